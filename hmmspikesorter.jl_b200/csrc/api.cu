@@ -1,0 +1,508 @@
+// api.cu -- the extern "C" boundary of libhmmcuda.so (include/hmmcuda.h).
+// Plain pointers and sizes in, status codes out; every exception is caught
+// here and turned into a code + thread-local message.  There is no CPU path:
+// without a device every compute entry point returns HMM_ENODEV.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "engines.h"
+
+using namespace hmm;
+
+static thread_local std::string g_err = "";
+static std::mutex g_entry;  // the library serialises concurrent entry (SURVEY 8b "Threading")
+
+static int set_err(int code, const std::string &m) {
+    g_err = m;
+    return code;
+}
+
+template <class F>
+static int guarded(F &&f) {
+    std::lock_guard<std::mutex> lk(g_entry);
+    try {
+        g_err.clear();
+        f();
+        return HMM_OK;
+    } catch (const Error &e) {
+        cudaGetLastError();
+        return set_err(e.code, e.msg);
+    } catch (const std::bad_alloc &) {
+        return set_err(HMM_ENOMEM, "host allocation failed");
+    } catch (const std::exception &e) {
+        return set_err(HMM_ECUDA, e.what());
+    }
+}
+
+static void require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        fail(HMM_ENODEV, "no CUDA device available (libhmmcuda has no CPU fallback): %s",
+             e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+}
+
+// Copies `bytes` from a host pointer of unknown kind (pageable or pinned) to the device.
+static void h2d(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    HMM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+}
+static void d2h(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    HMM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+}
+
+extern "C" {
+
+int hmm_version(void) { return 100; /* 0.1.0 */ }
+const char *hmm_last_error(void) { return g_err.c_str(); }
+
+int hmm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int hmm_set_device(int device) {
+    return guarded([&] {
+        require_device();
+        HMM_CUDA(cudaSetDevice(device));
+    });
+}
+
+int hmm_get_device(void) {
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return d;
+}
+
+int hmm_set_ring_params(int64_t chunk_len, int64_t warmup) {
+    if (chunk_len < 0 || warmup < 0) return set_err(HMM_EINVAL, "negative ring parameter");
+    ring_config().chunk_len = chunk_len;
+    ring_config().warmup = warmup;
+    return HMM_OK;
+}
+
+int hmm_host_alloc(void **ptr_out, uint64_t bytes) {
+    return guarded([&] {
+        require_device();
+        if (!ptr_out) fail(HMM_EINVAL, "null ptr_out");
+        HMM_CUDA(cudaHostAlloc(ptr_out, bytes ? bytes : 1, cudaHostAllocDefault));
+    });
+}
+int hmm_host_free(void *ptr) {
+    return guarded([&] {
+        if (ptr) HMM_CUDA(cudaFreeHost(ptr));
+    });
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Viterbi
+// ---------------------------------------------------------------------------
+namespace {
+
+struct BatchModels {
+    std::vector<HostModel> models;
+    FaithfulLayout layout;
+    char *blob_dev = nullptr;
+};
+
+void build_models(int C, const int16_t *states, int states_shared, int N, int K, int nstates, const hmm_trans *tr,
+                  int64_t ntrans, const double *mu, const double *sigma, BatchModels &B, cudaStream_t st) {
+    B.models.resize(C);
+    for (int c = 0; c < C; c++) {
+        const int16_t *stc = states_shared ? states : states + (size_t)c * N * nstates;
+        analyse_model(stc, N, K, nstates, tr + (size_t)c * ntrans, ntrans, mu + (size_t)c * K * N, sigma[c],
+                      B.models[c]);
+        if (c > 0 && (B.models[c].in_ptr != B.models[0].in_ptr || B.models[c].in_src != B.models[0].in_src))
+            fail(HMM_EINVAL, "channel %d has a different transition topology than channel 0", c);
+    }
+    B.layout = faithful_layout(nstates, ntrans);
+    std::vector<char> host((size_t)C * B.layout.bytes, 0);
+    for (int c = 0; c < C; c++) faithful_pack(B.models[c], B.layout, host.data() + (size_t)c * B.layout.bytes);
+    B.blob_dev = (char *)workspace().get(Workspace::MODEL, host.size());
+    // small pageable copy: synchronous w.r.t. the host buffer, so `host` may die afterwards
+    HMM_CUDA(cudaMemcpyAsync(B.blob_dev, host.data(), host.size(), cudaMemcpyHostToDevice, st));
+    HMM_CUDA(cudaStreamSynchronize(st));
+}
+
+// Core decode on device-resident y / x.
+void viterbi_core(const double *y_dev, int64_t T, int C, BatchModels &B, int16_t *x_dev, double *ll_host,
+                  double *T1_dev, int16_t *T2_dev, int mode, cudaStream_t st, hmm_info *info) {
+    const HostModel &M0 = B.models[0];
+    bool all_ring = true;
+    for (auto &m : B.models) all_ring = all_ring && m.is_ring;
+    bool want_trellis = T1_dev || T2_dev;
+    int engine;
+    if (mode == HMM_MODE_FAITHFUL || want_trellis)
+        engine = HMM_MODE_FAITHFUL;
+    else if (mode == HMM_MODE_RING) {
+        if (!all_ring) fail(HMM_EUNSUPPORTED, "HMM_MODE_RING requested but the model is not a non-overlap ring model");
+        if (!ring_supported(M0, T)) fail(HMM_EUNSUPPORTED, "HMM_MODE_RING: sequence too short or K/N outside the ring engine's range");
+        engine = HMM_MODE_RING;
+    } else
+        engine = (all_ring && ring_supported(M0, T) && T >= 32768) ? HMM_MODE_RING : HMM_MODE_FAITHFUL;
+    double *ll_dev = nullptr;
+    if (ll_host) ll_dev = (double *)workspace().get(Workspace::SCRATCH, sizeof(double) * C);
+    if (info) info->engine = engine;
+    if (engine == HMM_MODE_FAITHFUL)
+        faithful_viterbi_run(y_dev, T, T, C, B.layout, B.blob_dev, M0, x_dev, T, ll_dev, T1_dev, T2_dev,
+                             want_trellis ? T : 0, false, nullptr, st, info);
+    else
+        ring_viterbi_run(y_dev, T, T, C, B.models, B.layout, B.blob_dev, x_dev, T, ll_dev, st, info);
+    if (ll_host) d2h(ll_host, ll_dev, sizeof(double) * C, st);
+}
+
+int viterbi_host(const double *y, int64_t T, int C, const int16_t *states, int states_shared, int N, int K,
+                 int nstates, const hmm_trans *tr, int64_t ntrans, const double *mu, const double *sigma,
+                 int16_t *x_out, double *ll_out, int16_t *T2_out, double *T1_out, int mode, hmm_info *info) {
+    return guarded([&] {
+        if (info) memset(info, 0, sizeof *info);
+        if (!y || !x_out || !sigma) fail(HMM_EINVAL, "null y / x_out / sigma");
+        if (T < 1 || C < 1) fail(HMM_EINVAL, "T and C must be positive");
+        if ((T1_out || T2_out) && C != 1) fail(HMM_EINVAL, "trellis output is single-channel");
+        require_device();
+        cudaStream_t st = main_stream();
+        Workspace &ws = workspace();
+        Timer tall(st);
+        tall.start();
+        BatchModels B;
+        build_models(C, states, states_shared, N, K, nstates, tr, ntrans, mu, sigma, B, st);
+        double *y_dev = (double *)ws.get(Workspace::Y, sizeof(double) * (size_t)T * C);
+        int16_t *x_dev = (int16_t *)ws.get(Workspace::X, sizeof(int16_t) * (size_t)T * C);
+        double *T1_dev = T1_out ? (double *)ws.get(Workspace::T1, sizeof(double) * (size_t)T * nstates) : nullptr;
+        int16_t *T2_dev = T2_out ? (int16_t *)ws.get(Workspace::T2, sizeof(int16_t) * (size_t)T * nstates) : nullptr;
+        h2d(y_dev, y, sizeof(double) * (size_t)T * C, st);
+        Timer tk(st);
+        tk.start();
+        viterbi_core(y_dev, T, C, B, x_dev, ll_out, T1_dev, T2_dev, mode, st, info);
+        tk.stop();
+        d2h(x_out, x_dev, sizeof(int16_t) * (size_t)T * C, st);
+        if (T1_out) d2h(T1_out, T1_dev, sizeof(double) * (size_t)T * nstates, st);
+        if (T2_out) d2h(T2_out, T2_dev, sizeof(int16_t) * (size_t)T * nstates, st);
+        tall.stop();
+        HMM_CUDA(cudaStreamSynchronize(st));
+        if (info) {
+            info->device_ms = tall.ms();
+            info->kernel_ms = tk.ms();
+        }
+    });
+}
+
+}  // namespace
+
+extern "C" {
+
+int hmm_viterbi_f64(const double *y, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                    const hmm_trans *tr, int64_t ntrans, const double *mu, double sigma, int16_t *x_out,
+                    double *ll_out, int16_t *T2_out, double *T1_out) {
+    return viterbi_host(y, T, 1, states, 1, N, K, nstates, tr, ntrans, mu, &sigma, x_out, ll_out, T2_out, T1_out,
+                        HMM_MODE_AUTO, nullptr);
+}
+
+int hmm_viterbi_ex_f64(const double *y, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                       const hmm_trans *tr, int64_t ntrans, const double *mu, double sigma, int16_t *x_out,
+                       double *ll_out, int16_t *T2_out, double *T1_out, int32_t mode, hmm_info *info) {
+    return viterbi_host(y, T, 1, states, 1, N, K, nstates, tr, ntrans, mu, &sigma, x_out, ll_out, T2_out, T1_out,
+                        mode, info);
+}
+
+int hmm_viterbi_batch_f64(const double *y, int64_t T, int32_t C, const int16_t *states, int32_t states_shared,
+                          int32_t N, int32_t K, int32_t nstates, const hmm_trans *tr, int64_t ntrans,
+                          const double *mu, const double *sigma, int16_t *x_out, double *ll_out, int32_t mode,
+                          hmm_info *info) {
+    return viterbi_host(y, T, C, states, states_shared, N, K, nstates, tr, ntrans, mu, sigma, x_out, ll_out, nullptr,
+                        nullptr, mode, info);
+}
+
+int hmm_viterbi_dev_f64(const double *y_dev, int64_t T, int32_t C, const int16_t *states, int32_t states_shared,
+                        int32_t N, int32_t K, int32_t nstates, const hmm_trans *tr, int64_t ntrans,
+                        const double *mu, const double *sigma, int16_t *x_dev, double *ll_out, int32_t mode,
+                        hmm_info *info) {
+    return guarded([&] {
+        if (info) memset(info, 0, sizeof *info);
+        if (!y_dev || !x_dev || !sigma) fail(HMM_EINVAL, "null y_dev / x_dev / sigma");
+        if (T < 1 || C < 1) fail(HMM_EINVAL, "T and C must be positive");
+        require_device();
+        cudaStream_t st = main_stream();
+        BatchModels B;
+        build_models(C, states, states_shared, N, K, nstates, tr, ntrans, mu, sigma, B, st);
+        Timer tk(st);
+        tk.start();
+        viterbi_core(y_dev, T, C, B, x_dev, ll_out, nullptr, nullptr, mode, st, info);
+        tk.stop();
+        HMM_CUDA(cudaStreamSynchronize(st));
+        if (info) info->device_ms = info->kernel_ms = tk.ms();
+    });
+}
+
+// ---------------------------------------------------------------------------
+// forward / backward (dense output)
+// ---------------------------------------------------------------------------
+static int fb_host(bool backward, const double *V, int64_t T, const int16_t *states, int32_t N, int32_t K,
+                   int32_t nstates, const hmm_trans *tr, int64_t ntrans, const double *mu, double sigma, double *out) {
+    return guarded([&] {
+        if (!V || !out) fail(HMM_EINVAL, "null V / output");
+        if (T < 1) fail(HMM_EINVAL, "T must be positive");
+        require_device();
+        cudaStream_t st = main_stream();
+        Workspace &ws = workspace();
+        BatchModels B;
+        build_models(1, states, 1, N, K, nstates, tr, ntrans, mu, &sigma, B, st);
+        double *V_dev = (double *)ws.get(Workspace::Y, sizeof(double) * (size_t)T);
+        double *o_dev = (double *)ws.get(backward ? Workspace::BETA : Workspace::ALPHA,
+                                         sizeof(double) * (size_t)T * nstates);
+        h2d(V_dev, V, sizeof(double) * (size_t)T, st);
+        faithful_fb_run(backward, V_dev, T, B.layout, B.blob_dev, B.models[0], o_dev, st);
+        d2h(out, o_dev, sizeof(double) * (size_t)T * nstates, st);
+        HMM_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int hmm_forward_f64(const double *V, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                    const hmm_trans *tr, int64_t ntrans, const double *mu, double sigma, double *alpha_out) {
+    return fb_host(false, V, T, states, N, K, nstates, tr, ntrans, mu, sigma, alpha_out);
+}
+int hmm_backward_f64(const double *V, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                     const hmm_trans *tr, int64_t ntrans, const double *mu, double sigma, double *beta_out) {
+    return fb_host(true, V, T, states, N, K, nstates, tr, ntrans, mu, sigma, beta_out);
+}
+
+// ---------------------------------------------------------------------------
+// update / E-M step
+// ---------------------------------------------------------------------------
+static void export_em(const EmResult &r, const HostModel &M, double *mu_inout, double *sigma_inout, double *lp_out,
+                      double *pp_out, double *loglik_out) {
+    memcpy(mu_inout, r.mu.data(), sizeof(double) * (size_t)M.K * M.N);  // in place, src/baumwelch.jl:268
+    *sigma_inout = r.sigma;
+    if (lp_out) memcpy(lp_out, r.lp.data(), sizeof(double) * r.lp.size());
+    if (pp_out) memcpy(pp_out, r.pp.data(), sizeof(double) * M.nstates);
+    if (loglik_out) *loglik_out = r.loglik;
+}
+
+int hmm_update_f64(const double *alpha, const double *beta, int64_t T, const int16_t *states, int32_t N, int32_t K,
+                   int32_t nstates, const hmm_trans *tr, int64_t ntrans, double *mu_inout, double *sigma_inout,
+                   const double *x, double *lp_out, double *pp_out) {
+    return guarded([&] {
+        if (!alpha || !beta || !x || !mu_inout || !sigma_inout) fail(HMM_EINVAL, "null argument");
+        if (T < 2) fail(HMM_EINVAL, "T must be at least 2");
+        require_device();
+        cudaStream_t st = main_stream();
+        Workspace &ws = workspace();
+        HostModel M;
+        analyse_model(states, N, K, nstates, tr, ntrans, mu_inout, *sigma_inout, M);
+        size_t nb = sizeof(double) * (size_t)T * nstates;
+        double *a_dev = (double *)ws.get(Workspace::ALPHA, nb);
+        double *b_dev = (double *)ws.get(Workspace::BETA, nb);
+        double *x_dev = (double *)ws.get(Workspace::Y, sizeof(double) * (size_t)T);
+        h2d(a_dev, alpha, nb, st);
+        h2d(b_dev, beta, nb, st);
+        h2d(x_dev, x, sizeof(double) * (size_t)T, st);
+        EmResult r;
+        dense_update_run(a_dev, b_dev, x_dev, T, M, states, r, st);
+        export_em(r, M, mu_inout, sigma_inout, lp_out, pp_out, nullptr);
+    });
+}
+
+static void em_step_dev(const double *X_dev, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                        const hmm_trans *tr, int64_t ntrans, double *mu_inout, double *sigma_inout, double *lp_out,
+                        double *pp_out, double *loglik_out, int mode, cudaStream_t st, hmm_info *info) {
+    HostModel M;
+    analyse_model(states, N, K, nstates, tr, ntrans, mu_inout, *sigma_inout, M);
+    bool ring = M.is_ring && ring_supported(M, T);
+    if (mode == HMM_MODE_RING && !ring)
+        fail(HMM_EUNSUPPORTED, "HMM_MODE_RING requested but the model/sequence is outside the ring engine's range");
+    if (mode == HMM_MODE_FAITHFUL) ring = false;
+    EmResult r;
+    if (ring) {
+        if (info) info->engine = HMM_MODE_RING;
+        ring_em_run(X_dev, T, M, r, st, info);
+    } else {
+        // generic path: dense alpha/beta on the device (never cross the boundary), then update
+        if (info) info->engine = HMM_MODE_FAITHFUL;
+        Workspace &ws = workspace();
+        size_t nb = sizeof(double) * (size_t)T * nstates;
+        double *a_dev = (double *)ws.get(Workspace::ALPHA, nb);
+        double *b_dev = (double *)ws.get(Workspace::BETA, nb);
+        FaithfulLayout L = faithful_layout(nstates, ntrans);
+        std::vector<char> host(L.bytes, 0);
+        faithful_pack(M, L, host.data());
+        char *blob = (char *)ws.get(Workspace::MODEL, host.size());
+        HMM_CUDA(cudaMemcpyAsync(blob, host.data(), host.size(), cudaMemcpyHostToDevice, st));
+        HMM_CUDA(cudaStreamSynchronize(st));
+        faithful_fb_run(false, X_dev, T, L, blob, M, a_dev, st);
+        faithful_fb_run(true, X_dev, T, L, blob, M, b_dev, st);
+        dense_update_run(a_dev, b_dev, X_dev, T, M, states, r, st);
+        if (info) info->kernel_launches += 4;
+    }
+    export_em(r, M, mu_inout, sigma_inout, lp_out, pp_out, loglik_out);
+}
+
+int hmm_em_step_ex_f64(const double *X, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                       const hmm_trans *tr, int64_t ntrans, double *mu_inout, double *sigma_inout, double *lp_out,
+                       double *pp_out, double *loglik_out, int32_t mode, hmm_info *info) {
+    return guarded([&] {
+        if (info) memset(info, 0, sizeof *info);
+        if (!X || !mu_inout || !sigma_inout) fail(HMM_EINVAL, "null argument");
+        if (T < 2) fail(HMM_EINVAL, "T must be at least 2");
+        require_device();
+        cudaStream_t st = main_stream();
+        Timer tall(st);
+        tall.start();
+        double *X_dev = (double *)workspace().get(Workspace::Y, sizeof(double) * (size_t)T);
+        h2d(X_dev, X, sizeof(double) * (size_t)T, st);
+        em_step_dev(X_dev, T, states, N, K, nstates, tr, ntrans, mu_inout, sigma_inout, lp_out, pp_out, loglik_out,
+                    mode, st, info);
+        tall.stop();
+        HMM_CUDA(cudaStreamSynchronize(st));
+        if (info) info->device_ms = tall.ms();
+    });
+}
+
+int hmm_em_step_f64(const double *X, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                    const hmm_trans *tr, int64_t ntrans, double *mu_inout, double *sigma_inout, double *lp_out,
+                    double *pp_out, double *loglik_out) {
+    return hmm_em_step_ex_f64(X, T, states, N, K, nstates, tr, ntrans, mu_inout, sigma_inout, lp_out, pp_out,
+                              loglik_out, HMM_MODE_AUTO, nullptr);
+}
+
+struct hmm_train_ctx {
+    double *X_dev = nullptr;
+    int64_t T = 0;
+    bool owned = false;
+    int device = 0;
+};
+
+int hmm_train_create(const double *X, int64_t T, hmm_train_ctx **ctx_out) {
+    return guarded([&] {
+        if (!X || !ctx_out || T < 2) fail(HMM_EINVAL, "bad arguments");
+        require_device();
+        hmm_train_ctx *c = new hmm_train_ctx;
+        c->T = T;
+        c->owned = true;
+        HMM_CUDA(cudaGetDevice(&c->device));
+        cudaError_t e = cudaMalloc(&c->X_dev, sizeof(double) * (size_t)T);
+        if (e != cudaSuccess) {
+            delete c;
+            cudaGetLastError();
+            fail(HMM_ENOMEM, "device allocation failed: %s", cudaGetErrorString(e));
+        }
+        cudaStream_t st = main_stream();
+        h2d(c->X_dev, X, sizeof(double) * (size_t)T, st);
+        HMM_CUDA(cudaStreamSynchronize(st));
+        *ctx_out = c;
+    });
+}
+
+int hmm_train_create_dev(const double *X_dev, int64_t T, hmm_train_ctx **ctx_out) {
+    return guarded([&] {
+        if (!X_dev || !ctx_out || T < 2) fail(HMM_EINVAL, "bad arguments");
+        require_device();
+        hmm_train_ctx *c = new hmm_train_ctx;
+        c->T = T;
+        c->X_dev = const_cast<double *>(X_dev);
+        HMM_CUDA(cudaGetDevice(&c->device));
+        *ctx_out = c;
+    });
+}
+
+int hmm_train_em_step(hmm_train_ctx *ctx, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                      const hmm_trans *tr, int64_t ntrans, double *mu_inout, double *sigma_inout, double *lp_out,
+                      double *pp_out, double *loglik_out, hmm_info *info) {
+    return guarded([&] {
+        if (info) memset(info, 0, sizeof *info);
+        if (!ctx || !mu_inout || !sigma_inout) fail(HMM_EINVAL, "null argument");
+        require_device();
+        cudaStream_t st = main_stream();
+        Timer tall(st);
+        tall.start();
+        em_step_dev(ctx->X_dev, ctx->T, states, N, K, nstates, tr, ntrans, mu_inout, sigma_inout, lp_out, pp_out,
+                    loglik_out, HMM_MODE_AUTO, st, info);
+        tall.stop();
+        HMM_CUDA(cudaStreamSynchronize(st));
+        if (info) info->device_ms = tall.ms();
+    });
+}
+
+int hmm_train_destroy(hmm_train_ctx *ctx) {
+    return guarded([&] {
+        if (!ctx) return;
+        if (ctx->owned && ctx->X_dev) cudaFree(ctx->X_dev);
+        delete ctx;
+    });
+}
+
+// ---------------------------------------------------------------------------
+// reconstruct / unroll
+// ---------------------------------------------------------------------------
+static void check_model_small(const int16_t *states, int N, int K, int nstates, const double *mu) {
+    if (!states || !mu) fail(HMM_EINVAL, "null model array");
+    if (N < 1 || K < 1 || nstates < 1 || nstates > 32767) fail(HMM_EINVAL, "bad N/K/nstates");
+    for (size_t i = 0; i < (size_t)N * nstates; i++)
+        if (states[i] < 1 || states[i] > K) fail(HMM_EINVAL, "states[%zu]=%d outside 1..K=%d", i, (int)states[i], K);
+}
+
+int hmm_reconstruct_f64(const int16_t *x, int64_t T, const int16_t *states, int32_t N, int32_t nstates,
+                        const double *mu, int32_t K, double *Y_out) {
+    return guarded([&] {
+        if (!x || !Y_out) fail(HMM_EINVAL, "null x / Y_out");
+        if (T < 0) fail(HMM_EINVAL, "negative T");
+        check_model_small(states, N, K, nstates, mu);
+        require_device();
+        if (T == 0) return;
+        cudaStream_t st = main_stream();
+        Workspace &ws = workspace();
+        std::vector<double> m;
+        state_means(states, N, K, nstates, mu, m);
+        int16_t *x_dev = (int16_t *)ws.get(Workspace::X, sizeof(int16_t) * (size_t)T);
+        double *Y_dev = (double *)ws.get(Workspace::Y, sizeof(double) * (size_t)T);
+        h2d(x_dev, x, sizeof(int16_t) * (size_t)T, st);
+        reconstruct_run(x_dev, T, m, Y_dev, st);
+        d2h(Y_out, Y_dev, sizeof(double) * (size_t)T, st);
+        HMM_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int hmm_reconstruct_dev_f64(const int16_t *x_dev, int64_t T, const int16_t *states, int32_t N, int32_t nstates,
+                            const double *mu, int32_t K, double *Y_dev) {
+    return guarded([&] {
+        if (!x_dev || !Y_dev) fail(HMM_EINVAL, "null x_dev / Y_dev");
+        if (T < 0) fail(HMM_EINVAL, "negative T");
+        check_model_small(states, N, K, nstates, mu);
+        require_device();
+        if (T == 0) return;
+        std::vector<double> m;
+        state_means(states, N, K, nstates, mu, m);
+        reconstruct_run(x_dev, T, m, Y_dev, main_stream());
+    });
+}
+
+int hmm_unroll_mlseq_i16(const int16_t *x, int64_t T, const int16_t *states, int32_t N, int32_t nstates,
+                         int16_t *out) {
+    return guarded([&] {
+        if (!x || !out || !states) fail(HMM_EINVAL, "null argument");
+        if (T < 0 || N < 1 || nstates < 1) fail(HMM_EINVAL, "bad sizes");
+        require_device();
+        if (T == 0) return;
+        cudaStream_t st = main_stream();
+        Workspace &ws = workspace();
+        int16_t *x_dev = (int16_t *)ws.get(Workspace::X, sizeof(int16_t) * (size_t)T);
+        int16_t *o_dev = (int16_t *)ws.get(Workspace::T2, sizeof(int16_t) * (size_t)T * N);
+        h2d(x_dev, x, sizeof(int16_t) * (size_t)T, st);
+        unroll_run(x_dev, T, states, N, nstates, o_dev, st);
+        d2h(out, o_dev, sizeof(int16_t) * (size_t)T * N, st);
+        HMM_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+}  // extern "C"

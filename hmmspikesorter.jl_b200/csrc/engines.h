@@ -1,0 +1,61 @@
+// engines.h -- internal interfaces between the C-ABI layer (api.cu) and the
+// kernel translation units.
+#pragma once
+#include <cstring>
+
+#include "common.h"
+
+namespace hmm {
+
+// ---- faithful engine (faithful.cu) ----------------------------------------
+struct FaithfulLayout {  // byte offsets inside one channel's device model blob
+    size_t scal, m, in_lp, out_lp, in_ptr, in_src, out_ptr, out_dst, dec_slot, static_pred, bytes;
+};
+FaithfulLayout faithful_layout(int nstates, int64_t ntrans);
+void faithful_pack(const HostModel &M, const FaithfulLayout &L, char *dst);
+size_t faithful_smem_bytes(int ns, int64_t nt);
+
+// Decode C channels; y_dev [T x C] with column stride y_stride.  When
+// forward_only, stops after the forward sweep (used for the ring prologue).
+void faithful_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, const FaithfulLayout &L,
+                          const char *blob_dev, const HostModel &M0, int16_t *x_dev, int64_t x_stride, double *ll_dev,
+                          double *T1_dev, int16_t *T2_dev, int64_t trellis_cols, bool forward_only,
+                          double *final_col_dev, cudaStream_t st, hmm_info *info);
+void path_score_run(const double *y_dev, int64_t T, int64_t y_stride, int C, const FaithfulLayout &L,
+                    const char *blob_dev, const HostModel &M0, const int16_t *x_dev, int64_t x_stride, double *ll_dev,
+                    cudaStream_t st, hmm_info *info);
+void faithful_fb_run(bool backward, const double *V_dev, int64_t T, const FaithfulLayout &L, const char *blob_dev,
+                     const HostModel &M, double *out_dev, cudaStream_t st);
+
+// ---- ring engine, Viterbi (ring_viterbi.cu) --------------------------------
+struct RingConfig {
+    int64_t chunk_len = 0;  // 0 = auto
+    int64_t warmup = 0;     // 0 = default
+};
+RingConfig &ring_config();
+bool ring_supported(const HostModel &M, int64_t T);
+// models[C] must share topology (N, K).  Leaves x in x_dev; ll via path scoring.
+void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, const std::vector<HostModel> &models,
+                      const FaithfulLayout &L, const char *blob_dev, int16_t *x_dev, int64_t x_stride, double *ll_dev,
+                      cudaStream_t st, hmm_info *info);
+
+// ---- ring engine, E/M step (ring_em.cu) ------------------------------------
+struct EmResult {
+    std::vector<double> lp;  // [N]
+    std::vector<double> pp;  // [nstates] = gamma[:,1] (log)
+    std::vector<double> mu;  // [K x N]
+    double sigma = 0, loglik = 0;
+};
+void ring_em_run(const double *X_dev, int64_t T, const HostModel &M, EmResult &out, cudaStream_t st, hmm_info *info);
+
+// ---- generic E/M pieces (update.cu) ----------------------------------------
+// update() on dense alpha/beta (device pointers), src/baumwelch.jl:205-309
+void dense_update_run(const double *alpha_dev, const double *beta_dev, const double *x_dev, int64_t T,
+                      const HostModel &M, const int16_t *states_host, EmResult &out, cudaStream_t st);
+
+// ---- reconstruct (reconstruct.cu) ------------------------------------------
+void reconstruct_run(const int16_t *x_dev, int64_t T, const std::vector<double> &m, double *Y_dev, cudaStream_t st);
+void unroll_run(const int16_t *x_dev, int64_t T, const int16_t *states_host, int N, int nstates, int16_t *out_dev,
+                cudaStream_t st);
+
+}  // namespace hmm

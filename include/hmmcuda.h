@@ -1,0 +1,178 @@
+/*
+ * hmmcuda.h -- C ABI of libhmmcuda.so: the B200-native HMM inference hot path
+ * of grero/HMMSpikeSorter.jl (Viterbi decode, Baum-Welch E/M step,
+ * reconstruct_signal) behind the reference's own function signatures.
+ *
+ * The reference is pure Julia and has no FFI seam; these entry points are
+ * what a `ccall` shim replacing the Julia methods binds.
+ * Every array is caller-owned, column-major, with 1-based state indices,
+ * exactly as the Julia objects lay them out:
+ *
+ *   states  Int16  [N x nstates]   StateMatrix.states       (src/types.jl:2,150)
+ *   tr      24-byte records {Int64 src, Int64 dst, Float64 lp}, sorted by
+ *           (src, dst)             StateMatrix.transitions  (src/types.jl:3,115-127)
+ *   mu      Float64 [K x N]        templates, row 1 = silent (src/types.jl:17)
+ *   N = neurons, K = states per ring incl. the silent one   (src/types.jl:150)
+ *
+ * All functions return 0 on success, else an HMM_E* code; hmm_last_error()
+ * returns a thread-local message.  There is NO CPU fallback: without a CUDA
+ * device every compute entry point fails with HMM_ENODEV.
+ */
+#ifndef HMMCUDA_H
+#define HMMCUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMM_OK 0
+#define HMM_EINVAL 1       /* shape / index / ordering violation  -> Julia ArgumentError */
+#define HMM_ECUDA 2        /* CUDA runtime error                  -> Julia ErrorException */
+#define HMM_ENOMEM 3       /* host or device allocation failed */
+#define HMM_ENODEV 4       /* no CUDA device */
+#define HMM_EUNSUPPORTED 5 /* valid request outside what this build implements */
+
+/* == Julia Tuple{Int64,Int64,Float64}; src/types.jl:3 */
+typedef struct hmm_trans {
+    int64_t src; /* 1-based */
+    int64_t dst; /* 1-based */
+    double lp;
+} hmm_trans;
+
+/* Decode engines (hmm_viterbi_ex_f64 `mode`). */
+#define HMM_MODE_AUTO 0     /* ring fast path when the model is a non-overlap ring model and T is long, else faithful */
+#define HMM_MODE_FAITHFUL 1 /* sequential kernel in the reference's exact operation order (any StateMatrix) */
+#define HMM_MODE_RING 2     /* time-parallel ring kernels; HMM_EUNSUPPORTED if the model is not ring-structured */
+
+/* Diagnostics of one decode / E-M call (all optional outputs). */
+typedef struct hmm_info {
+    int32_t engine;           /* HMM_MODE_FAITHFUL or HMM_MODE_RING actually used */
+    int32_t n_chunks;         /* time chunks per channel (ring engine) */
+    int32_t fwd_repaired;     /* chunks whose speculative forward start failed verification and were re-run */
+    int32_t bwd_repaired;     /* same for the backward / traceback pass */
+    int64_t kernel_launches;  /* kernels launched by this call */
+    double device_ms;         /* CUDA-event time of the device work (H2D/D2H included for host-pointer entry points) */
+    double kernel_ms;         /* CUDA-event time of the kernels only */
+    double top_kernel_ms;     /* time of the dominant kernel (ring forward / E-step forward) */
+} hmm_info;
+
+/* ---- library / device ---------------------------------------------------- */
+int hmm_version(void);              /* major*10000 + minor*100 + patch */
+const char *hmm_last_error(void);   /* thread-local, never NULL */
+int hmm_device_count(void);         /* number of CUDA devices, 0 if none */
+int hmm_set_device(int device);     /* device used by subsequent calls from this thread */
+int hmm_get_device(void);
+
+/* Tunables of the ring engine (0 keeps the default): chunk length and
+ * speculative warm-up / look-ahead, in samples (rounded to multiples of 256). */
+int hmm_set_ring_params(int64_t chunk_len, int64_t warmup);
+
+/* ---- Viterbi ------------------------------------------------------------- */
+/*
+ * viterbi(y, lA::StateMatrix, mu, sigma) -> (x, ll)       src/viterbi.jl:44-98
+ * T2_out / T1_out: nullable [nstates x T]; when given, the dense trellis of
+ * src/viterbi.jl:52-53 is materialised (the `(x, T2, T1)` form of
+ * README.md:34).  Host pointers.
+ */
+int hmm_viterbi_f64(const double *y, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                    const hmm_trans *tr, int64_t ntrans, const double *mu, double sigma, int16_t *x_out,
+                    double *ll_out, int16_t *T2_out, double *T1_out);
+
+/* Same, with engine selection and diagnostics. */
+int hmm_viterbi_ex_f64(const double *y, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                       const hmm_trans *tr, int64_t ntrans, const double *mu, double sigma, int16_t *x_out,
+                       double *ll_out, int16_t *T2_out, double *T1_out, int32_t mode, hmm_info *info);
+
+/*
+ * Batched decode of C independent channels (BASELINE config 4; the reference
+ * sorts one channel per process, src/hmmsort.jl:79-83).  y is [T x C]
+ * column-major; every per-model array carries a leading channel stride:
+ * states [N x nstates x C] (or one shared copy if states_shared != 0),
+ * tr [ntrans x C], mu [K x N x C], sigma [C]; outputs x [T x C], ll [C].
+ * All channels share N, K, nstates, ntrans (same topology, own weights).
+ */
+int hmm_viterbi_batch_f64(const double *y, int64_t T, int32_t C, const int16_t *states, int32_t states_shared,
+                          int32_t N, int32_t K, int32_t nstates, const hmm_trans *tr, int64_t ntrans,
+                          const double *mu, const double *sigma, int16_t *x_out, double *ll_out, int32_t mode,
+                          hmm_info *info);
+
+/* Device-resident variant: y_dev [T x C] and x_dev [T x C] are DEVICE
+ * pointers on the current device (model arrays stay host pointers; they are
+ * tiny).  ll_out is a host pointer (nullable).  Used when the recording is
+ * already in HBM (bench `value`, multi-GPU orchestration). */
+int hmm_viterbi_dev_f64(const double *y_dev, int64_t T, int32_t C, const int16_t *states, int32_t states_shared,
+                        int32_t N, int32_t K, int32_t nstates, const hmm_trans *tr, int64_t ntrans,
+                        const double *mu, const double *sigma, int16_t *x_dev, double *ll_out, int32_t mode,
+                        hmm_info *info);
+
+/* ---- Baum-Welch ---------------------------------------------------------- */
+/* forward(V, lA, mu, sigma) -> alpha [nstates x T]          src/baumwelch.jl:25-51 */
+int hmm_forward_f64(const double *V, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                    const hmm_trans *tr, int64_t ntrans, const double *mu, double sigma, double *alpha_out);
+
+/* backward(V, lA, mu, sigma) -> beta [nstates x T]          src/baumwelch.jl:73-98 */
+int hmm_backward_f64(const double *V, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                     const hmm_trans *tr, int64_t ntrans, const double *mu, double sigma, double *beta_out);
+
+/*
+ * update(alpha, beta, lA, mu, sigma, x) -> (lA_new, mu, sigma)   src/baumwelch.jl:205-309
+ * mu_inout is overwritten in place like the reference's fill!(mu, 0.0)
+ * (src/baumwelch.jl:268); *sigma_inout receives the new sigma.  The new
+ * StateMatrix is rebuilt by the caller (the unchanged Julia constructor,
+ * src/types.jl:148-151) from lp_out [nxi-1] (= xb[2:end], :264-265, nxi =
+ * number of transitions out of state 1; == N for non-overlap models) and
+ * pp_out [nstates] (= gamma[:,1], :263).
+ */
+int hmm_update_f64(const double *alpha, const double *beta, int64_t T, const int16_t *states, int32_t N, int32_t K,
+                   int32_t nstates, const hmm_trans *tr, int64_t ntrans, double *mu_inout, double *sigma_inout,
+                   const double *x, double *lp_out, double *pp_out);
+
+/*
+ * One fused E/M step: train_model(X, lA, mu0, sigma0) of src/baumwelch.jl:362-370
+ * without alpha/beta/gamma crossing the boundary.  loglik_out (nullable)
+ * receives log p(X | model) = LSE_j alpha[j,T] (not returned by the
+ * reference).
+ */
+int hmm_em_step_f64(const double *X, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                    const hmm_trans *tr, int64_t ntrans, double *mu_inout, double *sigma_inout, double *lp_out,
+                    double *pp_out, double *loglik_out);
+
+int hmm_em_step_ex_f64(const double *X, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                       const hmm_trans *tr, int64_t ntrans, double *mu_inout, double *sigma_inout, double *lp_out,
+                       double *pp_out, double *loglik_out, int32_t mode, hmm_info *info);
+
+/*
+ * Device-resident training context: keeps X in HBM across the E/M
+ * iterations of train_model's outer loop (src/baumwelch.jl:324-354), so each
+ * iteration moves only the model (KBs) across PCIe.  The host loop (callback,
+ * yield, merge/prune) stays with the caller.
+ */
+typedef struct hmm_train_ctx hmm_train_ctx;
+int hmm_train_create(const double *X, int64_t T, hmm_train_ctx **ctx_out);          /* X: host pointer, copied once */
+int hmm_train_create_dev(const double *X_dev, int64_t T, hmm_train_ctx **ctx_out);  /* X_dev: device pointer, borrowed */
+int hmm_train_em_step(hmm_train_ctx *ctx, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                      const hmm_trans *tr, int64_t ntrans, double *mu_inout, double *sigma_inout, double *lp_out,
+                      double *pp_out, double *loglik_out, hmm_info *info);
+int hmm_train_destroy(hmm_train_ctx *ctx);
+
+/* ---- reconstruction ------------------------------------------------------ */
+/* reconstruct_signal(x, lA, mu, sigma) -> Y [T]             src/reconstruction.jl:1-9 */
+int hmm_reconstruct_f64(const int16_t *x, int64_t T, const int16_t *states, int32_t N, int32_t nstates,
+                        const double *mu, int32_t K, double *Y_out);
+/* device-pointer variant: x_dev, Y_dev on the current device */
+int hmm_reconstruct_dev_f64(const int16_t *x_dev, int64_t T, const int16_t *states, int32_t N, int32_t nstates,
+                            const double *mu, int32_t K, double *Y_dev);
+/* unroll_mlseq(mlseq, state_matrix) -> Int16 [N x T]        src/extraction.jl:4-13 */
+int hmm_unroll_mlseq_i16(const int16_t *x, int64_t T, const int16_t *states, int32_t N, int32_t nstates,
+                         int16_t *out);
+
+/* ---- pinned host memory for callers that want full PCIe rate ------------- */
+int hmm_host_alloc(void **ptr_out, uint64_t bytes);
+int hmm_host_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMMCUDA_H */
