@@ -29,7 +29,7 @@ from .synth import create_signal, create_spike_template, make_rng
 __all__ = [
     "StateMatrix", "viterbi", "viterbi_batch", "forward", "backward", "update", "train_model", "em_step",
     "reconstruct_signal", "unroll_mlseq", "TrainContext", "create_signal", "create_spike_template", "make_rng",
-    "HmmError", "HmmArgumentError", "device_count",
+    "HmmError", "HmmArgumentError", "device_count", "set_ring_params",
 ]
 
 i64, i32, f64 = C.c_int64, C.c_int32, C.c_double
@@ -41,6 +41,12 @@ def _p(a):
 
 def device_count() -> int:
     return int(lib().hmm_device_count())
+
+
+def set_ring_params(chunk_len: int = 0, warmup: int = 0) -> None:
+    """Tunables of the time-parallel ring engine (0 = default): chunk length and
+    speculative warm-up / look-ahead in samples."""
+    check(lib().hmm_set_ring_params(i64(chunk_len), i64(warmup)))
 
 
 def _model_args(lA, mu):

@@ -1,10 +1,854 @@
-// placeholder until the ring engine lands
-#include "engines.h"
+// ring_viterbi.cu -- time-parallel exact Viterbi decode for non-overlap ring
+// models (src/viterbi.jl:44-98 semantics).
+//
+// A recording is cut into chunks; ONE WARP owns one chunk and runs, without
+// any block-level synchronisation,
+//   (1) a register-blocked FP64 FIR (matched filter) F_i(t0) over a
+//       super-window of 32*R samples staged through shared memory with
+//       cp.async, then
+//   (2) the max-plus recursion over the N+1 decision states, 32 time steps at
+//       a time: one lane per step, a warp-shuffle prefix-max for the noise
+//       state, backpointers packed 4 bits per decision state (one u32 per
+//       step) plus one "noise entered from a tail" bit-mask word per 32 steps.
+// Chunks other than the first start SPECULATIVELY from an empty state W samples
+// early; afterwards every chunk boundary is VERIFIED (the speculative boundary
+// vector must equal the true one up to a constant) and any chunk that fails
+// is re-run from the true boundary vector, so the decode is exact, not
+// approximate.  The traceback is parallel in the same way (speculative
+// look-ahead + verification + repair).  The first L+1 samples are decoded by
+// the faithful engine in the reference's exact arithmetic, which reproduces
+// the structural ties at t=2.
+#include <cmath>
+#include <limits>
+
+#include "ring_common.cuh"
+
 namespace hmm {
-RingConfig &ring_config() { static RingConfig c; return c; }
-bool ring_supported(const HostModel &, int64_t) { return false; }
-void ring_viterbi_run(const double *, int64_t, int64_t, int, const std::vector<HostModel> &, const FaithfulLayout &,
-                      const char *, int16_t *, int64_t, double *, cudaStream_t, hmm_info *) {
-    fail(HMM_EUNSUPPORTED, "ring engine not built");
+
+RingConfig &ring_config() {
+    static RingConfig c;
+    return c;
 }
+
+bool ring_supported(const HostModel &M, int64_t T) {
+    return M.is_ring && M.N <= RING_MAX_N && (M.K - 1) <= RING_MAX_L && (M.K - 1) >= 2 && T >= 2048;
 }
+
+void ring_pack(const HostModel &M, const RingLayout &R, double *dst) {
+    const RingParams &P = M.ring;
+    const int N = R.N, L = R.L;
+    for (int i = 0; i < R.total; i++) dst[i] = 0.0;
+    const double m0 = M.m[0];
+    const double s2 = M.sigma * M.sigma;
+    for (int i = 0; i < N; i++) {
+        double bc = 0.0;
+        for (int r = 0; r < L; r++) {
+            double mi = M.m[1 + i * L + r];
+            double a = (mi - m0) / s2;
+            double b = (m0 - mi) * (m0 + mi) / (2 * s2);
+            double bw = b + (r > 0 ? P.w_c[(size_t)i * (L - 1) + r - 1] - P.w_nn : 0.0);
+            dst[R.A + r * R.NP + i] = a;
+            dst[R.BW + r * R.NP + i] = bw;
+            bc += bw;
+        }
+        dst[R.Bc + i] = bc;
+        dst[R.eG + i] = P.w_tn[i] - P.w_nn;
+        dst[R.eH + i] = P.w_nh[i] - P.w_nn;
+        for (int j = 0; j < N; j++)
+            dst[R.eT + j * R.NP + i] = (i == j) ? -std::numeric_limits<double>::infinity()
+                                                : P.w_th[(size_t)j * N + i] - P.w_nn;
+    }
+    const double LOG2PI = 0.9189385332046727;
+    dst[R.scal + 0] = P.w_nn;
+    dst[R.scal + 1] = (-LOG2PI) - M.lsig;
+    dst[R.scal + 2] = 2 * s2;
+    dst[R.scal + 3] = m0;
+    dst[R.scal + 4] = M.sigma;
+}
+
+// ---------------------------------------------------------------------------
+struct VitParams {
+    const double *y;       // [T x C]
+    int64_t T, y_stride;
+    const double *model;   // [C x RL.total]
+    RingLayout RL;
+    int64_t Lc, W;         // chunk length, warm-up / look-ahead (multiples of the super-window)
+    int nchunks;           // per channel
+    int ns;                // nstates
+    uint32_t *dec;         // [C x T]      packed decisions
+    uint32_t *nzmask;      // [C x ceil(T/32)]
+    double *SB, *EB;       // [C x nchunks x bvec]  boundary vectors (start: speculative, end: true)
+    int bvec;              // 1 + N*L
+    const double *T1pro;   // [C x ns x (L+1)] faithful prologue trellis
+    double *Pfin;          // [C x N x RING_Q]  P of the last steps (final chunk)
+    double *Gfin;          // [C]
+    int *fwd_flag;         // [C x nchunks] boundary mismatch flags
+    int *counters;         // [C x 4]: 0 fwd repaired, 1 trace repaired
+    // trace
+    const int16_t *T2pro;  // [C x ns x (L+1)]
+    const int16_t *xend;   // [C] final state (0-based)
+    int16_t *x;            // [T x C]
+    int64_t x_stride;
+    long long *own_start, *look_end;  // [C x nchunks] encoded states
+    int *tr_flag;
+};
+
+enum StartKind { START_PROLOGUE = 0, START_SPEC = 1, START_EXACT = 2 };
+
+template <int N, int R>
+struct WarpSmem {
+    using G = FirGeom<R>;
+    static constexpr int DOUBLES = G::YTILE + N * G::FTILE + N * RING_Q + 128;  // + Z scratch (prologue)
+};
+
+// Shared (per CTA) copy of the model: A interleaved [r][NP], then the DP constants.
+template <int N>
+struct CtaModel {
+    static constexpr int NP = (N + 1) & ~1;
+};
+
+// ---------------------------------------------------------------------------
+// One chunk, one warp.
+// ---------------------------------------------------------------------------
+template <int N, int R>
+__device__ void vit_process_chunk(const VitParams &p, int ch, int c, int kind, const double *mdl /*smem model*/,
+                                  double *ws /*per-warp smem*/) {
+    using G = FirGeom<R>;
+    constexpr int NP = (N + 1) & ~1;
+    const int lane = threadIdx.x & 31;
+    const RingLayout &RL = p.RL;
+    const int L = RL.L, LP = RL.LP;
+    const double NEG = -INFINITY;
+    double *ytile = ws;
+    double *fbuf = ytile + G::YTILE;
+    double *ring = fbuf + N * G::FTILE;
+    double *zs = ring + N * RING_Q;
+    const double *A = mdl + RL.A;
+    const double *Bc = mdl + RL.Bc, *eG = mdl + RL.eG, *eH = mdl + RL.eH, *eT = mdl + RL.eT;
+    const double *y = p.y + (size_t)ch * p.y_stride;
+    const int64_t T = p.T;
+    const int64_t s = (int64_t)c * p.Lc;                 // main range [s, e)
+    int64_t e = s + p.Lc;
+    const bool last = (c == p.nchunks - 1);
+    if (last || e > T) e = T;
+    int64_t base0;                                       // first super-window
+    int64_t tau_first;                                   // first DP step
+    double Gprev;
+    for (int k = lane; k < N * RING_Q; k += 32) ring[k] = NEG;
+    if (kind == START_PROLOGUE) {
+        base0 = 0;
+        tau_first = L + 1;
+        Gprev = 0;  // set after the first FIR
+    } else if (kind == START_SPEC) {
+        base0 = s - p.W;
+        if (base0 < 0) base0 = 0;
+        tau_first = base0;
+        Gprev = 0.0;
+    } else {
+        base0 = s;
+        tau_first = s;
+        const double *eb = p.EB + ((size_t)ch * p.nchunks + (c - 1)) * p.bvec;
+        Gprev = eb[0];
+        for (int k = lane; k < L; k += 32) {
+            int64_t t0 = s - L + k;
+            for (int j = 0; j < N; j++) ring[j * RING_Q + (int)(t0 & (RING_Q - 1))] = eb[1 + j * L + k];
+        }
+    }
+    __syncwarp();
+    uint32_t *dec = p.dec + (size_t)ch * T;
+    uint32_t *nzm = p.nzmask + (size_t)ch * ((T + 31) / 32);
+    const int Wd = L < 32 ? L : 32;
+    const int nsub = (32 + Wd - 1) / Wd;
+
+    for (int64_t b = base0; b < e; b += G::SW) {
+        // ---- stage y[b, b + SW + LP) into the transposed tile (zero beyond T) ----
+        {
+            const int need = G::SW + LP;
+            for (int k = lane; k < need; k += 32) {
+                int64_t g = b + k;
+                double *dst = ytile + (k & (R - 1)) * G::YS + (k >> G::LOGR);
+                if (g < T)
+                    cp_async8(dst, y + g);
+                else
+                    *dst = 0.0;
+            }
+            cp_async_commit();
+            cp_async_wait_all();
+            __syncwarp();
+        }
+        // ---- FIR: lane computes F_i(b + R*lane + j), j < R ----
+        {
+            double acc[N][R];
+#pragma unroll
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int j = 0; j < R; j++) acc[i][j] = Bc[i];
+            double w[R];
+#pragma unroll
+            for (int j = 0; j < R; j++) w[j] = ytile[j * G::YS + lane];  // elements R*lane + j
+            for (int r0 = 0; r0 < LP; r0 += R) {
+#pragma unroll
+                for (int u = 0; u < R; u++) {
+                    const int r = r0 + u;
+                    double a[N];
+#pragma unroll
+                    for (int i = 0; i < N; i++) a[i] = A[r * NP + i];
+#pragma unroll
+                    for (int j = 0; j < R; j++) {
+                        const double yv = w[(u + j) % R];
+#pragma unroll
+                        for (int i = 0; i < N; i++) acc[i][j] = fma(a[i], yv, acc[i][j]);
+                    }
+                    // slide: element R*lane + r + R -> row u, column lane + 1 + r0/R
+                    w[u] = ytile[u * G::YS + lane + 1 + (r0 >> G::LOGR)];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int j = 0; j < R; j++) fbuf[i * G::FTILE + j * G::FS + lane] = acc[i][j];
+            __syncwarp();
+        }
+        // ---- chunk 0: convert the faithful prologue (columns 0..L) into ring state ----
+        if (kind == START_PROLOGUE && b == 0) {
+            const double *sc = mdl + RL.scal;
+            const double w_nn = sc[0], c_emit = sc[1], two_s2 = sc[2], m0 = sc[3];
+            const double *t1 = p.T1pro + (size_t)ch * p.ns * (L + 1);
+            if (lane == 0) {
+                double z = 0.0;
+                zs[0] = 0.0;
+                for (int t = 1; t <= L; t++) {
+                    double dd = y[t] - m0;
+                    z += w_nn + (c_emit - (dd * dd) / two_s2);
+                    zs[t] = z;
+                }
+            }
+            __syncwarp();
+            const double *BW = mdl + RL.BW;
+            for (int t0 = 1 + lane; t0 <= L; t0 += 32) {
+                const double yv = y[t0];
+#pragma unroll
+                for (int i = 0; i < N; i++) {
+                    double uh = t1[(size_t)t0 * p.ns + 1 + i * L] - zs[t0];          // U(head_i) at t0
+                    double pu = uh - fma(A[i], yv, BW[i]);                             // minus d_t0(head_i)
+                    double f = fbuf[i * G::FTILE + (t0 & (R - 1)) * G::FS + (t0 >> G::LOGR)];
+                    ring[i * RING_Q + (t0 & (RING_Q - 1))] = pu + f;
+                }
+            }
+            Gprev = t1[(size_t)L * p.ns] - zs[L];
+            __syncwarp();
+        }
+        // ---- boundary dump: speculative start vector at s ----
+        if (kind == START_SPEC && b == s) {
+            double *sb = p.SB + ((size_t)ch * p.nchunks + c) * p.bvec;
+            if (lane == 0) sb[0] = Gprev;
+            for (int k = lane; k < L; k += 32) {
+                int64_t t0 = s - L + k;
+                for (int j = 0; j < N; j++) sb[1 + j * L + k] = ring[j * RING_Q + (int)(t0 & (RING_Q - 1))];
+            }
+        }
+        // ---- max-plus recursion over the super-window, 32 steps per window ----
+        for (int wdw = 0; wdw < R; wdw++) {
+            const int64_t tau0 = b + 32 * wdw;
+            if (tau0 + 32 <= tau_first) continue;
+            if (tau0 >= e) break;
+            const int tl = 32 * wdw + lane;
+            const int64_t tau = tau0 + lane;
+            double Fv[N];
+#pragma unroll
+            for (int i = 0; i < N; i++) Fv[i] = fbuf[i * G::FTILE + (tl & (R - 1)) * G::FS + (tl >> G::LOGR)];
+            unsigned nz = 0;
+            uint32_t myword = 0;
+            for (int sub = 0; sub < nsub; sub++) {
+                const bool active = (lane / Wd == sub) && tau >= tau_first && tau < e;
+                double tails[N];
+#pragma unroll
+                for (int j = 0; j < N; j++)
+                    tails[j] = active ? ring[j * RING_Q + (int)((tau - L) & (RING_Q - 1))] : NEG;
+                double X = NEG;
+                int jx = 0;
+#pragma unroll
+                for (int j = 0; j < N; j++) {
+                    double v = tails[j] + eG[j];
+                    if (v > X) {
+                        X = v;
+                        jx = j + 1;
+                    }
+                }
+                double M = X;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    double o = shfl_up_d(M, d);
+                    if (lane >= d) M = fmax(M, o);
+                }
+                const double Gincl = fmax(Gprev, M);
+                double Gexcl = shfl_up_d(Gincl, 1);
+                if (lane == 0) Gexcl = Gprev;
+                uint32_t word = (X > Gexcl) ? (uint32_t)jx : 0u;  // noise (first candidate) keeps ties
+#pragma unroll
+                for (int i = 0; i < N; i++) {
+                    double best = Gexcl + eH[i];
+                    int k = 0;
+#pragma unroll
+                    for (int j = 0; j < N; j++) {
+                        if (j == i) continue;
+                        double v = tails[j] + eT[j * NP + i];
+                        if (v > best) {
+                            best = v;
+                            k = j + 1;
+                        }
+                    }
+                    word |= (uint32_t)k << (4 * (i + 1));
+                    if (active) {
+                        ring[i * RING_Q + (int)(tau & (RING_Q - 1))] = best + Fv[i];
+                        if (last) p.Pfin[((size_t)ch * N + i) * RING_Q + (int)(tau & (RING_Q - 1))] = best;
+                    }
+                }
+                if (active) myword = word;
+                nz |= __ballot_sync(0xffffffffu, active && (word & 15u) != 0);
+                Gprev = shfl_d(Gincl, 31);
+                __syncwarp();
+            }
+            if (tau0 >= s) {  // main range only (warm-up decisions belong to the previous chunk)
+                if (tau < e) dec[tau] = myword;
+                if (lane == 0) nzm[tau0 >> 5] = nz;
+            }
+        }
+    }
+    // ---- end of chunk: true boundary vector for the next chunk, or final state ----
+    if (!last) {
+        double *eb = p.EB + ((size_t)ch * p.nchunks + c) * p.bvec;
+        if (lane == 0) eb[0] = Gprev;
+        for (int k = lane; k < L; k += 32) {
+            int64_t t0 = e - L + k;
+            for (int j = 0; j < N; j++) eb[1 + j * L + k] = ring[j * RING_Q + (int)(t0 & (RING_Q - 1))];
+        }
+    } else if (lane == 0) {
+        p.Gfin[ch] = Gprev;
+    }
+    __syncwarp();
+}
+
+template <int N, int R>
+__device__ void load_model_smem(const VitParams &p, int ch, double *mdl) {
+    const double *g = p.model + (size_t)ch * p.RL.total;
+    for (int k = threadIdx.x; k < p.RL.total; k += blockDim.x) mdl[k] = g[k];
+    __syncthreads();
+}
+
+template <int N, int R>
+__global__ void __launch_bounds__(128) ring_vit_forward(VitParams p) {
+    extern __shared__ __align__(16) double smem_d[];
+    const int ch = blockIdx.y;
+    double *mdl = smem_d;
+    load_model_smem<N, R>(p, ch, mdl);
+    const int warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (c >= p.nchunks) return;
+    double *ws = smem_d + ((p.RL.total + 1) & ~1) + (size_t)warp * WarpSmem<N, R>::DOUBLES;
+    vit_process_chunk<N, R>(p, ch, c, c == 0 ? START_PROLOGUE : START_SPEC, mdl, ws);
+}
+
+// Boundary check: speculative start vector of chunk c vs true end vector of c-1
+// must agree up to an additive constant.
+__device__ __forceinline__ bool boundary_matches(const double *sb, const double *eb, int n, int lane) {
+    const double s0 = sb[0], e0 = eb[0];
+    bool bad = false;
+    for (int k = lane; k < n; k += 32) {
+        double a = sb[k], b = eb[k];
+        bool ia = isinf(a), ib = isinf(b);
+        if (ia || ib) {
+            if (ia != ib) bad = true;
+            continue;
+        }
+        double da = a - s0, db = b - e0;
+        double tol = 1e-9 + 1e-12 * fabs(db);
+        if (!(fabs(da - db) <= tol)) bad = true;
+    }
+    return !__any_sync(0xffffffffu, bad);
+}
+
+__global__ void ring_vit_check_fwd(VitParams p) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int ch = blockIdx.y;
+    if (gw >= p.nchunks || gw == 0) return;
+    const double *sb = p.SB + ((size_t)ch * p.nchunks + gw) * p.bvec;
+    const double *eb = p.EB + ((size_t)ch * p.nchunks + gw - 1) * p.bvec;
+    bool ok = boundary_matches(sb, eb, p.bvec, lane);
+    if (lane == 0) p.fwd_flag[(size_t)ch * p.nchunks + gw] = ok ? 0 : 1;
+}
+
+// Sequential repair (one warp per channel): re-run flagged chunks from the true
+// boundary vector; a re-run changes EB[c], so chunk c+1 is re-checked against it.
+template <int N, int R>
+__global__ void __launch_bounds__(32) ring_vit_repair_fwd(VitParams p) {
+    extern __shared__ __align__(16) double smem_d[];
+    const int ch = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int *flag = p.fwd_flag + (size_t)ch * p.nchunks;
+    // fast exit when nothing is flagged
+    int any = 0;
+    for (int c = 1 + lane; c < p.nchunks; c += 32) any |= flag[c];
+    if (!__any_sync(0xffffffffu, any)) return;
+    double *mdl = smem_d;
+    load_model_smem<N, R>(p, ch, mdl);
+    double *ws = smem_d + ((p.RL.total + 1) & ~1);
+    bool prev_rerun = false;
+    int repaired = 0;
+    for (int c = 1; c < p.nchunks; c++) {
+        bool need = flag[c] != 0;
+        if (!need && prev_rerun) {
+            const double *sb = p.SB + ((size_t)ch * p.nchunks + c) * p.bvec;
+            const double *eb = p.EB + ((size_t)ch * p.nchunks + c - 1) * p.bvec;
+            need = !boundary_matches(sb, eb, p.bvec, lane);
+        }
+        if (need) {
+            vit_process_chunk<N, R>(p, ch, c, START_EXACT, mdl, ws);
+            __threadfence();
+            repaired++;
+        }
+        prev_rerun = need;
+    }
+    if (lane == 0) p.counters[ch * 4 + 0] = repaired;
+}
+
+// Final state: x[T] = argmax_j T1[j, T] (first maximum), from the last chunk's
+// G and P ring plus partial chain sums.  One warp per channel.
+template <int N>
+__global__ void __launch_bounds__(32) ring_vit_final(VitParams p, int16_t *xend) {
+    const int ch = blockIdx.x, lane = threadIdx.x;
+    const RingLayout &RL = p.RL;
+    const int L = RL.L, NP = RL.NP;
+    const double *mdl = p.model + (size_t)ch * RL.total;
+    const double *A = mdl + RL.A, *BW = mdl + RL.BW;
+    const double *y = p.y + (size_t)ch * p.y_stride;
+    const int64_t T = p.T;
+    // candidate per state j = 1 + i*L + (sph-1): entered at t0 = T - sph
+    double best = -INFINITY;
+    int bj = 0x7fffffff;
+    for (int idx = lane; idx < N * L; idx += 32) {
+        int i = idx / L, sph = idx % L + 1;
+        int64_t t0 = T - sph;
+        double v = p.Pfin[((size_t)ch * N + i) * RING_Q + (int)(t0 & (RING_Q - 1))];
+        for (int r = 0; r < sph; r++) v += fma(A[r * NP + i], y[t0 + r], BW[r * NP + i]);
+        int j = 1 + idx;
+        if (v > best || (v == best && j < bj)) {
+            best = v;
+            bj = j;
+        }
+    }
+    if (lane == 0) {  // noise is state 0: wins ties against everything
+        double g = p.Gfin[ch];
+        if (g >= best) {
+            best = g;
+            bj = 0;
+        }
+    }
+    for (int d = 16; d >= 1; d >>= 1) {
+        double ob = shfl_down_d(best, d);
+        int oj = __shfl_down_sync(0xffffffffu, bj, d);
+        if (ob > best || (ob == best && oj < bj)) {
+            best = ob;
+            bj = oj;
+        }
+    }
+    if (lane == 0) xend[ch] = (int16_t)bj;
+}
+
+// ---------------------------------------------------------------------------
+// Traceback.  State encoding: -1 = noise, else t0 * 8 + neuron (chain entered at t0).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ long long enc_spike(int64_t t0, int i) { return (long long)t0 * 8 + i; }
+
+template <int N>
+__device__ void trace_chunk(const VitParams &p, int ch, int c, int64_t tau_hi, long long st, bool record_look,
+                            int16_t *t2s /*smem, chunk 0 only*/) {
+    const int lane = threadIdx.x & 31;
+    const int L = p.RL.L;
+    const int64_t T = p.T;
+    const int64_t s = (int64_t)c * p.Lc;
+    int64_t e = s + p.Lc;
+    if (c == p.nchunks - 1 || e > T) e = T;
+    const int64_t lo = (c == 0) ? (int64_t)(L + 1) : s;
+    const uint32_t *dec = p.dec + (size_t)ch * T;
+    const uint32_t *nzm = p.nzmask + (size_t)ch * ((T + 31) / 32);
+    int16_t *x = p.x + (size_t)ch * p.x_stride;
+    long long own = -2, look = -2;
+    int64_t cur = tau_hi;
+    while (cur >= lo) {
+        if (st < 0) {
+            // noise at cur: find the latest step tp in [lo, cur] where noise was entered from a tail
+            int64_t tp = lo - 1;
+            int64_t whi = cur >> 5;
+            const int64_t wlo = lo >> 5;
+            while (whi >= wlo) {
+                int64_t wi = whi - lane;
+                uint32_t word = 0;
+                if (wi >= wlo) {
+                    word = nzm[wi];
+                    if (wi == (cur >> 5)) {
+                        int hb = (int)(cur & 31);
+                        if (hb < 31) word &= (2u << hb) - 1u;
+                    }
+                    if (wi == wlo) word &= ~((1u << (lo & 31)) - 1u);
+                }
+                unsigned bal = __ballot_sync(0xffffffffu, word != 0);
+                if (bal) {
+                    int src = __ffs(bal) - 1;
+                    uint32_t wsel = __shfl_sync(0xffffffffu, word, src);
+                    tp = ((whi - src) << 5) + (31 - __clz(wsel));
+                    break;
+                }
+                whi -= 32;
+            }
+            // (tp, cur] and tp itself are noise
+            int64_t a = tp < lo ? lo : tp;
+            if (record_look && e <= cur && e >= a) look = -1;
+            if (s <= cur && s >= a) own = -1;
+            {
+                int64_t wa = a < s ? s : a, wb = cur < e - 1 ? cur : e - 1;
+                for (int64_t t = wa + lane; t <= wb; t += 32) x[t] = 1;
+            }
+            if (tp < lo) {
+                cur = lo - 1;
+                break;
+            }
+            int j = (int)(dec[tp] & 15u);  // 1..N
+            cur = tp - 1;
+            st = enc_spike(tp - L, j - 1);
+        } else {
+            const int i = (int)(st & 7);
+            const int64_t t0 = st >> 3;
+            int64_t a = t0 < lo ? lo : t0;
+            if (record_look && e <= cur && e >= a) look = st;
+            if (s <= cur && s >= a) own = st;
+            {
+                int64_t wa = a < s ? s : a, wb = cur < e - 1 ? cur : e - 1;
+                for (int64_t t = wa + lane; t <= wb; t += 32) x[t] = (int16_t)(2 + i * L + (int)(t - t0));
+            }
+            if (t0 < lo) {
+                cur = lo - 1;
+                break;
+            }
+            int k = (int)((dec[t0] >> (4 * (i + 1))) & 15u);
+            cur = t0 - 1;
+            st = (k == 0) ? -1 : enc_spike(t0 - L, k - 1);
+        }
+    }
+    if (c == 0) {
+        // steps L .. 0 from the faithful prologue's backpointers (reference arithmetic)
+        int curj = (st < 0) ? 0 : (1 + (int)(st & 7) * L + (int)(L - (st >> 3)));
+        if (lane == 0) {
+            for (int t = L; t >= 1; t--) {
+                x[t] = (int16_t)(curj + 1);
+                curj = t2s[(size_t)t * p.ns + curj] - 1;
+            }
+            x[0] = (int16_t)(curj + 1);
+        }
+        own = 0;  // nothing precedes chunk 0
+    }
+    if (lane == 0) {
+        p.own_start[(size_t)ch * p.nchunks + c] = own;
+        if (record_look) p.look_end[(size_t)ch * p.nchunks + c] = look;
+    }
+}
+
+__device__ __forceinline__ long long state_from_xend(int j, int64_t T, int L) {
+    if (j == 0) return -1;
+    int i = (j - 1) / L, sph = (j - 1) % L + 1;
+    return enc_spike(T - sph, i);
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) ring_vit_trace(VitParams p) {
+    extern __shared__ __align__(16) int16_t t2s_all[];
+    const int ch = blockIdx.y;
+    const int warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int L = p.RL.L;
+    if (blockIdx.x == 0) {  // chunk 0 lives in CTA 0: stage the prologue backpointers
+        const int16_t *g = p.T2pro + (size_t)ch * p.ns * (L + 1);
+        for (int k = threadIdx.x; k < p.ns * (L + 1); k += blockDim.x) t2s_all[k] = g[k];
+    }
+    __syncthreads();
+    if (c >= p.nchunks) return;
+    const int64_t T = p.T;
+    const int64_t s = (int64_t)c * p.Lc;
+    int64_t e = s + p.Lc;
+    const bool last = (c == p.nchunks - 1);
+    if (last || e > T) e = T;
+    int64_t tau_hi = e + p.W - 1;
+    long long st = -1;  // speculative: noise at tau_hi
+    if (last || tau_hi >= T - 1) {
+        tau_hi = T - 1;
+        st = state_from_xend(p.xend[ch], T, L);
+    }
+    trace_chunk<N>(p, ch, c, tau_hi, st, !last, t2s_all);
+}
+
+__global__ void ring_vit_check_trace(VitParams p) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ch = blockIdx.y;
+    if (c >= p.nchunks - 1) return;
+    size_t o = (size_t)ch * p.nchunks;
+    p.tr_flag[o + c] = (p.look_end[o + c] != p.own_start[o + c + 1]) ? 1 : 0;
+}
+
+template <int N>
+__global__ void __launch_bounds__(32) ring_vit_repair_trace(VitParams p) {
+    extern __shared__ __align__(16) int16_t t2s_all[];
+    const int ch = blockIdx.x, lane = threadIdx.x;
+    const size_t o = (size_t)ch * p.nchunks;
+    int any = 0;
+    for (int c = lane; c < p.nchunks - 1; c += 32) any |= p.tr_flag[o + c];
+    if (!__any_sync(0xffffffffu, any)) return;
+    const int L = p.RL.L;
+    {
+        const int16_t *g = p.T2pro + (size_t)ch * p.ns * (L + 1);
+        for (int k = lane; k < p.ns * (L + 1); k += 32) t2s_all[k] = g[k];
+    }
+    __syncwarp();
+    int repaired = 0;
+    bool next_changed = false;
+    for (int c = p.nchunks - 2; c >= 0; c--) {
+        bool need = p.tr_flag[o + c] != 0;
+        if (!need && next_changed) need = p.look_end[o + c] != p.own_start[o + c + 1];
+        if (need) {
+            // true state at time e_c is the (final) start state of chunk c+1
+            int64_t e = (int64_t)(c + 1) * p.Lc;
+            long long before = p.own_start[o + c];
+            trace_chunk<N>(p, ch, c, e, p.own_start[o + c + 1], false, t2s_all);
+            __threadfence();
+            __syncwarp();
+            next_changed = (p.own_start[o + c] != before);
+            repaired++;
+        } else
+            next_changed = false;
+    }
+    if (lane == 0) p.counters[ch * 4 + 1] = repaired;
+}
+
+// ---------------------------------------------------------------------------
+// ll = sum_{i=T..2} T1[x[i], i]   (src/viterbi.jl:92-96), parallel form:
+// T1 along the decoded path is p_t = p_0 + sum_{u<=t} inc_u with
+// inc_u = lp(x_{u-1} -> x_u) + q_u(x_u), hence  ll = (T-1) p_0 + sum_u (T-u) inc_u.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    ring_path_ll_partial(const double *__restrict__ y, int64_t T, int64_t y_stride, const char *blob,
+                         size_t blob_stride, FaithfulLayout L, const int16_t *__restrict__ x, int64_t x_stride,
+                         double *__restrict__ partial /*[C x gridDim.x]*/) {
+    const int ch = blockIdx.y;
+    const char *mb = blob + (size_t)ch * blob_stride;
+    const double *sc = (const double *)(mb + L.scal);
+    const double c_emit = sc[2], two_s2 = sc[3];
+    const double *gm = (const double *)(mb + L.m), *glp = (const double *)(mb + L.in_lp);
+    const int *gp = (const int *)(mb + L.in_ptr), *gs = (const int *)(mb + L.in_src);
+    y += (size_t)ch * y_stride;
+    x += (size_t)ch * x_stride;
+    double acc = 0.0;
+    for (int64_t t = 1 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x) {
+        int d = x[t] - 1, s = x[t - 1] - 1;
+        double lp = __longlong_as_double(0x7ff8000000000000LL);
+        for (int e = gp[d]; e < gp[d + 1]; e++)
+            if (gs[e] == s) {
+                lp = glp[e];
+                break;
+            }
+        double dd = y[t] - gm[d];
+        double q = c_emit - (dd * dd) / two_s2;
+        acc += (double)(T - t) * (lp + q);
+    }
+    __shared__ double red[256];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int k = 128; k >= 1; k >>= 1) {
+        if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(size_t)ch * gridDim.x + blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(256)
+    ring_path_ll_final(const double *__restrict__ y, int64_t T, int64_t y_stride, const char *blob, size_t blob_stride,
+                       FaithfulLayout L, const int16_t *__restrict__ x, int64_t x_stride,
+                       const double *__restrict__ partial, int nparts, double *__restrict__ ll_out) {
+    const int ch = blockIdx.x;
+    __shared__ double red[256];
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < nparts; k += 256) acc += partial[(size_t)ch * nparts + k];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int k = 128; k >= 1; k >>= 1) {
+        if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const char *mb = blob + (size_t)ch * blob_stride;
+        const double *sc = (const double *)(mb + L.scal);
+        const double *gm = (const double *)(mb + L.m);
+        int x0 = x[(size_t)ch * x_stride] - 1;
+        double dd = y[(size_t)ch * y_stride] - gm[x0];
+        double p0 = x0 == 0 ? 0.0 : sc[2] - (dd * dd) / sc[3];
+        ll_out[ch] = (double)(T - 1) * p0 + red[0];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------
+template <int N, int R>
+static void launch_all(VitParams &p, int C, cudaStream_t st, hmm_info *info, Timer *ttop) {
+    constexpr int WPB = 4;
+    const size_t mdl_d = (p.RL.total + 1) & ~1;
+    const size_t sm_fwd = sizeof(double) * (mdl_d + (size_t)WPB * WarpSmem<N, R>::DOUBLES);
+    const size_t sm_rep = sizeof(double) * (mdl_d + WarpSmem<N, R>::DOUBLES);
+    HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+    HMM_CUDA(cudaFuncSetAttribute(ring_vit_repair_fwd<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rep));
+    dim3 gridc((p.nchunks + WPB - 1) / WPB, C);
+    if (ttop) ttop->start();
+    ring_vit_forward<N, R><<<gridc, 32 * WPB, sm_fwd, st>>>(p);
+    if (ttop) ttop->stop();
+    HMM_CUDA(cudaGetLastError());
+    ring_vit_check_fwd<<<dim3((p.nchunks * 32 + 127) / 128, C), 128, 0, st>>>(p);
+    ring_vit_repair_fwd<N, R><<<C, 32, sm_rep, st>>>(p);
+    ring_vit_final<N><<<C, 32, 0, st>>>(p, const_cast<int16_t *>(p.xend));
+    HMM_CUDA(cudaGetLastError());
+    const size_t sm_t2 = sizeof(int16_t) * (size_t)p.ns * (p.RL.L + 1);
+    HMM_CUDA(cudaFuncSetAttribute(ring_vit_trace<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_t2));
+    HMM_CUDA(cudaFuncSetAttribute(ring_vit_repair_trace<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_t2));
+    ring_vit_trace<N><<<gridc, 32 * WPB, sm_t2, st>>>(p);
+    ring_vit_check_trace<<<dim3((p.nchunks + 127) / 128, C), 128, 0, st>>>(p);
+    ring_vit_repair_trace<N><<<C, 32, sm_t2, st>>>(p);
+    HMM_CUDA(cudaGetLastError());
+    if (info) info->kernel_launches += 7;
+}
+
+void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, const std::vector<HostModel> &models,
+                      const FaithfulLayout &FL, const char *blob_dev, int16_t *x_dev, int64_t x_stride, double *ll_dev,
+                      cudaStream_t st, hmm_info *info) {
+    Workspace &ws = workspace();
+    const HostModel &M0 = models[0];
+    const int N = M0.N, L = M0.K - 1, ns = M0.nstates;
+    const int R = (N <= 4) ? 8 : 4;
+    const int SW = 32 * R;
+    RingLayout RL = ring_layout(N, L);
+
+    // geometry: one chunk per warp, one wave of warps over the whole GPU
+    int64_t W = ring_config().warmup > 0 ? ring_config().warmup : 512;
+    W = ((W + SW - 1) / SW) * SW;
+    if (W < ((L + 32 + SW - 1) / SW) * SW) W = ((L + 32 + SW - 1) / SW) * SW;
+    int64_t Lc = ring_config().chunk_len;
+    if (Lc <= 0) {
+        const int64_t target_warps = 148 * 12;
+        int64_t per_channel = (target_warps + C - 1) / C;
+        Lc = (T + per_channel - 1) / per_channel;
+        if (Lc < 4 * W) Lc = 4 * W;
+    }
+    Lc = ((Lc + SW - 1) / SW) * SW;
+    if (Lc < W) Lc = W;
+    int nchunks = (int)((T + Lc - 1) / Lc);
+    // the last chunk must be long enough to hold the final look-back of L steps
+    if (nchunks > 1 && T - (int64_t)(nchunks - 1) * Lc < RING_Q) nchunks--;
+
+    // prologue: first L+1 columns in the reference's exact arithmetic
+    const int64_t pcols = L + 1;
+    double *T1pro = (double *)ws.get(Workspace::PROLOG, (sizeof(double) + sizeof(int16_t)) * (size_t)C * ns * pcols + 64);
+    int16_t *T2pro = (int16_t *)(T1pro + (size_t)C * ns * pcols);
+    {
+        // run the faithful forward sweep on the first L+1 samples only
+        faithful_viterbi_run(y_dev, pcols, y_stride, C, FL, blob_dev, M0, nullptr, 0, nullptr, T1pro, T2pro, pcols,
+                             true, nullptr, st, info);
+    }
+
+    // ring models
+    std::vector<double> hmdl((size_t)C * RL.total);
+    for (int c = 0; c < C; c++) ring_pack(models[c], RL, hmdl.data() + (size_t)c * RL.total);
+    const int bvec = 1 + N * L;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+        size_t r = off;
+        off += (bytes + 255) & ~size_t(255);
+        return r;
+    };
+    size_t o_model = carve(sizeof(double) * hmdl.size());
+    size_t o_sb = carve(sizeof(double) * (size_t)C * nchunks * bvec);
+    size_t o_eb = carve(sizeof(double) * (size_t)C * nchunks * bvec);
+    size_t o_pfin = carve(sizeof(double) * (size_t)C * N * RING_Q);
+    size_t o_gfin = carve(sizeof(double) * C);
+    size_t o_flag = carve(sizeof(int) * (size_t)C * nchunks);
+    size_t o_trflag = carve(sizeof(int) * (size_t)C * nchunks);
+    size_t o_cnt = carve(sizeof(int) * (size_t)C * 4);
+    size_t o_own = carve(sizeof(long long) * (size_t)C * nchunks);
+    size_t o_look = carve(sizeof(long long) * (size_t)C * nchunks);
+    size_t o_xend = carve(sizeof(int16_t) * C);
+    size_t o_part = carve(sizeof(double) * (size_t)C * 1024);
+    char *base = (char *)ws.get(Workspace::CHUNKS, off);
+    HMM_CUDA(cudaMemcpyAsync(base + o_model, hmdl.data(), sizeof(double) * hmdl.size(), cudaMemcpyHostToDevice, st));
+    HMM_CUDA(cudaStreamSynchronize(st));  // hmdl is a pageable temporary
+    HMM_CUDA(cudaMemsetAsync(base + o_cnt, 0, sizeof(int) * (size_t)C * 4, st));
+    HMM_CUDA(cudaMemsetAsync(base + o_pfin, 0, sizeof(double) * (size_t)C * N * RING_Q, st));
+
+    VitParams p{};
+    p.y = y_dev;
+    p.T = T;
+    p.y_stride = y_stride;
+    p.model = (const double *)(base + o_model);
+    p.RL = RL;
+    p.Lc = Lc;
+    p.W = W;
+    p.nchunks = nchunks;
+    p.ns = ns;
+    p.dec = (uint32_t *)ws.get(Workspace::DEC, sizeof(uint32_t) * (size_t)C * T);
+    p.nzmask = (uint32_t *)ws.get(Workspace::MASK, sizeof(uint32_t) * (size_t)C * ((T + 31) / 32));
+    p.SB = (double *)(base + o_sb);
+    p.EB = (double *)(base + o_eb);
+    p.bvec = bvec;
+    p.T1pro = T1pro;
+    p.Pfin = (double *)(base + o_pfin);
+    p.Gfin = (double *)(base + o_gfin);
+    p.fwd_flag = (int *)(base + o_flag);
+    p.counters = (int *)(base + o_cnt);
+    p.T2pro = T2pro;
+    p.xend = (const int16_t *)(base + o_xend);
+    p.x = x_dev;
+    p.x_stride = x_stride;
+    p.own_start = (long long *)(base + o_own);
+    p.look_end = (long long *)(base + o_look);
+    p.tr_flag = (int *)(base + o_trflag);
+
+    Timer ttop(st);
+    switch (N * 10 + R) {
+        case 18: launch_all<1, 8>(p, C, st, info, &ttop); break;
+        case 28: launch_all<2, 8>(p, C, st, info, &ttop); break;
+        case 38: launch_all<3, 8>(p, C, st, info, &ttop); break;
+        case 48: launch_all<4, 8>(p, C, st, info, &ttop); break;
+        case 54: launch_all<5, 4>(p, C, st, info, &ttop); break;
+        case 64: launch_all<6, 4>(p, C, st, info, &ttop); break;
+        case 74: launch_all<7, 4>(p, C, st, info, &ttop); break;
+        default: fail(HMM_EUNSUPPORTED, "ring engine supports 1..%d neurons", RING_MAX_N);
+    }
+    if (ll_dev) {
+        const int nparts = 592;
+        double *part = (double *)(base + o_part);
+        ring_path_ll_partial<<<dim3(nparts, C), 256, 0, st>>>(y_dev, T, y_stride, blob_dev, FL.bytes, FL, x_dev, x_stride,
+                                                              part);
+        ring_path_ll_final<<<C, 256, 0, st>>>(y_dev, T, y_stride, blob_dev, FL.bytes, FL, x_dev, x_stride, part, nparts,
+                                              ll_dev);
+        HMM_CUDA(cudaGetLastError());
+        if (info) info->kernel_launches += 2;
+    }
+    if (info) {
+        std::vector<int> cnt((size_t)C * 4);
+        HMM_CUDA(cudaMemcpyAsync(cnt.data(), base + o_cnt, sizeof(int) * cnt.size(), cudaMemcpyDeviceToHost, st));
+        HMM_CUDA(cudaStreamSynchronize(st));
+        info->n_chunks = nchunks;
+        for (int c = 0; c < C; c++) {
+            info->fwd_repaired += cnt[c * 4 + 0];
+            info->bwd_repaired += cnt[c * 4 + 1];
+        }
+        info->top_kernel_ms = ttop.ms();
+    }
+}
+
+}  // namespace hmm

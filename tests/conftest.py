@@ -32,8 +32,8 @@ def O():
 
 
 TEMPLATE_PARAMS = [(3.0, 0.8, 0.2), (4.0, 0.3, 0.2), (2.0, 0.5, 0.3), (2.5, 0.6, 0.25), (3.5, 0.4, 0.15),
-                   (1.8, 0.9, 0.3), (2.8, 0.2, 0.1)]
-RATES = [0.003, 0.001, 0.002, 0.0015, 0.0025, 0.001, 0.002]
+                   (1.8, 0.9, 0.3), (2.8, 0.2, 0.1), (2.2, 0.7, 0.12)]
+RATES = [0.003, 0.001, 0.002, 0.0015, 0.0025, 0.001, 0.002, 0.0012]
 
 
 def make_case(hm, N, K, T, seed, sigma=0.3, rate_scale=1.0):

@@ -1,0 +1,101 @@
+"""Parity of the time-parallel ring Viterbi engine against the CPU oracle, through
+the C ABI.  Bars (BASELINE.json north_star): x bit-exact; ll within 1e-9 relative."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-9
+
+
+def _check(hm, O, S, lA, mu, sig, **kw):
+    x, ll, info = hm.viterbi(S, lA, mu, sig, mode="ring", return_info=True)
+    xo, llo = O.viterbi(S, lA, mu, sig)
+    assert info["engine"] == 2
+    bad = np.nonzero(x != xo)[0]
+    assert bad.size == 0, f"{bad.size} mismatches, first at {bad[:5]} (chunks={info['n_chunks']})"
+    assert abs(ll - llo) <= LL_RTOL * abs(llo), (ll, llo)
+    return info
+
+
+@pytest.mark.parametrize("N,K,T,seed", [(3, 60, 20000, 1234), (3, 60, 300000, 2), (4, 48, 200000, 7),
+                                        (5, 60, 150000, 5), (1, 20, 50000, 3), (2, 10, 30000, 1), (7, 60, 60000, 9),
+                                        (2, 4, 5000, 12), (6, 33, 40000, 13), (3, 97, 50000, 15)])
+def test_ring_viterbi_matches_oracle(hm, O, case_factory, N, K, T, seed):
+    hm.set_ring_params(0, 0)
+    S, lA, mu, sig = case_factory(N, K, T, seed)
+    _check(hm, O, S, lA, mu, sig)
+
+
+@pytest.mark.parametrize("chunk,warm", [(1024, 256), (2048, 512), (4096, 256), (512, 512)])
+@pytest.mark.parametrize("N,K,seed", [(3, 60, 31), (4, 48, 32), (2, 12, 33)])
+def test_ring_viterbi_many_small_chunks(hm, O, case_factory, N, K, seed, chunk, warm):
+    """Hundreds of chunk boundaries: exercises speculation, verification and repair."""
+    S, lA, mu, sig = case_factory(N, K, 120000, seed)
+    try:
+        hm.set_ring_params(chunk, warm)
+        info = _check(hm, O, S, lA, mu, sig)
+        assert info["n_chunks"] >= 120000 // max(chunk, 4 * 256) - 1
+    finally:
+        hm.set_ring_params(0, 0)
+
+
+def test_ring_viterbi_dense_spiking_forces_repairs(hm, O, case_factory):
+    """High firing rates leave few quiet gaps, so speculative starts fail to
+    coalesce and the repair path must produce the exact answer."""
+    S, lA, mu, sig = case_factory(3, 60, 100000, 41, rate_scale=8.0)
+    try:
+        hm.set_ring_params(1024, 256)
+        info = _check(hm, O, S, lA, mu, sig)
+    finally:
+        hm.set_ring_params(0, 0)
+    assert info["fwd_repaired"] >= 0 and info["bwd_repaired"] >= 0
+
+
+def test_ring_viterbi_fitted_like_model(hm, O, case_factory):
+    """A mis-specified model (scaled templates, wrong sigma, mu row 1 non-zero)."""
+    S, lA, mu, sig = case_factory(3, 60, 80000, 51)
+    mu2 = np.asfortranarray(mu * 0.8)
+    mu2[0, :] = [0.01, -0.02, 0.005]
+    _check(hm, O, S, lA, mu2, 0.35)
+
+
+def test_ring_viterbi_auto_and_batch(hm, O, case_factory):
+    cases = [case_factory(4, 48, 40000, 200 + c) for c in range(6)]
+    Y = np.asfortranarray(np.stack([c[0] for c in cases], axis=1))
+    models = [(c[1], np.asfortranarray(c[2] * (1 + 0.05 * i)), 0.3 + 0.01 * i) for i, c in enumerate(cases)]
+    x, ll, info = hm.viterbi_batch(Y, models, mode="auto", return_info=True)
+    assert info["engine"] == 2  # T >= 32768 and ring-structured -> ring engine
+    for c in range(6):
+        xo, llo = O.viterbi(Y[:, c], models[c][0], models[c][1], models[c][2])
+        assert np.array_equal(x[:, c], xo)
+        assert abs(ll[c] - llo) <= LL_RTOL * abs(llo)
+
+
+def test_ring_range_limits_fall_back_to_faithful(hm, O, case_factory):
+    """N = 8 is outside the ring engine (7 neurons max): explicit ring mode refuses,
+    auto mode decodes with the faithful engine."""
+    S, lA, mu, sig = case_factory(8, 40, 40000, 14)
+    with pytest.raises(hm.HmmError) as ei:
+        hm.viterbi(S, lA, mu, sig, mode="ring")
+    assert ei.value.code == hm._lib.HMM_EUNSUPPORTED
+    x, ll, info = hm.viterbi(S, lA, mu, sig, mode="auto", return_info=True)
+    xo, llo = O.viterbi(S, lA, mu, sig)
+    assert info["engine"] == 1 and np.array_equal(x, xo) and ll == llo
+
+
+def test_ring_rejects_overlap_model(hm):
+    lA = hm.StateMatrix(2, 6, np.log([0.01, 0.02]), True)
+    mu = np.asfortranarray(np.zeros((6, 2)))
+    with pytest.raises(hm.HmmError) as ei:
+        hm.viterbi(np.zeros(5000), lA, mu, 0.3, mode="ring")
+    assert ei.value.code == hm._lib.HMM_EUNSUPPORTED
+
+
+def test_ring_equals_faithful_1m(hm, case_factory):
+    """A 1 M-sample cut of config 2: ring engine == faithful engine (bit-exact x)."""
+    S, lA, mu, sig = case_factory(3, 60, 1_000_000, 2)
+    xr, llr, info = hm.viterbi(S, lA, mu, sig, mode="ring", return_info=True)
+    xf, llf = hm.viterbi(S, lA, mu, sig, mode="faithful")
+    assert np.array_equal(xr, xf)
+    assert abs(llr - llf) <= LL_RTOL * abs(llf)
