@@ -18,7 +18,9 @@
 // look-ahead + verification + repair).  The first L+1 samples are decoded by
 // the faithful engine in the reference's exact arithmetic, which reproduces
 // the structural ties at t=2.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <limits>
 
 #include "ring_common.cuh"
@@ -64,6 +66,15 @@ void ring_pack(const HostModel &M, const RingLayout &R, double *dst) {
     dst[R.scal + 2] = 2 * s2;
     dst[R.scal + 3] = m0;
     dst[R.scal + 4] = M.sigma;
+    // bounds used by the decision fast path: max finite tail->head weight, min noise->head weight
+    double eTmax = -std::numeric_limits<double>::infinity(), eHmin = std::numeric_limits<double>::infinity();
+    for (int i = 0; i < N; i++) {
+        eHmin = std::min(eHmin, dst[R.eH + i]);
+        for (int j = 0; j < N; j++)
+            if (i != j) eTmax = std::max(eTmax, dst[R.eT + j * R.NP + i]);
+    }
+    dst[R.scal + 5] = eTmax;  // -inf when N == 1
+    dst[R.scal + 6] = eHmin;
 }
 
 // ---------------------------------------------------------------------------
@@ -91,6 +102,8 @@ struct VitParams {
     int64_t x_stride;
     long long *own_start, *look_end;  // [C x nchunks] encoded states
     int *tr_flag;
+    int stagger_ns;        // start-up delay quantum that de-phases co-resident warps (FIR vs recursion)
+    int n_sm;
 };
 
 enum StartKind { START_PROLOGUE = 0, START_SPEC = 1, START_EXACT = 2 };
@@ -98,7 +111,10 @@ enum StartKind { START_PROLOGUE = 0, START_SPEC = 1, START_EXACT = 2 };
 template <int N, int R>
 struct WarpSmem {
     using G = FirGeom<R>;
-    static constexpr int DOUBLES = G::YTILE + N * G::FTILE + N * RING_Q + 128;  // + Z scratch (prologue)
+    // the F tile is written only after the FIR has consumed the y tile, so the two
+    // share storage; the prologue's Z scratch (chunk 0 only) lives behind the ring
+    static constexpr int TILE = (G::YTILE > N * G::FTILE) ? G::YTILE : N * G::FTILE;
+    static constexpr int DOUBLES = TILE + N * RING_Q + 104;
 };
 
 // Shared (per CTA) copy of the model: A interleaved [r][NP], then the DP constants.
@@ -120,11 +136,12 @@ __device__ void vit_process_chunk(const VitParams &p, int ch, int c, int kind, c
     const int L = RL.L, LP = RL.LP;
     const double NEG = -INFINITY;
     double *ytile = ws;
-    double *fbuf = ytile + G::YTILE;
-    double *ring = fbuf + N * G::FTILE;
-    double *zs = ring + N * RING_Q;
+    double *fbuf = ws;  // aliases ytile (see WarpSmem)
+    double *ring = ws + WarpSmem<N, R>::TILE;
+    double *zs = ring + N * RING_Q;  // [L+1] <= 97 doubles
     const double *A = mdl + RL.A;
     const double *Bc = mdl + RL.Bc, *eG = mdl + RL.eG, *eH = mdl + RL.eH, *eT = mdl + RL.eT;
+    const double eTmax = mdl[RL.scal + 5], eHmin = mdl[RL.scal + 6];
     const double *y = p.y + (size_t)ch * p.y_stride;
     const int64_t T = p.T;
     const int64_t s = (int64_t)c * p.Lc;                 // main range [s, e)
@@ -159,6 +176,10 @@ __device__ void vit_process_chunk(const VitParams &p, int ch, int c, int kind, c
     uint32_t *nzm = p.nzmask + (size_t)ch * ((T + 31) / 32);
     const int Wd = L < 32 ? L : 32;
     const int nsub = (32 + Wd - 1) / Wd;
+    const int mysub = lane / Wd;
+    const int tf_rel = (int)(tau_first - base0);  // steps are tracked relative to base0 in 32 bits
+    const int e_rel = (int)(e - base0);
+    const int s_rel = (int)(s - base0);
 
     for (int64_t b = base0; b < e; b += G::SW) {
         // ---- stage y[b, b + SW + LP) into the transposed tile (zero beyond T) ----
@@ -186,13 +207,23 @@ __device__ void vit_process_chunk(const VitParams &p, int ch, int c, int kind, c
             double w[R];
 #pragma unroll
             for (int j = 0; j < R; j++) w[j] = ytile[j * G::YS + lane];  // elements R*lane + j
+            double a[N], an[N];
+            auto load_coef = [&](int r, double *dst) {
+                const double2 *src = reinterpret_cast<const double2 *>(A + r * NP);
+#pragma unroll
+                for (int i2 = 0; i2 < NP / 2; i2++) {
+                    double2 v = src[i2];
+                    if (2 * i2 < N) dst[2 * i2] = v.x;
+                    if (2 * i2 + 1 < N) dst[2 * i2 + 1] = v.y;
+                }
+            };
+            load_coef(0, a);
             for (int r0 = 0; r0 < LP; r0 += R) {
 #pragma unroll
                 for (int u = 0; u < R; u++) {
                     const int r = r0 + u;
-                    double a[N];
-#pragma unroll
-                    for (int i = 0; i < N; i++) a[i] = A[r * NP + i];
+                    load_coef(r + 1 < LP ? r + 1 : r, an);  // one tap ahead
+                    const double ynew = ytile[u * G::YS + lane + 1 + (r0 >> G::LOGR)];
 #pragma unroll
                     for (int j = 0; j < R; j++) {
                         const double yv = w[(u + j) % R];
@@ -200,9 +231,12 @@ __device__ void vit_process_chunk(const VitParams &p, int ch, int c, int kind, c
                         for (int i = 0; i < N; i++) acc[i][j] = fma(a[i], yv, acc[i][j]);
                     }
                     // slide: element R*lane + r + R -> row u, column lane + 1 + r0/R
-                    w[u] = ytile[u * G::YS + lane + 1 + (r0 >> G::LOGR)];
+                    w[u] = ynew;
+#pragma unroll
+                    for (int i = 0; i < N; i++) a[i] = an[i];
                 }
             }
+            __syncwarp();  // all lanes are done with the y tile before F overwrites it
 #pragma unroll
             for (int i = 0; i < N; i++)
 #pragma unroll
@@ -248,69 +282,106 @@ __device__ void vit_process_chunk(const VitParams &p, int ch, int c, int kind, c
             }
         }
         // ---- max-plus recursion over the super-window, 32 steps per window ----
+        const int b_rel = (int)(b - base0);
         for (int wdw = 0; wdw < R; wdw++) {
-            const int64_t tau0 = b + 32 * wdw;
-            if (tau0 + 32 <= tau_first) continue;
-            if (tau0 >= e) break;
+            const int t0_rel = b_rel + 32 * wdw;
+            if (t0_rel + 32 <= tf_rel) continue;
+            if (t0_rel >= e_rel) break;
             const int tl = 32 * wdw + lane;
-            const int64_t tau = tau0 + lane;
+            const int t_rel = t0_rel + lane;
+            const bool in_range = t_rel >= tf_rel && t_rel < e_rel;
+            // ring slots: base0 is a multiple of RING_Q, so absolute and relative indices agree mod RING_Q
+            const int slot_w = t_rel & (RING_Q - 1);
+            const int slot_r = (t_rel - L) & (RING_Q - 1);
             double Fv[N];
 #pragma unroll
             for (int i = 0; i < N; i++) Fv[i] = fbuf[i * G::FTILE + (tl & (R - 1)) * G::FS + (tl >> G::LOGR)];
             unsigned nz = 0;
             uint32_t myword = 0;
             for (int sub = 0; sub < nsub; sub++) {
-                const bool active = (lane / Wd == sub) && tau >= tau_first && tau < e;
+                const bool active = in_range && (mysub == sub);
                 double tails[N];
 #pragma unroll
-                for (int j = 0; j < N; j++)
-                    tails[j] = active ? ring[j * RING_Q + (int)((tau - L) & (RING_Q - 1))] : NEG;
+                for (int j = 0; j < N; j++) tails[j] = active ? ring[j * RING_Q + slot_r] : NEG;
                 double X = NEG;
-                int jx = 0;
 #pragma unroll
                 for (int j = 0; j < N; j++) {
                     double v = tails[j] + eG[j];
-                    if (v > X) {
-                        X = v;
-                        jx = j + 1;
-                    }
+                    X = (v > X) ? v : X;
                 }
-                double M = X;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    double o = shfl_up_d(M, d);
-                    if (lane >= d) M = fmax(M, o);
-                }
-                const double Gincl = fmax(Gprev, M);
-                double Gexcl = shfl_up_d(Gincl, 1);
-                if (lane == 0) Gexcl = Gprev;
-                uint32_t word = (X > Gexcl) ? (uint32_t)jx : 0u;  // noise (first candidate) keeps ties
-#pragma unroll
-                for (int i = 0; i < N; i++) {
-                    double best = Gexcl + eH[i];
-                    int k = 0;
+                // Fast path 1: the noise score can only change inside this window if some
+                // X_t exceeds the window-start G (G is non-decreasing) -- true only where a
+                // chain has just ended.  Otherwise G is constant and no scan is needed.
+                double Gincl = Gprev, Gexcl = Gprev;
+                uint32_t word = 0;
+                const unsigned any_end = __ballot_sync(0xffffffffu, active && X > Gprev);
+                if (any_end) {
+                    int jx = 0;
+                    double Xi = NEG;
 #pragma unroll
                     for (int j = 0; j < N; j++) {
-                        if (j == i) continue;
-                        double v = tails[j] + eT[j * NP + i];
-                        if (v > best) {
-                            best = v;
-                            k = j + 1;
+                        double v = tails[j] + eG[j];
+                        if (v > Xi) {  // strict: first maximum in candidate order
+                            Xi = v;
+                            jx = j + 1;
                         }
                     }
-                    word |= (uint32_t)k << (4 * (i + 1));
-                    if (active) {
-                        ring[i * RING_Q + (int)(tau & (RING_Q - 1))] = best + Fv[i];
-                        if (last) p.Pfin[((size_t)ch * N + i) * RING_Q + (int)(tau & (RING_Q - 1))] = best;
+                    double M = X;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        double o = shfl_up_d(M, d);
+                        if (lane >= d && o > M) M = o;
+                    }
+                    Gincl = (M > Gprev) ? M : Gprev;
+                    Gexcl = shfl_up_d(Gincl, 1);
+                    if (lane == 0) Gexcl = Gprev;
+                    word = (X > Gexcl) ? (uint32_t)jx : 0u;  // noise (first candidate) keeps ties
+                }
+                // Fast path 2: a tail -> head candidate can win only if
+                // max_j tail_j + max eT > G + min eH (rounding is monotone, so this bound is exact).
+                double tmax = tails[0];
+#pragma unroll
+                for (int j = 1; j < N; j++) tmax = (tails[j] > tmax) ? tails[j] : tmax;
+                const unsigned any_th = __ballot_sync(0xffffffffu, active && (tmax + eTmax > Gexcl + eHmin));
+                double Pv[N];
+                if (any_th) {
+#pragma unroll
+                    for (int i = 0; i < N; i++) {
+                        double best = Gexcl + eH[i];
+                        int k = 0;
+#pragma unroll
+                        for (int j = 0; j < N; j++) {
+                            if (j == i) continue;
+                            double v = tails[j] + eT[j * NP + i];
+                            if (v > best) {
+                                best = v;
+                                k = j + 1;
+                            }
+                        }
+                        word |= (uint32_t)k << (4 * (i + 1));
+                        Pv[i] = best;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < N; i++) Pv[i] = Gexcl + eH[i];
+                }
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < N; i++) {
+                        ring[i * RING_Q + slot_w] = Pv[i] + Fv[i];
+                        if (last) p.Pfin[((size_t)ch * N + i) * RING_Q + slot_w] = Pv[i];
                     }
                 }
                 if (active) myword = word;
-                nz |= __ballot_sync(0xffffffffu, active && (word & 15u) != 0);
-                Gprev = shfl_d(Gincl, 31);
+                if (any_end) {
+                    nz |= __ballot_sync(0xffffffffu, active && (word & 15u) != 0);
+                    Gprev = shfl_d(Gincl, 31);
+                }
                 __syncwarp();
             }
-            if (tau0 >= s) {  // main range only (warm-up decisions belong to the previous chunk)
-                if (tau < e) dec[tau] = myword;
+            if (t0_rel >= s_rel) {  // main range only (warm-up decisions belong to the previous chunk)
+                const int64_t tau0 = base0 + t0_rel;
+                if (t_rel < e_rel) dec[tau0 + lane] = myword;
                 if (lane == 0) nzm[tau0 >> 5] = nz;
             }
         }
@@ -337,7 +408,7 @@ __device__ void load_model_smem(const VitParams &p, int ch, double *mdl) {
 }
 
 template <int N, int R>
-__global__ void __launch_bounds__(128) ring_vit_forward(VitParams p) {
+__global__ void __launch_bounds__(128, 4) ring_vit_forward(VitParams p) {
     extern __shared__ __align__(16) double smem_d[];
     const int ch = blockIdx.y;
     double *mdl = smem_d;
@@ -346,6 +417,12 @@ __global__ void __launch_bounds__(128) ring_vit_forward(VitParams p) {
     const int c = blockIdx.x * (blockDim.x >> 5) + warp;
     if (c >= p.nchunks) return;
     double *ws = smem_d + ((p.RL.total + 1) & ~1) + (size_t)warp * WarpSmem<N, R>::DOUBLES;
+    if (p.stagger_ns > 0) {
+        // Co-resident CTAs start in lockstep and would alternate between an FP64-pipe-bound
+        // phase (FIR) and a latency-bound phase (recursion) together; offset them.
+        int k = (int)((blockIdx.x / (unsigned)p.n_sm) & 3u);
+        for (int q = 0; q < k; q++) __nanosleep(p.stagger_ns);
+    }
     vit_process_chunk<N, R>(p, ch, c, c == 0 ? START_PROLOGUE : START_SPEC, mdl, ws);
 }
 
@@ -724,6 +801,29 @@ static void launch_all(VitParams &p, int C, cudaStream_t st, hmm_info *info, Tim
     if (info) info->kernel_launches += 7;
 }
 
+template <int N, int R>
+static int fwd_warps_per_sm(const RingLayout &RL) {
+    constexpr int WPB = 4;
+    const size_t sm_fwd = sizeof(double) * (((RL.total + 1) & ~1) + (size_t)WPB * WarpSmem<N, R>::DOUBLES);
+    HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+    int nb = 0;
+    HMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ring_vit_forward<N, R>, 32 * WPB, sm_fwd));
+    return (nb > 0 ? nb : 1) * WPB;
+}
+
+static int fwd_warps_per_sm_dispatch(int N, const RingLayout &RL) {
+    switch (N) {
+        case 1: return fwd_warps_per_sm<1, 8>(RL);
+        case 2: return fwd_warps_per_sm<2, 8>(RL);
+        case 3: return fwd_warps_per_sm<3, 8>(RL);
+        case 4: return fwd_warps_per_sm<4, 8>(RL);
+        case 5: return fwd_warps_per_sm<5, 4>(RL);
+        case 6: return fwd_warps_per_sm<6, 4>(RL);
+        case 7: return fwd_warps_per_sm<7, 4>(RL);
+    }
+    fail(HMM_EUNSUPPORTED, "ring engine supports 1..%d neurons", RING_MAX_N);
+}
+
 void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, const std::vector<HostModel> &models,
                       const FaithfulLayout &FL, const char *blob_dev, int16_t *x_dev, int64_t x_stride, double *ll_dev,
                       cudaStream_t st, hmm_info *info) {
@@ -740,7 +840,11 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
     if (W < ((L + 32 + SW - 1) / SW) * SW) W = ((L + 32 + SW - 1) / SW) * SW;
     int64_t Lc = ring_config().chunk_len;
     if (Lc <= 0) {
-        const int64_t target_warps = 148 * 12;
+        int dev = 0, sms = 148;
+        HMM_CUDA(cudaGetDevice(&dev));
+        HMM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        // one chunk per resident warp: a single, full wave over the whole GPU
+        const int64_t target_warps = (int64_t)sms * fwd_warps_per_sm_dispatch(N, RL);
         int64_t per_channel = (target_warps + C - 1) / C;
         Lc = (T + per_channel - 1) / per_channel;
         if (Lc < 4 * W) Lc = 4 * W;
@@ -816,6 +920,13 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
     p.own_start = (long long *)(base + o_own);
     p.look_end = (long long *)(base + o_look);
     p.tr_flag = (int *)(base + o_trflag);
+    {
+        const char *e = getenv("HMMCUDA_STAGGER_NS");
+        p.stagger_ns = e ? atoi(e) : 0;
+        int dev = 0;
+        HMM_CUDA(cudaGetDevice(&dev));
+        HMM_CUDA(cudaDeviceGetAttribute(&p.n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
 
     Timer ttop(st);
     switch (N * 10 + R) {
