@@ -26,7 +26,7 @@ constexpr int RING_Q = 128;      // ring-buffer length (>= L + 32), power of two
 // Per-channel ring model, a flat array of doubles on the device.
 struct RingLayout {
     int N, L, LP, NP;            // LP = L rounded up to 8; NP = N rounded up to even
-    int A, BW, Bc, eG, eH, eT, scal, total;  // offsets in doubles
+    int A, BW, B0, BWsuf, Bc, eG, eH, eT, scal, hot, total;  // offsets in doubles
 };
 // scal[]: 0 w_nn, 1 c_emit, 2 two_s2, 3 m0, 4 sigma
 __host__ __device__ inline RingLayout ring_layout(int N, int L) {
@@ -36,13 +36,18 @@ __host__ __device__ inline RingLayout ring_layout(int N, int L) {
     R.LP = (L + 7) & ~7;
     R.NP = (N + 1) & ~1;
     int o = 0;
+    // hot prefix (copied to shared memory by the recursion kernels)
     R.A = o;  o += R.LP * R.NP;   // A[r*NP + i]
-    R.BW = o; o += R.LP * R.NP;   // BW[r*NP + i] = b[i][r] + (r>0 ? w_c[i][r-1]-w_nn : 0)
     R.Bc = o; o += R.NP;
     R.eG = o; o += R.NP;
     R.eH = o; o += R.NP;
     R.eT = o; o += N * R.NP;      // eT[j*NP + i]
     R.scal = o; o += 8;
+    R.hot = o;
+    // cold part (boundary handling only; read from global memory)
+    R.BW = o; o += R.LP * R.NP;   // BW[r*NP + i] = b[i][r] + (r>0 ? w_c[i][r-1]-w_nn : 0)
+    R.B0 = o; o += R.LP * R.NP;   // B0[r*NP + i] = b[i][r]
+    R.BWsuf = o; o += (R.LP + 1) * R.NP;  // BWsuf[k*NP + i] = sum_{r>=k} BW[r][i]
     R.total = o;
     return R;
 }
@@ -73,5 +78,100 @@ struct FirGeom {
     static constexpr int YTILE = R * YS;                    // doubles
     static constexpr int FTILE = R * FS;                    // doubles per neuron
 };
+
+// Stage y[b, b + SW + LP) into the transposed tile with cp.async (zero beyond T),
+// then run the register-blocked FIR: lane computes F_i(b + R*lane + j), j < R,
+// F_i(t0) = Bc[i] + sum_r A[r][i] * y[t0 + r], and leaves the results in `fbuf`
+// (element t0-b = R*l + j of neuron i at fbuf[i*FTILE + j*FS + l]).
+// `fbuf` may alias `ytile`.  A is the shared-memory copy [LP][NP] (zero padded).
+template <int N, int R>
+__device__ __forceinline__ void fir_superwindow(const double *__restrict__ y, int64_t T, int64_t b,
+                                                const double *A, const double *Bc, int LP, double *ytile,
+                                                double *fbuf, int lane) {
+    using G = FirGeom<R>;
+    constexpr int NP = (N + 1) & ~1;
+    {
+        const int need = G::SW + LP;
+        for (int k = lane; k < need; k += 32) {
+            int64_t g = b + k;
+            double *dst = ytile + (k & (R - 1)) * G::YS + (k >> G::LOGR);
+            if (g < T)
+                cp_async8(dst, y + g);
+            else
+                *dst = 0.0;
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncwarp();
+    }
+    double acc[N][R];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j < R; j++) acc[i][j] = Bc[i];
+    double w[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) w[j] = ytile[j * G::YS + lane];  // elements R*lane + j
+    auto load_coef = [&](int r, double *dst) {
+        const double2 *src = reinterpret_cast<const double2 *>(A + r * NP);
+#pragma unroll
+        for (int i2 = 0; i2 < NP / 2; i2++) {
+            double2 v = src[i2];
+            if (2 * i2 < N) dst[2 * i2] = v.x;
+            if (2 * i2 + 1 < N) dst[2 * i2 + 1] = v.y;
+        }
+    };
+    double a0[N], a1[N];
+    load_coef(0, a0);
+    for (int r0 = 0; r0 < LP; r0 += R) {
+        const int col = lane + 1 + (r0 >> G::LOGR);
+#pragma unroll
+        for (int u = 0; u < R; u += 2) {
+            // coefficients are fetched one tap ahead into the other register set
+            load_coef(r0 + u + 1, a1);
+            double ynew = ytile[u * G::YS + col];  // element R*lane + (r0+u) + R
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                const double yv = w[(u + j) % R];
+#pragma unroll
+                for (int i = 0; i < N; i++) acc[i][j] = fma(a0[i], yv, acc[i][j]);
+            }
+            w[u] = ynew;
+            load_coef(r0 + u + 2 < LP ? r0 + u + 2 : LP - 1, a0);
+            ynew = ytile[(u + 1) * G::YS + col];
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                const double yv = w[(u + 1 + j) % R];
+#pragma unroll
+                for (int i = 0; i < N; i++) acc[i][j] = fma(a1[i], yv, acc[i][j]);
+            }
+            w[u + 1] = ynew;
+        }
+    }
+    __syncwarp();  // every lane is done with the y tile before F overwrites it
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j < R; j++) fbuf[i * G::FTILE + j * G::FS + lane] = acc[i][j];
+    __syncwarp();
+}
+
+// F value of step (local index tl in the super-window) for the lane-per-step mapping
+template <int R>
+__device__ __forceinline__ int fbuf_index(int tl) {
+    using G = FirGeom<R>;
+    return (tl & (R - 1)) * G::FS + (tl >> G::LOGR);
+}
+
+// log(exp(a) + exp(b)); exact shortcut when the smaller term is below half an ulp
+// of the larger (log1p(exp(d)) < 2^-54 for d < -37.5), which is also what the
+// reference's logsumexpl (src/utils.jl:24-32) rounds to.
+__device__ __forceinline__ double lse2(double a, double b) {
+    double hi = a > b ? a : b, lo = a > b ? b : a;
+    if (lo == -INFINITY) return hi;
+    double d = lo - hi;
+    if (d > -37.5) hi += log1p(exp(d));
+    return hi;
+}
 
 }  // namespace hmm

@@ -1,6 +1,822 @@
-#include "engines.h"
+// ring_em.cu -- one fused Baum-Welch E/M step for non-overlap ring models
+// (forward + backward + update of src/baumwelch.jl:25-51, 73-98, 205-309,
+// 362-370) without ever materialising alpha, beta or gamma (nstates x T).
+//
+// Because a chain is a delay line, being in chain state (i, s) at time t is
+// the same event as "chain i was entered at t0 = t - s + 1", so
+//     gamma_t(i, s) = pi_i(t - s + 1)
+// and the whole E-step reduces to, per sample, the noise posterior, one
+// entry posterior per neuron, and the FIR scores F_i(t0) (ring_common.cuh):
+//   forward : lg_t  = LSE(lg_{t-1}, ltail_{t-1}(j) + lA_j)
+//             lp_t(i)= LSE(lg_{t-1} + lH_i, ltail_{t-1}(j) + lC_ji)
+//             ltail_t(i) = lp_{t-L+1}(i) + F_i(t-L+1)
+//   backward: lh_t  = LSE(lh_{t+1}, lH_i + lr_{t+1}(i))
+//             le_t(i)= LSE(lA_i + lh_{t+1}, lC_ij + lr_{t+1}(j))
+//             lr_t(i)= F_i(t) + le_{t+L-1}(i)
+// all in the log domain, normalised by the all-noise path, 32 time steps per
+// warp pass with a warp-shuffle log-sum-exp scan for the noise state.
+// M-step statistics: S0 = sum pi, S1[s] = sum pi(t0) y[t0+s] (a sparse
+// correlation), xi counts for lA, sum y^2 -- fused reductions (pass 3).
+// Time is cut into chunks with speculative warm-up, verified and repaired
+// exactly like the Viterbi engine (ring_viterbi.cu).
+#include <cmath>
+#include <cstdlib>
+#include <limits>
+
+#include "ring_common.cuh"
+
 namespace hmm {
-void ring_em_run(const double *, int64_t, const HostModel &, EmResult &, cudaStream_t, hmm_info *) {
-    fail(HMM_EUNSUPPORTED, "ring E/M engine not built");
+
+struct EmParams {
+    const double *y;
+    int64_t T;
+    const double *model;  // one channel
+    RingLayout RL;
+    int64_t Lc, W;
+    int nchunks, ns;
+    double *Fg, *LG, *LQ, *LH, *LE;  // per-step arrays: Fg/LQ/LE are [N][T]
+    double *LQneg;                    // [N][L]: virtual chains already running at t=0 (entered at -r0)
+    double *SBf, *EBf, *SBb, *EBb;    // boundary vectors [nchunks][bvec]
+    int bvec;
+    int *flag_f, *flag_b;
+    double *kappa, *lambda;           // per-chunk log offsets (forward / backward)
+    double *lS;                       // [1] log of the normalised total likelihood
+    int *counters;                    // [0] fwd repaired [1] bwd repaired
+    double *part;                     // [nblk][PSTRIDE] statistic partials
+    int nblk, pstride;
+    double *out;                      // finalize output
+};
+
+enum { EM_INIT = 0, EM_SPEC = 1, EM_EXACT = 2 };
+constexpr int S1_LAGS = 96;  // == RING_MAX_L
+
+template <int N, int R>
+struct EmWarpSmem {
+    using G = FirGeom<R>;
+    static constexpr int TILE = (G::YTILE > N * G::FTILE) ? G::YTILE : N * G::FTILE;
+    static constexpr int DOUBLES = TILE + N * RING_Q;
+};
+
+// Inclusive log-sum-exp scan over the lanes of a warp (lane 0 first).
+__device__ __forceinline__ double lse_scan(double v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        double o = shfl_up_d(v, d);
+        if (lane >= d) v = lse2(v, o);
+    }
+    return v;
 }
+
+// ---------------------------------------------------------------------------
+// forward, one chunk per warp
+// ---------------------------------------------------------------------------
+template <int N, int R>
+__device__ void em_fwd_chunk(const EmParams &p, int c, int kind, const double *mdl, double *ws) {
+    using G = FirGeom<R>;
+    constexpr int NP = (N + 1) & ~1;
+    const int lane = threadIdx.x & 31;
+    const RingLayout &RL = p.RL;
+    const int L = RL.L, LP = RL.LP;
+    const double NEG = -INFINITY;
+    double *ytile = ws, *fbuf = ws;
+    double *ring = ws + EmWarpSmem<N, R>::TILE;
+    const double *A = mdl + RL.A, *Bc = mdl + RL.Bc, *lA = mdl + RL.eG, *lH = mdl + RL.eH, *lC = mdl + RL.eT;
+    const double *cold = p.model;
+    const double *y = p.y;
+    const int64_t T = p.T;
+    const int64_t s = (int64_t)c * p.Lc;
+    int64_t e = s + p.Lc;
+    const bool last = (c == p.nchunks - 1);
+    if (last || e > T) e = T;
+    int64_t base0, tau_first;
+    double lgprev;
+    for (int k = lane; k < N * RING_Q; k += 32) ring[k] = NEG;
+    __syncwarp();
+    if (kind == EM_INIT) {
+        base0 = 0;
+        tau_first = 1;
+        lgprev = 0.0;  // alpha_1(noise) / itself
+        // chains already running at t = 0: state (i, r0+1) <-> entered at tau0 = -r0 with weight 1
+        const double *BW = cold + RL.BW, *B0 = cold + RL.B0;
+        for (int idx = lane; idx < N * L; idx += 32) {
+            int i = idx / L, r0 = idx % L;
+            double f = 0.0;
+            for (int r = r0; r < L; r++) f += fma(cold[RL.A + r * NP + i], y[r - r0], BW[r * NP + i]);
+            if (r0 >= 1) f -= BW[r0 * NP + i] - B0[r0 * NP + i];  // no chain transition INTO the first sample
+            ring[i * RING_Q + ((-r0) & (RING_Q - 1))] = f;
+            p.LQneg[i * L + r0] = f;
+        }
+    } else if (kind == EM_SPEC) {
+        base0 = s - p.W;
+        if (base0 < 0) base0 = 0;
+        tau_first = base0;
+        lgprev = 0.0;
+    } else {
+        base0 = s;
+        tau_first = s;
+        const double *eb = p.EBf + (size_t)(c - 1) * p.bvec;
+        lgprev = eb[0];
+        for (int k = lane; k < L; k += 32) {
+            int64_t t0 = s - L + k;
+            for (int j = 0; j < N; j++) ring[j * RING_Q + (int)(t0 & (RING_Q - 1))] = eb[1 + j * L + k];
+        }
+    }
+    __syncwarp();
+    const int Wd = L < 32 ? L : 32;
+    const int nsub = (32 + Wd - 1) / Wd;
+    const int mysub = lane / Wd;
+    const int tf_rel = (int)(tau_first - base0), e_rel = (int)(e - base0), s_rel = (int)(s - base0);
+
+    for (int64_t b = base0; b < e; b += G::SW) {
+        fir_superwindow<N, R>(y, T, b, A, Bc, LP, ytile, fbuf, lane);
+        if (kind == EM_SPEC && b == s) {
+            double *sb = p.SBf + (size_t)c * p.bvec;
+            if (lane == 0) sb[0] = lgprev;
+            for (int k = lane; k < L; k += 32) {
+                int64_t t0 = s - L + k;
+                for (int j = 0; j < N; j++) sb[1 + j * L + k] = ring[j * RING_Q + (int)(t0 & (RING_Q - 1))];
+            }
+        }
+        const int b_rel = (int)(b - base0);
+        for (int wdw = 0; wdw < R; wdw++) {
+            const int t0_rel = b_rel + 32 * wdw;
+            if (t0_rel >= e_rel) break;
+            const int tl = 32 * wdw + lane;
+            const int t_rel = t0_rel + lane;
+            const int64_t tau = base0 + t_rel;
+            double Fv[N];
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                double f = fbuf[i * G::FTILE + fbuf_index<R>(tl)];
+                // chains that run past the end of the recording: drop the terms beyond T-1
+                if (tau > T - L && tau < T) f -= cold[RL.BWsuf + (int)(T - tau) * NP + i];
+                Fv[i] = f;
+            }
+            if (t0_rel >= s_rel && tau < e) {
+#pragma unroll
+                for (int i = 0; i < N; i++) p.Fg[(size_t)i * T + tau] = Fv[i];
+            }
+            const bool in_range = t_rel >= tf_rel && t_rel < e_rel;
+            const int slot_w = t_rel & (RING_Q - 1);
+            const int slot_r = (t_rel - L) & (RING_Q - 1);
+            if (kind == EM_INIT && tau == 0) {
+                p.LG[0] = 0.0;
+#pragma unroll
+                for (int i = 0; i < N; i++) {
+                    p.LQ[(size_t)i * T] = Fv[i];
+                    ring[i * RING_Q] = Fv[i];
+                }
+            }
+            __syncwarp();
+            for (int sub = 0; sub < nsub; sub++) {
+                const bool active = in_range && (mysub == sub);
+                double lt[N];
+#pragma unroll
+                for (int j = 0; j < N; j++) lt[j] = active ? ring[j * RING_Q + slot_r] : NEG;
+                double lX = NEG;
+#pragma unroll
+                for (int j = 0; j < N; j++) lX = lse2(lX, lt[j] + lA[j]);
+                const double lCs = lse_scan(lX, lane);
+                const double lg = lse2(lgprev, lCs);
+                double lgm1 = shfl_up_d(lg, 1);
+                if (lane == 0) lgm1 = lgprev;
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < N; i++) {
+                        double lp = lgm1 + lH[i];
+#pragma unroll
+                        for (int j = 0; j < N; j++)
+                            if (j != i) lp = lse2(lp, lt[j] + lC[j * NP + i]);
+                        const double lq = lp + Fv[i];
+                        ring[i * RING_Q + slot_w] = lq;
+                        if (t0_rel >= s_rel) p.LQ[(size_t)i * T + tau] = lq;
+                    }
+                    if (t0_rel >= s_rel) p.LG[tau] = lg;
+                }
+                lgprev = shfl_d(lg, 31);
+                __syncwarp();
+            }
+        }
+    }
+    if (!last) {
+        double *eb = p.EBf + (size_t)c * p.bvec;
+        if (lane == 0) eb[0] = lgprev;
+        for (int k = lane; k < L; k += 32) {
+            int64_t t0 = e - L + k;
+            for (int j = 0; j < N; j++) eb[1 + j * L + k] = ring[j * RING_Q + (int)(t0 & (RING_Q - 1))];
+        }
+    }
+    __syncwarp();
 }
+
+template <int N, int R>
+__global__ void __launch_bounds__(128) em_forward(EmParams p) {
+    extern __shared__ __align__(16) double smem_d[];
+    double *mdl = smem_d;
+    for (int k = threadIdx.x; k < p.RL.hot; k += blockDim.x) mdl[k] = p.model[k];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (c >= p.nchunks) return;
+    double *ws = smem_d + ((p.RL.hot + 1) & ~1) + (size_t)warp * EmWarpSmem<N, R>::DOUBLES;
+    em_fwd_chunk<N, R>(p, c, c == 0 ? EM_INIT : EM_SPEC, mdl, ws);
+}
+
+// Two boundary vectors describe the same distribution iff they differ by a
+// constant; entries more than 745 below the maximum cannot influence a double.
+__device__ __forceinline__ bool em_boundary_matches(const double *sb, const double *eb, int n, int lane) {
+    double ms = -INFINITY, me = -INFINITY;
+    for (int k = lane; k < n; k += 32) {
+        ms = fmax(ms, sb[k]);
+        me = fmax(me, eb[k]);
+    }
+    for (int d = 16; d >= 1; d >>= 1) {
+        ms = fmax(ms, __shfl_xor_sync(0xffffffffu, ms, d));
+        me = fmax(me, __shfl_xor_sync(0xffffffffu, me, d));
+    }
+    bool bad = false;
+    for (int k = lane; k < n; k += 32) {
+        double a = sb[k] - ms, b = eb[k] - me;
+        if (a < -745.0 && b < -745.0) continue;
+        if (!(fabs(a - b) <= 1e-11 + 1e-13 * fabs(b))) bad = true;
+    }
+    return !__any_sync(0xffffffffu, bad);
+}
+
+__global__ void em_check(EmParams p, int backward) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (!backward) {
+        if (gw >= p.nchunks || gw == 0) return;
+        bool ok = em_boundary_matches(p.SBf + (size_t)gw * p.bvec, p.EBf + (size_t)(gw - 1) * p.bvec, p.bvec, lane);
+        if (lane == 0) p.flag_f[gw] = ok ? 0 : 1;
+    } else {
+        if (gw >= p.nchunks - 1) return;
+        bool ok = em_boundary_matches(p.SBb + (size_t)gw * p.bvec, p.EBb + (size_t)(gw + 1) * p.bvec, p.bvec, lane);
+        if (lane == 0) p.flag_b[gw] = ok ? 0 : 1;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// backward, one chunk per warp
+// ---------------------------------------------------------------------------
+template <int N>
+__device__ void em_bwd_chunk(const EmParams &p, int c, int kind, const double *mdl, double *ring) {
+    constexpr int NP = (N + 1) & ~1;
+    const int lane = threadIdx.x & 31;
+    const RingLayout &RL = p.RL;
+    const int L = RL.L;
+    const double *lA = mdl + RL.eG, *lH = mdl + RL.eH, *lC = mdl + RL.eT;
+    const int64_t T = p.T;
+    const int64_t s = (int64_t)c * p.Lc;
+    int64_t e = s + p.Lc;
+    const bool last = (c == p.nchunks - 1);
+    if (last || e > T) e = T;
+    // state is known (or assumed) at time `hi`; steps hi-1 .. s are computed
+    int64_t hi;
+    double lhprev = 0.0;
+    for (int k = lane; k < N * RING_Q; k += 32) ring[k] = 0.0;  // beyond-the-end chains contribute e = 1
+    __syncwarp();
+    bool true_end = false;
+    if (kind == EM_EXACT) {
+        hi = e;  // boundary vector of chunk c+1 lives at time e
+        const double *eb = p.EBb + (size_t)(c + 1) * p.bvec;
+        lhprev = eb[0];
+        for (int k = lane; k < L; k += 32)
+            for (int j = 0; j < N; j++) ring[j * RING_Q + (int)((e + k) & (RING_Q - 1))] = eb[1 + j * L + k];
+    } else {
+        hi = e + p.W;
+        if (last || hi >= T - 1) {
+            hi = T - 1;
+            true_end = true;
+        }
+        if (true_end && e == T && lane == 0) {  // beta_T = 0 (src/baumwelch.jl:80)
+            p.LH[T - 1] = 0.0;
+            for (int i = 0; i < N; i++) p.LE[(size_t)i * T + T - 1] = 0.0;
+        }
+    }
+    __syncwarp();
+    const int Wd = L < 32 ? L : 32;
+    const int nsub = (32 + Wd - 1) / Wd;
+    const int mysub = lane / Wd;
+    // windows of 32 steps, descending; lane 0 is the latest step of the window
+    for (int64_t wtop = ((hi - 1) | 31); wtop >= s; wtop -= 32) {
+        const int64_t t = wtop - lane;
+        const bool in_range = t <= hi - 1 && t >= s;
+        double Fn[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) Fn[i] = (in_range) ? p.Fg[(size_t)i * T + t + 1] : 0.0;
+        // F of the warm-up region belongs to the next chunk and is complete: the forward pass has finished
+        for (int sub = 0; sub < nsub; sub++) {
+            const bool active = in_range && (mysub == sub);
+            double lr[N];
+#pragma unroll
+            for (int j = 0; j < N; j++)
+                lr[j] = active ? Fn[j] + ring[j * RING_Q + (int)((t + L) & (RING_Q - 1))] : -INFINITY;
+            double lY = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < N; j++) lY = lse2(lY, lH[j] + lr[j]);
+            const double sc = lse_scan(lY, lane);
+            const double lh = lse2(lhprev, sc);
+            double lhp1 = shfl_up_d(lh, 1);  // lh_{t+1}
+            if (lane == 0) lhp1 = lhprev;
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < N; i++) {
+                    double le = lA[i] + lhp1;
+#pragma unroll
+                    for (int j = 0; j < N; j++)
+                        if (j != i) le = lse2(le, lC[i * NP + j] + lr[j]);
+                    ring[i * RING_Q + (int)(t & (RING_Q - 1))] = le;
+                    if (t < e) p.LE[(size_t)i * T + t] = le;
+                }
+                if (t < e) p.LH[t] = lh;
+            }
+            lhprev = shfl_d(lh, 31);
+            __syncwarp();
+        }
+        // speculative boundary vector at time e (after the window whose lowest step is e)
+        if (kind == EM_SPEC && !last && wtop - 31 == e) {
+            double *sb = p.SBb + (size_t)c * p.bvec;
+            if (lane == 0) sb[0] = lhprev;
+            for (int k = lane; k < L; k += 32)
+                for (int j = 0; j < N; j++) sb[1 + j * L + k] = ring[j * RING_Q + (int)((e + k) & (RING_Q - 1))];
+            __syncwarp();
+        }
+    }
+    if (c > 0) {  // true boundary vector at time s for chunk c-1
+        double *eb = p.EBb + (size_t)c * p.bvec;
+        if (lane == 0) eb[0] = lhprev;
+        for (int k = lane; k < L; k += 32)
+            for (int j = 0; j < N; j++) eb[1 + j * L + k] = ring[j * RING_Q + (int)((s + k) & (RING_Q - 1))];
+    }
+    __syncwarp();
+}
+
+template <int N>
+__global__ void __launch_bounds__(128) em_backward(EmParams p) {
+    extern __shared__ __align__(16) double smem_d[];
+    double *mdl = smem_d;
+    for (int k = threadIdx.x; k < p.RL.hot; k += blockDim.x) mdl[k] = p.model[k];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (c >= p.nchunks) return;
+    double *ring = smem_d + ((p.RL.hot + 1) & ~1) + (size_t)warp * N * RING_Q;
+    em_bwd_chunk<N>(p, c, EM_SPEC, mdl, ring);
+}
+
+// ---------------------------------------------------------------------------
+// sequential repair + per-chunk log offsets (one warp)
+// ---------------------------------------------------------------------------
+template <int N, int R>
+__global__ void __launch_bounds__(32) em_repair_fwd(EmParams p) {
+    extern __shared__ __align__(16) double smem_d[];
+    const int lane = threadIdx.x;
+    int any = 0;
+    for (int c = 1 + lane; c < p.nchunks; c += 32) any |= p.flag_f[c];
+    int repaired = 0;
+    if (__any_sync(0xffffffffu, any)) {
+        double *mdl = smem_d;
+        for (int k = lane; k < p.RL.hot; k += 32) mdl[k] = p.model[k];
+        __syncwarp();
+        double *ws = smem_d + ((p.RL.hot + 1) & ~1);
+        bool prev = false;
+        for (int c = 1; c < p.nchunks; c++) {
+            bool need = p.flag_f[c] != 0;
+            if (!need && prev)
+                need = !em_boundary_matches(p.SBf + (size_t)c * p.bvec, p.EBf + (size_t)(c - 1) * p.bvec, p.bvec, lane);
+            if (need) {
+                em_fwd_chunk<N, R>(p, c, EM_EXACT, mdl, ws);
+                // an exactly restarted chunk continues chunk c-1's normalisation
+                if (lane == 0) p.SBf[(size_t)c * p.bvec] = p.EBf[(size_t)(c - 1) * p.bvec];
+                __threadfence();
+                __syncwarp();
+                repaired++;
+            }
+            prev = need;
+        }
+    }
+    if (lane == 0) p.counters[0] = repaired;
+}
+
+template <int N>
+__global__ void __launch_bounds__(32) em_repair_bwd(EmParams p) {
+    extern __shared__ __align__(16) double smem_d[];
+    const int lane = threadIdx.x;
+    int any = 0;
+    for (int c = lane; c < p.nchunks - 1; c += 32) any |= p.flag_b[c];
+    int repaired = 0;
+    if (__any_sync(0xffffffffu, any)) {
+        double *mdl = smem_d;
+        for (int k = lane; k < p.RL.hot; k += 32) mdl[k] = p.model[k];
+        __syncwarp();
+        double *ring = smem_d + ((p.RL.hot + 1) & ~1);
+        bool prev = false;
+        for (int c = p.nchunks - 2; c >= 0; c--) {
+            bool need = p.flag_b[c] != 0;
+            if (!need && prev)
+                need = !em_boundary_matches(p.SBb + (size_t)c * p.bvec, p.EBb + (size_t)(c + 1) * p.bvec, p.bvec, lane);
+            if (need) {
+                em_bwd_chunk<N>(p, c, EM_EXACT, mdl, ring);
+                if (lane == 0) p.SBb[(size_t)c * p.bvec] = p.EBb[(size_t)(c + 1) * p.bvec];
+                __threadfence();
+                __syncwarp();
+                repaired++;
+            }
+            prev = need;
+        }
+    }
+    if (lane == 0) p.counters[1] = repaired;
+}
+
+// kappa_c = sum_{k<=c} (EBf[k-1].lg - SBf[k].lg);  lambda_c = sum_{k>=c} (EBb[k+1].lh - SBb[k].lh)
+// plus lS = kappa_last + LSE(alpha-hat at T-1).  Single block.
+template <int N>
+__global__ void __launch_bounds__(256) em_offsets(EmParams p, int backward) {
+    __shared__ double buf[256];
+    __shared__ double carry;
+    const int n = p.nchunks;
+    if (threadIdx.x == 0) carry = 0.0;
+    __syncthreads();
+    if (!backward) {
+        for (int base = 0; base < n; base += 256) {
+            int c = base + threadIdx.x;
+            double d = (c >= 1 && c < n) ? p.EBf[(size_t)(c - 1) * p.bvec] - p.SBf[(size_t)c * p.bvec] : 0.0;
+            buf[threadIdx.x] = d;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double a = carry;
+                for (int k = 0; k < 256 && base + k < n; k++) {
+                    a += buf[k];
+                    buf[k] = a;
+                }
+                carry = a;
+            }
+            __syncthreads();
+            if (c < n) p.kappa[c] = buf[threadIdx.x];
+            __syncthreads();
+        }
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x, L = p.RL.L;
+            const int64_t T = p.T;
+            double v = -INFINITY;
+            for (int idx = lane; idx < N * L; idx += 32) {
+                int i = idx / L, k = idx % L;  // t0 = T - L + k
+                v = lse2(v, p.LQ[(size_t)i * T + (T - L + k)]);
+            }
+            if (lane == 0) v = lse2(v, p.LG[T - 1]);
+            for (int d = 16; d >= 1; d >>= 1) v = lse2(v, __shfl_xor_sync(0xffffffffu, v, d));
+            if (lane == 0) p.lS[0] = v + carry;  // carry == kappa of the last chunk
+        }
+    } else {
+        for (int top = n - 1; top >= 0; top -= 256) {
+            int c = top - threadIdx.x;
+            double d = (c >= 0 && c < n - 1) ? p.EBb[(size_t)(c + 1) * p.bvec] - p.SBb[(size_t)c * p.bvec] : 0.0;
+            buf[threadIdx.x] = d;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double a = carry;
+                for (int k = 0; k < 256 && top - k >= 0; k++) {
+                    a += buf[k];
+                    buf[k] = a;
+                }
+                carry = a;
+            }
+            __syncthreads();
+            if (c >= 0) p.lambda[c] = buf[threadIdx.x];
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// pass 3: posteriors and M-step sufficient statistics (fused reductions)
+// partial layout: [0] sum gamma0 (t <= T-2)  [1] sum y  [2] sum y^2  [3] sum gamma0 (all t)
+//                 [4 .. 4+N) xi_i   [4+N .. 4+2N) S0tot_i   then S1[i][lag], lag < S1_LAGS
+// ---------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(128) em_stats(EmParams p) {
+    extern __shared__ __align__(16) double smem_d[];
+    constexpr int WPB = 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const RingLayout &RL = p.RL;
+    const int L = RL.L;
+    const int64_t T = p.T;
+    const double lS = p.lS[0];
+    const double *lH = p.model + RL.eH;
+    double *ysm = smem_d + warp * (160 + N * 32);  // y[t0 .. t0+32+L) then pi[i][32]
+    double *pism = ysm + 160;
+    double a_g0 = 0, a_y = 0, a_y2 = 0, a_g0all = 0;
+    double a_xi[N], a_s0[N], a_s1[N][3];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        a_xi[i] = 0;
+        a_s0[i] = 0;
+        a_s1[i][0] = a_s1[i][1] = a_s1[i][2] = 0;
+    }
+    const int64_t nwin = (T + 31) / 32;
+    const int64_t gw = (int64_t)blockIdx.x * WPB + warp, nw = (int64_t)gridDim.x * WPB;
+    for (int64_t w = gw; w < nwin; w += nw) {
+        const int64_t t = w * 32 + lane;
+        const bool ok = t < T;
+        const int c = ok ? (int)(t / p.Lc) < p.nchunks ? (int)(t / p.Lc) : p.nchunks - 1 : 0;
+        double yv = 0.0;
+        for (int k = lane; k < 32 + L; k += 32) {
+            int64_t g = w * 32 + k;
+            double v = g < T ? p.y[g] : 0.0;
+            ysm[k] = v;
+            if (k == lane) yv = v;
+        }
+        double pi[N];
+        double pmax = 0.0;
+        if (ok) {
+            const double kap = p.kappa[c], lam = p.lambda[c];
+            const double g0 = exp(p.LG[t] + kap + p.LH[t] + lam - lS);
+            a_g0all += g0;
+            if (t <= T - 2) a_g0 += g0;
+            a_y += yv;
+            a_y2 += yv * yv;
+            const int64_t te = t + L - 1;  // chain entered at t ends here
+            int ce = (int)(te / p.Lc);
+            if (ce >= p.nchunks) ce = p.nchunks - 1;
+            const double lame = te <= T - 1 ? p.lambda[ce] : 0.0;
+            const int64_t tx = t + L;  // for xi: chain entered at t+1 ends at t+L
+            int cx = (int)(tx / p.Lc);
+            if (cx >= p.nchunks) cx = p.nchunks - 1;
+            const double lamx = tx <= T - 1 ? p.lambda[cx] : 0.0;
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                const double le = te <= T - 1 ? p.LE[(size_t)i * T + te] + lame : 0.0;
+                pi[i] = exp(p.LQ[(size_t)i * T + t] + kap + le - lS);
+                a_s0[i] += pi[i];
+                pmax = fmax(pmax, pi[i]);
+                if (t <= T - 2) {
+                    const double lex = tx <= T - 1 ? p.LE[(size_t)i * T + tx] + lamx : 0.0;
+                    a_xi[i] += exp(p.LG[t] + kap + lH[i] + p.Fg[(size_t)i * T + t + 1] + lex - lS);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; i++) pi[i] = 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < N; i++) pism[i * 32 + lane] = pi[i];
+        __syncwarp();
+        // S1[i][lag] += pi_i(t0) * y[t0 + lag]; entries below 1e-30 cannot change a double sum >= ~1
+        unsigned sig = __ballot_sync(0xffffffffu, pmax > 1e-30);
+        while (sig) {
+            const int k = __ffs(sig) - 1;
+            sig &= sig - 1;
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const int lag = lane + 32 * q;
+                if (lag < L) {
+                    const double yy = ysm[k + lag];
+#pragma unroll
+                    for (int i = 0; i < N; i++) a_s1[i][q] = fma(pism[i * 32 + k], yy, a_s1[i][q]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // block reduction (fixed order -> deterministic)
+    __syncthreads();
+    double *red = smem_d;  // reuse: [WPB][pstride]
+    auto wsum = [&](double v) {
+        for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        return v;
+    };
+    double r_g0 = wsum(a_g0), r_y = wsum(a_y), r_y2 = wsum(a_y2), r_g0all = wsum(a_g0all);
+    double *mine = red + (size_t)warp * p.pstride;
+    if (lane == 0) {
+        mine[0] = r_g0;
+        mine[1] = r_y;
+        mine[2] = r_y2;
+        mine[3] = r_g0all;
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        double rx = wsum(a_xi[i]), rs = wsum(a_s0[i]);
+        if (lane == 0) {
+            mine[4 + i] = rx;
+            mine[4 + N + i] = rs;
+        }
+#pragma unroll
+        for (int q = 0; q < 3; q++) mine[4 + 2 * N + i * S1_LAGS + lane + 32 * q] = a_s1[i][q];
+    }
+    __syncthreads();
+    double *dst = p.part + (size_t)blockIdx.x * p.pstride;
+    for (int k = threadIdx.x; k < p.pstride; k += blockDim.x) {
+        double v = 0.0;
+        for (int w2 = 0; w2 < WPB; w2++) v += red[(size_t)w2 * p.pstride + k];
+        dst[k] = v;
+    }
+}
+
+// out layout: [0] sigma [1] loglik [2..2+N) lp  then mu [K*N] then pp [ns]
+template <int N>
+__global__ void __launch_bounds__(128) em_finalize(EmParams p) {
+    extern __shared__ __align__(16) double sm[];  // tot[pstride] then S0[N][S1_LAGS]
+    const RingLayout &RL = p.RL;
+    const int L = RL.L, K = L + 1;
+    const int64_t T = p.T;
+    double *tot = sm;
+    double *S0 = sm + p.pstride;
+    for (int k = threadIdx.x; k < p.pstride; k += blockDim.x) {
+        double v = 0.0;
+        for (int b = 0; b < p.nblk; b++) v += p.part[(size_t)b * p.pstride + k];
+        tot[k] = v;
+    }
+    __syncthreads();
+    const double lS = p.lS[0];
+    const double lam0 = p.lambda[0];
+    const double kapl = p.kappa[p.nchunks - 1];
+    double *S1 = tot + 4 + 2 * N;
+    for (int idx = threadIdx.x; idx < N * L; idx += blockDim.x) {
+        const int i = idx / L, sph = idx % L;  // 0-based phase: template row sph+1
+        double s0 = tot[4 + N + i], s1 = S1[i * S1_LAGS + sph];
+        // chains entered in the last L-1 samples never reach phases >= T - t0
+        for (int64_t t0 = T - sph; t0 <= T - 1; t0++)
+            if (t0 > T - L && t0 >= 0) s0 -= exp(p.LQ[(size_t)i * T + t0] + kapl - lS);
+        // chains already running at t = 0 (entered at -r0, r0 = 1..L-1) reach phases >= r0
+        for (int r0 = 1; r0 <= sph; r0++) {
+            const int te = L - 1 - r0;  // their last sample
+            const double pi = exp(p.LQneg[i * L + r0] + p.LE[(size_t)i * T + te] + lam0 - lS);
+            s0 += pi;
+            s1 = fma(pi, p.y[sph - r0], s1);
+        }
+        S0[i * S1_LAGS + sph] = s0;
+        S1[i * S1_LAGS + sph] = s1;
+    }
+    __syncthreads();
+    double *out = p.out;
+    double *mu = out + 2 + N, *pp = mu + (size_t)K * N;
+    for (int idx = threadIdx.x; idx < N * L; idx += blockDim.x) {
+        const int i = idx / L, sph = idx % L;
+        mu[(sph + 1) + (size_t)K * i] = S1[i * S1_LAGS + sph] / S0[i * S1_LAGS + sph];  // src/baumwelch.jl:283-287
+        // pp = gamma[:,1] (log), src/baumwelch.jl:263
+        pp[1 + i * L + sph] = p.LQneg[i * L + sph] + p.LE[(size_t)i * T + (L - 1 - sph)] + lam0 - lS;
+    }
+    if (threadIdx.x < N) mu[(size_t)K * threadIdx.x] = 0.0;  // row 1 stays 0 (src/baumwelch.jl:268)
+    if (threadIdx.x == 0) {
+        pp[0] = p.LG[0] + p.LH[0] + lam0 - lS;
+        double q = 0.0;
+        for (int i = 0; i < N; i++)
+            for (int sph = 0; sph < L; sph++) {
+                double s1 = S1[i * S1_LAGS + sph];
+                q += s1 * s1 / S0[i * S1_LAGS + sph];
+            }
+        // sigma^2 = sum_t sum_j gamma (y - m_j_new)^2 / sum gamma, with m_noise_new = 0 and
+        // m_(i,s)_new = S1/S0  =>  (sum y^2 - sum S1^2/S0) / T      (src/baumwelch.jl:288-307)
+        out[0] = sqrt((tot[2] - q) / (double)T);
+        const double *sc = p.model + RL.scal;
+        const double w_nn = sc[0], c_emit = sc[1], two_s2 = sc[2], m0 = sc[3];
+        const double ssq = tot[2] - 2.0 * m0 * tot[1] + (double)T * m0 * m0;
+        out[1] = (double)T * c_emit - ssq / two_s2 + (double)(T - 1) * w_nn + lS;
+        for (int i = 0; i < N; i++) out[2 + i] = log(tot[4 + i]) - log(tot[0]);  // xb[2:end], :254-265
+    }
+}
+
+// ---------------------------------------------------------------------------
+template <int N, int R>
+static void em_launch(EmParams &p, cudaStream_t st, hmm_info *info, Timer &ttop) {
+    constexpr int WPB = 4;
+    const size_t mdl_d = (p.RL.hot + 1) & ~1;
+    const size_t sm_fwd = sizeof(double) * (mdl_d + (size_t)WPB * EmWarpSmem<N, R>::DOUBLES);
+    const size_t sm_frep = sizeof(double) * (mdl_d + EmWarpSmem<N, R>::DOUBLES);
+    const size_t sm_bwd = sizeof(double) * (mdl_d + (size_t)WPB * N * RING_Q);
+    const size_t sm_brep = sizeof(double) * (mdl_d + (size_t)N * RING_Q);
+    const size_t sm_stats = sizeof(double) * std::max<size_t>((size_t)WPB * (160 + N * 32), (size_t)WPB * p.pstride);
+    const size_t sm_fin = sizeof(double) * ((size_t)p.pstride + (size_t)N * S1_LAGS);
+    HMM_CUDA(cudaFuncSetAttribute(em_forward<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+    HMM_CUDA(cudaFuncSetAttribute(em_repair_fwd<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_frep));
+    HMM_CUDA(cudaFuncSetAttribute(em_stats<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stats));
+    const int gridc = (p.nchunks + WPB - 1) / WPB;
+    const int gchk = (p.nchunks * 32 + 127) / 128;
+    ttop.start();
+    em_forward<N, R><<<gridc, 32 * WPB, sm_fwd, st>>>(p);
+    ttop.stop();
+    em_check<<<gchk, 128, 0, st>>>(p, 0);
+    em_repair_fwd<N, R><<<1, 32, sm_frep, st>>>(p);
+    em_offsets<N><<<1, 256, 0, st>>>(p, 0);
+    em_backward<N><<<gridc, 32 * WPB, sm_bwd, st>>>(p);
+    em_check<<<gchk, 128, 0, st>>>(p, 1);
+    em_repair_bwd<N><<<1, 32, sm_brep, st>>>(p);
+    em_offsets<N><<<1, 256, 0, st>>>(p, 1);
+    em_stats<N><<<p.nblk, 32 * WPB, sm_stats, st>>>(p);
+    em_finalize<N><<<1, 128, sm_fin, st>>>(p);
+    HMM_CUDA(cudaGetLastError());
+    if (info) info->kernel_launches += 10;
+}
+
+void ring_em_run(const double *X_dev, int64_t T, const HostModel &M, EmResult &out, cudaStream_t st, hmm_info *info) {
+    Workspace &ws = workspace();
+    const int N = M.N, L = M.K - 1, K = M.K, ns = M.nstates;
+    const int R = (N <= 4) ? 8 : 4, SW = 32 * R;
+    RingLayout RL = ring_layout(N, L);
+    int64_t W = ring_config().warmup > 0 ? ring_config().warmup : 512;
+    W = ((W + SW - 1) / SW) * SW;
+    if (W < ((L + 32 + SW - 1) / SW) * SW) W = ((L + 32 + SW - 1) / SW) * SW;
+    int64_t Lc = ring_config().chunk_len;
+    if (Lc <= 0) {
+        int dev = 0, sms = 148;
+        HMM_CUDA(cudaGetDevice(&dev));
+        HMM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        Lc = (T + (int64_t)sms * 16 - 1) / ((int64_t)sms * 16);
+        if (Lc < 4 * W) Lc = 4 * W;
+    }
+    Lc = ((Lc + SW - 1) / SW) * SW;
+    if (Lc < W) Lc = W;
+    if (Lc < 256) Lc = 256;
+    int nchunks = (int)((T + Lc - 1) / Lc);
+    if (nchunks > 1 && T - (int64_t)(nchunks - 1) * Lc < RING_Q) nchunks--;
+
+    std::vector<double> hmdl(RL.total);
+    ring_pack(M, RL, hmdl.data());
+    const int bvec = 1 + N * L;
+    const int pstride = 4 + 2 * N + N * S1_LAGS;
+    const int nblk = 148 * 2;
+    const int nout = 2 + N + K * N + ns;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+        size_t r = off;
+        off += (bytes + 255) & ~size_t(255);
+        return r;
+    };
+    size_t o_model = carve(sizeof(double) * hmdl.size());
+    size_t o_neg = carve(sizeof(double) * N * L);
+    size_t o_b = carve(sizeof(double) * 4 * (size_t)nchunks * bvec);
+    size_t o_flag = carve(sizeof(int) * 2 * (size_t)nchunks);
+    size_t o_kl = carve(sizeof(double) * 2 * (size_t)nchunks);
+    size_t o_ls = carve(sizeof(double) * 2);
+    size_t o_cnt = carve(sizeof(int) * 4);
+    size_t o_part = carve(sizeof(double) * (size_t)nblk * pstride);
+    size_t o_out = carve(sizeof(double) * nout);
+    char *base = (char *)ws.get(Workspace::CHUNKS, off);
+    double *steps = (double *)ws.get(Workspace::FWDQ, sizeof(double) * (size_t)T * (3 * N + 2));
+    HMM_CUDA(cudaMemcpyAsync(base + o_model, hmdl.data(), sizeof(double) * hmdl.size(), cudaMemcpyHostToDevice, st));
+    HMM_CUDA(cudaStreamSynchronize(st));
+    HMM_CUDA(cudaMemsetAsync(base + o_cnt, 0, sizeof(int) * 4, st));
+
+    EmParams p{};
+    p.y = X_dev;
+    p.T = T;
+    p.model = (const double *)(base + o_model);
+    p.RL = RL;
+    p.Lc = Lc;
+    p.W = W;
+    p.nchunks = nchunks;
+    p.ns = ns;
+    p.Fg = steps;
+    p.LQ = steps + (size_t)N * T;
+    p.LE = steps + (size_t)2 * N * T;
+    p.LG = steps + (size_t)3 * N * T;
+    p.LH = p.LG + T;
+    p.LQneg = (double *)(base + o_neg);
+    p.SBf = (double *)(base + o_b);
+    p.EBf = p.SBf + (size_t)nchunks * bvec;
+    p.SBb = p.EBf + (size_t)nchunks * bvec;
+    p.EBb = p.SBb + (size_t)nchunks * bvec;
+    p.bvec = bvec;
+    p.flag_f = (int *)(base + o_flag);
+    p.flag_b = p.flag_f + nchunks;
+    p.kappa = (double *)(base + o_kl);
+    p.lambda = p.kappa + nchunks;
+    p.lS = (double *)(base + o_ls);
+    p.counters = (int *)(base + o_cnt);
+    p.part = (double *)(base + o_part);
+    p.nblk = nblk;
+    p.pstride = pstride;
+    p.out = (double *)(base + o_out);
+
+    Timer ttop(st);
+    switch (N) {
+        case 1: em_launch<1, 8>(p, st, info, ttop); break;
+        case 2: em_launch<2, 8>(p, st, info, ttop); break;
+        case 3: em_launch<3, 8>(p, st, info, ttop); break;
+        case 4: em_launch<4, 8>(p, st, info, ttop); break;
+        case 5: em_launch<5, 4>(p, st, info, ttop); break;
+        case 6: em_launch<6, 4>(p, st, info, ttop); break;
+        case 7: em_launch<7, 4>(p, st, info, ttop); break;
+        default: fail(HMM_EUNSUPPORTED, "ring E/M engine supports 1..%d neurons", RING_MAX_N);
+    }
+    std::vector<double> h(nout);
+    int cnt[4] = {0, 0, 0, 0};
+    HMM_CUDA(cudaMemcpyAsync(h.data(), p.out, sizeof(double) * nout, cudaMemcpyDeviceToHost, st));
+    HMM_CUDA(cudaMemcpyAsync(cnt, p.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+    HMM_CUDA(cudaStreamSynchronize(st));
+    out.sigma = h[0];
+    out.loglik = h[1];
+    out.lp.assign(h.begin() + 2, h.begin() + 2 + N);
+    out.mu.assign(h.begin() + 2 + N, h.begin() + 2 + N + (size_t)K * N);
+    out.pp.assign(h.begin() + 2 + N + (size_t)K * N, h.end());
+    if (info) {
+        info->n_chunks = nchunks;
+        info->fwd_repaired = cnt[0];
+        info->bwd_repaired = cnt[1];
+        info->top_kernel_ms = ttop.ms();
+    }
+}
+
+}  // namespace hmm

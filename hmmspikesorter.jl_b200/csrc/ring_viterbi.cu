@@ -51,7 +51,15 @@ void ring_pack(const HostModel &M, const RingLayout &R, double *dst) {
             double bw = b + (r > 0 ? P.w_c[(size_t)i * (L - 1) + r - 1] - P.w_nn : 0.0);
             dst[R.A + r * R.NP + i] = a;
             dst[R.BW + r * R.NP + i] = bw;
+            dst[R.B0 + r * R.NP + i] = b;
             bc += bw;
+        }
+        {
+            double suf = 0.0;
+            for (int r = L - 1; r >= 0; r--) {
+                suf += dst[R.BW + r * R.NP + i];
+                dst[R.BWsuf + r * R.NP + i] = suf;
+            }
         }
         dst[R.Bc + i] = bc;
         dst[R.eG + i] = P.w_tn[i] - P.w_nn;
@@ -182,67 +190,8 @@ __device__ void vit_process_chunk(const VitParams &p, int ch, int c, int kind, c
     const int s_rel = (int)(s - base0);
 
     for (int64_t b = base0; b < e; b += G::SW) {
-        // ---- stage y[b, b + SW + LP) into the transposed tile (zero beyond T) ----
-        {
-            const int need = G::SW + LP;
-            for (int k = lane; k < need; k += 32) {
-                int64_t g = b + k;
-                double *dst = ytile + (k & (R - 1)) * G::YS + (k >> G::LOGR);
-                if (g < T)
-                    cp_async8(dst, y + g);
-                else
-                    *dst = 0.0;
-            }
-            cp_async_commit();
-            cp_async_wait_all();
-            __syncwarp();
-        }
-        // ---- FIR: lane computes F_i(b + R*lane + j), j < R ----
-        {
-            double acc[N][R];
-#pragma unroll
-            for (int i = 0; i < N; i++)
-#pragma unroll
-                for (int j = 0; j < R; j++) acc[i][j] = Bc[i];
-            double w[R];
-#pragma unroll
-            for (int j = 0; j < R; j++) w[j] = ytile[j * G::YS + lane];  // elements R*lane + j
-            double a[N], an[N];
-            auto load_coef = [&](int r, double *dst) {
-                const double2 *src = reinterpret_cast<const double2 *>(A + r * NP);
-#pragma unroll
-                for (int i2 = 0; i2 < NP / 2; i2++) {
-                    double2 v = src[i2];
-                    if (2 * i2 < N) dst[2 * i2] = v.x;
-                    if (2 * i2 + 1 < N) dst[2 * i2 + 1] = v.y;
-                }
-            };
-            load_coef(0, a);
-            for (int r0 = 0; r0 < LP; r0 += R) {
-#pragma unroll
-                for (int u = 0; u < R; u++) {
-                    const int r = r0 + u;
-                    load_coef(r + 1 < LP ? r + 1 : r, an);  // one tap ahead
-                    const double ynew = ytile[u * G::YS + lane + 1 + (r0 >> G::LOGR)];
-#pragma unroll
-                    for (int j = 0; j < R; j++) {
-                        const double yv = w[(u + j) % R];
-#pragma unroll
-                        for (int i = 0; i < N; i++) acc[i][j] = fma(a[i], yv, acc[i][j]);
-                    }
-                    // slide: element R*lane + r + R -> row u, column lane + 1 + r0/R
-                    w[u] = ynew;
-#pragma unroll
-                    for (int i = 0; i < N; i++) a[i] = an[i];
-                }
-            }
-            __syncwarp();  // all lanes are done with the y tile before F overwrites it
-#pragma unroll
-            for (int i = 0; i < N; i++)
-#pragma unroll
-                for (int j = 0; j < R; j++) fbuf[i * G::FTILE + j * G::FS + lane] = acc[i][j];
-            __syncwarp();
-        }
+        // ---- stage y and run the FIR: F_i(b + t) for the whole super-window ----
+        fir_superwindow<N, R>(y, T, b, A, Bc, LP, ytile, fbuf, lane);
         // ---- chunk 0: convert the faithful prologue (columns 0..L) into ring state ----
         if (kind == START_PROLOGUE && b == 0) {
             const double *sc = mdl + RL.scal;
@@ -258,7 +207,7 @@ __device__ void vit_process_chunk(const VitParams &p, int ch, int c, int kind, c
                 }
             }
             __syncwarp();
-            const double *BW = mdl + RL.BW;
+            const double *BW = p.model + (size_t)ch * RL.total + RL.BW;  // cold part: global memory
             for (int t0 = 1 + lane; t0 <= L; t0 += 32) {
                 const double yv = y[t0];
 #pragma unroll
@@ -403,7 +352,7 @@ __device__ void vit_process_chunk(const VitParams &p, int ch, int c, int kind, c
 template <int N, int R>
 __device__ void load_model_smem(const VitParams &p, int ch, double *mdl) {
     const double *g = p.model + (size_t)ch * p.RL.total;
-    for (int k = threadIdx.x; k < p.RL.total; k += blockDim.x) mdl[k] = g[k];
+    for (int k = threadIdx.x; k < p.RL.hot; k += blockDim.x) mdl[k] = g[k];
     __syncthreads();
 }
 
@@ -416,7 +365,7 @@ __global__ void __launch_bounds__(128, 4) ring_vit_forward(VitParams p) {
     const int warp = threadIdx.x >> 5;
     const int c = blockIdx.x * (blockDim.x >> 5) + warp;
     if (c >= p.nchunks) return;
-    double *ws = smem_d + ((p.RL.total + 1) & ~1) + (size_t)warp * WarpSmem<N, R>::DOUBLES;
+    double *ws = smem_d + ((p.RL.hot + 1) & ~1) + (size_t)warp * WarpSmem<N, R>::DOUBLES;
     if (p.stagger_ns > 0) {
         // Co-resident CTAs start in lockstep and would alternate between an FP64-pipe-bound
         // phase (FIR) and a latency-bound phase (recursion) together; offset them.
@@ -470,7 +419,7 @@ __global__ void __launch_bounds__(32) ring_vit_repair_fwd(VitParams p) {
     if (!__any_sync(0xffffffffu, any)) return;
     double *mdl = smem_d;
     load_model_smem<N, R>(p, ch, mdl);
-    double *ws = smem_d + ((p.RL.total + 1) & ~1);
+    double *ws = smem_d + ((p.RL.hot + 1) & ~1);
     bool prev_rerun = false;
     int repaired = 0;
     for (int c = 1; c < p.nchunks; c++) {
@@ -777,7 +726,7 @@ __global__ void __launch_bounds__(256)
 template <int N, int R>
 static void launch_all(VitParams &p, int C, cudaStream_t st, hmm_info *info, Timer *ttop) {
     constexpr int WPB = 4;
-    const size_t mdl_d = (p.RL.total + 1) & ~1;
+    const size_t mdl_d = (p.RL.hot + 1) & ~1;
     const size_t sm_fwd = sizeof(double) * (mdl_d + (size_t)WPB * WarpSmem<N, R>::DOUBLES);
     const size_t sm_rep = sizeof(double) * (mdl_d + WarpSmem<N, R>::DOUBLES);
     HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
@@ -804,7 +753,7 @@ static void launch_all(VitParams &p, int C, cudaStream_t st, hmm_info *info, Tim
 template <int N, int R>
 static int fwd_warps_per_sm(const RingLayout &RL) {
     constexpr int WPB = 4;
-    const size_t sm_fwd = sizeof(double) * (((RL.total + 1) & ~1) + (size_t)WPB * WarpSmem<N, R>::DOUBLES);
+    const size_t sm_fwd = sizeof(double) * (((RL.hot + 1) & ~1) + (size_t)WPB * WarpSmem<N, R>::DOUBLES);
     HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
     int nb = 0;
     HMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ring_vit_forward<N, R>, 32 * WPB, sm_fwd));

