@@ -132,3 +132,39 @@ def test_reconstruct_and_unroll(hm, O, case_factory):
     u = hm.unroll_mlseq(mlseq, sm)
     assert u[0].tolist() == [1, 1, 1, 2, 3, 4, 5, 1, 1, 1, 1, 1, 1, 2, 3, 4, 5, 1]
     assert u[1].tolist() == [1, 1, 1, 1, 1, 1, 1, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 1]
+
+
+@pytest.mark.parametrize("N,K,T,seed,ov", [(3, 60, 3000, 3, False), (2, 10, 1500, 1, False), (2, 6, 1200, 5, True)])
+def test_update_dense(hm, O, case_factory, N, K, T, seed, ov):
+    """update(alpha, beta, lA, mu, sigma, x) on dense alpha/beta (src/baumwelch.jl:205-309),
+    for ring and overlap models; mu is overwritten in place."""
+    S, lA_no, mu_true, sig = case_factory(N, K, T, seed, rate_scale=min(4.0, 60.0 / K))
+    lA = hm.StateMatrix(N, K, np.log(np.full(N, 0.01)), ov)
+    mu0 = np.asfortranarray(0.7 * mu_true)
+    s0 = float(np.std(S))
+    ao, bo = O.forward(S, lA, mu0, s0), O.backward(S, lA, mu0, s0)
+    lpo, ppo, muo, so = O.update(ao, bo, lA, mu0, s0, S)
+    mu = mu0.copy(order="F")
+    lA2, mu_out, s2 = hm.update(ao, bo, lA, mu, s0, S)
+    assert mu_out is mu
+    assert np.abs(mu - muo).max() < 1e-9 and abs(s2 - so) < 1e-9
+    ref = hm.StateMatrix.from_states(lA.states, ppo, K, lpo, ov)
+    assert np.abs(lA2.transitions["lp"] - ref.transitions["lp"]).max() < 1e-9
+    fin = np.isfinite(ppo)
+    assert np.allclose(lA2.pi[fin], ppo[fin], atol=1e-8)
+
+
+def test_em_step_generic_path_overlap(hm, O):
+    """One E/M step on an overlap model goes through the generic path (dense alpha/beta
+    kept on the device) and matches the oracle."""
+    K, N, T = 8, 2, 2500
+    temps = np.stack([hm.create_spike_template(K, 3.0, 0.8, 0.2), hm.create_spike_template(K, 4.0, 0.3, 0.2)], 1)
+    S = hm.create_signal(T, 0.3, np.array([0.02, 0.01]), temps, hm.make_rng(7))
+    lA = hm.StateMatrix(N, K, np.log([0.01, 0.01]), True)
+    mu0 = np.asfortranarray(0.7 * temps)
+    mu0[0, :] = 0
+    r = hm.em_step(S, lA, mu0, 0.4, return_info=True)
+    o = O.em_step(S, lA, mu0, 0.4)
+    assert r[5]["engine"] == 1
+    assert np.abs(r[0] - o[0]).max() < 1e-8 and np.abs(r[2] - o[2]).max() < 1e-8
+    assert abs(r[3] - o[3]) < 1e-9
