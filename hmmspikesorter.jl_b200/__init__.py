@@ -25,6 +25,7 @@ from . import _lib
 from ._lib import MODES, HmmArgumentError, HmmError, HmmInfo, check, lib
 from .statematrix import TRANS_DTYPE, StateMatrix, generate_states, get_valid_transitions
 from .synth import create_signal, create_spike_template, make_rng
+from . import sharding
 
 __all__ = [
     "StateMatrix", "viterbi", "viterbi_batch", "forward", "backward", "update", "train_model", "em_step",

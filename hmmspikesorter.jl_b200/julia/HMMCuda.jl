@@ -1,0 +1,131 @@
+# HMMCuda.jl -- the `ccall` shim that makes libhmmcuda.so a drop-in for the
+# hot-path methods of HMMSpikeSorter.jl.  `include` it AFTER the package's own
+# files (src/HMMSpikeSorter.jl:14-20): the methods below have the same
+# signatures as the reference's and therefore REPLACE them, so every caller
+# (src/fit.jl:7,23,45,50,55; README.md:33-35; test/runtests.jl) keeps working
+# unmodified.
+#
+# NOTE: Julia is not installed in the environment this library is built and
+# tested in, so this file has not been executed there.  It is kept mechanical
+# on purpose: every call passes exactly the arrays the Python ctypes mirror
+# (hmmspikesorter.jl_b200/__init__.py) passes to the same symbols, and that
+# mirror is what the test-suite exercises.
+#
+# Memory layout facts relied upon (src/types.jl:1-9):
+#   lA.states       :: Matrix{Int16}  [N x nstates], column-major, 1-based ring phases
+#   lA.transitions  :: Vector{Tuple{Int64,Int64,Float64}}  isbits => contiguous 24-byte records
+#   μ               :: Matrix{Float64} [K x N], column-major
+
+const libhmmcuda = get(ENV, "LIBHMMCUDA", "libhmmcuda.so")
+
+const HMM_EINVAL = 1
+
+struct HmmInfo
+    engine::Int32; n_chunks::Int32; fwd_repaired::Int32; bwd_repaired::Int32
+    kernel_launches::Int64; device_ms::Float64; kernel_ms::Float64; top_kernel_ms::Float64
+end
+
+function _check(rc::Integer)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:hmm_last_error, libhmmcuda), Cstring, ()))
+    rc == HMM_EINVAL ? throw(ArgumentError(msg)) : error("libhmmcuda: $msg")
+end
+
+_vec(y::Vector{Float64}) = y
+_vec(y::SubArray{Float64,1,Vector{Float64},<:Tuple{UnitRange},true}) = y   # contiguous view (src/fit.jl:23)
+_vec(y::AbstractVector{Float64}) = collect(y)                               # anything else is collected
+
+# ---- viterbi(y, lA, μ, σ) -> (x, ll)                      replaces src/viterbi.jl:44-98
+function viterbi(y::AbstractArray{Float64,1}, lA::StateMatrix, μ::Array{Float64,2}, σ::Float64)
+    yv = _vec(y); T = length(yv)
+    x = Vector{Int16}(undef, T); ll = Ref{Float64}(0.0)
+    tr = lA.transitions
+    GC.@preserve yv lA μ x begin
+        _check(ccall((:hmm_viterbi_f64, libhmmcuda), Cint,
+            (Ptr{Float64}, Int64, Ptr{Int16}, Int32, Int32, Int32, Ptr{Cvoid}, Int64, Ptr{Float64}, Float64,
+             Ptr{Int16}, Ref{Float64}, Ptr{Int16}, Ptr{Float64}),
+            pointer(yv), T, lA.states, lA.N, lA.K, lA.nstates, pointer(tr), length(tr), μ, σ,
+            x, ll, C_NULL, C_NULL))
+    end
+    return x, ll[]
+end
+
+# ---- (x, T2, T1) form of README.md:34 / src/example.jl:32 -- trellis materialised on request
+function viterbi_trellis(y::AbstractArray{Float64,1}, lA::StateMatrix, μ::Array{Float64,2}, σ::Float64)
+    yv = _vec(y); T = length(yv)
+    x = Vector{Int16}(undef, T); ll = Ref{Float64}(0.0)
+    T1 = Matrix{Float64}(undef, lA.nstates, T); T2 = Matrix{Int16}(undef, lA.nstates, T)
+    tr = lA.transitions
+    GC.@preserve yv lA μ x T1 T2 begin
+        _check(ccall((:hmm_viterbi_f64, libhmmcuda), Cint,
+            (Ptr{Float64}, Int64, Ptr{Int16}, Int32, Int32, Int32, Ptr{Cvoid}, Int64, Ptr{Float64}, Float64,
+             Ptr{Int16}, Ref{Float64}, Ptr{Int16}, Ptr{Float64}),
+            pointer(yv), T, lA.states, lA.N, lA.K, lA.nstates, pointer(tr), length(tr), μ, σ, x, ll, T2, T1))
+    end
+    return x, T2, T1
+end
+
+# ---- forward / backward                                   replace src/baumwelch.jl:25-51, 73-98
+for (fn, sym) in ((:forward, :hmm_forward_f64), (:backward, :hmm_backward_f64))
+    @eval function $fn(V::Array{Float64,1}, lA::StateMatrix, μ::Array{Float64,2}, σ::Float64)
+        T = length(V); out = Matrix{Float64}(undef, lA.nstates, T); tr = lA.transitions
+        GC.@preserve V lA μ out begin
+            _check(ccall(($(QuoteNode(sym)), libhmmcuda), Cint,
+                (Ptr{Float64}, Int64, Ptr{Int16}, Int32, Int32, Int32, Ptr{Cvoid}, Int64, Ptr{Float64}, Float64, Ptr{Float64}),
+                V, T, lA.states, lA.N, lA.K, lA.nstates, pointer(tr), length(tr), μ, σ, out))
+        end
+        out
+    end
+end
+
+_nxi(lA::StateMatrix) = count(q -> q[1] == 1, lA.transitions)
+
+# ---- update(α, β, lA, μ, σ, x) -> (lA_new, μ, σ)          replaces src/baumwelch.jl:205-309
+# μ is overwritten in place exactly like the reference's fill!(μ, 0.0) (:268).
+function update(α::Array{Float64,2}, β::Array{Float64,2}, lA::StateMatrix, μ::Array{Float64,2}, σ::Float64, x::Array{Float64,1})
+    lp = Vector{Float64}(undef, max(_nxi(lA) - 1, 1)); pp = Vector{Float64}(undef, lA.nstates)
+    s = Ref{Float64}(σ); tr = lA.transitions
+    GC.@preserve α β lA μ x lp pp begin
+        _check(ccall((:hmm_update_f64, libhmmcuda), Cint,
+            (Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Int16}, Int32, Int32, Int32, Ptr{Cvoid}, Int64,
+             Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            α, β, length(x), lA.states, lA.N, lA.K, lA.nstates, pointer(tr), length(tr), μ, s, x, lp, pp))
+    end
+    # the UNCHANGED Julia constructor rebuilds the transitions (src/baumwelch.jl:265, src/types.jl:148-151)
+    lA_new = StateMatrix(lA.states .- one(Int16), pp, lA.K, lp[1:_nxi(lA)-1]; allow_overlaps=lA.resolve_overlaps)
+    lA_new, μ, s[]
+end
+
+# ---- one fused E/M step: train_model(X, lA, μ0, σ0)       replaces src/baumwelch.jl:362-370
+function train_model(X::Array{Float64,1}, state_matrix::StateMatrix, μ0::Array{Float64,2}, σ0::Float64; verbose=0)
+    lA = state_matrix
+    lp = Vector{Float64}(undef, max(_nxi(lA) - 1, 1)); pp = Vector{Float64}(undef, lA.nstates)
+    s = Ref{Float64}(σ0); ll = Ref{Float64}(0.0); tr = lA.transitions
+    GC.@preserve X lA μ0 lp pp begin
+        _check(ccall((:hmm_em_step_f64, libhmmcuda), Cint,
+            (Ptr{Float64}, Int64, Ptr{Int16}, Int32, Int32, Int32, Ptr{Cvoid}, Int64,
+             Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
+            X, length(X), lA.states, lA.N, lA.K, lA.nstates, pointer(tr), length(tr), μ0, s, lp, pp, ll))
+    end
+    lA_new = StateMatrix(lA.states .- one(Int16), pp, lA.K, lp[1:_nxi(lA)-1]; allow_overlaps=lA.resolve_overlaps)
+    lA_new, μ0, s[]
+end
+# The outer loop train_model(X, sm, μ, σ, nsteps, callback) (src/baumwelch.jl:324-354) is
+# unchanged Julia: it calls the method above once per iteration, so callback(μ), yield() and
+# the merge/prune phase behave exactly as before.  To keep X resident in HBM across the
+# iterations, wrap the loop in hmm_train_create / hmm_train_em_step / hmm_train_destroy.
+
+# ---- reconstruct_signal(x, lA, μ, σ)                      replaces src/reconstruction.jl:1-9
+function reconstruct_signal(x::Array{T,1}, lA::StateMatrix, μ::Array{Float64,2}, σ::Float64) where T <: Integer
+    xi = T === Int16 ? x : begin
+        all(1 .<= x .<= lA.nstates) || throw(BoundsError(lA.states, (1, x)))
+        convert(Vector{Int16}, x)
+    end
+    Y = Vector{Float64}(undef, length(xi))
+    GC.@preserve xi lA μ Y begin
+        _check(ccall((:hmm_reconstruct_f64, libhmmcuda), Cint,
+            (Ptr{Int16}, Int64, Ptr{Int16}, Int32, Int32, Ptr{Float64}, Int32, Ptr{Float64}),
+            xi, length(xi), lA.states, lA.N, lA.nstates, μ, lA.K, Y))
+    end
+    Y
+end

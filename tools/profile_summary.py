@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""Turn ncu exports brought back in gpurun_out/ into the tracked summaries under profiles/.
+
+  python tools/profile_summary.py launches gpurun_out/launches.csv profiles/r01_launches_c2.md
+  python tools/profile_summary.py kernel   gpurun_out/prof_fwd2.ncu-rep profiles/r01_ring_vit_forward.md
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+
+def launches(src, dst):
+    lines = [l for l in open(src) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        if row.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        agg.setdefault(row["Kernel Name"], []).append(float(row["Metric Value"].replace(",", "")))
+    tot = sum(sum(v) / len(v) for v in agg.values())
+    with open(dst, "w") as f:
+        f.write("# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare SHARES)\n\n")
+        f.write(f"source: `{src}`\n\n| kernel | launches | mean us | share of step |\n|---|---|---|---|\n")
+        for k, v in agg.items():
+            m = sum(v) / len(v)
+            f.write(f"| `{k[:90]}` | {len(v)} | {m / 1e3:.1f} | {100 * m / tot:.1f}% |\n")
+        f.write(f"\nsum of per-kernel means: {tot / 1e3:.1f} us per step\n")
+
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__average_warps_issue_stalled"]
+
+
+def kernel(rep, dst):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full summary\n\nsource: `{rep}` (kept in gpurun_out/, not tracked)\n")
+        for vals in rows[2:]:
+            d = dict(zip(hdr, vals))
+            f.write(f"\n## {d.get('Kernel Name', '?')}\n\n| metric | value | unit |\n|---|---|---|\n")
+            for h, u, v in zip(hdr, units, vals):
+                if any(h == w or (w.endswith("stalled") and w in h and "per_issue_active" in h) for w in WANT):
+                    f.write(f"| {h} | {v} | {u} |\n")
+            try:
+                tr = (float(d["dram__bytes_read.sum"]) + float(d["dram__bytes_write.sum"]))
+                f.write(f"\ntraffic (dram read + write) = {tr:.1f} {units[hdr.index('dram__bytes_read.sum')]}\n")
+            except Exception:
+                pass
+
+
+if __name__ == "__main__":
+    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
