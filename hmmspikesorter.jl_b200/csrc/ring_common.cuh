@@ -26,7 +26,7 @@ constexpr int RING_Q = 128;      // ring-buffer length (>= L + 32), power of two
 // Per-channel ring model, a flat array of doubles on the device.
 struct RingLayout {
     int N, L, LP, NP;            // LP = L rounded up to 8; NP = N rounded up to even
-    int A, BW, B0, BWsuf, Bc, eG, eH, eT, scal, hot, total;  // offsets in doubles
+    int A, BW, B0, BWsuf, Bc, eG, eH, eT, scal, cL, hot, total;  // offsets in doubles
 };
 // scal[]: 0 w_nn, 1 c_emit, 2 two_s2, 3 m0, 4 sigma
 __host__ __device__ inline RingLayout ring_layout(int N, int L) {
@@ -43,6 +43,7 @@ __host__ __device__ inline RingLayout ring_layout(int N, int L) {
     R.eH = o; o += R.NP;
     R.eT = o; o += N * R.NP;      // eT[j*NP + i]
     R.scal = o; o += 8;
+    R.cL = o; o += R.NP;          // liveness margin per neuron (ring_viterbi.cu)
     R.hot = o;
     // cold part (boundary handling only; read from global memory)
     R.BW = o; o += R.LP * R.NP;   // BW[r*NP + i] = b[i][r] + (r>0 ? w_c[i][r-1]-w_nn : 0)
@@ -149,6 +150,71 @@ __device__ __forceinline__ void fir_superwindow(const double *__restrict__ y, in
         }
     }
     __syncwarp();  // every lane is done with the y tile before F overwrites it
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j < R; j++) fbuf[i * G::FTILE + j * G::FS + lane] = acc[i][j];
+    __syncwarp();
+}
+
+// FIR coefficients passed BY VALUE as a kernel parameter: they live in the
+// constant bank, and with the tap loop fully unrolled every DFMA takes its
+// coefficient as a c[0x0][imm] operand.  A DFMA with three distinct 64-bit
+// register operands is limited by register-file read bandwidth to one per 3
+// cycles per SM sub-partition; with a constant operand it issues at the FP64
+// pipe rate (one per 2 cycles) and the coefficient LDS traffic disappears.
+template <int N, int LPC>
+struct FirCoef {
+    double a[(LPC > 0 ? LPC : 1) * N];  // a[r*N + i]
+};
+
+template <int N, int R, int LPC>
+__device__ __forceinline__ void fir_superwindow_c(const double *__restrict__ y, int64_t T, int64_t b,
+                                                  const FirCoef<N, LPC> &coef, const double *Bc, double *ytile,
+                                                  double *fbuf, int lane) {
+    using G = FirGeom<R>;
+    {
+        const int need = G::SW + LPC;
+        for (int k = lane; k < need; k += 32) {
+            int64_t g = b + k;
+            double *dst = ytile + (k & (R - 1)) * G::YS + (k >> G::LOGR);
+            if (g < T)
+                cp_async8(dst, y + g);
+            else
+                *dst = 0.0;
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncwarp();
+    }
+    double acc[N][R];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j < R; j++) acc[i][j] = Bc[i];
+    double w[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) w[j] = ytile[j * G::YS + lane];
+    // Fully unrolled so that every coefficient is a compile-time constant-bank offset (the
+    // compiler keeps them in uniform registers: LDCU + DFMA R, R, UR, R).  Measured at C2:
+    // full unroll 0.42 ms (28 KB of code; ncu shows stall_no_instruction), unroll-by-2 with
+    // vector-register coefficients 0.47 ms, shared-memory coefficients 0.52 ms.
+#pragma unroll
+    for (int r0 = 0; r0 < LPC; r0 += R) {
+#pragma unroll
+        for (int u = 0; u < R; u++) {
+            const int r = r0 + u;
+            const double ynew = ytile[u * G::YS + lane + 1 + (r0 >> G::LOGR)];
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                const double yv = w[(u + j) % R];
+#pragma unroll
+                for (int i = 0; i < N; i++) acc[i][j] = fma(coef.a[r * N + i], yv, acc[i][j]);
+            }
+            w[u] = ynew;
+        }
+    }
+    __syncwarp();
 #pragma unroll
     for (int i = 0; i < N; i++)
 #pragma unroll

@@ -83,6 +83,15 @@ void ring_pack(const HostModel &M, const RingLayout &R, double *dst) {
     }
     dst[R.scal + 5] = eTmax;  // -inf when N == 1
     dst[R.scal + 6] = eHmin;
+    // Liveness margin: a pending chain score Q_j created at t0 can influence a later decision
+    // only if Q_j + cL[j] > G_t0 (G is non-decreasing): it must beat the noise path either into
+    // the noise state (eG) or into some head (eT[j][i] - eH[i]).  1e-9 covers all rounding.
+    for (int j = 0; j < N; j++) {
+        double c = dst[R.eG + j];
+        for (int i = 0; i < N; i++)
+            if (i != j) c = std::max(c, dst[R.eT + j * R.NP + i] - dst[R.eH + i]);
+        dst[R.cL + j] = c + 1e-9;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -110,6 +119,8 @@ struct VitParams {
     int64_t x_stride;
     long long *own_start, *look_end;  // [C x nchunks] encoded states
     int *tr_flag;
+    int debug_skip;        // debug: 1 = skip the recursion (time the FIR alone), 2 = skip the FIR
+    int *sm_slots;         // [256] per-SM CTA arrival counters (stagger)
     int stagger_ns;        // start-up delay quantum that de-phases co-resident warps (FIR vs recursion)
     int n_sm;
 };
@@ -134,9 +145,9 @@ struct CtaModel {
 // ---------------------------------------------------------------------------
 // One chunk, one warp.
 // ---------------------------------------------------------------------------
-template <int N, int R>
-__device__ void vit_process_chunk(const VitParams &p, int ch, int c, int kind, const double *mdl /*smem model*/,
-                                  double *ws /*per-warp smem*/) {
+template <int N, int R, int LPC>
+__device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coef, int ch, int c, int kind,
+                                  const double *mdl /*smem model*/, double *ws /*per-warp smem*/) {
     using G = FirGeom<R>;
     constexpr int NP = (N + 1) & ~1;
     const int lane = threadIdx.x & 31;
@@ -150,6 +161,7 @@ __device__ void vit_process_chunk(const VitParams &p, int ch, int c, int kind, c
     const double *A = mdl + RL.A;
     const double *Bc = mdl + RL.Bc, *eG = mdl + RL.eG, *eH = mdl + RL.eH, *eT = mdl + RL.eT;
     const double eTmax = mdl[RL.scal + 5], eHmin = mdl[RL.scal + 6];
+    const double *cL = mdl + RL.cL;
     const double *y = p.y + (size_t)ch * p.y_stride;
     const int64_t T = p.T;
     const int64_t s = (int64_t)c * p.Lc;                 // main range [s, e)
@@ -185,13 +197,32 @@ __device__ void vit_process_chunk(const VitParams &p, int ch, int c, int kind, c
     const int Wd = L < 32 ? L : 32;
     const int nsub = (32 + Wd - 1) / Wd;
     const int mysub = lane / Wd;
+    // window-invariant constants in registers (the compiler cannot hoist them past the ring stores)
+    double eHr[N], cLr[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        eHr[i] = eH[i];
+        cLr[i] = cL[i];
+    }
+    // "live" masks of the last four 32-step windows (bit = a chain score created at that step
+    // may still win a decision when it arrives L steps later); see the quiet-window fast path
+    uint32_t lq1, lq2, lq3, lq4;
+    lq1 = lq2 = lq3 = lq4 = (kind == START_SPEC) ? 0u : 0xffffffffu;
+    const int qq = (L >> 5) + ((L & 31) ? 1 : 0);  // windows back to the first word holding step t-L
+    const int lsh = (32 - (L & 31)) & 31;
     const int tf_rel = (int)(tau_first - base0);  // steps are tracked relative to base0 in 32 bits
     const int e_rel = (int)(e - base0);
     const int s_rel = (int)(s - base0);
 
     for (int64_t b = base0; b < e; b += G::SW) {
         // ---- stage y and run the FIR: F_i(b + t) for the whole super-window ----
-        fir_superwindow<N, R>(y, T, b, A, Bc, LP, ytile, fbuf, lane);
+        if (p.debug_skip != 2) {
+            if constexpr (LPC > 0)
+                fir_superwindow_c<N, R, LPC>(y, T, b, coef, Bc, ytile, fbuf, lane);
+            else
+                fir_superwindow<N, R>(y, T, b, A, Bc, LP, ytile, fbuf, lane);
+        }
+        if (p.debug_skip == 1) continue;
         // ---- chunk 0: convert the faithful prologue (columns 0..L) into ring state ----
         if (kind == START_PROLOGUE && b == 0) {
             const double *sc = mdl + RL.scal;
@@ -234,19 +265,48 @@ __device__ void vit_process_chunk(const VitParams &p, int ch, int c, int kind, c
         const int b_rel = (int)(b - base0);
         for (int wdw = 0; wdw < R; wdw++) {
             const int t0_rel = b_rel + 32 * wdw;
-            if (t0_rel + 32 <= tf_rel) continue;
+            if (t0_rel + 32 <= tf_rel) {  // before the first recursion step: pre-loaded entries only
+                lq4 = lq3; lq3 = lq2; lq2 = lq1;
+                lq1 = (kind == START_SPEC) ? 0u : 0xffffffffu;
+                continue;
+            }
             if (t0_rel >= e_rel) break;
             const int tl = 32 * wdw + lane;
             const int t_rel = t0_rel + lane;
-            const bool in_range = t_rel >= tf_rel && t_rel < e_rel;
             // ring slots: base0 is a multiple of RING_Q, so absolute and relative indices agree mod RING_Q
             const int slot_w = t_rel & (RING_Q - 1);
-            const int slot_r = (t_rel - L) & (RING_Q - 1);
             double Fv[N];
 #pragma unroll
             for (int i = 0; i < N; i++) Fv[i] = fbuf[i * G::FTILE + (tl & (R - 1)) * G::FS + (tl >> G::LOGR)];
+            // Quiet-window fast path: if none of the pending chain scores that arrive in this
+            // window was live when it was created, no tail can win any decision here: G stays,
+            // every head is entered from noise and all backpointers are 0 (the decision arrays
+            // are pre-zeroed) -- the tails are not even read.
+            if (L >= 32 && t0_rel >= tf_rel && t0_rel + 32 <= e_rel) {
+                const uint32_t lo = qq == 1 ? lq1 : qq == 2 ? lq2 : qq == 3 ? lq3 : lq4;
+                const uint32_t hi = qq == 1 ? 0u : qq == 2 ? lq1 : qq == 3 ? lq2 : lq3;
+                if (__funnelshift_r(lo, hi, lsh) == 0u) {
+                    const double marg = 1e-13 * fabs(Gprev);
+                    bool live = false;
+#pragma unroll
+                    for (int i = 0; i < N; i++) {
+                        const double gh = Gprev + eHr[i];
+                        const double q = gh + Fv[i];
+                        ring[i * RING_Q + slot_w] = q;
+                        if (last) p.Pfin[((size_t)ch * N + i) * RING_Q + slot_w] = gh;
+                        live = live || (q + cLr[i] + marg > Gprev);
+                    }
+                    lq4 = lq3; lq3 = lq2; lq2 = lq1;
+                    lq1 = __ballot_sync(0xffffffffu, live);
+                    __syncwarp();
+                    continue;
+                }
+            }
+            const bool in_range = t_rel >= tf_rel && t_rel < e_rel;
+            const int slot_r = (t_rel - L) & (RING_Q - 1);
             unsigned nz = 0;
             uint32_t myword = 0;
+            unsigned lvw = 0;
             for (int sub = 0; sub < nsub; sub++) {
                 const bool active = in_range && (mysub == sub);
                 double tails[N];
@@ -314,13 +374,19 @@ __device__ void vit_process_chunk(const VitParams &p, int ch, int c, int kind, c
 #pragma unroll
                     for (int i = 0; i < N; i++) Pv[i] = Gexcl + eH[i];
                 }
+                bool live = false;
                 if (active) {
 #pragma unroll
                     for (int i = 0; i < N; i++) {
-                        ring[i * RING_Q + slot_w] = Pv[i] + Fv[i];
+                        const double q = Pv[i] + Fv[i];
+                        ring[i * RING_Q + slot_w] = q;
                         if (last) p.Pfin[((size_t)ch * N + i) * RING_Q + slot_w] = Pv[i];
+                        live = live || (q + cLr[i] + 1e-13 * fabs(Gexcl) > Gexcl);
                     }
                 }
+                // entries pre-loaded before the first recursion step (prologue) stay live
+                if (sub == 0 && kind != START_SPEC && t_rel < tf_rel) live = true;
+                lvw |= __ballot_sync(0xffffffffu, live);
                 if (active) myword = word;
                 if (any_end) {
                     nz |= __ballot_sync(0xffffffffu, active && (word & 15u) != 0);
@@ -328,6 +394,8 @@ __device__ void vit_process_chunk(const VitParams &p, int ch, int c, int kind, c
                 }
                 __syncwarp();
             }
+            lq4 = lq3; lq3 = lq2; lq2 = lq1;
+            lq1 = lvw;
             if (t0_rel >= s_rel) {  // main range only (warm-up decisions belong to the previous chunk)
                 const int64_t tau0 = base0 + t0_rel;
                 if (t_rel < e_rel) dec[tau0 + lane] = myword;
@@ -356,8 +424,9 @@ __device__ void load_model_smem(const VitParams &p, int ch, double *mdl) {
     __syncthreads();
 }
 
-template <int N, int R>
-__global__ void __launch_bounds__(128, 4) ring_vit_forward(VitParams p) {
+template <int N, int R, int LPC>
+__global__ void __launch_bounds__(128, (R == 8) ? 4 : 6)
+    ring_vit_forward(const __grid_constant__ VitParams p, const __grid_constant__ FirCoef<N, LPC> coef) {
     extern __shared__ __align__(16) double smem_d[];
     const int ch = blockIdx.y;
     double *mdl = smem_d;
@@ -369,10 +438,17 @@ __global__ void __launch_bounds__(128, 4) ring_vit_forward(VitParams p) {
     if (p.stagger_ns > 0) {
         // Co-resident CTAs start in lockstep and would alternate between an FP64-pipe-bound
         // phase (FIR) and a latency-bound phase (recursion) together; offset them.
-        int k = (int)((blockIdx.x / (unsigned)p.n_sm) & 3u);
-        for (int q = 0; q < k; q++) __nanosleep(p.stagger_ns);
+        // arrival order of this CTA on its SM decides its phase offset
+        __shared__ int slot_s;
+        if (threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            slot_s = atomicAdd(p.sm_slots + (smid & 255), 1) & 3;
+        }
+        __syncthreads();
+        for (int q = 0; q < slot_s; q++) __nanosleep(p.stagger_ns);
     }
-    vit_process_chunk<N, R>(p, ch, c, c == 0 ? START_PROLOGUE : START_SPEC, mdl, ws);
+    vit_process_chunk<N, R, LPC>(p, coef, ch, c, c == 0 ? START_PROLOGUE : START_SPEC, mdl, ws);
 }
 
 // Boundary check: speculative start vector of chunk c vs true end vector of c-1
@@ -430,7 +506,7 @@ __global__ void __launch_bounds__(32) ring_vit_repair_fwd(VitParams p) {
             need = !boundary_matches(sb, eb, p.bvec, lane);
         }
         if (need) {
-            vit_process_chunk<N, R>(p, ch, c, START_EXACT, mdl, ws);
+            vit_process_chunk<N, R, 0>(p, FirCoef<N, 0>{}, ch, c, START_EXACT, mdl, ws);
             __threadfence();
             repaired++;
         }
@@ -723,17 +799,39 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------
-template <int N, int R>
-static void launch_all(VitParams &p, int C, cudaStream_t st, hmm_info *info, Timer *ttop) {
+template <int N, int R, int LPC>
+static size_t fwd_smem_bytes(const RingLayout &RL) {
+    constexpr int WPB = 4;
+    return sizeof(double) * (((RL.hot + 1) & ~1) + (size_t)WPB * WarpSmem<N, R>::DOUBLES);
+}
+
+// Resident warps per SM of the forward kernel (sets the one-wave chunk count).
+template <int N, int R, int LPC>
+static int fwd_warps_per_sm(const RingLayout &RL) {
+    constexpr int WPB = 4;
+    const size_t sm_fwd = fwd_smem_bytes<N, R, LPC>(RL);
+    HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward<N, R, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+    int nb = 0;
+    HMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ring_vit_forward<N, R, LPC>, 32 * WPB, sm_fwd));
+    return (nb > 0 ? nb : 1) * WPB;
+}
+
+template <int N, int R, int LPC>
+static void launch_all(VitParams &p, const double *hmodel /*host ring model of channel 0*/, int C, cudaStream_t st,
+                       hmm_info *info, Timer *ttop) {
     constexpr int WPB = 4;
     const size_t mdl_d = (p.RL.hot + 1) & ~1;
-    const size_t sm_fwd = sizeof(double) * (mdl_d + (size_t)WPB * WarpSmem<N, R>::DOUBLES);
+    const size_t sm_fwd = fwd_smem_bytes<N, R, LPC>(p.RL);
     const size_t sm_rep = sizeof(double) * (mdl_d + WarpSmem<N, R>::DOUBLES);
-    HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+    HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward<N, R, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
     HMM_CUDA(cudaFuncSetAttribute(ring_vit_repair_fwd<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rep));
+    FirCoef<N, LPC> coef{};
+    if (LPC > 0)
+        for (int r = 0; r < LPC; r++)
+            for (int i = 0; i < N; i++) coef.a[r * N + i] = hmodel[p.RL.A + r * p.RL.NP + i];
     dim3 gridc((p.nchunks + WPB - 1) / WPB, C);
     if (ttop) ttop->start();
-    ring_vit_forward<N, R><<<gridc, 32 * WPB, sm_fwd, st>>>(p);
+    ring_vit_forward<N, R, LPC><<<gridc, 32 * WPB, sm_fwd, st>>>(p, coef);
     if (ttop) ttop->stop();
     HMM_CUDA(cudaGetLastError());
     ring_vit_check_fwd<<<dim3((p.nchunks * 32 + 127) / 128, C), 128, 0, st>>>(p);
@@ -750,25 +848,32 @@ static void launch_all(VitParams &p, int C, cudaStream_t st, hmm_info *info, Tim
     if (info) info->kernel_launches += 7;
 }
 
-template <int N, int R>
-static int fwd_warps_per_sm(const RingLayout &RL) {
-    constexpr int WPB = 4;
-    const size_t sm_fwd = sizeof(double) * (((RL.hot + 1) & ~1) + (size_t)WPB * WarpSmem<N, R>::DOUBLES);
-    HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
-    int nb = 0;
-    HMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ring_vit_forward<N, R>, 32 * WPB, sm_fwd));
-    return (nb > 0 ? nb : 1) * WPB;
+// (N, LP) -> kernel variant.  LPC > 0: FIR coefficients as constant-bank operands
+// (single channel per launch; K = 48 and K = 60 models); LPC = 0: generic, coefficients
+// in shared memory (any K <= 97, any number of channels per launch).
+struct VitVariant {
+    int (*warps_per_sm)(const RingLayout &);
+    void (*launch)(VitParams &, const double *, int, cudaStream_t, hmm_info *, Timer *);
+};
+template <int N, int R, int LPC>
+static VitVariant make_variant() {
+    return VitVariant{&fwd_warps_per_sm<N, R, LPC>, &launch_all<N, R, LPC>};
 }
-
-static int fwd_warps_per_sm_dispatch(int N, const RingLayout &RL) {
+template <int N, int R>
+static VitVariant pick_lp(int LP, bool const_ok) {
+    if (const_ok && LP == 64) return make_variant<N, R, 64>();
+    if (const_ok && LP == 48) return make_variant<N, R, 48>();
+    return make_variant<N, R, 0>();
+}
+static VitVariant pick_variant(int N, int LP, bool const_ok) {
     switch (N) {
-        case 1: return fwd_warps_per_sm<1, 8>(RL);
-        case 2: return fwd_warps_per_sm<2, 8>(RL);
-        case 3: return fwd_warps_per_sm<3, 8>(RL);
-        case 4: return fwd_warps_per_sm<4, 8>(RL);
-        case 5: return fwd_warps_per_sm<5, 4>(RL);
-        case 6: return fwd_warps_per_sm<6, 4>(RL);
-        case 7: return fwd_warps_per_sm<7, 4>(RL);
+        case 1: return pick_lp<1, 8>(LP, const_ok);
+        case 2: return pick_lp<2, 8>(LP, const_ok);
+        case 3: return pick_lp<3, 8>(LP, const_ok);
+        case 4: return pick_lp<4, 8>(LP, const_ok);
+        case 5: return pick_lp<5, 4>(LP, const_ok);
+        case 6: return make_variant<6, 4, 0>();
+        case 7: return make_variant<7, 4, 0>();
     }
     fail(HMM_EUNSUPPORTED, "ring engine supports 1..%d neurons", RING_MAX_N);
 }
@@ -782,6 +887,19 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
     const int R = (N <= 4) ? 8 : 4;
     const int SW = 32 * R;
     RingLayout RL = ring_layout(N, L);
+    // Long recordings: one channel per launch (each already fills the GPU), which lets the
+    // FIR take its coefficients from the constant bank.
+    const bool no_const = getenv("HMMCUDA_NO_CONST_FIR") && atoi(getenv("HMMCUDA_NO_CONST_FIR")) != 0;
+    if (C > 1 && T >= 262144 && !no_const) {
+        for (int ch = 0; ch < C; ch++) {
+            std::vector<HostModel> one(1, models[ch]);
+            ring_viterbi_run(y_dev + (size_t)ch * y_stride, T, y_stride, 1, one, FL, blob_dev + (size_t)ch * FL.bytes,
+                             x_dev + (size_t)ch * x_stride, x_stride, ll_dev ? ll_dev + ch : nullptr, st, info);
+        }
+        if (info) info->n_chunks /= 1;
+        return;
+    }
+    const VitVariant variant = pick_variant(N, RL.LP, C == 1 && !no_const);
 
     // geometry: one chunk per warp, one wave of warps over the whole GPU
     int64_t W = ring_config().warmup > 0 ? ring_config().warmup : 512;
@@ -793,7 +911,7 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
         HMM_CUDA(cudaGetDevice(&dev));
         HMM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         // one chunk per resident warp: a single, full wave over the whole GPU
-        const int64_t target_warps = (int64_t)sms * fwd_warps_per_sm_dispatch(N, RL);
+        const int64_t target_warps = (int64_t)sms * variant.warps_per_sm(RL);
         int64_t per_channel = (target_warps + C - 1) / C;
         Lc = (T + per_channel - 1) / per_channel;
         if (Lc < 4 * W) Lc = 4 * W;
@@ -836,10 +954,12 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
     size_t o_look = carve(sizeof(long long) * (size_t)C * nchunks);
     size_t o_xend = carve(sizeof(int16_t) * C);
     size_t o_part = carve(sizeof(double) * (size_t)C * 1024);
+    size_t o_slots = carve(sizeof(int) * 256);
     char *base = (char *)ws.get(Workspace::CHUNKS, off);
     HMM_CUDA(cudaMemcpyAsync(base + o_model, hmdl.data(), sizeof(double) * hmdl.size(), cudaMemcpyHostToDevice, st));
     HMM_CUDA(cudaStreamSynchronize(st));  // hmdl is a pageable temporary
     HMM_CUDA(cudaMemsetAsync(base + o_cnt, 0, sizeof(int) * (size_t)C * 4, st));
+    HMM_CUDA(cudaMemsetAsync(base + o_slots, 0, sizeof(int) * 256, st));
     HMM_CUDA(cudaMemsetAsync(base + o_pfin, 0, sizeof(double) * (size_t)C * N * RING_Q, st));
 
     VitParams p{};
@@ -854,6 +974,8 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
     p.ns = ns;
     p.dec = (uint32_t *)ws.get(Workspace::DEC, sizeof(uint32_t) * (size_t)C * T);
     p.nzmask = (uint32_t *)ws.get(Workspace::MASK, sizeof(uint32_t) * (size_t)C * ((T + 31) / 32));
+    HMM_CUDA(cudaMemsetAsync(p.dec, 0, sizeof(uint32_t) * (size_t)C * T, st));
+    HMM_CUDA(cudaMemsetAsync(p.nzmask, 0, sizeof(uint32_t) * (size_t)C * ((T + 31) / 32), st));
     p.SB = (double *)(base + o_sb);
     p.EB = (double *)(base + o_eb);
     p.bvec = bvec;
@@ -869,25 +991,19 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
     p.own_start = (long long *)(base + o_own);
     p.look_end = (long long *)(base + o_look);
     p.tr_flag = (int *)(base + o_trflag);
+    p.sm_slots = (int *)(base + o_slots);
     {
         const char *e = getenv("HMMCUDA_STAGGER_NS");
         p.stagger_ns = e ? atoi(e) : 0;
+        const char *e2 = getenv("HMMCUDA_DEBUG_SKIP");
+        p.debug_skip = e2 ? atoi(e2) : 0;
         int dev = 0;
         HMM_CUDA(cudaGetDevice(&dev));
         HMM_CUDA(cudaDeviceGetAttribute(&p.n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
 
     Timer ttop(st);
-    switch (N * 10 + R) {
-        case 18: launch_all<1, 8>(p, C, st, info, &ttop); break;
-        case 28: launch_all<2, 8>(p, C, st, info, &ttop); break;
-        case 38: launch_all<3, 8>(p, C, st, info, &ttop); break;
-        case 48: launch_all<4, 8>(p, C, st, info, &ttop); break;
-        case 54: launch_all<5, 4>(p, C, st, info, &ttop); break;
-        case 64: launch_all<6, 4>(p, C, st, info, &ttop); break;
-        case 74: launch_all<7, 4>(p, C, st, info, &ttop); break;
-        default: fail(HMM_EUNSUPPORTED, "ring engine supports 1..%d neurons", RING_MAX_N);
-    }
+    variant.launch(p, hmdl.data(), C, st, info, &ttop);
     if (ll_dev) {
         const int nparts = 592;
         double *part = (double *)(base + o_part);
