@@ -9,6 +9,7 @@
 #include <cfloat>
 
 #include "engines.h"
+#include "faithful_dev.cuh"
 
 namespace hmm {
 
@@ -55,11 +56,6 @@ void faithful_pack(const HostModel &M, const FaithfulLayout &L, char *dst) {
     memcpy(dst + L.static_pred, M.static_pred.data(), sizeof(int) * M.nstates);
 }
 
-// Gaussian log-emission, src/utils.jl:3-4: (-log2pi - l_sigma) - (dd*dd)/(2*sigma2)
-__device__ __forceinline__ double emit_rn(double x, double mu, double c_emit, double two_s2) {
-    double dd = __dsub_rn(x, mu);
-    return __dsub_rn(c_emit, __ddiv_rn(__dmul_rn(dd, dd), two_s2));
-}
 
 // src/utils.jl:24-32
 __device__ __forceinline__ double logsumexpl_dev(double xp, double yp) {

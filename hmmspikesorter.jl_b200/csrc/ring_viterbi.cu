@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <limits>
 
+#include "faithful_dev.cuh"
 #include "ring_common.cuh"
 
 namespace hmm {
@@ -107,14 +108,17 @@ struct VitParams {
     uint32_t *nzmask;      // [C x ceil(T/32)]
     double *SB, *EB;       // [C x nchunks x bvec]  boundary vectors (start: speculative, end: true)
     int bvec;              // 1 + N*L
-    const double *T1pro;   // [C x ns x (L+1)] faithful prologue trellis
+    const char *fblob;     // faithful model blobs (prologue in the reference's arithmetic)
+    size_t fblob_stride;
+    FaithfulLayout FL;
+    double *T1pro;         // [C x ns x (L+1)] prologue trellis, written by chunk 0's warp
     double *Pfin;          // [C x N x RING_Q]  P of the last steps (final chunk)
     double *Gfin;          // [C]
     int *fwd_flag;         // [C x nchunks] boundary mismatch flags
     int *counters;         // [C x 4]: 0 fwd repaired, 1 trace repaired
     // trace
-    const int16_t *T2pro;  // [C x ns x (L+1)]
-    const int16_t *xend;   // [C] final state (0-based)
+    int16_t *T2pro;        // [C x ns x (L+1)]
+    int16_t *xend;         // [C] final state (0-based), written by the last chunk's warp
     int16_t *x;            // [T x C]
     int64_t x_stride;
     long long *own_start, *look_end;  // [C x nchunks] encoded states
@@ -141,6 +145,117 @@ template <int N>
 struct CtaModel {
     static constexpr int NP = (N + 1) & ~1;
 };
+
+// ---------------------------------------------------------------------------
+// The first L+1 columns of the trellis in the reference's exact arithmetic
+// (src/viterbi.jl:55-88).  This is where the reference's initialisation creates
+// exact ties, so the decisions must come from bit-identical scores.
+// One CTA per channel, one thread per state.  All (L+1) x nstates emissions are
+// computed first, in parallel (the FP64 division is the long-latency part), so the
+// sequential sweep is an add / compare / select per step.  Writes T1pro / T2pro.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) ring_vit_prologue(VitParams p) {
+    extern __shared__ __align__(16) double psm[];
+    const int ch = blockIdx.x;
+    const int ns = p.ns, L = p.RL.L, cols = L + 1;
+    const char *mb = p.fblob + (size_t)ch * p.fblob_stride;
+    const double *sc = (const double *)(mb + p.FL.scal);
+    const double c_emit = sc[2], two_s2 = sc[3];
+    const double *gm = (const double *)(mb + p.FL.m), *glp = (const double *)(mb + p.FL.in_lp);
+    const int *gp = (const int *)(mb + p.FL.in_ptr), *gs = (const int *)(mb + p.FL.in_src);
+    const double *y = p.y + (size_t)ch * p.y_stride;
+    double *t1 = p.T1pro + (size_t)ch * ns * cols;
+    int16_t *t2 = p.T2pro + (size_t)ch * ns * cols;
+    double *q = psm;                    // [cols][ns]
+    double *c0 = q + (size_t)cols * ns, *c1 = c0 + ns;
+    for (int idx = threadIdx.x; idx < cols * ns; idx += blockDim.x) {
+        const int t = idx / ns, j = idx - t * ns;
+        q[idx] = emit_rn(y[t], gm[j], c_emit, two_s2);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < ns; j += blockDim.x) {
+        const double v = j == 0 ? 0.0 : q[j];  // :55-63
+        c0[j] = v;
+        t1[j] = v;
+        t2[j] = 1;
+    }
+    __syncthreads();
+    double *prev = c0, *cur = c1;
+    for (int t = 1; t <= L; t++) {
+        for (int j = threadIdx.x; j < ns; j += blockDim.x) {
+            double best = -INFINITY;
+            int bp = 0;
+            const int e1 = gp[j + 1];
+            for (int e = gp[j]; e < e1; e++) {
+                const int k2 = gs[e];
+                const double tt = __dadd_rn(prev[k2], glp[e]);
+                if (tt > best) {  // strict: first candidate in list order wins ties
+                    best = tt;
+                    bp = k2;
+                }
+            }
+            const double v = __dadd_rn(best, q[(size_t)t * ns + j]);
+            cur[j] = v;
+            t1[(size_t)t * ns + j] = v;
+            t2[(size_t)t * ns + j] = (int16_t)(bp + 1);
+        }
+        __syncthreads();
+        double *tmp = prev;
+        prev = cur;
+        cur = tmp;
+    }
+}
+
+// Final state: x[T] = argmax_j T1[j, T] (first maximum, src/viterbi.jl:90), from the last
+// chunk's G and P ring plus partial chain sums.  One CTA per channel, one thread per state.
+template <int N>
+__global__ void __launch_bounds__(256) ring_vit_final(VitParams p) {
+    const int ch = blockIdx.x;
+    const RingLayout &RL = p.RL;
+    const int L = RL.L, NP = RL.NP;
+    const double *mdl = p.model + (size_t)ch * RL.total;
+    const double *A = mdl + RL.A, *BW = mdl + RL.BW;
+    const double *y = p.y + (size_t)ch * p.y_stride;
+    const int64_t T = p.T;
+    // candidate per state j = 1 + i*L + (sph-1): entered at t0 = T - sph
+    double best = -INFINITY;
+    int bj = 0x7fffffff;
+    for (int idx = threadIdx.x; idx < N * L; idx += blockDim.x) {
+        int i = idx / L, sph = idx % L + 1;
+        int64_t t0 = T - sph;
+        double v = p.Pfin[((size_t)ch * N + i) * RING_Q + (int)(t0 & (RING_Q - 1))];
+        for (int r = 0; r < sph; r++) v += fma(A[r * NP + i], y[t0 + r], BW[r * NP + i]);
+        int j = 1 + idx;
+        if (v > best || (v == best && j < bj)) {
+            best = v;
+            bj = j;
+        }
+    }
+    if (threadIdx.x == 0) {  // noise is state 0: wins ties against everything
+        const double g = p.Gfin[ch];
+        if (g >= best) {
+            best = g;
+            bj = 0;
+        }
+    }
+    __shared__ double sb[256];
+    __shared__ int sj[256];
+    sb[threadIdx.x] = best;
+    sj[threadIdx.x] = bj;
+    __syncthreads();
+    for (int k = 128; k >= 1; k >>= 1) {
+        if (threadIdx.x < k) {
+            double ob = sb[threadIdx.x + k];
+            int oj = sj[threadIdx.x + k];
+            if (ob > sb[threadIdx.x] || (ob == sb[threadIdx.x] && oj < sj[threadIdx.x])) {
+                sb[threadIdx.x] = ob;
+                sj[threadIdx.x] = oj;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) p.xend[ch] = (int16_t)sj[0];
+}
 
 // ---------------------------------------------------------------------------
 // One chunk, one warp.
@@ -515,49 +630,6 @@ __global__ void __launch_bounds__(32) ring_vit_repair_fwd(VitParams p) {
     if (lane == 0) p.counters[ch * 4 + 0] = repaired;
 }
 
-// Final state: x[T] = argmax_j T1[j, T] (first maximum), from the last chunk's
-// G and P ring plus partial chain sums.  One warp per channel.
-template <int N>
-__global__ void __launch_bounds__(32) ring_vit_final(VitParams p, int16_t *xend) {
-    const int ch = blockIdx.x, lane = threadIdx.x;
-    const RingLayout &RL = p.RL;
-    const int L = RL.L, NP = RL.NP;
-    const double *mdl = p.model + (size_t)ch * RL.total;
-    const double *A = mdl + RL.A, *BW = mdl + RL.BW;
-    const double *y = p.y + (size_t)ch * p.y_stride;
-    const int64_t T = p.T;
-    // candidate per state j = 1 + i*L + (sph-1): entered at t0 = T - sph
-    double best = -INFINITY;
-    int bj = 0x7fffffff;
-    for (int idx = lane; idx < N * L; idx += 32) {
-        int i = idx / L, sph = idx % L + 1;
-        int64_t t0 = T - sph;
-        double v = p.Pfin[((size_t)ch * N + i) * RING_Q + (int)(t0 & (RING_Q - 1))];
-        for (int r = 0; r < sph; r++) v += fma(A[r * NP + i], y[t0 + r], BW[r * NP + i]);
-        int j = 1 + idx;
-        if (v > best || (v == best && j < bj)) {
-            best = v;
-            bj = j;
-        }
-    }
-    if (lane == 0) {  // noise is state 0: wins ties against everything
-        double g = p.Gfin[ch];
-        if (g >= best) {
-            best = g;
-            bj = 0;
-        }
-    }
-    for (int d = 16; d >= 1; d >>= 1) {
-        double ob = shfl_down_d(best, d);
-        int oj = __shfl_down_sync(0xffffffffu, bj, d);
-        if (ob > best || (ob == best && oj < bj)) {
-            best = ob;
-            bj = oj;
-        }
-    }
-    if (lane == 0) xend[ch] = (int16_t)bj;
-}
-
 // ---------------------------------------------------------------------------
 // Traceback.  State encoding: -1 = noise, else t0 * 8 + neuron (chain entered at t0).
 // ---------------------------------------------------------------------------
@@ -738,28 +810,68 @@ __global__ void __launch_bounds__(32) ring_vit_repair_trace(VitParams p) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     ring_path_ll_partial(const double *__restrict__ y, int64_t T, int64_t y_stride, const char *blob,
-                         size_t blob_stride, FaithfulLayout L, const int16_t *__restrict__ x, int64_t x_stride,
-                         double *__restrict__ partial /*[C x gridDim.x]*/) {
+                         size_t blob_stride, FaithfulLayout L, int ns, int nt, const int16_t *__restrict__ x,
+                         int64_t x_stride, double *__restrict__ partial /*[C x gridDim.x]*/) {
+    extern __shared__ __align__(16) char llsm[];
     const int ch = blockIdx.y;
     const char *mb = blob + (size_t)ch * blob_stride;
     const double *sc = (const double *)(mb + L.scal);
-    const double c_emit = sc[2], two_s2 = sc[3];
-    const double *gm = (const double *)(mb + L.m), *glp = (const double *)(mb + L.in_lp);
-    const int *gp = (const int *)(mb + L.in_ptr), *gs = (const int *)(mb + L.in_src);
+    const double c_emit = sc[2], inv2s2 = 1.0 / sc[3];
+    double *sm_m = (double *)llsm, *sm_lp = sm_m + ns;
+    int *sm_ptr = (int *)(sm_lp + nt), *sm_src = sm_ptr + ns + 1;
+    {
+        const double *gm = (const double *)(mb + L.m), *glp = (const double *)(mb + L.in_lp);
+        const int *gp = (const int *)(mb + L.in_ptr), *gs = (const int *)(mb + L.in_src);
+        for (int i = threadIdx.x; i < ns; i += blockDim.x) sm_m[i] = gm[i];
+        for (int i = threadIdx.x; i <= ns; i += blockDim.x) sm_ptr[i] = gp[i];
+        for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+            sm_lp[i] = glp[i];
+            sm_src[i] = gs[i];
+        }
+    }
+    __syncthreads();
     y += (size_t)ch * y_stride;
     x += (size_t)ch * x_stride;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
     double acc = 0.0;
-    for (int64_t t = 1 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x) {
-        int d = x[t] - 1, s = x[t - 1] - 1;
-        double lp = __longlong_as_double(0x7ff8000000000000LL);
-        for (int e = gp[d]; e < gp[d + 1]; e++)
-            if (gs[e] == s) {
-                lp = glp[e];
-                break;
+    const int64_t ngroups = (T + 7) / 8;  // group g covers steps [8g, 8g+8)
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < ngroups; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t0 = g * 8;
+        int16_t xs[8];
+        double ys[8];
+        if (aligned && t0 + 8 <= T) {
+            *reinterpret_cast<int4 *>(xs) = __ldg(reinterpret_cast<const int4 *>(x + t0));
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+                double2 v = __ldg(reinterpret_cast<const double2 *>(y + t0 + k));
+                ys[k] = v.x;
+                ys[k + 1] = v.y;
             }
-        double dd = y[t] - gm[d];
-        double q = c_emit - (dd * dd) / two_s2;
-        acc += (double)(T - t) * (lp + q);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                xs[k] = t0 + k < T ? x[t0 + k] : (int16_t)1;
+                ys[k] = t0 + k < T ? y[t0 + k] : 0.0;
+            }
+        }
+        int s = t0 > 0 ? x[t0 - 1] - 1 : 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int64_t t = t0 + k;
+            const int d = xs[k] - 1;
+            if (t >= 1 && t < T) {
+                double lp = __longlong_as_double(0x7ff8000000000000LL);
+                for (int e = sm_ptr[d]; e < sm_ptr[d + 1]; e++)
+                    if (sm_src[e] == s) {
+                        lp = sm_lp[e];
+                        break;
+                    }
+                const double dd = ys[k] - sm_m[d];
+                const double q = c_emit - (dd * dd) * inv2s2;
+                acc = fma((double)(T - t), lp + q, acc);
+            }
+            s = d;
+        }
     }
     __shared__ double red[256];
     red[threadIdx.x] = acc;
@@ -830,13 +942,20 @@ static void launch_all(VitParams &p, const double *hmodel /*host ring model of c
         for (int r = 0; r < LPC; r++)
             for (int i = 0; i < N; i++) coef.a[r * N + i] = hmodel[p.RL.A + r * p.RL.NP + i];
     dim3 gridc((p.nchunks + WPB - 1) / WPB, C);
+    {
+        const size_t sm_pro = sizeof(double) * ((size_t)(p.RL.L + 1) * p.ns + 2 * (size_t)p.ns);
+        if (sm_pro > 227 * 1024) fail(HMM_EUNSUPPORTED, "prologue does not fit shared memory");
+        HMM_CUDA(cudaFuncSetAttribute(ring_vit_prologue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pro));
+        int th = ((p.ns + 31) / 32) * 32;
+        ring_vit_prologue<<<C, th > 1024 ? 1024 : th, sm_pro, st>>>(p);
+    }
     if (ttop) ttop->start();
     ring_vit_forward<N, R, LPC><<<gridc, 32 * WPB, sm_fwd, st>>>(p, coef);
     if (ttop) ttop->stop();
     HMM_CUDA(cudaGetLastError());
     ring_vit_check_fwd<<<dim3((p.nchunks * 32 + 127) / 128, C), 128, 0, st>>>(p);
     ring_vit_repair_fwd<N, R><<<C, 32, sm_rep, st>>>(p);
-    ring_vit_final<N><<<C, 32, 0, st>>>(p, const_cast<int16_t *>(p.xend));
+    ring_vit_final<N><<<C, 256, 0, st>>>(p);
     HMM_CUDA(cudaGetLastError());
     const size_t sm_t2 = sizeof(int16_t) * (size_t)p.ns * (p.RL.L + 1);
     HMM_CUDA(cudaFuncSetAttribute(ring_vit_trace<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_t2));
@@ -845,7 +964,7 @@ static void launch_all(VitParams &p, const double *hmodel /*host ring model of c
     ring_vit_check_trace<<<dim3((p.nchunks + 127) / 128, C), 128, 0, st>>>(p);
     ring_vit_repair_trace<N><<<C, 32, sm_t2, st>>>(p);
     HMM_CUDA(cudaGetLastError());
-    if (info) info->kernel_launches += 7;
+    if (info) info->kernel_launches += 8;
 }
 
 // (N, LP) -> kernel variant.  LPC > 0: FIR coefficients as constant-bank operands
@@ -926,12 +1045,6 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
     const int64_t pcols = L + 1;
     double *T1pro = (double *)ws.get(Workspace::PROLOG, (sizeof(double) + sizeof(int16_t)) * (size_t)C * ns * pcols + 64);
     int16_t *T2pro = (int16_t *)(T1pro + (size_t)C * ns * pcols);
-    {
-        // run the faithful forward sweep on the first L+1 samples only
-        faithful_viterbi_run(y_dev, pcols, y_stride, C, FL, blob_dev, M0, nullptr, 0, nullptr, T1pro, T2pro, pcols,
-                             true, nullptr, st, info);
-    }
-
     // ring models
     std::vector<double> hmdl((size_t)C * RL.total);
     for (int c = 0; c < C; c++) ring_pack(models[c], RL, hmdl.data() + (size_t)c * RL.total);
@@ -979,13 +1092,16 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
     p.SB = (double *)(base + o_sb);
     p.EB = (double *)(base + o_eb);
     p.bvec = bvec;
+    p.fblob = blob_dev;
+    p.fblob_stride = FL.bytes;
+    p.FL = FL;
     p.T1pro = T1pro;
     p.Pfin = (double *)(base + o_pfin);
     p.Gfin = (double *)(base + o_gfin);
     p.fwd_flag = (int *)(base + o_flag);
     p.counters = (int *)(base + o_cnt);
     p.T2pro = T2pro;
-    p.xend = (const int16_t *)(base + o_xend);
+    p.xend = (int16_t *)(base + o_xend);
     p.x = x_dev;
     p.x_stride = x_stride;
     p.own_start = (long long *)(base + o_own);
@@ -1007,8 +1123,9 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
     if (ll_dev) {
         const int nparts = 592;
         double *part = (double *)(base + o_part);
-        ring_path_ll_partial<<<dim3(nparts, C), 256, 0, st>>>(y_dev, T, y_stride, blob_dev, FL.bytes, FL, x_dev, x_stride,
-                                                              part);
+        const size_t llsm = sizeof(double) * ((size_t)ns + M0.ntrans) + sizeof(int) * ((size_t)ns + 1 + M0.ntrans) + 16;
+        ring_path_ll_partial<<<dim3(nparts, C), 256, llsm, st>>>(y_dev, T, y_stride, blob_dev, FL.bytes, FL, ns,
+                                                                 (int)M0.ntrans, x_dev, x_stride, part);
         ring_path_ll_final<<<C, 256, 0, st>>>(y_dev, T, y_stride, blob_dev, FL.bytes, FL, x_dev, x_stride, part, nparts,
                                               ll_dev);
         HMM_CUDA(cudaGetLastError());
