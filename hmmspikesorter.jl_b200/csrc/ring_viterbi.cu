@@ -168,9 +168,17 @@ __global__ void __launch_bounds__(1024) ring_vit_prologue(VitParams p) {
     int16_t *t2 = p.T2pro + (size_t)ch * ns * cols;
     double *q = psm;                    // [cols][ns]
     double *c0 = q + (size_t)cols * ns, *c1 = c0 + ns;
-    for (int idx = threadIdx.x; idx < cols * ns; idx += blockDim.x) {
-        const int t = idx / ns, j = idx - t * ns;
-        q[idx] = emit_rn(y[t], gm[j], c_emit, two_s2);
+    // emissions: thread (tq, j) strides over the columns; no integer division in the loop
+    {
+        const int tpc = blockDim.x / ns > 0 ? blockDim.x / ns : 1;  // columns processed concurrently
+        const int tq = threadIdx.x / ns, j = threadIdx.x - tq * ns;
+        if (tq < tpc && blockDim.x >= (unsigned)ns) {
+            const double mj = gm[j];
+            for (int t = tq; t < cols; t += tpc) q[(size_t)t * ns + j] = emit_rn(y[t], mj, c_emit, two_s2);
+        } else if (blockDim.x < (unsigned)ns) {
+            for (int idx = threadIdx.x; idx < cols * ns; idx += blockDim.x)
+                q[idx] = emit_rn(y[idx / ns], gm[idx % ns], c_emit, two_s2);
+        }
     }
     __syncthreads();
     for (int j = threadIdx.x; j < ns; j += blockDim.x) {
@@ -181,23 +189,61 @@ __global__ void __launch_bounds__(1024) ring_vit_prologue(VitParams p) {
     }
     __syncthreads();
     double *prev = c0, *cur = c1;
+    const bool one_state = blockDim.x >= (unsigned)ns;  // thread j owns state j: keep its first edge in registers
+    int my_deg = 0, my_src = 0, my_e0 = 0;
+    double my_w = 0.0;
+    if (one_state && threadIdx.x < (unsigned)ns) {
+        my_e0 = gp[threadIdx.x];
+        my_deg = gp[threadIdx.x + 1] - my_e0;
+        if (my_deg > 0) {
+            my_src = gs[my_e0];
+            my_w = glp[my_e0];
+        }
+    }
     for (int t = 1; t <= L; t++) {
-        for (int j = threadIdx.x; j < ns; j += blockDim.x) {
-            double best = -INFINITY;
-            int bp = 0;
-            const int e1 = gp[j + 1];
-            for (int e = gp[j]; e < e1; e++) {
-                const int k2 = gs[e];
-                const double tt = __dadd_rn(prev[k2], glp[e]);
-                if (tt > best) {  // strict: first candidate in list order wins ties
-                    best = tt;
-                    bp = k2;
+        if (one_state) {
+            const int j = threadIdx.x;
+            if (j < ns) {
+                double best = -INFINITY;
+                int bp = 0;
+                if (my_deg > 0) {
+                    const double tt = __dadd_rn(prev[my_src], my_w);
+                    if (tt > best) {
+                        best = tt;
+                        bp = my_src;
+                    }
+                    for (int e = my_e0 + 1; e < my_e0 + my_deg; e++) {
+                        const int k2 = gs[e];
+                        const double t3 = __dadd_rn(prev[k2], glp[e]);
+                        if (t3 > best) {  // strict: first candidate in list order wins ties
+                            best = t3;
+                            bp = k2;
+                        }
+                    }
                 }
+                const double v = __dadd_rn(best, q[(size_t)t * ns + j]);
+                cur[j] = v;
+                t1[(size_t)t * ns + j] = v;
+                t2[(size_t)t * ns + j] = (int16_t)(bp + 1);
             }
-            const double v = __dadd_rn(best, q[(size_t)t * ns + j]);
-            cur[j] = v;
-            t1[(size_t)t * ns + j] = v;
-            t2[(size_t)t * ns + j] = (int16_t)(bp + 1);
+        } else {
+            for (int j = threadIdx.x; j < ns; j += blockDim.x) {
+                double best = -INFINITY;
+                int bp = 0;
+                const int e1 = gp[j + 1];
+                for (int e = gp[j]; e < e1; e++) {
+                    const int k2 = gs[e];
+                    const double tt = __dadd_rn(prev[k2], glp[e]);
+                    if (tt > best) {
+                        best = tt;
+                        bp = k2;
+                    }
+                }
+                const double v = __dadd_rn(best, q[(size_t)t * ns + j]);
+                cur[j] = v;
+                t1[(size_t)t * ns + j] = v;
+                t2[(size_t)t * ns + j] = (int16_t)(bp + 1);
+            }
         }
         __syncthreads();
         double *tmp = prev;
@@ -217,6 +263,14 @@ __global__ void __launch_bounds__(256) ring_vit_final(VitParams p) {
     const double *A = mdl + RL.A, *BW = mdl + RL.BW;
     const double *y = p.y + (size_t)ch * p.y_stride;
     const int64_t T = p.T;
+    __shared__ double sA[RING_MAX_L * RING_MAX_N], sB[RING_MAX_L * RING_MAX_N], sy[RING_MAX_L];
+    for (int k = threadIdx.x; k < N * L; k += blockDim.x) {
+        const int i = k / L, r = k % L;
+        sA[k] = A[r * NP + i];
+        sB[k] = BW[r * NP + i];
+    }
+    for (int k = threadIdx.x; k < L; k += blockDim.x) sy[k] = y[T - L + k];
+    __syncthreads();
     // candidate per state j = 1 + i*L + (sph-1): entered at t0 = T - sph
     double best = -INFINITY;
     int bj = 0x7fffffff;
@@ -224,7 +278,7 @@ __global__ void __launch_bounds__(256) ring_vit_final(VitParams p) {
         int i = idx / L, sph = idx % L + 1;
         int64_t t0 = T - sph;
         double v = p.Pfin[((size_t)ch * N + i) * RING_Q + (int)(t0 & (RING_Q - 1))];
-        for (int r = 0; r < sph; r++) v += fma(A[r * NP + i], y[t0 + r], BW[r * NP + i]);
+        for (int r = 0; r < sph; r++) v += fma(sA[i * L + r], sy[L - sph + r], sB[i * L + r]);
         int j = 1 + idx;
         if (v > best || (v == best && j < bj)) {
             best = v;
@@ -635,9 +689,14 @@ __global__ void __launch_bounds__(32) ring_vit_repair_fwd(VitParams p) {
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ long long enc_spike(int64_t t0, int i) { return (long long)t0 * 8 + i; }
 
+// Per-warp shared workspace of the traceback: one tile of 8192 steps.
+constexpr int TR_TILE_W = 256;  // mask words per tile
+constexpr int TR_CAP = 512;     // pre-fetched decision entries per tile
+constexpr int TR_WARP_U32 = TR_TILE_W /*mw*/ + TR_TILE_W /*pre*/ + 2 * TR_CAP /*ent*/ + TR_CAP / 2 /*pos, u16*/;
+
 template <int N>
 __device__ void trace_chunk(const VitParams &p, int ch, int c, int64_t tau_hi, long long st, bool record_look,
-                            int16_t *t2s /*smem, chunk 0 only*/) {
+                            int16_t *t2s /*smem, chunk 0 only*/, uint32_t *tws /*per-warp, TR_WARP_U32 words*/) {
     const int lane = threadIdx.x & 31;
     const int L = p.RL.L;
     const int64_t T = p.T;
@@ -648,64 +707,136 @@ __device__ void trace_chunk(const VitParams &p, int ch, int c, int64_t tau_hi, l
     const uint32_t *dec = p.dec + (size_t)ch * T;
     const uint32_t *nzm = p.nzmask + (size_t)ch * ((T + 31) / 32);
     int16_t *x = p.x + (size_t)ch * p.x_stride;
+    uint32_t *mw = tws, *pre = mw + TR_TILE_W, *ent = pre + TR_TILE_W;
+    uint16_t *pos = reinterpret_cast<uint16_t *>(ent + 2 * TR_CAP);
     long long own = -2, look = -2;
     int64_t cur = tau_hi;
+    int64_t tile_wlo = 0, tile_whi = -1;  // invalid
+    const int64_t wlo = lo >> 5;
+    // segment [a, b] is decoded as `state`: remember what the chunk boundaries see, write x
+    auto emit_noise = [&](int64_t a, int64_t b) {
+        if (record_look && e <= b && e >= a) look = -1;
+        if (s <= b && s >= a) own = -1;
+        int64_t wa = a < s ? s : a, wb = b < e - 1 ? b : e - 1;
+        for (int64_t t = wa + lane; t <= wb; t += 32) x[t] = 1;
+    };
+    auto emit_spike = [&](int64_t a, int64_t b, long long state) {
+        const int i = (int)(state & 7);
+        const int64_t t0 = state >> 3;
+        if (record_look && e <= b && e >= a) look = state;
+        if (s <= b && s >= a) own = state;
+        int64_t wa = a < s ? s : a, wb = b < e - 1 ? b : e - 1;
+        for (int64_t t = wa + lane; t <= wb; t += 32) x[t] = (int16_t)(2 + i * L + (int)(t - t0));
+    };
     while (cur >= lo) {
         if (st < 0) {
-            // noise at cur: find the latest step tp in [lo, cur] where noise was entered from a tail
-            int64_t tp = lo - 1;
-            int64_t whi = cur >> 5;
-            const int64_t wlo = lo >> 5;
-            while (whi >= wlo) {
-                int64_t wi = whi - lane;
+            // ---- make sure the tile holding `cur` is staged: mask words, ranks, decision entries ----
+            const int64_t wc = cur >> 5;
+            if (wc > tile_whi || wc < tile_wlo) {
+                tile_whi = wc;
+                tile_wlo = wc - (TR_TILE_W - 1);
+                if (tile_wlo < wlo) tile_wlo = wlo;
+                const int nW = (int)(tile_whi - tile_wlo + 1);
+                __syncwarp();
+                for (int k = lane; k < TR_TILE_W; k += 32) {
+                    uint32_t word = k < nW ? nzm[tile_wlo + k] : 0u;
+                    if (tile_wlo + k == wlo) word &= ~((1u << (lo & 31)) - 1u);
+                    mw[k] = word;
+                }
+                __syncwarp();
+                int cnt = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) cnt += __popc(mw[8 * lane + q]);
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += o;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                int r = incl - cnt;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    uint32_t w = mw[8 * lane + q];
+                    pre[8 * lane + q] = (uint32_t)r;
+                    while (w) {
+                        const int bpos = __ffs(w) - 1;
+                        w &= w - 1;
+                        if (r < TR_CAP) pos[r] = (uint16_t)((8 * lane + q) * 32 + bpos);
+                        r++;
+                    }
+                }
+                __syncwarp();
+                const int n = total < TR_CAP ? total : TR_CAP;
+                for (int q = lane; q < n; q += 32) {
+                    const int64_t tp = (tile_wlo << 5) + pos[q];
+                    ent[2 * q] = dec[tp];
+                    ent[2 * q + 1] = tp >= L ? dec[tp - L] : 0u;
+                }
+                __syncwarp();
+            }
+            // ---- latest step tp <= cur in this tile where noise was entered from a tail ----
+            int64_t tp = -1;
+            uint32_t wsel = 0;
+            for (int64_t whi = wc; whi >= tile_wlo; whi -= 32) {
+                const int64_t wi = whi - lane;
                 uint32_t word = 0;
-                if (wi >= wlo) {
-                    word = nzm[wi];
-                    if (wi == (cur >> 5)) {
-                        int hb = (int)(cur & 31);
+                if (wi >= tile_wlo) {
+                    word = mw[wi - tile_wlo];
+                    if (wi == wc) {
+                        const int hb = (int)(cur & 31);
                         if (hb < 31) word &= (2u << hb) - 1u;
                     }
-                    if (wi == wlo) word &= ~((1u << (lo & 31)) - 1u);
                 }
-                unsigned bal = __ballot_sync(0xffffffffu, word != 0);
+                const unsigned bal = __ballot_sync(0xffffffffu, word != 0);
                 if (bal) {
-                    int src = __ffs(bal) - 1;
-                    uint32_t wsel = __shfl_sync(0xffffffffu, word, src);
+                    const int src = __ffs(bal) - 1;
+                    wsel = __shfl_sync(0xffffffffu, word, src);
                     tp = ((whi - src) << 5) + (31 - __clz(wsel));
                     break;
                 }
-                whi -= 32;
             }
-            // (tp, cur] and tp itself are noise
-            int64_t a = tp < lo ? lo : tp;
-            if (record_look && e <= cur && e >= a) look = -1;
-            if (s <= cur && s >= a) own = -1;
+            if (tp < 0) {  // noise all the way down to the bottom of the tile
+                const int64_t bottom = (tile_wlo << 5) < lo ? lo : (tile_wlo << 5);
+                emit_noise(bottom, cur);
+                cur = bottom - 1;
+                continue;  // reaches lo -> loop ends; otherwise the next tile is staged
+            }
+            emit_noise(tp, cur);  // (tp, cur] and tp itself are noise
+            uint32_t d1, d2;
             {
-                int64_t wa = a < s ? s : a, wb = cur < e - 1 ? cur : e - 1;
-                for (int64_t t = wa + lane; t <= wb; t += 32) x[t] = 1;
+                const int widx = (int)((tp >> 5) - tile_wlo);
+                const int rank = (int)pre[widx] + __popc(mw[widx] & ((1u << (tp & 31)) - 1u));
+                if (rank < TR_CAP) {
+                    d1 = ent[2 * rank];
+                    d2 = ent[2 * rank + 1];
+                } else {
+                    d1 = dec[tp];
+                    d2 = tp >= L ? dec[tp - L] : 0u;
+                }
             }
-            if (tp < lo) {
+            const int j = (int)(d1 & 15u);  // 1..N: noise at tp was entered from tail_j at tp-1
+            const int64_t t0 = tp - L;      // that chain was entered at t0 and occupies [t0, tp-1]
+            const long long sp = enc_spike(t0, j - 1);
+            emit_spike(t0 < lo ? lo : t0, tp - 1, sp);
+            if (t0 < lo) {
+                st = sp;
                 cur = lo - 1;
                 break;
             }
-            int j = (int)(dec[tp] & 15u);  // 1..N
-            cur = tp - 1;
-            st = enc_spike(tp - L, j - 1);
+            const int k = (int)((d2 >> (4 * j)) & 15u);
+            cur = t0 - 1;
+            st = (k == 0) ? -1 : enc_spike(t0 - L, k - 1);
         } else {
+            // chain state at cur (start state, or chains entered directly from another chain's tail)
             const int i = (int)(st & 7);
             const int64_t t0 = st >> 3;
-            int64_t a = t0 < lo ? lo : t0;
-            if (record_look && e <= cur && e >= a) look = st;
-            if (s <= cur && s >= a) own = st;
-            {
-                int64_t wa = a < s ? s : a, wb = cur < e - 1 ? cur : e - 1;
-                for (int64_t t = wa + lane; t <= wb; t += 32) x[t] = (int16_t)(2 + i * L + (int)(t - t0));
-            }
+            emit_spike(t0 < lo ? lo : t0, cur, st);
             if (t0 < lo) {
                 cur = lo - 1;
                 break;
             }
-            int k = (int)((dec[t0] >> (4 * (i + 1))) & 15u);
+            const int k = (int)((dec[t0] >> (4 * (i + 1))) & 15u);
             cur = t0 - 1;
             st = (k == 0) ? -1 : enc_spike(t0 - L, k - 1);
         }
@@ -736,9 +867,11 @@ __device__ __forceinline__ long long state_from_xend(int j, int64_t T, int L) {
 
 template <int N>
 __global__ void __launch_bounds__(128) ring_vit_trace(VitParams p) {
-    extern __shared__ __align__(16) int16_t t2s_all[];
+    extern __shared__ __align__(16) uint32_t trsm[];
     const int ch = blockIdx.y;
     const int warp = threadIdx.x >> 5;
+    uint32_t *tws = trsm + (size_t)warp * TR_WARP_U32;
+    int16_t *t2s_all = reinterpret_cast<int16_t *>(trsm + (size_t)(blockDim.x >> 5) * TR_WARP_U32);
     const int c = blockIdx.x * (blockDim.x >> 5) + warp;
     const int L = p.RL.L;
     if (blockIdx.x == 0) {  // chunk 0 lives in CTA 0: stage the prologue backpointers
@@ -758,7 +891,7 @@ __global__ void __launch_bounds__(128) ring_vit_trace(VitParams p) {
         tau_hi = T - 1;
         st = state_from_xend(p.xend[ch], T, L);
     }
-    trace_chunk<N>(p, ch, c, tau_hi, st, !last, t2s_all);
+    trace_chunk<N>(p, ch, c, tau_hi, st, !last, t2s_all, tws);
 }
 
 __global__ void ring_vit_check_trace(VitParams p) {
@@ -771,7 +904,9 @@ __global__ void ring_vit_check_trace(VitParams p) {
 
 template <int N>
 __global__ void __launch_bounds__(32) ring_vit_repair_trace(VitParams p) {
-    extern __shared__ __align__(16) int16_t t2s_all[];
+    extern __shared__ __align__(16) uint32_t trsm[];
+    uint32_t *tws = trsm;
+    int16_t *t2s_all = reinterpret_cast<int16_t *>(trsm + TR_WARP_U32);
     const int ch = blockIdx.x, lane = threadIdx.x;
     const size_t o = (size_t)ch * p.nchunks;
     int any = 0;
@@ -792,7 +927,7 @@ __global__ void __launch_bounds__(32) ring_vit_repair_trace(VitParams p) {
             // true state at time e_c is the (final) start state of chunk c+1
             int64_t e = (int64_t)(c + 1) * p.Lc;
             long long before = p.own_start[o + c];
-            trace_chunk<N>(p, ch, c, e, p.own_start[o + c + 1], false, t2s_all);
+            trace_chunk<N>(p, ch, c, e, p.own_start[o + c + 1], false, t2s_all, tws);
             __threadfence();
             __syncwarp();
             next_changed = (p.own_start[o + c] != before);
@@ -946,8 +1081,7 @@ static void launch_all(VitParams &p, const double *hmodel /*host ring model of c
         const size_t sm_pro = sizeof(double) * ((size_t)(p.RL.L + 1) * p.ns + 2 * (size_t)p.ns);
         if (sm_pro > 227 * 1024) fail(HMM_EUNSUPPORTED, "prologue does not fit shared memory");
         HMM_CUDA(cudaFuncSetAttribute(ring_vit_prologue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pro));
-        int th = ((p.ns + 31) / 32) * 32;
-        ring_vit_prologue<<<C, th > 1024 ? 1024 : th, sm_pro, st>>>(p);
+        ring_vit_prologue<<<C, 1024, sm_pro, st>>>(p);
     }
     if (ttop) ttop->start();
     ring_vit_forward<N, R, LPC><<<gridc, 32 * WPB, sm_fwd, st>>>(p, coef);
@@ -957,12 +1091,14 @@ static void launch_all(VitParams &p, const double *hmodel /*host ring model of c
     ring_vit_repair_fwd<N, R><<<C, 32, sm_rep, st>>>(p);
     ring_vit_final<N><<<C, 256, 0, st>>>(p);
     HMM_CUDA(cudaGetLastError());
-    const size_t sm_t2 = sizeof(int16_t) * (size_t)p.ns * (p.RL.L + 1);
-    HMM_CUDA(cudaFuncSetAttribute(ring_vit_trace<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_t2));
-    HMM_CUDA(cudaFuncSetAttribute(ring_vit_repair_trace<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_t2));
-    ring_vit_trace<N><<<gridc, 32 * WPB, sm_t2, st>>>(p);
+    const size_t sm_t2 = sizeof(int16_t) * (size_t)p.ns * (p.RL.L + 1) + 16;
+    const size_t sm_tr = sm_t2 + sizeof(uint32_t) * (size_t)WPB * TR_WARP_U32;
+    const size_t sm_trr = sm_t2 + sizeof(uint32_t) * (size_t)TR_WARP_U32;
+    HMM_CUDA(cudaFuncSetAttribute(ring_vit_trace<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_tr));
+    HMM_CUDA(cudaFuncSetAttribute(ring_vit_repair_trace<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_trr));
+    ring_vit_trace<N><<<gridc, 32 * WPB, sm_tr, st>>>(p);
     ring_vit_check_trace<<<dim3((p.nchunks + 127) / 128, C), 128, 0, st>>>(p);
-    ring_vit_repair_trace<N><<<C, 32, sm_t2, st>>>(p);
+    ring_vit_repair_trace<N><<<C, 32, sm_trr, st>>>(p);
     HMM_CUDA(cudaGetLastError());
     if (info) info->kernel_launches += 8;
 }
