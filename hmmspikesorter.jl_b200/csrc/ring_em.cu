@@ -81,6 +81,16 @@ __device__ void em_fwd_chunk(const EmParams &p, int c, int kind, const double *m
     double *ytile = ws, *fbuf = ws;
     double *ring = ws + EmWarpSmem<N, R>::TILE;
     const double *A = mdl + RL.A, *Bc = mdl + RL.Bc, *lA = mdl + RL.eG, *lH = mdl + RL.eH, *lC = mdl + RL.eT;
+    // cF[j] = max(lA_j, max_i(lC_ji - lH_i)): how much a tail of neuron j can gain on the noise term
+    double cF[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        double c = lA[j];
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            if (i != j) c = fmax(c, lC[j * NP + i] - lH[i]);
+        cF[j] = c;
+    }
     const double *cold = p.model;
     const double *y = p.y;
     const int64_t T = p.T;
@@ -173,6 +183,28 @@ __device__ void em_fwd_chunk(const EmParams &p, int c, int kind, const double *m
                 double lt[N];
 #pragma unroll
                 for (int j = 0; j < N; j++) lt[j] = active ? ring[j * RING_Q + slot_r] : NEG;
+                // Dead-window fast path: if every arriving tail is more than e^-43 below the noise
+                // term in every sum it enters, each lse2 below would take its "smaller term is under
+                // half an ulp" shortcut (32 lanes x N terms of e^-43 still sum to < e^-37.5), so
+                // lg stays and lp_i = lg + lH_i exactly -- no transcendental, no scan.
+                {
+                    bool alive = false;
+#pragma unroll
+                    for (int j = 0; j < N; j++) alive = alive || (lt[j] + cF[j] > lgprev - 43.0);
+                    if (!__any_sync(0xffffffffu, active && alive)) {
+                        if (active) {
+#pragma unroll
+                            for (int i = 0; i < N; i++) {
+                                const double lq = (lgprev + lH[i]) + Fv[i];
+                                ring[i * RING_Q + slot_w] = lq;
+                                if (t0_rel >= s_rel) p.LQ[(size_t)i * T + tau] = lq;
+                            }
+                            if (t0_rel >= s_rel) p.LG[tau] = lgprev;
+                        }
+                        __syncwarp();
+                        continue;
+                    }
+                }
                 double lX = NEG;
 #pragma unroll
                 for (int j = 0; j < N; j++) lX = lse2(lX, lt[j] + lA[j]);
@@ -267,6 +299,16 @@ __device__ void em_bwd_chunk(const EmParams &p, int c, int kind, const double *m
     const RingLayout &RL = p.RL;
     const int L = RL.L;
     const double *lA = mdl + RL.eG, *lH = mdl + RL.eH, *lC = mdl + RL.eT;
+    // cB[j] = max(lH_j, max_i(lC_ij - lA_i)): how much entering chain j can gain on the noise term
+    double cB[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        double c2 = lH[j];
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            if (i != j) c2 = fmax(c2, lC[i * NP + j] - lA[i]);
+        cB[j] = c2;
+    }
     const int64_t T = p.T;
     const int64_t s = (int64_t)c * p.Lc;
     int64_t e = s + p.Lc;
@@ -313,6 +355,26 @@ __device__ void em_bwd_chunk(const EmParams &p, int c, int kind, const double *m
 #pragma unroll
             for (int j = 0; j < N; j++)
                 lr[j] = active ? Fn[j] + ring[j * RING_Q + (int)((t + L) & (RING_Q - 1))] : -INFINITY;
+            // Dead-window fast path (see em_fwd_chunk): every entry term is more than e^-43 below
+            // the noise continuation, so lh stays and le_i = lA_i + lh exactly.
+            {
+                bool alive = false;
+#pragma unroll
+                for (int j = 0; j < N; j++) alive = alive || (lr[j] + cB[j] > lhprev - 43.0);
+                if (!__any_sync(0xffffffffu, active && alive)) {
+                    if (active) {
+#pragma unroll
+                        for (int i = 0; i < N; i++) {
+                            const double le = lA[i] + lhprev;
+                            ring[i * RING_Q + (int)(t & (RING_Q - 1))] = le;
+                            if (t < e) p.LE[(size_t)i * T + t] = le;
+                        }
+                        if (t < e) p.LH[t] = lhprev;
+                    }
+                    __syncwarp();
+                    continue;
+                }
+            }
             double lY = -INFINITY;
 #pragma unroll
             for (int j = 0; j < N; j++) lY = lse2(lY, lH[j] + lr[j]);
@@ -432,31 +494,40 @@ __global__ void __launch_bounds__(32) em_repair_bwd(EmParams p) {
 
 // kappa_c = sum_{k<=c} (EBf[k-1].lg - SBf[k].lg);  lambda_c = sum_{k>=c} (EBb[k+1].lh - SBb[k].lh)
 // plus lS = kappa_last + LSE(alpha-hat at T-1).  Single block.
+// Block-wide inclusive scan of one double per thread (256 threads), fixed order.
+__device__ __forceinline__ double block_scan_256(double v, double *wsum) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        double o = shfl_up_d(v, d);
+        if (lane >= d) v += o;
+    }
+    if (lane == 31) wsum[warp] = v;
+    __syncthreads();
+    double base = 0.0;
+    for (int w = 0; w < warp; w++) base += wsum[w];
+    __syncthreads();
+    return v + base;
+}
+
 template <int N>
 __global__ void __launch_bounds__(256) em_offsets(EmParams p, int backward) {
-    __shared__ double buf[256];
-    __shared__ double carry;
+    __shared__ double wsum[8];
     const int n = p.nchunks;
-    if (threadIdx.x == 0) carry = 0.0;
-    __syncthreads();
+    const int per = (n + 255) / 256;  // contiguous chunks per thread
+    const int c0 = threadIdx.x * per;
     if (!backward) {
-        for (int base = 0; base < n; base += 256) {
-            int c = base + threadIdx.x;
-            double d = (c >= 1 && c < n) ? p.EBf[(size_t)(c - 1) * p.bvec] - p.SBf[(size_t)c * p.bvec] : 0.0;
-            buf[threadIdx.x] = d;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double a = carry;
-                for (int k = 0; k < 256 && base + k < n; k++) {
-                    a += buf[k];
-                    buf[k] = a;
-                }
-                carry = a;
-            }
-            __syncthreads();
-            if (c < n) p.kappa[c] = buf[threadIdx.x];
-            __syncthreads();
+        // kappa_c = sum_{k<=c} d_k,  d_k = EBf[k-1].lg - SBf[k].lg  (d_0 = 0)
+        double loc = 0.0;
+        for (int c = c0; c < c0 + per && c < n; c++)
+            if (c >= 1) loc += p.EBf[(size_t)(c - 1) * p.bvec] - p.SBf[(size_t)c * p.bvec];
+        const double incl = block_scan_256(loc, wsum);
+        double run = incl - loc;
+        for (int c = c0; c < c0 + per && c < n; c++) {
+            if (c >= 1) run += p.EBf[(size_t)(c - 1) * p.bvec] - p.SBf[(size_t)c * p.bvec];
+            p.kappa[c] = run;
         }
+        __syncthreads();
         if (threadIdx.x < 32) {
             const int lane = threadIdx.x, L = p.RL.L;
             const int64_t T = p.T;
@@ -467,25 +538,21 @@ __global__ void __launch_bounds__(256) em_offsets(EmParams p, int backward) {
             }
             if (lane == 0) v = lse2(v, p.LG[T - 1]);
             for (int d = 16; d >= 1; d >>= 1) v = lse2(v, __shfl_xor_sync(0xffffffffu, v, d));
-            if (lane == 0) p.lS[0] = v + carry;  // carry == kappa of the last chunk
+            if (lane == 0) p.lS[0] = v + p.kappa[n - 1];
         }
     } else {
-        for (int top = n - 1; top >= 0; top -= 256) {
-            int c = top - threadIdx.x;
-            double d = (c >= 0 && c < n - 1) ? p.EBb[(size_t)(c + 1) * p.bvec] - p.SBb[(size_t)c * p.bvec] : 0.0;
-            buf[threadIdx.x] = d;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                double a = carry;
-                for (int k = 0; k < 256 && top - k >= 0; k++) {
-                    a += buf[k];
-                    buf[k] = a;
-                }
-                carry = a;
-            }
-            __syncthreads();
-            if (c >= 0) p.lambda[c] = buf[threadIdx.x];
-            __syncthreads();
+        // lambda_c = sum_{k>=c} d_k,  d_k = EBb[k+1].lh - SBb[k].lh  (d_{n-1} = 0): scan the reversed order
+        double loc = 0.0;
+        for (int r = c0; r < c0 + per && r < n; r++) {
+            const int c = n - 1 - r;
+            if (c < n - 1) loc += p.EBb[(size_t)(c + 1) * p.bvec] - p.SBb[(size_t)c * p.bvec];
+        }
+        const double incl = block_scan_256(loc, wsum);
+        double run = incl - loc;
+        for (int r = c0; r < c0 + per && r < n; r++) {
+            const int c = n - 1 - r;
+            if (c < n - 1) run += p.EBb[(size_t)(c + 1) * p.bvec] - p.SBb[(size_t)c * p.bvec];
+            p.lambda[c] = run;
         }
     }
 }
@@ -616,19 +683,30 @@ __global__ void __launch_bounds__(128) em_stats(EmParams p) {
 
 // out layout: [0] sigma [1] loglik [2..2+N) lp  then mu [K*N] then pp [ns]
 template <int N>
-__global__ void __launch_bounds__(128) em_finalize(EmParams p) {
+__global__ void __launch_bounds__(1024) em_finalize(EmParams p) {
     extern __shared__ __align__(16) double sm[];  // tot[pstride] then S0[N][S1_LAGS]
     const RingLayout &RL = p.RL;
     const int L = RL.L, K = L + 1;
     const int64_t T = p.T;
     double *tot = sm;
     double *S0 = sm + p.pstride;
-    for (int k = threadIdx.x; k < p.pstride; k += blockDim.x) {
-        double v = 0.0;
-        for (int b = 0; b < p.nblk; b++) v += p.part[(size_t)b * p.pstride + k];
-        tot[k] = v;
+    {
+        // column sums of the per-CTA partials: 4 row groups per column, combined in a fixed order
+        double *grp = S0;  // scratch [4][pstride] (S0 is filled later); sized by the host
+        const int ngrp = 4;
+        const int rows = (p.nblk + ngrp - 1) / ngrp;
+        for (int idx = threadIdx.x; idx < ngrp * p.pstride; idx += blockDim.x) {
+            const int g = idx / p.pstride, k = idx - g * p.pstride;
+            double v = 0.0;
+            const int b1 = (g + 1) * rows < p.nblk ? (g + 1) * rows : p.nblk;
+            for (int b = g * rows; b < b1; b++) v += p.part[(size_t)b * p.pstride + k];
+            grp[idx] = v;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < p.pstride; k += blockDim.x)
+            tot[k] = ((grp[k] + grp[p.pstride + k]) + grp[2 * p.pstride + k]) + grp[3 * p.pstride + k];
+        __syncthreads();
     }
-    __syncthreads();
     const double lS = p.lS[0];
     const double lam0 = p.lambda[0];
     const double kapl = p.kappa[p.nchunks - 1];
@@ -688,7 +766,7 @@ static void em_launch(EmParams &p, cudaStream_t st, hmm_info *info, Timer &ttop)
     const size_t sm_bwd = sizeof(double) * (mdl_d + (size_t)WPB * N * RING_Q);
     const size_t sm_brep = sizeof(double) * (mdl_d + (size_t)N * RING_Q);
     const size_t sm_stats = sizeof(double) * std::max<size_t>((size_t)WPB * (160 + N * 32), (size_t)WPB * p.pstride);
-    const size_t sm_fin = sizeof(double) * ((size_t)p.pstride + (size_t)N * S1_LAGS);
+    const size_t sm_fin = sizeof(double) * ((size_t)p.pstride + std::max<size_t>((size_t)N * S1_LAGS, 4 * (size_t)p.pstride));
     HMM_CUDA(cudaFuncSetAttribute(em_forward<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
     HMM_CUDA(cudaFuncSetAttribute(em_repair_fwd<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_frep));
     HMM_CUDA(cudaFuncSetAttribute(em_stats<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stats));
@@ -705,7 +783,8 @@ static void em_launch(EmParams &p, cudaStream_t st, hmm_info *info, Timer &ttop)
     em_repair_bwd<N><<<1, 32, sm_brep, st>>>(p);
     em_offsets<N><<<1, 256, 0, st>>>(p, 1);
     em_stats<N><<<p.nblk, 32 * WPB, sm_stats, st>>>(p);
-    em_finalize<N><<<1, 128, sm_fin, st>>>(p);
+    HMM_CUDA(cudaFuncSetAttribute(em_finalize<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fin));
+    em_finalize<N><<<1, 1024, sm_fin, st>>>(p);
     HMM_CUDA(cudaGetLastError());
     if (info) info->kernel_launches += 10;
 }
@@ -715,7 +794,9 @@ void ring_em_run(const double *X_dev, int64_t T, const HostModel &M, EmResult &o
     const int N = M.N, L = M.K - 1, K = M.K, ns = M.nstates;
     const int R = (N <= 4) ? 8 : 4, SW = 32 * R;
     RingLayout RL = ring_layout(N, L);
-    int64_t W = ring_config().warmup > 0 ? ring_config().warmup : 512;
+    // The E-step is latency-bound per warp (log-sum-exp chains), so short chunks and a short
+    // warm-up pay: every boundary is verified (and repaired if needed) anyway.
+    int64_t W = ring_config().warmup > 0 ? ring_config().warmup : 256;
     W = ((W + SW - 1) / SW) * SW;
     if (W < ((L + 32 + SW - 1) / SW) * SW) W = ((L + 32 + SW - 1) / SW) * SW;
     int64_t Lc = ring_config().chunk_len;
@@ -724,7 +805,7 @@ void ring_em_run(const double *X_dev, int64_t T, const HostModel &M, EmResult &o
         HMM_CUDA(cudaGetDevice(&dev));
         HMM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         Lc = (T + (int64_t)sms * 16 - 1) / ((int64_t)sms * 16);
-        if (Lc < 4 * W) Lc = 4 * W;
+        if (Lc < 3 * W) Lc = 3 * W;
     }
     Lc = ((Lc + SW - 1) / SW) * SW;
     if (Lc < W) Lc = W;
@@ -736,7 +817,7 @@ void ring_em_run(const double *X_dev, int64_t T, const HostModel &M, EmResult &o
     ring_pack(M, RL, hmdl.data());
     const int bvec = 1 + N * L;
     const int pstride = 4 + 2 * N + N * S1_LAGS;
-    const int nblk = 148 * 2;
+    const int nblk = 148 * 6;
     const int nout = 2 + N + K * N + ns;
     size_t off = 0;
     auto carve = [&](size_t bytes) {

@@ -76,6 +76,50 @@ def get_valid_transitions(states0: np.ndarray, K: int, lp: np.ndarray, row_block
     return np.concatenate(out) if out else np.empty(0, dtype=TRANS_DTYPE)
 
 
+_TOPOLOGY_CACHE: dict = {}
+
+
+def _topology(states0: np.ndarray, K: int, allow_overlaps: bool):
+    """(src, dst, codes) of the finite transitions of a state layout.  Which transitions are
+    finite does not depend on lp (src/types.jl:94-113), only their weights do, so the
+    O(nstates^2 N) scan is done once per layout; codes[e, i] says which term neuron i adds to
+    edge e: 0 -> lpz, 1 -> lp[i], 2 -> 0.0."""
+    N, n = states0.shape
+    key = (N, int(K), bool(allow_overlaps), n, hash(states0.tobytes()))
+    hit = _TOPOLOGY_CACHE.get(key)
+    if hit is not None:
+        return hit
+    tr = get_valid_transitions(states0, K, np.full(N, np.log(0.5 / max(N, 1))))
+    src = tr["src"].astype(np.int64) - 1
+    dst = tr["dst"].astype(np.int64) - 1
+    s1 = states0[:, src].astype(np.int32).T  # [ntrans, N]
+    s2 = states0[:, dst].astype(np.int32).T
+    codes = np.where((s1 == 0) & (s2 == 0), 0, np.where((s1 == 0) & (s2 == 1), 1, 2)).astype(np.int8)
+    out = (tr["src"].copy(), tr["dst"].copy(), codes)
+    if len(_TOPOLOGY_CACHE) > 32:
+        _TOPOLOGY_CACHE.clear()
+    _TOPOLOGY_CACHE[key] = out
+    return out
+
+
+def transitions_fast(states0: np.ndarray, K: int, lp, allow_overlaps: bool) -> np.ndarray:
+    """Same records as get_valid_transitions, bit for bit (the per-neuron terms are added in
+    the same order), using the cached topology."""
+    src, dst, codes = _topology(states0, K, allow_overlaps)
+    lp = np.asarray(lp, dtype=np.float64)
+    N = states0.shape[0]
+    lpz = lpz_of(lp[:N])
+    lpt = np.zeros(src.size, dtype=np.float64)
+    for i in range(N):
+        c = codes[:, i]
+        lpt = lpt + np.where(c == 0, lpz, np.where(c == 1, lp[i], 0.0))
+    if not np.all(np.isfinite(lpt)):  # degenerate lp (e.g. -Inf): the set of finite edges changes
+        return get_valid_transitions(states0, K, lp)
+    rec = np.empty(src.size, dtype=TRANS_DTYPE)
+    rec["src"], rec["dst"], rec["lp"] = src, dst, lpt
+    return rec
+
+
 class StateMatrix:
     """Fields as src/types.jl:1-9.  NOTE the reference's field comments are
     swapped; as in the constructor call (src/types.jl:150) `K` is states per
@@ -91,7 +135,7 @@ class StateMatrix:
         lp = np.ascontiguousarray(lp, dtype=np.float64)
         if pp is None:  # src/types.jl:138 log.(ones(nstates)./nstates)
             pp = np.log(np.ones(nstates) / nstates)
-        self.transitions = get_valid_transitions(states0, K, lp)
+        self.transitions = transitions_fast(states0, K, lp, allow_overlaps)
         self.states = np.asfortranarray(states0 + np.int16(1))  # src/types.jl:150
         self.pi = np.ascontiguousarray(pp, dtype=np.float64)
         self.K = int(K)
