@@ -261,7 +261,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": 2 * T + 8, "host_memory": "pinned", "same_result_as_resident": same},
             "gpu_launches": int(launches),
             "kernel_ms_per_step": round(float(np.mean(kern_ms)), 4),
-            "roofline": {"bound": "hbm", "kernel": "ring_vit_forward<3,8>", "achieved": round(achieved, 1),
+            "roofline": {"bound": "hbm", "kernel": "ring_vit_forward<3,8,64>", "achieved": round(achieved, 1),
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": None, "kernel_ms": round(top, 4),
                          "note": "algorithmic 10 B/sample; the kernel is FP64-issue bound (FIR), see DESIGN.md"},

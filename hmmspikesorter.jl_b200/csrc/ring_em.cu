@@ -587,7 +587,28 @@ __global__ void __launch_bounds__(128) em_stats(EmParams p) {
     for (int64_t w = gw; w < nwin; w += nw) {
         const int64_t t = w * 32 + lane;
         const bool ok = t < T;
-        const int c = ok ? (int)(t / p.Lc) < p.nchunks ? (int)(t / p.Lc) : p.nchunks - 1 : 0;
+        // chunk indices without per-lane 64-bit divisions: Lc is a multiple of 256, so the whole
+        // window lies in one chunk; t+L-1 and t+L are at most one chunk further (L < Lc)
+        int c = (int)((w * 32) / p.Lc);
+        if (c >= p.nchunks) c = p.nchunks - 1;
+        const int64_t cend = (c == p.nchunks - 1) ? T : (int64_t)(c + 1) * p.Lc;
+        const int64_t tc = ok ? t : T - 1;
+        const int64_t te = tc + L - 1;  // the chain entered at t ends here
+        const int64_t tx = tc + L;      // for xi: the chain entered at t+1 ends here
+        const int ce = (te >= cend) ? c + 1 : c, cx = (tx >= cend) ? c + 1 : c;
+        const bool e_in = te <= T - 1, x_in = tx <= T - 1, has_next = tc <= T - 2;
+        // ---- issue every global load of the window up front (independent, clamped indices) ----
+        const double kap = p.kappa[c], lam = p.lambda[c];
+        const double lame = p.lambda[e_in ? ce : c], lamx = p.lambda[x_in ? cx : c];
+        const double vLG = p.LG[tc], vLH = p.LH[tc];
+        double vLQ[N], vLEe[N], vLEx[N], vFn[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            vLQ[i] = p.LQ[(size_t)i * T + tc];
+            vLEe[i] = p.LE[(size_t)i * T + (e_in ? te : T - 1)];
+            vLEx[i] = p.LE[(size_t)i * T + (x_in ? tx : T - 1)];
+            vFn[i] = p.Fg[(size_t)i * T + (has_next ? tc + 1 : T - 1)];
+        }
         double yv = 0.0;
         for (int k = lane; k < 32 + L; k += 32) {
             int64_t g = w * 32 + k;
@@ -598,29 +619,20 @@ __global__ void __launch_bounds__(128) em_stats(EmParams p) {
         double pi[N];
         double pmax = 0.0;
         if (ok) {
-            const double kap = p.kappa[c], lam = p.lambda[c];
-            const double g0 = exp(p.LG[t] + kap + p.LH[t] + lam - lS);
+            const double g0 = exp(vLG + kap + vLH + lam - lS);
             a_g0all += g0;
-            if (t <= T - 2) a_g0 += g0;
+            if (has_next) a_g0 += g0;
             a_y += yv;
             a_y2 += yv * yv;
-            const int64_t te = t + L - 1;  // chain entered at t ends here
-            int ce = (int)(te / p.Lc);
-            if (ce >= p.nchunks) ce = p.nchunks - 1;
-            const double lame = te <= T - 1 ? p.lambda[ce] : 0.0;
-            const int64_t tx = t + L;  // for xi: chain entered at t+1 ends at t+L
-            int cx = (int)(tx / p.Lc);
-            if (cx >= p.nchunks) cx = p.nchunks - 1;
-            const double lamx = tx <= T - 1 ? p.lambda[cx] : 0.0;
 #pragma unroll
             for (int i = 0; i < N; i++) {
-                const double le = te <= T - 1 ? p.LE[(size_t)i * T + te] + lame : 0.0;
-                pi[i] = exp(p.LQ[(size_t)i * T + t] + kap + le - lS);
+                const double le = e_in ? vLEe[i] + lame : 0.0;
+                pi[i] = exp(vLQ[i] + kap + le - lS);
                 a_s0[i] += pi[i];
                 pmax = fmax(pmax, pi[i]);
-                if (t <= T - 2) {
-                    const double lex = tx <= T - 1 ? p.LE[(size_t)i * T + tx] + lamx : 0.0;
-                    a_xi[i] += exp(p.LG[t] + kap + lH[i] + p.Fg[(size_t)i * T + t + 1] + lex - lS);
+                if (has_next) {
+                    const double lex = x_in ? vLEx[i] + lamx : 0.0;
+                    a_xi[i] += exp(vLG + kap + lH[i] + vFn[i] + lex - lS);
                 }
             }
         } else {
@@ -711,16 +723,27 @@ __global__ void __launch_bounds__(1024) em_finalize(EmParams p) {
     const double lam0 = p.lambda[0];
     const double kapl = p.kappa[p.nchunks - 1];
     double *S1 = tot + 4 + 2 * N;
+    // boundary posteriors, computed once in parallel:
+    //   piv[i][r0]: chains already running at t = 0 (entered at -r0, r0 = 1..L-1)
+    //   pie[i][k] : chains entered at t0 = T-1-k (k = 0..L-2), which run past the end
+    double *piv = S0 + (size_t)N * S1_LAGS, *pie = piv + (size_t)N * S1_LAGS;
+    for (int idx = threadIdx.x; idx < N * L; idx += blockDim.x) {
+        const int i = idx / L, r = idx % L;
+        double v = 0.0, w2 = 0.0;
+        if (r >= 1) v = exp(p.LQneg[i * L + r] + p.LE[(size_t)i * T + (L - 1 - r)] + lam0 - lS);
+        if (r <= L - 2) w2 = exp(p.LQ[(size_t)i * T + (T - 1 - r)] + kapl - lS);
+        piv[i * S1_LAGS + r] = v;
+        pie[i * S1_LAGS + r] = w2;
+    }
+    __syncthreads();
     for (int idx = threadIdx.x; idx < N * L; idx += blockDim.x) {
         const int i = idx / L, sph = idx % L;  // 0-based phase: template row sph+1
         double s0 = tot[4 + N + i], s1 = S1[i * S1_LAGS + sph];
-        // chains entered in the last L-1 samples never reach phases >= T - t0
-        for (int64_t t0 = T - sph; t0 <= T - 1; t0++)
-            if (t0 > T - L && t0 >= 0) s0 -= exp(p.LQ[(size_t)i * T + t0] + kapl - lS);
-        // chains already running at t = 0 (entered at -r0, r0 = 1..L-1) reach phases >= r0
+        // chains entered in the last sph samples (t0 >= T - sph) never reach phase sph
+        for (int k = 0; k < sph; k++) s0 -= pie[i * S1_LAGS + k];
+        // chains already running at t = 0 reach phases >= r0; at phase sph they sit on y[sph - r0]
         for (int r0 = 1; r0 <= sph; r0++) {
-            const int te = L - 1 - r0;  // their last sample
-            const double pi = exp(p.LQneg[i * L + r0] + p.LE[(size_t)i * T + te] + lam0 - lS);
+            const double pi = piv[i * S1_LAGS + r0];
             s0 += pi;
             s1 = fma(pi, p.y[sph - r0], s1);
         }
@@ -766,7 +789,7 @@ static void em_launch(EmParams &p, cudaStream_t st, hmm_info *info, Timer &ttop)
     const size_t sm_bwd = sizeof(double) * (mdl_d + (size_t)WPB * N * RING_Q);
     const size_t sm_brep = sizeof(double) * (mdl_d + (size_t)N * RING_Q);
     const size_t sm_stats = sizeof(double) * std::max<size_t>((size_t)WPB * (160 + N * 32), (size_t)WPB * p.pstride);
-    const size_t sm_fin = sizeof(double) * ((size_t)p.pstride + std::max<size_t>((size_t)N * S1_LAGS, 4 * (size_t)p.pstride));
+    const size_t sm_fin = sizeof(double) * ((size_t)p.pstride + std::max<size_t>(3 * (size_t)N * S1_LAGS, 4 * (size_t)p.pstride));
     HMM_CUDA(cudaFuncSetAttribute(em_forward<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
     HMM_CUDA(cudaFuncSetAttribute(em_repair_fwd<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_frep));
     HMM_CUDA(cudaFuncSetAttribute(em_stats<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stats));

@@ -1,0 +1,152 @@
+"""BASELINE.json full-size configurations through the C ABI.  The CPU oracle cannot
+decode these in seconds, so parity is carried by size-independent properties:
+  * chunk-geometry invariance: two different time-chunkings give the bit-identical x
+    (every chunk boundary is a speculative start that must reproduce the sequential answer);
+  * every step of x is a valid transition of the StateMatrix and the chain structure holds;
+  * ll recomputed independently from (x, y) in numpy matches the reported ll to 1e-9;
+  * a 2 M-sample prefix equals the faithful (reference-order) engine away from the cut;
+plus config 1 (README example) end to end against the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _c2(hm, T, seed):
+    K, N = 60, 3
+    temps = np.stack([hm.create_spike_template(K, 3.0, 0.8, 0.2), hm.create_spike_template(K, 4.0, 0.3, 0.2),
+                      hm.create_spike_template(K, 2.0, 0.5, 0.3)], axis=1)
+    pp = np.array([0.003, 0.001, 0.002])
+    S = hm.create_signal(T, 0.3, pp, temps, hm.make_rng(seed))
+    mu = np.asfortranarray(temps.copy())
+    mu[0, :] = 0.0
+    return S, hm.StateMatrix(N, K, np.log(pp), False), mu, 0.3
+
+
+def _ll_numpy(y, x, lA, mu, sigma):
+    """sum_{i=2..T} T1[x[i], i] along the decoded path (src/viterbi.jl:92-96), vectorised."""
+    ns = lA.nstates
+    W = np.full((ns, ns), np.nan)
+    W[lA.transitions["src"] - 1, lA.transitions["dst"] - 1] = lA.transitions["lp"]
+    m = np.array([sum(mu[lA.states[l, j] - 1, l] for l in range(lA.N)) for j in range(ns)])
+    xs = x.astype(np.int64) - 1
+    w = W[xs[:-1], xs[1:]]
+    assert not np.isnan(w).any(), "decoded path uses a transition that is not in the StateMatrix"
+    q = -0.9189385332046727 - np.log(sigma) - (y - m[xs]) ** 2 / (2 * sigma * sigma)
+    p0 = 0.0 if xs[0] == 0 else q[0]
+    inc = w + q[1:]
+    T = y.size
+    return (T - 1) * p0 + float(np.dot(np.arange(T - 1, 0, -1, dtype=np.float64), inc))
+
+
+def _check_structure(x, lA):
+    """Inside a chain the state index increases by one per step; chains start at a head."""
+    L = lA.K - 1
+    xs = x.astype(np.int64) - 1
+    ph = np.where(xs > 0, (xs - 1) % L, -1)  # 0-based phase, -1 for noise
+    nxt_ok = (ph[:-1] < 0) | (ph[:-1] == L - 1) | (xs[1:] == xs[:-1] + 1)
+    assert nxt_ok.all()
+    starts_ok = (ph[1:] != 0) | (ph[:-1] < 0) | (ph[:-1] == L - 1)
+    assert starts_ok.all()
+
+
+def test_config2_full_size_properties(hm):
+    T = 18_000_000
+    S, lA, mu, sig = _c2(hm, T, 2)
+    hm.set_ring_params(0, 0)
+    x, ll, info = hm.viterbi(S, lA, mu, sig, mode="ring", return_info=True)
+    assert info["engine"] == 2 and x.shape == (T,)
+    try:
+        hm.set_ring_params(12288, 1024)
+        x2, ll2, info2 = hm.viterbi(S, lA, mu, sig, mode="ring", return_info=True)
+    finally:
+        hm.set_ring_params(0, 0)
+    assert info2["n_chunks"] != info["n_chunks"]
+    assert np.array_equal(x, x2) and abs(ll - ll2) <= 1e-12 * abs(ll)
+    _check_structure(x, lA)
+    assert abs(ll - _ll_numpy(S, x, lA, mu, sig)) <= 1e-9 * abs(ll)
+    # prefix vs the faithful engine (bit-exact reference order); the decode of a prefix can
+    # only differ from the full decode near the cut
+    Tp = 2_000_000
+    xf, _ = hm.viterbi(S[:Tp], lA, mu, sig, mode="faithful")
+    assert np.array_equal(xf[:Tp - 4096], x[:Tp - 4096])
+    Y = hm.reconstruct_signal(x, lA, mu, sig)
+    assert 0.5 < 1 - np.std(Y - S) / np.std(S) < 0.7
+
+
+def test_config5_long_sequence_properties(hm):
+    """Config 5: single channel, 1 h at 30 kHz (108 M samples), N=5 x K=60."""
+    T, N, K = 108_000_000, 5, 60
+    params = [(3.0, 0.8, 0.2), (4.0, 0.3, 0.2), (2.0, 0.5, 0.3), (2.5, 0.6, 0.25), (3.5, 0.4, 0.15)]
+    temps = np.stack([hm.create_spike_template(K, *q) for q in params], axis=1)
+    pp = np.array([0.003, 0.001, 0.002, 0.0015, 0.0025])
+    S = hm.create_signal(T, 0.3, pp, temps, hm.make_rng(5))
+    mu = np.asfortranarray(temps.copy())
+    mu[0, :] = 0.0
+    lA = hm.StateMatrix(N, K, np.log(pp), False)
+    x, ll, info = hm.viterbi(S, lA, mu, 0.3, mode="ring", return_info=True)
+    try:
+        hm.set_ring_params(65536, 512)
+        x2, ll2, _ = hm.viterbi(S, lA, mu, 0.3, mode="ring", return_info=True)
+    finally:
+        hm.set_ring_params(0, 0)
+    assert np.array_equal(x, x2)
+    del x2
+    _check_structure(x, lA)
+    Tq = 20_000_000  # ll check on a slice of the path keeps host memory modest
+    xq, llq = hm.viterbi(S[:Tq], lA, mu, 0.3, mode="ring")
+    assert abs(llq - _ll_numpy(S[:Tq], xq, lA, mu, 0.3)) <= 1e-9 * abs(llq)
+
+
+def test_config4_channel_batch(hm, O):
+    """Config 4 style: independent per-channel HMMs (N=4, K=48), batched decode; two of the
+    channels are checked against the oracle on a prefix-sized recording."""
+    C, T, N, K = 6, 400_000, 4, 48
+    rng = np.random.default_rng(1000)
+    models, cols = [], []
+    for c in range(C):
+        prm = [(rng.uniform(2, 4), rng.uniform(0.3, 0.9), rng.uniform(0.1, 0.3)) for _ in range(N)]
+        temps = np.stack([hm.create_spike_template(K, *q) for q in prm], axis=1)
+        pp = rng.uniform(0.0005, 0.004, size=N)
+        cols.append(hm.create_signal(T, 0.3, pp, temps, hm.make_rng(1000 + c)))
+        mu = np.asfortranarray(temps.copy())
+        mu[0, :] = 0.0
+        models.append((hm.StateMatrix(N, K, np.log(pp), False), mu, 0.3))
+    Y = np.asfortranarray(np.stack(cols, axis=1))
+    x, ll, info = hm.viterbi_batch(Y, models, mode="ring", return_info=True)
+    assert info["engine"] == 2
+    for c in (0, C - 1):
+        xo, llo = O.viterbi(Y[:, c], *models[c])
+        assert np.array_equal(x[:, c], xo) and abs(ll[c] - llo) <= 1e-9 * abs(llo)
+    for c in range(C):
+        _check_structure(x[:, c], models[c][0])
+
+
+def test_config1_readme_example(hm, O):
+    """Config 1: create_signal(20_000, 0.3, [0.003, 0.001]) from two 60-sample templates;
+    10 E/M steps of a 3-neuron K=60 non-overlap model from an explicit seeded init (the
+    reference's own init uses Julia's RNG), then viterbi + reconstruct_signal --
+    every stage against the oracle."""
+    K, N, T = 60, 3, 20_000
+    temps2 = np.stack([hm.create_spike_template(K, 3.0, 0.8, 0.2), hm.create_spike_template(K, 4.0, 0.3, 0.2)], 1)
+    S = hm.create_signal(T, 0.3, np.array([0.003, 0.001]), temps2, hm.make_rng(1234))
+    rng = np.random.default_rng(7)
+    sig0 = float(np.std(S))
+    mu0 = np.asfortranarray(np.stack([hm.create_spike_template(K, 3 * sig0 * rng.random(), 0.5 + 0.1 * rng.normal(),
+                                                               1.5 * rng.random()) for _ in range(N)], 1))
+    mu0[0, :] = 0.0
+    p0 = 2.0 ** (-3 * K / 2)  # src/baumwelch.jl:311
+    lA = hm.StateMatrix(N, K, np.log(np.full(N, p0)), False)
+    mu = mu0.copy(order="F")
+    lA_fit, mu_fit, s_fit = hm.train_model(S, lA, mu, sig0, 10)
+    smo, muo, so = O.OracleStateMatrix(N, K, np.log(np.full(N, p0)), False), mu0.copy(order="F"), sig0
+    for _ in range(10):
+        lpo, ppo, muo, so, _ = O.em_step(S, smo, muo, so)
+        smo = O.OracleStateMatrix(N, K, lpo, False)
+    assert np.abs(mu_fit - muo).max() < 1e-6 and abs(s_fit - so) < 1e-6
+    assert np.abs(lA_fit.transitions["lp"] - smo.transitions["lp"]).max() < 1e-6
+    x, ll = hm.viterbi(S, lA_fit, mu_fit, s_fit)
+    xo, llo = O.viterbi(S, smo, muo, so)
+    assert np.array_equal(x, xo) and abs(ll - llo) <= 1e-9 * abs(llo)
+    Y = hm.reconstruct_signal(x, lA_fit, mu_fit, s_fit)
+    assert np.allclose(Y, O.reconstruct_signal(xo, smo, muo), atol=1e-6)
