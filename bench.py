@@ -42,6 +42,8 @@ import __graft_entry__ as ge  # noqa: E402
 T_C2 = 18_000_000
 T_C3 = 1_800_000
 BYTES_PER_SAMPLE = 10  # 8 B read of S + 2 B write of x
+NCU_TRAFFIC_BYTES = 169545216  # ring_vit_forward<3,8,64>: dram read + write per launch (profiles/r01_ring_vit_forward_ncu.md)
+FP64_PEAK_GDFMA = 18421.7  # measured FP64 FMA issue rate, profiles/r01_fp64_peak.jsonl
 
 
 def make_c2(hm, seed, T=T_C2):
@@ -245,6 +247,7 @@ def run_ours(args):
         peak, peak_src = measured_peak_hbm()
         top = float(np.mean(top_ms))
         achieved = BYTES_PER_SAMPLE * T / (top * 1e-3) / 1e9
+        dfma = (T + chunks * 512.0) * lA.N * 64  # LP = 64 taps for K = 60; 512-sample warm-up per chunk
         out = {
             "metric": "Viterbi Msamples/s (N=3,K=60; Baum-Welch iters/s in `baum_welch`)",
             "value": round(value, 2), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
@@ -263,8 +266,14 @@ def run_ours(args):
             "kernel_ms_per_step": round(float(np.mean(kern_ms)), 4),
             "roofline": {"bound": "hbm", "kernel": "ring_vit_forward<3,8,64>", "achieved": round(achieved, 1),
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                         "traffic": None, "kernel_ms": round(top, 4),
-                         "note": "algorithmic 10 B/sample; the kernel is FP64-issue bound (FIR), see DESIGN.md"},
+                         "traffic": NCU_TRAFFIC_BYTES, "kernel_ms": round(top, 4),
+                         "note": "algorithmic 10 B/sample; traffic = dram read+write per launch from the ncu --set "
+                                 "full capture in profiles/; the kernel is FP64-issue bound (FIR), see `fp64_issue`"},
+            "fp64_issue": {"achieved": round(dfma / (top * 1e-3) / 1e9, 1), "peak": FP64_PEAK_GDFMA, "unit": "GDFMA/s",
+                           "frac": round(dfma / (top * 1e-3) / 1e9 / FP64_PEAK_GDFMA, 4),
+                           "peak_source": "measured with tools/fp64_peak.cu on this pool's B200 "
+                                          "(profiles/r01_fp64_peak.jsonl)",
+                           "work": "FIR: (samples + chunks*warmup) x N x LP fused multiply-adds"},
             "cpu_baseline": cpu,
             "baum_welch": bw,
             "clocks": clocks,
