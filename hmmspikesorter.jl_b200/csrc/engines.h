@@ -39,6 +39,45 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
                       const FaithfulLayout &L, const char *blob_dev, int16_t *x_dev, int64_t x_stride, double *ll_dev,
                       cudaStream_t st, hmm_info *info);
 
+// Staged decode (used directly by the time-shard API in api.cu).
+struct VitParams;
+class VitPlan {
+  public:
+    VitPlan();
+    ~VitPlan();
+    VitPlan(const VitPlan &) = delete;
+    VitPlan &operator=(const VitPlan &) = delete;
+    bool own_memory = false;  // false: thread-local grow-only workspace; true: cudaMalloc owned by the plan
+    void build(const double *y_dev, int64_t T, int64_t y_stride, int C, const std::vector<HostModel> &models,
+               const FaithfulLayout &FL, const char *blob_dev, int16_t *x_dev, int64_t x_stride, int64_t Lc, int64_t W,
+               bool first_prologue, bool last_true_end, cudaStream_t st);
+    void forward(cudaStream_t st, Timer *ttop);
+    void verify_fwd(cudaStream_t st);    // boundary check + repair (+ final state when the sequence really ends)
+    void trace(cudaStream_t st);
+    void verify_trace(cudaStream_t st);  // boundary check + repair
+    void path_ll(cudaStream_t st, double *ll_dev, int64_t t_lo, int64_t t_hi, int64_t t_off, int64_t T_glob, bool with_p0);
+    void read_counters(cudaStream_t st, int *fwd_rep, int *bwd_rep);
+    int nchunks() const;
+    int bvec() const;
+    double *eb_ptr(int chunk);              // device pointer: true end-boundary vector of `chunk` (channel 0)
+    long long *own_start_ptr(int chunk);    // device pointer: traceback state at the start of `chunk`
+    void *alloc(int slot, size_t bytes);
+
+  private:
+    struct Impl;
+    Impl *impl;
+    VitParams *p_;  // owned; defined in ring_viterbi.cu
+    std::vector<void *> owned;
+    std::vector<double> hmdl;
+    HostModel M0;
+    FaithfulLayout FL;
+    const char *blob_dev = nullptr;
+    double *part = nullptr;
+    int C = 1;
+};
+// Default chunk length / warm-up for a recording of T_total samples decoded on n_gpus GPUs.
+int ring_default_chunking(const HostModel &M0, int64_t T_total, int C, int n_gpus, int64_t *Lc_out, int64_t *W_out);
+
 // ---- ring engine, E/M step (ring_em.cu) ------------------------------------
 struct EmResult {
     std::vector<double> lp;  // [N]

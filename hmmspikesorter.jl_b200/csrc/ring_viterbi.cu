@@ -123,6 +123,8 @@ struct VitParams {
     int64_t x_stride;
     long long *own_start, *look_end;  // [C x nchunks] encoded states
     int *tr_flag;
+    int first_prologue;    // chunk 0 starts from the reference's initial condition (else: ghost chunk of a time shard)
+    int last_true_end;     // the sequence really ends at T (else: ghost chunk; traceback starts speculatively)
     int debug_skip;        // debug: 1 = skip the recursion (time the FIR alone), 2 = skip the FIR
     int *sm_slots;         // [256] per-SM CTA arrival counters (stagger)
     int stagger_ns;        // start-up delay quantum that de-phases co-resident warps (FIR vs recursion)
@@ -617,7 +619,7 @@ __global__ void __launch_bounds__(128, (R == 8) ? 4 : 6)
         __syncthreads();
         for (int q = 0; q < slot_s; q++) __nanosleep(p.stagger_ns);
     }
-    vit_process_chunk<N, R, LPC>(p, coef, ch, c, c == 0 ? START_PROLOGUE : START_SPEC, mdl, ws);
+    vit_process_chunk<N, R, LPC>(p, coef, ch, c, (c == 0 && p.first_prologue) ? START_PROLOGUE : START_SPEC, mdl, ws);
 }
 
 // Boundary check: speculative start vector of chunk c vs true end vector of c-1
@@ -703,7 +705,7 @@ __device__ void trace_chunk(const VitParams &p, int ch, int c, int64_t tau_hi, l
     const int64_t s = (int64_t)c * p.Lc;
     int64_t e = s + p.Lc;
     if (c == p.nchunks - 1 || e > T) e = T;
-    const int64_t lo = (c == 0) ? (int64_t)(L + 1) : s;
+    const int64_t lo = (c == 0 && p.first_prologue) ? (int64_t)(L + 1) : s;
     const uint32_t *dec = p.dec + (size_t)ch * T;
     const uint32_t *nzm = p.nzmask + (size_t)ch * ((T + 31) / 32);
     int16_t *x = p.x + (size_t)ch * p.x_stride;
@@ -841,7 +843,7 @@ __device__ void trace_chunk(const VitParams &p, int ch, int c, int64_t tau_hi, l
             st = (k == 0) ? -1 : enc_spike(t0 - L, k - 1);
         }
     }
-    if (c == 0) {
+    if (c == 0 && p.first_prologue) {
         // steps L .. 0 from the faithful prologue's backpointers (reference arithmetic)
         int curj = (st < 0) ? 0 : (1 + (int)(st & 7) * L + (int)(L - (st >> 3)));
         if (lane == 0) {
@@ -874,7 +876,7 @@ __global__ void __launch_bounds__(128) ring_vit_trace(VitParams p) {
     int16_t *t2s_all = reinterpret_cast<int16_t *>(trsm + (size_t)(blockDim.x >> 5) * TR_WARP_U32);
     const int c = blockIdx.x * (blockDim.x >> 5) + warp;
     const int L = p.RL.L;
-    if (blockIdx.x == 0) {  // chunk 0 lives in CTA 0: stage the prologue backpointers
+    if (blockIdx.x == 0 && p.first_prologue) {  // chunk 0 lives in CTA 0: stage the prologue backpointers
         const int16_t *g = p.T2pro + (size_t)ch * p.ns * (L + 1);
         for (int k = threadIdx.x; k < p.ns * (L + 1); k += blockDim.x) t2s_all[k] = g[k];
     }
@@ -889,7 +891,7 @@ __global__ void __launch_bounds__(128) ring_vit_trace(VitParams p) {
     long long st = -1;  // speculative: noise at tau_hi
     if (last || tau_hi >= T - 1) {
         tau_hi = T - 1;
-        st = state_from_xend(p.xend[ch], T, L);
+        if (p.last_true_end) st = state_from_xend(p.xend[ch], T, L);  // else: ghost chunk, speculative noise
     }
     trace_chunk<N>(p, ch, c, tau_hi, st, !last, t2s_all, tws);
 }
@@ -913,7 +915,7 @@ __global__ void __launch_bounds__(32) ring_vit_repair_trace(VitParams p) {
     for (int c = lane; c < p.nchunks - 1; c += 32) any |= p.tr_flag[o + c];
     if (!__any_sync(0xffffffffu, any)) return;
     const int L = p.RL.L;
-    {
+    if (p.first_prologue) {
         const int16_t *g = p.T2pro + (size_t)ch * p.ns * (L + 1);
         for (int k = lane; k < p.ns * (L + 1); k += 32) t2s_all[k] = g[k];
     }
@@ -946,7 +948,9 @@ __global__ void __launch_bounds__(32) ring_vit_repair_trace(VitParams p) {
 __global__ void __launch_bounds__(256)
     ring_path_ll_partial(const double *__restrict__ y, int64_t T, int64_t y_stride, const char *blob,
                          size_t blob_stride, FaithfulLayout L, int ns, int nt, const int16_t *__restrict__ x,
-                         int64_t x_stride, double *__restrict__ partial /*[C x gridDim.x]*/) {
+                         int64_t x_stride, double *__restrict__ partial /*[C x gridDim.x]*/, int64_t t_lo,
+                         int64_t t_hi, int64_t t_off, int64_t T_glob) {
+    // steps t in [t_lo, t_hi) of this (local) buffer; global time = t + t_off, weights use T_glob
     extern __shared__ __align__(16) char llsm[];
     const int ch = blockIdx.y;
     const char *mb = blob + (size_t)ch * blob_stride;
@@ -994,7 +998,7 @@ __global__ void __launch_bounds__(256)
         for (int k = 0; k < 8; k++) {
             const int64_t t = t0 + k;
             const int d = xs[k] - 1;
-            if (t >= 1 && t < T) {
+            if (t >= 1 && t < T && t >= t_lo && t < t_hi && t + t_off >= 1) {
                 double lp = __longlong_as_double(0x7ff8000000000000LL);
                 for (int e = sm_ptr[d]; e < sm_ptr[d + 1]; e++)
                     if (sm_src[e] == s) {
@@ -1003,7 +1007,7 @@ __global__ void __launch_bounds__(256)
                     }
                 const double dd = ys[k] - sm_m[d];
                 const double q = c_emit - (dd * dd) * inv2s2;
-                acc = fma((double)(T - t), lp + q, acc);
+                acc = fma((double)(T_glob - (t + t_off)), lp + q, acc);
             }
             s = d;
         }
@@ -1021,7 +1025,8 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     ring_path_ll_final(const double *__restrict__ y, int64_t T, int64_t y_stride, const char *blob, size_t blob_stride,
                        FaithfulLayout L, const int16_t *__restrict__ x, int64_t x_stride,
-                       const double *__restrict__ partial, int nparts, double *__restrict__ ll_out) {
+                       const double *__restrict__ partial, int nparts, double *__restrict__ ll_out, int with_p0,
+                       int64_t T_glob) {
     const int ch = blockIdx.x;
     __shared__ double red[256];
     double acc = 0.0;
@@ -1039,7 +1044,7 @@ __global__ void __launch_bounds__(256)
         int x0 = x[(size_t)ch * x_stride] - 1;
         double dd = y[(size_t)ch * y_stride] - gm[x0];
         double p0 = x0 == 0 ? 0.0 : sc[2] - (dd * dd) / sc[3];
-        ll_out[ch] = (double)(T - 1) * p0 + red[0];
+        ll_out[ch] = (with_p0 ? (double)(T_glob - 1) * p0 : 0.0) + red[0];
     }
 }
 
@@ -1064,20 +1069,17 @@ static int fwd_warps_per_sm(const RingLayout &RL) {
 }
 
 template <int N, int R, int LPC>
-static void launch_all(VitParams &p, const double *hmodel /*host ring model of channel 0*/, int C, cudaStream_t st,
-                       hmm_info *info, Timer *ttop) {
+static void stage_forward(VitParams &p, const double *hmodel /*host ring model of channel 0*/, int C, cudaStream_t st,
+                          Timer *ttop) {
     constexpr int WPB = 4;
-    const size_t mdl_d = (p.RL.hot + 1) & ~1;
     const size_t sm_fwd = fwd_smem_bytes<N, R, LPC>(p.RL);
-    const size_t sm_rep = sizeof(double) * (mdl_d + WarpSmem<N, R>::DOUBLES);
     HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward<N, R, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
-    HMM_CUDA(cudaFuncSetAttribute(ring_vit_repair_fwd<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rep));
     FirCoef<N, LPC> coef{};
     if (LPC > 0)
         for (int r = 0; r < LPC; r++)
             for (int i = 0; i < N; i++) coef.a[r * N + i] = hmodel[p.RL.A + r * p.RL.NP + i];
     dim3 gridc((p.nchunks + WPB - 1) / WPB, C);
-    {
+    if (p.first_prologue) {
         const size_t sm_pro = sizeof(double) * ((size_t)(p.RL.L + 1) * p.ns + 2 * (size_t)p.ns);
         if (sm_pro > 227 * 1024) fail(HMM_EUNSUPPORTED, "prologue does not fit shared memory");
         HMM_CUDA(cudaFuncSetAttribute(ring_vit_prologue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pro));
@@ -1087,20 +1089,37 @@ static void launch_all(VitParams &p, const double *hmodel /*host ring model of c
     ring_vit_forward<N, R, LPC><<<gridc, 32 * WPB, sm_fwd, st>>>(p, coef);
     if (ttop) ttop->stop();
     HMM_CUDA(cudaGetLastError());
+}
+
+template <int N, int R, int LPC>
+static void stage_verify_fwd(VitParams &p, int C, cudaStream_t st) {
+    const size_t sm_rep = sizeof(double) * (((p.RL.hot + 1) & ~1) + WarpSmem<N, R>::DOUBLES);
+    HMM_CUDA(cudaFuncSetAttribute(ring_vit_repair_fwd<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rep));
     ring_vit_check_fwd<<<dim3((p.nchunks * 32 + 127) / 128, C), 128, 0, st>>>(p);
     ring_vit_repair_fwd<N, R><<<C, 32, sm_rep, st>>>(p);
-    ring_vit_final<N><<<C, 256, 0, st>>>(p);
+    if (p.last_true_end) ring_vit_final<N><<<C, 256, 0, st>>>(p);
     HMM_CUDA(cudaGetLastError());
+}
+
+template <int N, int R, int LPC>
+static void stage_trace(VitParams &p, int C, cudaStream_t st) {
+    constexpr int WPB = 4;
     const size_t sm_t2 = sizeof(int16_t) * (size_t)p.ns * (p.RL.L + 1) + 16;
     const size_t sm_tr = sm_t2 + sizeof(uint32_t) * (size_t)WPB * TR_WARP_U32;
-    const size_t sm_trr = sm_t2 + sizeof(uint32_t) * (size_t)TR_WARP_U32;
     HMM_CUDA(cudaFuncSetAttribute(ring_vit_trace<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_tr));
-    HMM_CUDA(cudaFuncSetAttribute(ring_vit_repair_trace<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_trr));
+    dim3 gridc((p.nchunks + WPB - 1) / WPB, C);
     ring_vit_trace<N><<<gridc, 32 * WPB, sm_tr, st>>>(p);
+    HMM_CUDA(cudaGetLastError());
+}
+
+template <int N, int R, int LPC>
+static void stage_verify_trace(VitParams &p, int C, cudaStream_t st) {
+    const size_t sm_t2 = sizeof(int16_t) * (size_t)p.ns * (p.RL.L + 1) + 16;
+    const size_t sm_trr = sm_t2 + sizeof(uint32_t) * (size_t)TR_WARP_U32;
+    HMM_CUDA(cudaFuncSetAttribute(ring_vit_repair_trace<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_trr));
     ring_vit_check_trace<<<dim3((p.nchunks + 127) / 128, C), 128, 0, st>>>(p);
     ring_vit_repair_trace<N><<<C, 32, sm_trr, st>>>(p);
     HMM_CUDA(cudaGetLastError());
-    if (info) info->kernel_launches += 8;
 }
 
 // (N, LP) -> kernel variant.  LPC > 0: FIR coefficients as constant-bank operands
@@ -1108,11 +1127,15 @@ static void launch_all(VitParams &p, const double *hmodel /*host ring model of c
 // in shared memory (any K <= 97, any number of channels per launch).
 struct VitVariant {
     int (*warps_per_sm)(const RingLayout &);
-    void (*launch)(VitParams &, const double *, int, cudaStream_t, hmm_info *, Timer *);
+    void (*forward)(VitParams &, const double *, int, cudaStream_t, Timer *);
+    void (*verify_fwd)(VitParams &, int, cudaStream_t);
+    void (*trace)(VitParams &, int, cudaStream_t);
+    void (*verify_trace)(VitParams &, int, cudaStream_t);
 };
 template <int N, int R, int LPC>
 static VitVariant make_variant() {
-    return VitVariant{&fwd_warps_per_sm<N, R, LPC>, &launch_all<N, R, LPC>};
+    return VitVariant{&fwd_warps_per_sm<N, R, LPC>, &stage_forward<N, R, LPC>, &stage_verify_fwd<N, R, LPC>,
+                      &stage_trace<N, R, LPC>, &stage_verify_trace<N, R, LPC>};
 }
 template <int N, int R>
 static VitVariant pick_lp(int LP, bool const_ok) {
@@ -1133,30 +1156,39 @@ static VitVariant pick_variant(int N, int LP, bool const_ok) {
     fail(HMM_EUNSUPPORTED, "ring engine supports 1..%d neurons", RING_MAX_N);
 }
 
-void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, const std::vector<HostModel> &models,
-                      const FaithfulLayout &FL, const char *blob_dev, int16_t *x_dev, int64_t x_stride, double *ll_dev,
-                      cudaStream_t st, hmm_info *info) {
-    Workspace &ws = workspace();
-    const HostModel &M0 = models[0];
-    const int N = M0.N, L = M0.K - 1, ns = M0.nstates;
-    const int R = (N <= 4) ? 8 : 4;
-    const int SW = 32 * R;
-    RingLayout RL = ring_layout(N, L);
-    // Long recordings: one channel per launch (each already fills the GPU), which lets the
-    // FIR take its coefficients from the constant bank.
-    const bool no_const = getenv("HMMCUDA_NO_CONST_FIR") && atoi(getenv("HMMCUDA_NO_CONST_FIR")) != 0;
-    if (C > 1 && T >= 262144 && !no_const) {
-        for (int ch = 0; ch < C; ch++) {
-            std::vector<HostModel> one(1, models[ch]);
-            ring_viterbi_run(y_dev + (size_t)ch * y_stride, T, y_stride, 1, one, FL, blob_dev + (size_t)ch * FL.bytes,
-                             x_dev + (size_t)ch * x_stride, x_stride, ll_dev ? ll_dev + ch : nullptr, st, info);
-        }
-        if (info) info->n_chunks /= 1;
-        return;
-    }
-    const VitVariant variant = pick_variant(N, RL.LP, C == 1 && !no_const);
+// ---------------------------------------------------------------------------
+// VitPlan: buffers + staged launches of one decode (whole recording, or one time
+// shard of it with ghost chunks on either side)
+// ---------------------------------------------------------------------------
+struct VitPlan::Impl {
+    VitVariant variant;
+};
 
-    // geometry: one chunk per warp, one wave of warps over the whole GPU
+VitPlan::VitPlan() : impl(new Impl), p_(new VitParams{}) {}
+VitPlan::~VitPlan() {
+    for (void *q : owned) cudaFree(q);
+    delete impl;
+    delete p_;
+}
+
+void *VitPlan::alloc(int slot, size_t bytes) {
+    if (!own_memory) return workspace().get((Workspace::Slot)slot, bytes);
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fail(HMM_ENOMEM, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    owned.push_back(q);
+    return q;
+}
+
+int ring_default_chunking(const HostModel &M0, int64_t T_total, int C, int n_gpus, int64_t *Lc_out, int64_t *W_out) {
+    const int N = M0.N, L = M0.K - 1;
+    const int R = (N <= 4) ? 8 : 4, SW = 32 * R;
+    RingLayout RL = ring_layout(N, L);
+    const bool no_const = getenv("HMMCUDA_NO_CONST_FIR") && atoi(getenv("HMMCUDA_NO_CONST_FIR")) != 0;
+    const VitVariant variant = pick_variant(N, RL.LP, C == 1 && !no_const);
     int64_t W = ring_config().warmup > 0 ? ring_config().warmup : 512;
     W = ((W + SW - 1) / SW) * SW;
     if (W < ((L + 32 + SW - 1) / SW) * SW) W = ((L + 32 + SW - 1) / SW) * SW;
@@ -1165,24 +1197,39 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
         int dev = 0, sms = 148;
         HMM_CUDA(cudaGetDevice(&dev));
         HMM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        // one chunk per resident warp: a single, full wave over the whole GPU
-        const int64_t target_warps = (int64_t)sms * variant.warps_per_sm(RL);
+        // one chunk per resident warp: a single, full wave over every GPU
+        const int64_t target_warps = (int64_t)sms * variant.warps_per_sm(RL) * (n_gpus > 0 ? n_gpus : 1);
         int64_t per_channel = (target_warps + C - 1) / C;
-        Lc = (T + per_channel - 1) / per_channel;
+        Lc = (T_total + per_channel - 1) / per_channel;
         if (Lc < 4 * W) Lc = 4 * W;
     }
     Lc = ((Lc + SW - 1) / SW) * SW;
     if (Lc < W) Lc = W;
+    *Lc_out = Lc;
+    *W_out = W;
+    return SW;
+}
+
+void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, const std::vector<HostModel> &models,
+                    const FaithfulLayout &FL_, const char *blob_dev_, int16_t *x_dev, int64_t x_stride, int64_t Lc,
+                    int64_t W, bool first_prologue, bool last_true_end, cudaStream_t st) {
+    VitParams &p = *p_;
+    C = C_;
+    FL = FL_;
+    blob_dev = blob_dev_;
+    M0 = models[0];
+    const int N = M0.N, L = M0.K - 1, ns = M0.nstates;
+    RingLayout RL = ring_layout(N, L);
+    const bool no_const = getenv("HMMCUDA_NO_CONST_FIR") && atoi(getenv("HMMCUDA_NO_CONST_FIR")) != 0;
+    impl->variant = pick_variant(N, RL.LP, C == 1 && !no_const);
     int nchunks = (int)((T + Lc - 1) / Lc);
     // the last chunk must be long enough to hold the final look-back of L steps
     if (nchunks > 1 && T - (int64_t)(nchunks - 1) * Lc < RING_Q) nchunks--;
 
-    // prologue: first L+1 columns in the reference's exact arithmetic
     const int64_t pcols = L + 1;
-    double *T1pro = (double *)ws.get(Workspace::PROLOG, (sizeof(double) + sizeof(int16_t)) * (size_t)C * ns * pcols + 64);
+    double *T1pro = (double *)alloc(Workspace::PROLOG, (sizeof(double) + sizeof(int16_t)) * (size_t)C * ns * pcols + 64);
     int16_t *T2pro = (int16_t *)(T1pro + (size_t)C * ns * pcols);
-    // ring models
-    std::vector<double> hmdl((size_t)C * RL.total);
+    hmdl.assign((size_t)C * RL.total, 0.0);
     for (int c = 0; c < C; c++) ring_pack(models[c], RL, hmdl.data() + (size_t)c * RL.total);
     const int bvec = 1 + N * L;
     size_t off = 0;
@@ -1204,14 +1251,14 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
     size_t o_xend = carve(sizeof(int16_t) * C);
     size_t o_part = carve(sizeof(double) * (size_t)C * 1024);
     size_t o_slots = carve(sizeof(int) * 256);
-    char *base = (char *)ws.get(Workspace::CHUNKS, off);
+    char *base = (char *)alloc(Workspace::CHUNKS, off);
+    // pageable source: the copy is staged before cudaMemcpyAsync returns, and hmdl outlives it anyway
     HMM_CUDA(cudaMemcpyAsync(base + o_model, hmdl.data(), sizeof(double) * hmdl.size(), cudaMemcpyHostToDevice, st));
-    HMM_CUDA(cudaStreamSynchronize(st));  // hmdl is a pageable temporary
     HMM_CUDA(cudaMemsetAsync(base + o_cnt, 0, sizeof(int) * (size_t)C * 4, st));
     HMM_CUDA(cudaMemsetAsync(base + o_slots, 0, sizeof(int) * 256, st));
     HMM_CUDA(cudaMemsetAsync(base + o_pfin, 0, sizeof(double) * (size_t)C * N * RING_Q, st));
 
-    VitParams p{};
+    p = VitParams{};
     p.y = y_dev;
     p.T = T;
     p.y_stride = y_stride;
@@ -1221,8 +1268,8 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
     p.W = W;
     p.nchunks = nchunks;
     p.ns = ns;
-    p.dec = (uint32_t *)ws.get(Workspace::DEC, sizeof(uint32_t) * (size_t)C * T);
-    p.nzmask = (uint32_t *)ws.get(Workspace::MASK, sizeof(uint32_t) * (size_t)C * ((T + 31) / 32));
+    p.dec = (uint32_t *)alloc(Workspace::DEC, sizeof(uint32_t) * (size_t)C * T);
+    p.nzmask = (uint32_t *)alloc(Workspace::MASK, sizeof(uint32_t) * (size_t)C * ((T + 31) / 32));
     HMM_CUDA(cudaMemsetAsync(p.dec, 0, sizeof(uint32_t) * (size_t)C * T, st));
     HMM_CUDA(cudaMemsetAsync(p.nzmask, 0, sizeof(uint32_t) * (size_t)C * ((T + 31) / 32), st));
     p.SB = (double *)(base + o_sb);
@@ -1244,6 +1291,9 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
     p.look_end = (long long *)(base + o_look);
     p.tr_flag = (int *)(base + o_trflag);
     p.sm_slots = (int *)(base + o_slots);
+    p.first_prologue = first_prologue ? 1 : 0;
+    p.last_true_end = last_true_end ? 1 : 0;
+    part = (double *)(base + o_part);
     {
         const char *e = getenv("HMMCUDA_STAGGER_NS");
         p.stagger_ns = e ? atoi(e) : 0;
@@ -1253,30 +1303,81 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
         HMM_CUDA(cudaGetDevice(&dev));
         HMM_CUDA(cudaDeviceGetAttribute(&p.n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
+}
 
+void VitPlan::forward(cudaStream_t st, Timer *ttop) { impl->variant.forward(*p_, hmdl.data(), C, st, ttop); }
+void VitPlan::verify_fwd(cudaStream_t st) { impl->variant.verify_fwd(*p_, C, st); }
+void VitPlan::trace(cudaStream_t st) { impl->variant.trace(*p_, C, st); }
+void VitPlan::verify_trace(cudaStream_t st) { impl->variant.verify_trace(*p_, C, st); }
+
+void VitPlan::path_ll(cudaStream_t st, double *ll_dev, int64_t t_lo, int64_t t_hi, int64_t t_off, int64_t T_glob,
+                      bool with_p0) {
+    VitParams &p = *p_;
+    const int nparts = 592;
+    const int ns = M0.nstates;
+    const size_t llsm = sizeof(double) * ((size_t)ns + M0.ntrans) + sizeof(int) * ((size_t)ns + 1 + M0.ntrans) + 16;
+    ring_path_ll_partial<<<dim3(nparts, C), 256, llsm, st>>>(p.y, p.T, p.y_stride, blob_dev, FL.bytes, FL, ns,
+                                                             (int)M0.ntrans, p.x, p.x_stride, part, t_lo, t_hi, t_off,
+                                                             T_glob);
+    ring_path_ll_final<<<C, 256, 0, st>>>(p.y, p.T, p.y_stride, blob_dev, FL.bytes, FL, p.x, p.x_stride, part, nparts,
+                                          ll_dev, with_p0 ? 1 : 0, T_glob);
+    HMM_CUDA(cudaGetLastError());
+}
+
+void VitPlan::read_counters(cudaStream_t st, int *fwd_rep, int *bwd_rep) {
+    VitParams &p = *p_;
+    std::vector<int> cnt((size_t)C * 4);
+    HMM_CUDA(cudaMemcpyAsync(cnt.data(), p.counters, sizeof(int) * cnt.size(), cudaMemcpyDeviceToHost, st));
+    HMM_CUDA(cudaStreamSynchronize(st));
+    *fwd_rep = *bwd_rep = 0;
+    for (int c = 0; c < C; c++) {
+        *fwd_rep += cnt[c * 4 + 0];
+        *bwd_rep += cnt[c * 4 + 1];
+    }
+}
+
+int VitPlan::nchunks() const { return p_->nchunks; }
+int VitPlan::bvec() const { return p_->bvec; }
+double *VitPlan::eb_ptr(int chunk) { return p_->EB + (size_t)chunk * p_->bvec; }
+long long *VitPlan::own_start_ptr(int chunk) { return p_->own_start + chunk; }
+
+void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, const std::vector<HostModel> &models,
+                      const FaithfulLayout &FL, const char *blob_dev, int16_t *x_dev, int64_t x_stride, double *ll_dev,
+                      cudaStream_t st, hmm_info *info) {
+    // Long recordings: one channel per launch (each already fills the GPU), which lets the
+    // FIR take its coefficients from the constant bank.
+    const bool no_const = getenv("HMMCUDA_NO_CONST_FIR") && atoi(getenv("HMMCUDA_NO_CONST_FIR")) != 0;
+    if (C > 1 && T >= 262144 && !no_const) {
+        for (int ch = 0; ch < C; ch++) {
+            std::vector<HostModel> one(1, models[ch]);
+            ring_viterbi_run(y_dev + (size_t)ch * y_stride, T, y_stride, 1, one, FL, blob_dev + (size_t)ch * FL.bytes,
+                             x_dev + (size_t)ch * x_stride, x_stride, ll_dev ? ll_dev + ch : nullptr, st, info);
+        }
+        return;
+    }
+    int64_t Lc = 0, W = 0;
+    ring_default_chunking(models[0], T, C, 1, &Lc, &W);
+    VitPlan plan;
+    plan.build(y_dev, T, y_stride, C, models, FL, blob_dev, x_dev, x_stride, Lc, W, true, true, st);
     Timer ttop(st);
-    variant.launch(p, hmdl.data(), C, st, info, &ttop);
+    plan.forward(st, &ttop);
+    plan.verify_fwd(st);
+    plan.trace(st);
+    plan.verify_trace(st);
+    if (info) info->kernel_launches += 8;
     if (ll_dev) {
-        const int nparts = 592;
-        double *part = (double *)(base + o_part);
-        const size_t llsm = sizeof(double) * ((size_t)ns + M0.ntrans) + sizeof(int) * ((size_t)ns + 1 + M0.ntrans) + 16;
-        ring_path_ll_partial<<<dim3(nparts, C), 256, llsm, st>>>(y_dev, T, y_stride, blob_dev, FL.bytes, FL, ns,
-                                                                 (int)M0.ntrans, x_dev, x_stride, part);
-        ring_path_ll_final<<<C, 256, 0, st>>>(y_dev, T, y_stride, blob_dev, FL.bytes, FL, x_dev, x_stride, part, nparts,
-                                              ll_dev);
-        HMM_CUDA(cudaGetLastError());
+        plan.path_ll(st, ll_dev, 0, T, 0, T, true);
         if (info) info->kernel_launches += 2;
     }
     if (info) {
-        std::vector<int> cnt((size_t)C * 4);
-        HMM_CUDA(cudaMemcpyAsync(cnt.data(), base + o_cnt, sizeof(int) * cnt.size(), cudaMemcpyDeviceToHost, st));
-        HMM_CUDA(cudaStreamSynchronize(st));
-        info->n_chunks = nchunks;
-        for (int c = 0; c < C; c++) {
-            info->fwd_repaired += cnt[c * 4 + 0];
-            info->bwd_repaired += cnt[c * 4 + 1];
-        }
+        int f = 0, b = 0;
+        plan.read_counters(st, &f, &b);
+        info->n_chunks = plan.nchunks();
+        info->fwd_repaired += f;
+        info->bwd_repaired += b;
         info->top_kernel_ms = ttop.ms();
+    } else {
+        HMM_CUDA(cudaStreamSynchronize(st));  // plan.hmdl must outlive the (already staged) upload; be explicit
     }
 }
 
