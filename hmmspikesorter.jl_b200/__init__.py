@@ -26,11 +26,13 @@ from ._lib import MODES, HmmArgumentError, HmmError, HmmInfo, check, lib
 from .statematrix import TRANS_DTYPE, StateMatrix, generate_states, get_valid_transitions
 from .synth import create_signal, create_spike_template, make_rng
 from . import sharding
+from . import timeshard
+from .timeshard import viterbi_time_sharded
 
 __all__ = [
     "StateMatrix", "viterbi", "viterbi_batch", "forward", "backward", "update", "train_model", "em_step",
     "reconstruct_signal", "unroll_mlseq", "TrainContext", "create_signal", "create_spike_template", "make_rng",
-    "HmmError", "HmmArgumentError", "device_count", "set_ring_params",
+    "HmmError", "HmmArgumentError", "device_count", "set_ring_params", "viterbi_time_sharded",
 ]
 
 i64, i32, f64 = C.c_int64, C.c_int32, C.c_double

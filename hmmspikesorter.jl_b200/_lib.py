@@ -50,6 +50,9 @@ EXPORTS = [
     "hmm_forward_f64", "hmm_backward_f64", "hmm_update_f64", "hmm_em_step_f64", "hmm_em_step_ex_f64",
     "hmm_train_create", "hmm_train_create_dev", "hmm_train_em_step", "hmm_train_destroy",
     "hmm_reconstruct_f64", "hmm_reconstruct_dev_f64", "hmm_unroll_mlseq_i16", "hmm_host_alloc", "hmm_host_free",
+    "hmm_vshard_chunking", "hmm_vshard_create", "hmm_vshard_bvec", "hmm_vshard_forward", "hmm_vshard_fwd_boundary_get",
+    "hmm_vshard_fwd_boundary_set", "hmm_vshard_fwd_verify", "hmm_vshard_trace", "hmm_vshard_trace_boundary_get",
+    "hmm_vshard_trace_boundary_set", "hmm_vshard_trace_verify", "hmm_vshard_finish", "hmm_vshard_destroy",
 ]
 
 

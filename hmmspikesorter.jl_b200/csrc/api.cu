@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <mutex>
 
 #include "engines.h"
@@ -243,6 +244,246 @@ int hmm_viterbi_dev_f64(const double *y_dev, int64_t T, int32_t C, const int16_t
         tk.stop();
         HMM_CUDA(cudaStreamSynchronize(st));
         if (info) info->device_ms = info->kernel_ms = tk.ms();
+    });
+}
+
+// ---------------------------------------------------------------------------
+// time-sharded decode of one recording (config 5)
+// ---------------------------------------------------------------------------
+struct hmm_vshard {
+    VitPlan plan;
+    std::vector<HostModel> models;
+    FaithfulLayout FL;
+    char *blob_dev = nullptr;
+    double *y_dev = nullptr;
+    bool y_owned = false;
+    int16_t *x_loc = nullptr;
+    double *ll_dev = nullptr;
+    int64_t local_begin = 0, local_end = 0, main_begin = 0, main_end = 0, T_global = 0, Lc = 0;
+    bool first = false, last = false;
+    int c_main0 = 0, c_main1 = 0;  // local chunk index range of the main span [c_main0, c_main1)
+    int device = 0;
+    int last_fwd_rep = 0, last_bwd_rep = 0;
+    std::vector<void *> owned;
+    ~hmm_vshard() {
+        for (void *q : owned) cudaFree(q);
+    }
+};
+
+static void *shard_alloc(hmm_vshard *h, size_t bytes) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fail(HMM_ENOMEM, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    h->owned.push_back(q);
+    return q;
+}
+
+int hmm_vshard_chunking(int64_t T_global, int32_t n_ranks, int32_t N, int32_t K, int64_t *chunk_len_out,
+                        int64_t *warmup_out) {
+    return guarded([&] {
+        if (!chunk_len_out || !warmup_out || T_global < 1 || n_ranks < 1) fail(HMM_EINVAL, "bad arguments");
+        require_device();
+        HostModel M;
+        M.N = N;
+        M.K = K;
+        M.nstates = 1 + N * (K - 1);
+        M.is_ring = true;
+        if (!ring_supported(M, T_global)) fail(HMM_EUNSUPPORTED, "model/sequence outside the ring engine's range");
+        ring_default_chunking(M, T_global, 1, n_ranks, chunk_len_out, warmup_out);
+    });
+}
+
+int hmm_vshard_create(const double *y_local, int32_t y_is_host, int64_t local_begin, int64_t local_end,
+                      int64_t main_begin, int64_t main_end, int64_t T_global, int64_t chunk_len, int64_t warmup,
+                      const int16_t *states, int32_t N, int32_t K, int32_t nstates, const hmm_trans *tr,
+                      int64_t ntrans, const double *mu, double sigma, hmm_vshard **out) {
+    return guarded([&] {
+        if (!y_local || !out) fail(HMM_EINVAL, "null argument");
+        if (!(0 <= local_begin && local_begin <= main_begin && main_begin < main_end && main_end <= local_end &&
+              local_end <= T_global))
+            fail(HMM_EINVAL, "inconsistent shard spans");
+        if (chunk_len < 256 || warmup < 0 || warmup > chunk_len) fail(HMM_EINVAL, "bad chunk_len / warmup");
+        const bool first = main_begin == 0, last = main_end == T_global;
+        if ((main_begin - local_begin) % chunk_len || (!last && (main_end - local_begin) % chunk_len))
+            fail(HMM_EINVAL, "shard spans must be multiples of chunk_len from local_begin");
+        if (first != (local_begin == 0)) fail(HMM_EINVAL, "only the first shard may start at sample 0");
+        if (!first && main_begin - local_begin != chunk_len) fail(HMM_EINVAL, "left ghost must be exactly one chunk");
+        if (!last && local_end - main_end < warmup + 128) fail(HMM_EINVAL, "right ghost shorter than the look-ahead");
+        require_device();
+        std::unique_ptr<hmm_vshard> h(new hmm_vshard);
+        HMM_CUDA(cudaGetDevice(&h->device));
+        cudaStream_t st = main_stream();
+        h->models.resize(1);
+        analyse_model(states, N, K, nstates, tr, ntrans, mu, sigma, h->models[0]);
+        const int64_t Tl = local_end - local_begin;
+        if (!h->models[0].is_ring || !ring_supported(h->models[0], Tl))
+            fail(HMM_EUNSUPPORTED, "time sharding needs a non-overlap ring model within the ring engine's range");
+        h->FL = faithful_layout(nstates, ntrans);
+        std::vector<char> hostblob(h->FL.bytes, 0);
+        faithful_pack(h->models[0], h->FL, hostblob.data());
+        h->blob_dev = (char *)shard_alloc(h.get(), hostblob.size());
+        HMM_CUDA(cudaMemcpyAsync(h->blob_dev, hostblob.data(), hostblob.size(), cudaMemcpyHostToDevice, st));
+        HMM_CUDA(cudaStreamSynchronize(st));
+        if (y_is_host) {
+            h->y_dev = (double *)shard_alloc(h.get(), sizeof(double) * (size_t)Tl);
+            HMM_CUDA(cudaMemcpyAsync(h->y_dev, y_local, sizeof(double) * (size_t)Tl, cudaMemcpyHostToDevice, st));
+        } else
+            h->y_dev = const_cast<double *>(y_local);
+        h->x_loc = (int16_t *)shard_alloc(h.get(), sizeof(int16_t) * (size_t)Tl);
+        h->ll_dev = (double *)shard_alloc(h.get(), sizeof(double));
+        h->local_begin = local_begin;
+        h->local_end = local_end;
+        h->main_begin = main_begin;
+        h->main_end = main_end;
+        h->T_global = T_global;
+        h->Lc = chunk_len;
+        h->first = first;
+        h->last = last;
+        h->plan.own_memory = true;
+        h->plan.build(h->y_dev, Tl, Tl, 1, h->models, h->FL, h->blob_dev, h->x_loc, Tl, chunk_len, warmup, first, last,
+                      st);
+        h->c_main0 = (int)((main_begin - local_begin) / chunk_len);
+        h->c_main1 = last ? h->plan.nchunks() : (int)((main_end - local_begin) / chunk_len);
+        if (h->c_main1 > h->plan.nchunks()) h->c_main1 = h->plan.nchunks();
+        if (!last && h->c_main1 >= h->plan.nchunks()) fail(HMM_EINVAL, "right ghost chunk missing");
+        HMM_CUDA(cudaStreamSynchronize(st));
+        *out = h.release();
+    });
+}
+
+int hmm_vshard_bvec(const hmm_vshard *h) { return h ? h->plan.bvec() : 0; }
+
+static void shard_dev(hmm_vshard *h) {
+    if (!h) fail(HMM_EINVAL, "null shard");
+    HMM_CUDA(cudaSetDevice(h->device));
+}
+
+int hmm_vshard_forward(hmm_vshard *h) {
+    return guarded([&] {
+        shard_dev(h);
+        h->plan.forward(main_stream(), nullptr);
+    });
+}
+
+int hmm_vshard_fwd_boundary_get(hmm_vshard *h, double *out, int32_t out_is_device) {
+    return guarded([&] {
+        shard_dev(h);
+        if (!out) fail(HMM_EINVAL, "null out");
+        if (h->last) fail(HMM_EINVAL, "the last shard has no right neighbour");
+        cudaStream_t st = main_stream();
+        HMM_CUDA(cudaMemcpyAsync(out, h->plan.eb_ptr(h->c_main1 - 1), sizeof(double) * h->plan.bvec(),
+                                 out_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        HMM_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int hmm_vshard_fwd_boundary_set(hmm_vshard *h, const double *in, int32_t in_is_device) {
+    return guarded([&] {
+        shard_dev(h);
+        if (!in) fail(HMM_EINVAL, "null in");
+        if (h->first) fail(HMM_EINVAL, "the first shard has no left neighbour");
+        cudaStream_t st = main_stream();
+        // the left ghost chunk's own (speculative) end vector is replaced by the neighbour's true one
+        HMM_CUDA(cudaMemcpyAsync(h->plan.eb_ptr(h->c_main0 - 1), in, sizeof(double) * h->plan.bvec(),
+                                 in_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        HMM_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int hmm_vshard_fwd_verify(hmm_vshard *h, int32_t *n_repaired) {
+    return guarded([&] {
+        shard_dev(h);
+        cudaStream_t st = main_stream();
+        h->plan.reset_counters(st);
+        h->plan.verify_fwd(st);
+        int f = 0, b = 0;
+        h->plan.read_counters(st, &f, &b);
+        h->last_fwd_rep = f;
+        if (n_repaired) *n_repaired = f;
+    });
+}
+
+int hmm_vshard_trace(hmm_vshard *h) {
+    return guarded([&] {
+        shard_dev(h);
+        h->plan.trace(main_stream());
+    });
+}
+
+int hmm_vshard_trace_boundary_get(hmm_vshard *h, int64_t *out, int32_t out_is_device) {
+    return guarded([&] {
+        shard_dev(h);
+        if (!out) fail(HMM_EINVAL, "null out");
+        if (h->first) fail(HMM_EINVAL, "the first shard has no left neighbour");
+        cudaStream_t st = main_stream();
+        long long v = 0;
+        HMM_CUDA(cudaMemcpyAsync(&v, h->plan.own_start_ptr(h->c_main0), sizeof v, cudaMemcpyDeviceToHost, st));
+        HMM_CUDA(cudaStreamSynchronize(st));
+        if (v >= 0) v += 8 * (long long)h->local_begin;  // chain entry time: local -> global
+        int64_t g = (int64_t)v;
+        if (out_is_device)
+            HMM_CUDA(cudaMemcpy(out, &g, sizeof g, cudaMemcpyHostToDevice));
+        else
+            *out = g;
+    });
+}
+
+int hmm_vshard_trace_boundary_set(hmm_vshard *h, const int64_t *in, int32_t in_is_device) {
+    return guarded([&] {
+        shard_dev(h);
+        if (!in) fail(HMM_EINVAL, "null in");
+        if (h->last) fail(HMM_EINVAL, "the last shard has no right neighbour");
+        int64_t g = 0;
+        if (in_is_device)
+            HMM_CUDA(cudaMemcpy(&g, in, sizeof g, cudaMemcpyDeviceToHost));
+        else
+            g = *in;
+        long long v = (long long)g;
+        if (v >= 0) v -= 8 * (long long)h->local_begin;  // global -> local
+        // traceback state at main_end = start of the right ghost chunk
+        HMM_CUDA(cudaMemcpy(h->plan.own_start_ptr(h->c_main1), &v, sizeof v, cudaMemcpyHostToDevice));
+    });
+}
+
+int hmm_vshard_trace_verify(hmm_vshard *h, int32_t *n_repaired) {
+    return guarded([&] {
+        shard_dev(h);
+        cudaStream_t st = main_stream();
+        h->plan.reset_counters(st);
+        h->plan.verify_trace(st);
+        int f = 0, b = 0;
+        h->plan.read_counters(st, &f, &b);
+        h->last_bwd_rep = b;
+        if (n_repaired) *n_repaired = b;
+    });
+}
+
+int hmm_vshard_finish(hmm_vshard *h, int16_t *x_main_out, int32_t x_is_device, double *ll_partial_out) {
+    return guarded([&] {
+        shard_dev(h);
+        if (!x_main_out) fail(HMM_EINVAL, "null x_main_out");
+        cudaStream_t st = main_stream();
+        const int64_t lo = h->main_begin - h->local_begin, hi = h->main_end - h->local_begin;
+        if (ll_partial_out) {
+            // sum over the main span of (T_global - t) * (lp + q) with global t, plus the t = 0 term on the first shard
+            h->plan.path_ll(st, h->ll_dev, lo, hi, h->local_begin, h->T_global, h->first);
+            HMM_CUDA(cudaMemcpyAsync(ll_partial_out, h->ll_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
+        }
+        HMM_CUDA(cudaMemcpyAsync(x_main_out, h->x_loc + lo, sizeof(int16_t) * (size_t)(hi - lo),
+                                 x_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        HMM_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int hmm_vshard_destroy(hmm_vshard *h) {
+    return guarded([&] {
+        if (!h) return;
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        delete h;
     });
 }
 

@@ -57,6 +57,7 @@ class VitPlan {
     void verify_trace(cudaStream_t st);  // boundary check + repair
     void path_ll(cudaStream_t st, double *ll_dev, int64_t t_lo, int64_t t_hi, int64_t t_off, int64_t T_glob, bool with_p0);
     void read_counters(cudaStream_t st, int *fwd_rep, int *bwd_rep);
+    void reset_counters(cudaStream_t st);
     int nchunks() const;
     int bvec() const;
     double *eb_ptr(int chunk);              // device pointer: true end-boundary vector of `chunk` (channel 0)

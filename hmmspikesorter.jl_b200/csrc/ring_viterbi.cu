@@ -1336,6 +1336,10 @@ void VitPlan::read_counters(cudaStream_t st, int *fwd_rep, int *bwd_rep) {
     }
 }
 
+void VitPlan::reset_counters(cudaStream_t st) {
+    HMM_CUDA(cudaMemsetAsync(p_->counters, 0, sizeof(int) * (size_t)C * 4, st));
+}
+
 int VitPlan::nchunks() const { return p_->nchunks; }
 int VitPlan::bvec() const { return p_->bvec; }
 double *VitPlan::eb_ptr(int chunk) { return p_->EB + (size_t)chunk * p_->bvec; }

@@ -1,0 +1,265 @@
+"""Time-sharded decode of ONE long recording (BASELINE config 5): contiguous spans of
+the recording are decoded on different GPUs (or, for testing, as several shards on one
+GPU) and stitched EXACTLY: each shard carries one ghost chunk on either side, decodes
+speculatively, and the shard boundaries are verified -- and repaired when needed -- with
+two tiny messages per neighbour pair, the forward boundary vector (1 + N*(K-1) doubles)
+travelling right and the traceback state (one int64) travelling left.  The reference's
+only long-sequence mechanism, fit(..., chunksize) (src/fit.jl:11-42), is approximate;
+this replaces it without approximation.
+
+`viterbi_time_sharded`      all shards driven from one process (shards may sit on
+                            different devices); messages go through host memory.
+`viterbi_time_sharded_dist` one shard per torch.distributed rank; messages are
+                            NCCL (or gloo) point-to-point sends of device tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._lib import check, lib
+from .statematrix import TRANS_DTYPE
+
+i64, i32, f64 = C.c_int64, C.c_int32, C.c_double
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def shard_plan(T: int, n_shards: int, chunk_len: int) -> List[Tuple[int, int, int, int]]:
+    """(local_begin, local_end, main_begin, main_end) per shard: main spans are whole chunks,
+    balanced over the shards; one ghost chunk on either side."""
+    nchunks = -(-T // chunk_len)
+    if n_shards > nchunks:
+        raise ValueError("more shards than chunks")
+    q, r = divmod(nchunks, n_shards)
+    out, c0 = [], 0
+    for s in range(n_shards):
+        c1 = c0 + q + (1 if s < r else 0)
+        mb, me = c0 * chunk_len, min(T, c1 * chunk_len)
+        out.append((max(0, mb - chunk_len), min(T, me + chunk_len), mb, me))
+        c0 = c1
+    # a final main span shorter than the engine's look-back is merged into its neighbour's ghost
+    return out
+
+
+def default_chunking(T: int, n_ranks: int, N: int, K: int) -> Tuple[int, int]:
+    lc, w = i64(0), i64(0)
+    check(lib().hmm_vshard_chunking(i64(T), i32(n_ranks), i32(N), i32(K), C.byref(lc), C.byref(w)))
+    return int(lc.value), int(w.value)
+
+
+class Shard:
+    """One hmm_vshard handle."""
+
+    def __init__(self, y_local, y_is_host, span, T, chunk_len, warmup, lA, mu, sigma, device=None):
+        L = lib()
+        if device is not None:
+            check(L.hmm_set_device(i32(device)))
+        self.device = device
+        self.span = span
+        st = np.asfortranarray(lA.states, dtype=np.int16)
+        tr = np.ascontiguousarray(lA.transitions, dtype=TRANS_DTYPE)
+        mu = np.asfortranarray(mu, dtype=np.float64)
+        self._h = C.c_void_p()
+        yp = _p(y_local) if y_is_host else C.c_void_p(int(y_local))
+        check(L.hmm_vshard_create(yp, i32(1 if y_is_host else 0), i64(span[0]), i64(span[1]), i64(span[2]), i64(span[3]),
+                                  i64(T), i64(chunk_len), i64(warmup), _p(st), i32(lA.N), i32(lA.K), i32(lA.nstates),
+                                  _p(tr), i64(tr.size), _p(mu), f64(sigma), C.byref(self._h)))
+        self.bvec = int(L.hmm_vshard_bvec(self._h))
+        self.first = span[2] == 0
+        self.last = span[3] == T
+
+    def _dev(self):
+        if self.device is not None:
+            check(lib().hmm_set_device(i32(self.device)))
+
+    def forward(self):
+        self._dev()
+        check(lib().hmm_vshard_forward(self._h))
+
+    def fwd_get(self, out_ptr=None):
+        self._dev()
+        if out_ptr is not None:
+            check(lib().hmm_vshard_fwd_boundary_get(self._h, C.c_void_p(out_ptr), i32(1)))
+            return None
+        v = np.empty(self.bvec, dtype=np.float64)
+        check(lib().hmm_vshard_fwd_boundary_get(self._h, _p(v), i32(0)))
+        return v
+
+    def fwd_set(self, v=None, in_ptr=None):
+        self._dev()
+        if in_ptr is not None:
+            check(lib().hmm_vshard_fwd_boundary_set(self._h, C.c_void_p(in_ptr), i32(1)))
+        else:
+            v = np.ascontiguousarray(v, dtype=np.float64)
+            check(lib().hmm_vshard_fwd_boundary_set(self._h, _p(v), i32(0)))
+
+    def fwd_verify(self) -> int:
+        self._dev()
+        n = i32(0)
+        check(lib().hmm_vshard_fwd_verify(self._h, C.byref(n)))
+        return int(n.value)
+
+    def trace(self):
+        self._dev()
+        check(lib().hmm_vshard_trace(self._h))
+
+    def trace_get(self, out_ptr=None):
+        self._dev()
+        if out_ptr is not None:
+            check(lib().hmm_vshard_trace_boundary_get(self._h, C.c_void_p(out_ptr), i32(1)))
+            return None
+        v = i64(0)
+        check(lib().hmm_vshard_trace_boundary_get(self._h, C.byref(v), i32(0)))
+        return int(v.value)
+
+    def trace_set(self, v=None, in_ptr=None):
+        self._dev()
+        if in_ptr is not None:
+            check(lib().hmm_vshard_trace_boundary_set(self._h, C.c_void_p(in_ptr), i32(1)))
+        else:
+            vv = i64(int(v))
+            check(lib().hmm_vshard_trace_boundary_set(self._h, C.byref(vv), i32(0)))
+
+    def trace_verify(self) -> int:
+        self._dev()
+        n = i32(0)
+        check(lib().hmm_vshard_trace_verify(self._h, C.byref(n)))
+        return int(n.value)
+
+    def finish(self, x_out=None, x_ptr=None, want_ll=True):
+        self._dev()
+        ll = f64(0)
+        if x_ptr is not None:
+            check(lib().hmm_vshard_finish(self._h, C.c_void_p(x_ptr), i32(1), C.byref(ll) if want_ll else None))
+        else:
+            check(lib().hmm_vshard_finish(self._h, _p(x_out), i32(0), C.byref(ll) if want_ll else None))
+        return ll.value
+
+    def close(self):
+        if self._h:
+            self._dev()
+            lib().hmm_vshard_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def viterbi_time_sharded(y, lA, mu, sigma, n_shards: int, *, devices: Optional[Sequence[int]] = None,
+                         chunk_len: int = 0, warmup: int = 0, return_info: bool = False):
+    """Decode `y` as `n_shards` time shards driven from this process; returns (x, ll) identical
+    to viterbi(y, lA, mu, sigma).  `devices[s]` places shard s (default: the current device)."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    T = y.size
+    if not chunk_len:
+        chunk_len, warmup = default_chunking(T, n_shards, lA.N, lA.K)
+    plan = shard_plan(T, n_shards, chunk_len)
+    shards = [Shard(y[sp[0]:sp[1]], True, sp, T, chunk_len, warmup, lA, mu, sigma,
+                    None if devices is None else devices[s]) for s, sp in enumerate(plan)]
+    info = {"n_shards": n_shards, "chunk_len": chunk_len, "warmup": warmup, "fwd_rounds": 0, "trace_rounds": 0,
+            "fwd_repaired": 0, "trace_repaired": 0}
+    try:
+        for sh in shards:
+            sh.forward()
+        while True:  # forward boundary vectors travel right until no shard repairs anything
+            msgs = [sh.fwd_get() if not sh.last else None for sh in shards]
+            for s in range(1, n_shards):
+                shards[s].fwd_set(msgs[s - 1])
+            rep = sum(sh.fwd_verify() for sh in shards)
+            info["fwd_rounds"] += 1
+            info["fwd_repaired"] += rep
+            if rep == 0 or info["fwd_rounds"] > n_shards:
+                break
+        for sh in shards:
+            sh.trace()
+        while True:  # traceback states travel left
+            msgs = [sh.trace_get() if not sh.first else None for sh in shards]
+            for s in range(n_shards - 1):
+                shards[s].trace_set(msgs[s + 1])
+            rep = sum(sh.trace_verify() for sh in shards)
+            info["trace_rounds"] += 1
+            info["trace_repaired"] += rep
+            if rep == 0 or info["trace_rounds"] > n_shards:
+                break
+        x = np.empty(T, dtype=np.int16)
+        ll = 0.0
+        for sh in shards:
+            ll += sh.finish(x_out=x[sh.span[2]:sh.span[3]])
+    finally:
+        for sh in shards:
+            sh.close()
+    return (x, ll, info) if return_info else (x, ll)
+
+
+def viterbi_time_sharded_dist(y_local_dev_ptr: int, span, T: int, chunk_len: int, warmup: int, lA, mu, sigma,
+                              x_main_dev_ptr: int, device):
+    """One shard per torch.distributed rank.  `y_local_dev_ptr` points at this rank's samples
+    [span[0], span[1]) in HBM, `x_main_dev_ptr` receives x for [span[2], span[3]).  Boundary
+    messages are point-to-point sends of device tensors (NCCL over NVLink on a GPU box).
+    Returns (ll summed over ranks, info)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    sh = Shard(y_local_dev_ptr, False, span, T, chunk_len, warmup, lA, mu, sigma)
+    info = {"fwd_rounds": 0, "trace_rounds": 0, "fwd_repaired": 0, "trace_repaired": 0}
+    try:
+        sh.forward()
+        vec_out = torch.empty(sh.bvec, dtype=torch.float64, device=device)
+        vec_in = torch.empty(sh.bvec, dtype=torch.float64, device=device)
+        cnt = torch.zeros(1, dtype=torch.int64, device=device)
+        while True:
+            ops = []
+            if not sh.last:
+                sh.fwd_get(out_ptr=vec_out.data_ptr())
+                ops.append(dist.P2POp(dist.isend, vec_out, rank + 1))
+            if not sh.first:
+                ops.append(dist.P2POp(dist.irecv, vec_in, rank - 1))
+            if ops:
+                for r in dist.batch_isend_irecv(ops):
+                    r.wait()
+                torch.cuda.synchronize(device) if torch.cuda.is_available() else None
+            if not sh.first:
+                sh.fwd_set(in_ptr=vec_in.data_ptr())
+            cnt[0] = sh.fwd_verify()
+            dist.all_reduce(cnt)
+            info["fwd_rounds"] += 1
+            info["fwd_repaired"] += int(cnt.item())
+            if int(cnt.item()) == 0 or info["fwd_rounds"] > world:
+                break
+        sh.trace()
+        s_out = torch.zeros(1, dtype=torch.int64, device=device)
+        s_in = torch.zeros(1, dtype=torch.int64, device=device)
+        while True:
+            ops = []
+            if not sh.first:
+                sh.trace_get(out_ptr=s_out.data_ptr())
+                ops.append(dist.P2POp(dist.isend, s_out, rank - 1))
+            if not sh.last:
+                ops.append(dist.P2POp(dist.irecv, s_in, rank + 1))
+            if ops:
+                for r in dist.batch_isend_irecv(ops):
+                    r.wait()
+                torch.cuda.synchronize(device) if torch.cuda.is_available() else None
+            if not sh.last:
+                sh.trace_set(in_ptr=s_in.data_ptr())
+            cnt[0] = sh.trace_verify()
+            dist.all_reduce(cnt)
+            info["trace_rounds"] += 1
+            info["trace_repaired"] += int(cnt.item())
+            if int(cnt.item()) == 0 or info["trace_rounds"] > world:
+                break
+        ll = sh.finish(x_ptr=x_main_dev_ptr)
+        t = torch.tensor([ll], dtype=torch.float64, device=device)
+        dist.all_reduce(t)
+        return float(t.item()), info
+    finally:
+        sh.close()

@@ -107,6 +107,43 @@ int hmm_viterbi_dev_f64(const double *y_dev, int64_t T, int32_t C, const int16_t
                         const double *mu, const double *sigma, int16_t *x_dev, double *ll_out, int32_t mode,
                         hmm_info *info);
 
+/* ---- time-sharded decode of ONE long recording across GPUs (BASELINE config 5) ------------- */
+/*
+ * Every rank owns a contiguous span [main_begin, main_end) of the recording (multiples of
+ * chunk_len, except the global end) and holds the samples [local_begin, local_end) with one
+ * "ghost" chunk on either side: local_begin = main_begin - chunk_len (0 on the first rank),
+ * local_end = min(T_global, main_end + chunk_len).  The ghost chunks are decoded speculatively
+ * and thrown away; the shard boundaries are then verified exactly like the chunk boundaries
+ * inside one GPU, with two tiny messages per neighbour pair (exchanged by the caller, e.g. over
+ * NCCL): the forward boundary vector (hmm_vshard_bvec() doubles) travelling right and the
+ * traceback state (one int64) travelling left.  Protocol (all ranks, same order):
+ *   create -> forward -> [send fwd boundary to r+1 / set from r-1] -> fwd_verify
+ *          (repeat exchange + fwd_verify while any rank reports repairs)
+ *          -> trace -> [send trace boundary to r-1 / set from r+1] -> trace_verify (repeat likewise)
+ *          -> finish (x of the main span, partial ll to be summed over ranks) -> destroy
+ * y_local is a DEVICE pointer unless y_is_host != 0 (then it is copied once).  Boundary buffers
+ * are device pointers when *_is_device != 0, host pointers otherwise.  Single channel, ring
+ * models only.
+ */
+typedef struct hmm_vshard hmm_vshard;
+int hmm_vshard_chunking(int64_t T_global, int32_t n_ranks, int32_t N, int32_t K, int64_t *chunk_len_out,
+                        int64_t *warmup_out);
+int hmm_vshard_create(const double *y_local, int32_t y_is_host, int64_t local_begin, int64_t local_end,
+                      int64_t main_begin, int64_t main_end, int64_t T_global, int64_t chunk_len, int64_t warmup,
+                      const int16_t *states, int32_t N, int32_t K, int32_t nstates, const hmm_trans *tr,
+                      int64_t ntrans, const double *mu, double sigma, hmm_vshard **out);
+int hmm_vshard_bvec(const hmm_vshard *h);
+int hmm_vshard_forward(hmm_vshard *h);
+int hmm_vshard_fwd_boundary_get(hmm_vshard *h, double *out, int32_t out_is_device);        /* at main_end  -> rank r+1 */
+int hmm_vshard_fwd_boundary_set(hmm_vshard *h, const double *in, int32_t in_is_device);   /* at main_begin <- rank r-1 */
+int hmm_vshard_fwd_verify(hmm_vshard *h, int32_t *n_repaired);
+int hmm_vshard_trace(hmm_vshard *h);
+int hmm_vshard_trace_boundary_get(hmm_vshard *h, int64_t *out, int32_t out_is_device);      /* at main_begin -> rank r-1 */
+int hmm_vshard_trace_boundary_set(hmm_vshard *h, const int64_t *in, int32_t in_is_device); /* at main_end   <- rank r+1 */
+int hmm_vshard_trace_verify(hmm_vshard *h, int32_t *n_repaired);
+int hmm_vshard_finish(hmm_vshard *h, int16_t *x_main_out, int32_t x_is_device, double *ll_partial_out);
+int hmm_vshard_destroy(hmm_vshard *h);
+
 /* ---- Baum-Welch ---------------------------------------------------------- */
 /* forward(V, lA, mu, sigma) -> alpha [nstates x T]          src/baumwelch.jl:25-51 */
 int hmm_forward_f64(const double *V, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
