@@ -85,6 +85,11 @@ int hmm_get_device(void) {
     return d;
 }
 
+int hmm_set_stream(void *cuda_stream) {
+    set_external_stream((cudaStream_t)cuda_stream, cuda_stream != nullptr);
+    return HMM_OK;
+}
+
 int hmm_set_ring_params(int64_t chunk_len, int64_t warmup) {
     if (chunk_len < 0 || warmup < 0) return set_err(HMM_EINVAL, "negative ring parameter");
     ring_config().chunk_len = chunk_len;
@@ -250,6 +255,12 @@ int hmm_viterbi_dev_f64(const double *y_dev, int64_t T, int32_t C, const int16_t
 // ---------------------------------------------------------------------------
 // time-sharded decode of one recording (config 5)
 // ---------------------------------------------------------------------------
+// traceback state codes carry a chain entry time (code = 8*t0 + neuron, -1 = noise)
+__global__ void shift_state_kernel(const long long *src, long long *dst, long long delta) {
+    long long v = *src;
+    *dst = v >= 0 ? v + delta : v;
+}
+
 struct hmm_vshard {
     VitPlan plan;
     std::vector<HostModel> models;
@@ -376,7 +387,7 @@ int hmm_vshard_fwd_boundary_get(hmm_vshard *h, double *out, int32_t out_is_devic
         cudaStream_t st = main_stream();
         HMM_CUDA(cudaMemcpyAsync(out, h->plan.eb_ptr(h->c_main1 - 1), sizeof(double) * h->plan.bvec(),
                                  out_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-        HMM_CUDA(cudaStreamSynchronize(st));
+        if (!out_is_device) HMM_CUDA(cudaStreamSynchronize(st));
     });
 }
 
@@ -389,7 +400,7 @@ int hmm_vshard_fwd_boundary_set(hmm_vshard *h, const double *in, int32_t in_is_d
         // the left ghost chunk's own (speculative) end vector is replaced by the neighbour's true one
         HMM_CUDA(cudaMemcpyAsync(h->plan.eb_ptr(h->c_main0 - 1), in, sizeof(double) * h->plan.bvec(),
                                  in_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-        HMM_CUDA(cudaStreamSynchronize(st));
+        if (!in_is_device) HMM_CUDA(cudaStreamSynchronize(st));
     });
 }
 
@@ -397,12 +408,13 @@ int hmm_vshard_fwd_verify(hmm_vshard *h, int32_t *n_repaired) {
     return guarded([&] {
         shard_dev(h);
         cudaStream_t st = main_stream();
-        h->plan.reset_counters(st);
+        if (n_repaired) h->plan.reset_counters(st);
         h->plan.verify_fwd(st);
-        int f = 0, b = 0;
-        h->plan.read_counters(st, &f, &b);
-        h->last_fwd_rep = f;
-        if (n_repaired) *n_repaired = f;
+        if (n_repaired) {
+            int f = 0, b = 0;
+            h->plan.read_counters(st, &f, &b);
+            *n_repaired = f;
+        }
     });
 }
 
@@ -419,15 +431,17 @@ int hmm_vshard_trace_boundary_get(hmm_vshard *h, int64_t *out, int32_t out_is_de
         if (!out) fail(HMM_EINVAL, "null out");
         if (h->first) fail(HMM_EINVAL, "the first shard has no left neighbour");
         cudaStream_t st = main_stream();
+        if (out_is_device) {  // chain entry time: local -> global, on the device, asynchronous
+            shift_state_kernel<<<1, 1, 0, st>>>(h->plan.own_start_ptr(h->c_main0), (long long *)out,
+                                                8 * (long long)h->local_begin);
+            HMM_CUDA(cudaGetLastError());
+            return;
+        }
         long long v = 0;
         HMM_CUDA(cudaMemcpyAsync(&v, h->plan.own_start_ptr(h->c_main0), sizeof v, cudaMemcpyDeviceToHost, st));
         HMM_CUDA(cudaStreamSynchronize(st));
-        if (v >= 0) v += 8 * (long long)h->local_begin;  // chain entry time: local -> global
-        int64_t g = (int64_t)v;
-        if (out_is_device)
-            HMM_CUDA(cudaMemcpy(out, &g, sizeof g, cudaMemcpyHostToDevice));
-        else
-            *out = g;
+        if (v >= 0) v += 8 * (long long)h->local_begin;
+        *out = (int64_t)v;
     });
 }
 
@@ -436,15 +450,18 @@ int hmm_vshard_trace_boundary_set(hmm_vshard *h, const int64_t *in, int32_t in_i
         shard_dev(h);
         if (!in) fail(HMM_EINVAL, "null in");
         if (h->last) fail(HMM_EINVAL, "the last shard has no right neighbour");
-        int64_t g = 0;
-        if (in_is_device)
-            HMM_CUDA(cudaMemcpy(&g, in, sizeof g, cudaMemcpyDeviceToHost));
-        else
-            g = *in;
-        long long v = (long long)g;
-        if (v >= 0) v -= 8 * (long long)h->local_begin;  // global -> local
-        // traceback state at main_end = start of the right ghost chunk
-        HMM_CUDA(cudaMemcpy(h->plan.own_start_ptr(h->c_main1), &v, sizeof v, cudaMemcpyHostToDevice));
+        // traceback state at main_end = start of the right ghost chunk; global -> local entry time
+        cudaStream_t st = main_stream();
+        if (in_is_device) {
+            shift_state_kernel<<<1, 1, 0, st>>>((const long long *)in, h->plan.own_start_ptr(h->c_main1),
+                                                -8 * (long long)h->local_begin);
+            HMM_CUDA(cudaGetLastError());
+            return;
+        }
+        long long v = (long long)*in;
+        if (v >= 0) v -= 8 * (long long)h->local_begin;
+        HMM_CUDA(cudaMemcpyAsync(h->plan.own_start_ptr(h->c_main1), &v, sizeof v, cudaMemcpyHostToDevice, st));
+        HMM_CUDA(cudaStreamSynchronize(st));
     });
 }
 
@@ -452,12 +469,13 @@ int hmm_vshard_trace_verify(hmm_vshard *h, int32_t *n_repaired) {
     return guarded([&] {
         shard_dev(h);
         cudaStream_t st = main_stream();
-        h->plan.reset_counters(st);
+        if (n_repaired) h->plan.reset_counters(st);
         h->plan.verify_trace(st);
-        int f = 0, b = 0;
-        h->plan.read_counters(st, &f, &b);
-        h->last_bwd_rep = b;
-        if (n_repaired) *n_repaired = b;
+        if (n_repaired) {
+            int f = 0, b = 0;
+            h->plan.read_counters(st, &f, &b);
+            *n_repaired = b;
+        }
     });
 }
 
@@ -475,6 +493,16 @@ int hmm_vshard_finish(hmm_vshard *h, int16_t *x_main_out, int32_t x_is_device, d
         HMM_CUDA(cudaMemcpyAsync(x_main_out, h->x_loc + lo, sizeof(int16_t) * (size_t)(hi - lo),
                                  x_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
         HMM_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int hmm_vshard_repairs(hmm_vshard *h, int32_t *fwd_repaired, int32_t *trace_repaired) {
+    return guarded([&] {
+        shard_dev(h);
+        int f = 0, b = 0;
+        h->plan.read_counters(main_stream(), &f, &b);
+        if (fwd_repaired) *fwd_repaired = f;
+        if (trace_repaired) *trace_repaired = b;
     });
 }
 

@@ -56,6 +56,7 @@ class Workspace {
 Workspace &workspace();      // per host thread
 cudaStream_t main_stream();  // per host thread, non-blocking stream
 cudaStream_t copy_stream();
+void set_external_stream(cudaStream_t s, bool use);  // per host thread
 
 // ---------------------------------------------------------------------------
 // Host-side analysis of one StateMatrix + templates (one channel).

@@ -57,6 +57,12 @@ struct Streams {
     cudaStream_t main = nullptr, copy = nullptr;
     int dev = -1;
 };
+static thread_local cudaStream_t g_external = nullptr;
+static thread_local bool g_use_external = false;
+void set_external_stream(cudaStream_t s, bool use) {
+    g_external = s;
+    g_use_external = use;
+}
 static Streams &streams() {
     static thread_local Streams st;
     int dev = 0;
@@ -71,7 +77,7 @@ static Streams &streams() {
     }
     return st;
 }
-cudaStream_t main_stream() { return streams().main; }
+cudaStream_t main_stream() { return g_use_external ? g_external : streams().main; }
 cudaStream_t copy_stream() { return streams().copy; }
 
 // ---------------------------------------------------------------------------

@@ -1254,9 +1254,6 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     char *base = (char *)alloc(Workspace::CHUNKS, off);
     // pageable source: the copy is staged before cudaMemcpyAsync returns, and hmdl outlives it anyway
     HMM_CUDA(cudaMemcpyAsync(base + o_model, hmdl.data(), sizeof(double) * hmdl.size(), cudaMemcpyHostToDevice, st));
-    HMM_CUDA(cudaMemsetAsync(base + o_cnt, 0, sizeof(int) * (size_t)C * 4, st));
-    HMM_CUDA(cudaMemsetAsync(base + o_slots, 0, sizeof(int) * 256, st));
-    HMM_CUDA(cudaMemsetAsync(base + o_pfin, 0, sizeof(double) * (size_t)C * N * RING_Q, st));
 
     p = VitParams{};
     p.y = y_dev;
@@ -1270,8 +1267,6 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     p.ns = ns;
     p.dec = (uint32_t *)alloc(Workspace::DEC, sizeof(uint32_t) * (size_t)C * T);
     p.nzmask = (uint32_t *)alloc(Workspace::MASK, sizeof(uint32_t) * (size_t)C * ((T + 31) / 32));
-    HMM_CUDA(cudaMemsetAsync(p.dec, 0, sizeof(uint32_t) * (size_t)C * T, st));
-    HMM_CUDA(cudaMemsetAsync(p.nzmask, 0, sizeof(uint32_t) * (size_t)C * ((T + 31) / 32), st));
     p.SB = (double *)(base + o_sb);
     p.EB = (double *)(base + o_eb);
     p.bvec = bvec;
@@ -1305,7 +1300,16 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     }
 }
 
-void VitPlan::forward(cudaStream_t st, Timer *ttop) { impl->variant.forward(*p_, hmdl.data(), C, st, ttop); }
+void VitPlan::forward(cudaStream_t st, Timer *ttop) {
+    VitParams &p = *p_;
+    // a plan can be run repeatedly: everything the kernels accumulate into is re-zeroed here
+    HMM_CUDA(cudaMemsetAsync(p.dec, 0, sizeof(uint32_t) * (size_t)C * p.T, st));
+    HMM_CUDA(cudaMemsetAsync(p.nzmask, 0, sizeof(uint32_t) * (size_t)C * ((p.T + 31) / 32), st));
+    HMM_CUDA(cudaMemsetAsync(p.counters, 0, sizeof(int) * (size_t)C * 4, st));
+    HMM_CUDA(cudaMemsetAsync(p.sm_slots, 0, sizeof(int) * 256, st));
+    HMM_CUDA(cudaMemsetAsync(p.Pfin, 0, sizeof(double) * (size_t)C * p.RL.N * RING_Q, st));
+    impl->variant.forward(p, hmdl.data(), C, st, ttop);
+}
 void VitPlan::verify_fwd(cudaStream_t st) { impl->variant.verify_fwd(*p_, C, st); }
 void VitPlan::trace(cudaStream_t st) { impl->variant.trace(*p_, C, st); }
 void VitPlan::verify_trace(cudaStream_t st) { impl->variant.verify_trace(*p_, C, st); }

@@ -98,8 +98,11 @@ class Shard:
             v = np.ascontiguousarray(v, dtype=np.float64)
             check(lib().hmm_vshard_fwd_boundary_set(self._h, _p(v), i32(0)))
 
-    def fwd_verify(self) -> int:
+    def fwd_verify(self, count: bool = True) -> int:
         self._dev()
+        if not count:  # asynchronous: no read-back
+            check(lib().hmm_vshard_fwd_verify(self._h, None))
+            return 0
         n = i32(0)
         check(lib().hmm_vshard_fwd_verify(self._h, C.byref(n)))
         return int(n.value)
@@ -125,11 +128,21 @@ class Shard:
             vv = i64(int(v))
             check(lib().hmm_vshard_trace_boundary_set(self._h, C.byref(vv), i32(0)))
 
-    def trace_verify(self) -> int:
+    def trace_verify(self, count: bool = True) -> int:
         self._dev()
+        if not count:
+            check(lib().hmm_vshard_trace_verify(self._h, None))
+            return 0
         n = i32(0)
         check(lib().hmm_vshard_trace_verify(self._h, C.byref(n)))
         return int(n.value)
+
+    def repairs(self):
+        """(forward, traceback) chunks repaired since the last forward()."""
+        self._dev()
+        f, b = i32(0), i32(0)
+        check(lib().hmm_vshard_repairs(self._h, C.byref(f), C.byref(b)))
+        return int(f.value), int(b.value)
 
     def finish(self, x_out=None, x_ptr=None, want_ll=True):
         self._dev()

@@ -64,6 +64,10 @@ const char *hmm_last_error(void);   /* thread-local, never NULL */
 int hmm_device_count(void);         /* number of CUDA devices, 0 if none */
 int hmm_set_device(int device);     /* device used by subsequent calls from this thread */
 int hmm_get_device(void);
+/* Run the calling thread's subsequent work on `cuda_stream` (a cudaStream_t owned by the caller, e.g.
+ * torch.cuda.current_stream().cuda_stream) so that it is stream-ordered with the caller's own kernels
+ * and NCCL collectives; NULL restores the library's private stream. */
+int hmm_set_stream(void *cuda_stream);
 
 /* Tunables of the ring engine (0 keeps the default): chunk length and
  * speculative warm-up / look-ahead, in samples (rounded to multiples of 256). */
@@ -122,8 +126,10 @@ int hmm_viterbi_dev_f64(const double *y_dev, int64_t T, int32_t C, const int16_t
  *          -> trace -> [send trace boundary to r-1 / set from r+1] -> trace_verify (repeat likewise)
  *          -> finish (x of the main span, partial ll to be summed over ranks) -> destroy
  * y_local is a DEVICE pointer unless y_is_host != 0 (then it is copied once).  Boundary buffers
- * are device pointers when *_is_device != 0, host pointers otherwise.  Single channel, ring
- * models only.
+ * are device pointers when *_is_device != 0 (then get/set are asynchronous on the library's
+ * stream, see hmm_set_stream), host pointers otherwise.  fwd_verify / trace_verify with a NULL
+ * n_repaired do not synchronise; hmm_vshard_repairs reads both counters afterwards.  A handle can
+ * be re-run (forward ... finish) any number of times.  Single channel, ring models only.
  */
 typedef struct hmm_vshard hmm_vshard;
 int hmm_vshard_chunking(int64_t T_global, int32_t n_ranks, int32_t N, int32_t K, int64_t *chunk_len_out,
@@ -142,6 +148,7 @@ int hmm_vshard_trace_boundary_get(hmm_vshard *h, int64_t *out, int32_t out_is_de
 int hmm_vshard_trace_boundary_set(hmm_vshard *h, const int64_t *in, int32_t in_is_device); /* at main_end   <- rank r+1 */
 int hmm_vshard_trace_verify(hmm_vshard *h, int32_t *n_repaired);
 int hmm_vshard_finish(hmm_vshard *h, int16_t *x_main_out, int32_t x_is_device, double *ll_partial_out);
+int hmm_vshard_repairs(hmm_vshard *h, int32_t *fwd_repaired, int32_t *trace_repaired); /* counters since forward */
 int hmm_vshard_destroy(hmm_vshard *h);
 
 /* ---- Baum-Welch ---------------------------------------------------------- */
