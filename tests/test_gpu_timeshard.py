@@ -34,12 +34,3 @@ def test_time_sharded_dense_spiking_repairs_across_shards(hm, O, case_factory):
     x_ref, ll_ref = O.viterbi(S, lA, mu, sig)
     x, ll, info = hm.viterbi_time_sharded(S, lA, mu, sig, 5, chunk_len=1024, warmup=256, return_info=True)
     assert np.array_equal(x, x_ref) and abs(ll - ll_ref) <= 1e-9 * abs(ll_ref)
-
-
-def test_shard_plan(hm):
-    plan = hm.timeshard.shard_plan(108_000_000, 8, 7680)
-    assert plan[0][0] == 0 and plan[0][2] == 0 and plan[-1][3] == 108_000_000 and plan[-1][1] == 108_000_000
-    for (lb, le, mb, me), (lb2, le2, mb2, me2) in zip(plan, plan[1:]):
-        assert me == mb2 and lb2 == mb2 - 7680 and le == me + 7680 and mb % 7680 == 0
-    with pytest.raises(ValueError):
-        hm.timeshard.shard_plan(10_000, 8, 4096)

@@ -38,6 +38,18 @@ def test_shard_time(hm):
     assert spans[0][2] == 0 and spans[-1][3] == T
 
 
+def test_time_shard_plan(hm):
+    """Config 5 style time sharding: whole chunks per shard, one ghost chunk on either side."""
+    plan = hm.timeshard.shard_plan(108_000_000, 8, 7680)
+    assert plan[0][0] == 0 and plan[0][2] == 0 and plan[-1][3] == 108_000_000 and plan[-1][1] == 108_000_000
+    for (lb, le, mb, me), (lb2, le2, mb2, me2) in zip(plan, plan[1:]):
+        assert me == mb2 and lb2 == mb2 - 7680 and le == me + 7680 and mb % 7680 == 0
+    sizes = [me - mb for _, _, mb, me in plan]
+    assert max(sizes) - min(sizes) <= 7680
+    with pytest.raises(ValueError):
+        hm.timeshard.shard_plan(10_000, 8, 4096)
+
+
 WORKER = textwrap.dedent("""
     import os, sys, json
     import numpy as np
