@@ -45,7 +45,7 @@ def test_time_shard_plan(hm):
     for (lb, le, mb, me), (lb2, le2, mb2, me2) in zip(plan, plan[1:]):
         assert me == mb2 and lb2 == mb2 - 7680 and le == me + 7680 and mb % 7680 == 0
     sizes = [me - mb for _, _, mb, me in plan]
-    assert max(sizes) - min(sizes) <= 7680
+    assert max(sizes) - min(sizes) <= 2 * 7680  # one chunk of imbalance + the partial last chunk
     with pytest.raises(ValueError):
         hm.timeshard.shard_plan(10_000, 8, 4096)
 
