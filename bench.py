@@ -446,7 +446,14 @@ def bench_bw(hm, args, rank):
             lA = hm.StateMatrix.from_states(lA.states, pp, K, lp, False)
             launches += info["kernel_launches"]
         dt = time.perf_counter() - t0
+    peak, peak_src = measured_peak_hbm()
+    alg = 16.0 * (lA.nstates + 1) * T  # S twice + alpha written and read once, per iteration
+    ach = alg / (dt / iters) / 1e9
     return {"value": round(iters / dt, 3), "unit": "iters/s", "iterations": iters, "T": T,
+            "roofline": {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(ach / peak, 4), "traffic": None,
+                         "note": "algorithmic 16*(nstates+1) B/sample/iteration assumes alpha is materialised; the "
+                                 "semi-Markov E-step writes (3N+2)*8 = 88 B/sample instead, hence frac > 1"},
             "config": "BASELINE config 3: 30 kHz x 1 min, N=3 x K=60, 20 Baum-Welch iterations, X resident in HBM, "
                       "host StateMatrix rebuild each iteration inside the timed region",
             "ms_per_iter": round(dt / iters * 1e3, 3), "final_sigma": sigma, "final_loglik": ll,

@@ -4,6 +4,7 @@
 // without a device every compute entry point returns HMM_ENODEV.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -532,7 +533,11 @@ static int fb_host(bool backward, const double *V, int64_t T, const int16_t *sta
         double *o_dev = (double *)ws.get(backward ? Workspace::BETA : Workspace::ALPHA,
                                          sizeof(double) * (size_t)T * nstates);
         h2d(V_dev, V, sizeof(double) * (size_t)T, st);
-        faithful_fb_run(backward, V_dev, T, B.layout, B.blob_dev, B.models[0], o_dev, st);
+        const bool no_ring = getenv("HMMCUDA_DENSE_FB_FAITHFUL") && atoi(getenv("HMMCUDA_DENSE_FB_FAITHFUL"));
+        if (B.models[0].is_ring && ring_supported(B.models[0], T) && !no_ring)
+            ring_fb_dense_run(V_dev, T, B.models[0], backward ? nullptr : o_dev, backward ? o_dev : nullptr, st);
+        else
+            faithful_fb_run(backward, V_dev, T, B.layout, B.blob_dev, B.models[0], o_dev, st);
         d2h(out, o_dev, sizeof(double) * (size_t)T * nstates, st);
         HMM_CUDA(cudaStreamSynchronize(st));
     });

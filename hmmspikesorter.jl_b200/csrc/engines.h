@@ -87,6 +87,9 @@ struct EmResult {
     double sigma = 0, loglik = 0;
 };
 void ring_em_run(const double *X_dev, int64_t T, const HostModel &M, EmResult &out, cudaStream_t st, hmm_info *info);
+// dense alpha and/or beta [nstates x T] (device pointers, nullable) from the semi-Markov engine
+void ring_fb_dense_run(const double *X_dev, int64_t T, const HostModel &M, double *alpha_dev, double *beta_dev,
+                       cudaStream_t st);
 
 // ---- generic E/M pieces (update.cu) ----------------------------------------
 // update() on dense alpha/beta (device pointers), src/baumwelch.jl:205-309

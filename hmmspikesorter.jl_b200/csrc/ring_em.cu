@@ -780,8 +780,105 @@ __global__ void __launch_bounds__(1024) em_finalize(EmParams p) {
 }
 
 // ---------------------------------------------------------------------------
+// Dense alpha / beta on request (forward / backward of src/baumwelch.jl:25-51, 73-98 as
+// stand-alone calls): materialised from the semi-Markov quantities.
+//   alpha[noise, t]  = Z_t + lg_t                     Z_t = sum_{tau<=t} q_tau(noise) + t * w_nn
+//   alpha[(i,s), t]  = Z_t + lp_{t-s}(i) + sum_{r<=s} (a[i][r] y[t-s+r] + bw[i][r])
+//   beta[noise, t]   = (Z_{T-1} - Z_t) + lh_t
+//   beta[(i,s), t]   = (Z_{T-1} - Z_t) + le_{t-s+L-1}(i) + sum_{r>s} (a[i][r] y[t-s+r] + bw[i][r])
+// One thread per chain entry time t0 walks its chain and writes one column entry per step.
+// ---------------------------------------------------------------------------
+constexpr int ZS_ITEMS = 16;  // samples per thread in the Z prefix scan (256 threads -> 4096 per block)
+
+__global__ void __launch_bounds__(256) fb_zscan(EmParams p, double *Zs, double *bsum) {
+    __shared__ double wsum[8];
+    const double *sc = p.model + p.RL.scal;
+    const double w_nn = sc[0], c_emit = sc[1], two_s2 = sc[2], m0 = sc[3];
+    const int64_t base = ((int64_t)blockIdx.x * 256 + threadIdx.x) * ZS_ITEMS;
+    double v[ZS_ITEMS];
+    double loc = 0.0;
+#pragma unroll
+    for (int k = 0; k < ZS_ITEMS; k++) {
+        const int64_t t = base + k;
+        double inc = 0.0;
+        if (t < p.T) {
+            const double dd = p.y[t] - m0;
+            inc = (c_emit - (dd * dd) / two_s2) + (t > 0 ? w_nn : 0.0);
+        }
+        loc += inc;
+        v[k] = loc;
+    }
+    const double incl = block_scan_256(loc, wsum);
+    const double off = incl - loc;
+#pragma unroll
+    for (int k = 0; k < ZS_ITEMS; k++)
+        if (base + k < p.T) Zs[base + k] = v[k] + off;
+    if (threadIdx.x == 255) bsum[blockIdx.x] = incl;
+}
+
+__global__ void fb_zscan_blocks(double *bsum, int nb) {  // exclusive scan of the block totals, in place
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double a = 0.0;
+        for (int b = 0; b < nb; b++) {
+            double v = bsum[b];
+            bsum[b] = a;
+            a += v;
+        }
+    }
+}
+
+__device__ __forceinline__ double zval(const double *Zs, const double *boff, int64_t t) {
+    return Zs[t] + boff[t / (256 * ZS_ITEMS)];
+}
+
+template <int N, bool BETA>
+__global__ void __launch_bounds__(128) fb_dense(EmParams p, const double *Zs, const double *boff, double *out) {
+    const RingLayout &RL = p.RL;
+    const int L = RL.L, NP = RL.NP, ns = p.ns;
+    const int64_t T = p.T;
+    const double *A = p.model + RL.A, *BW = p.model + RL.BW, *B0 = p.model + RL.B0;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - (L - 1);
+    if (t0 > T - 1) return;
+    const double ZT = zval(Zs, boff, T - 1);
+    auto chunk_of = [&](int64_t t) {
+        int c = (int)(t / p.Lc);
+        return c >= p.nchunks ? p.nchunks - 1 : c;
+    };
+    if (t0 >= 0) {  // noise row
+        const int c = chunk_of(t0);
+        const double z = zval(Zs, boff, t0);
+        out[(size_t)ns * t0] = BETA ? (ZT - z) + p.LH[t0] + p.lambda[c] : z + p.LG[t0] + p.kappa[c];
+    }
+    const int r_lo = t0 < 0 ? (int)(-t0) : 0;                        // first phase with a sample
+    const int r_hi = (t0 + L - 1 <= T - 1) ? L - 1 : (int)(T - 1 - t0);  // last phase with a sample
+#pragma unroll 1
+    for (int i = 0; i < N; i++) {
+        if (!BETA) {
+            double acc = t0 >= 0 ? (p.LQ[(size_t)i * T + t0] - p.Fg[(size_t)i * T + t0]) + p.kappa[chunk_of(t0)] : 0.0;
+            for (int r = r_lo; r <= r_hi; r++) {
+                const int64_t t = t0 + r;
+                // a chain already running at t = 0 has no transition INTO its first sample
+                const double bw = (t0 < 0 && r == r_lo) ? B0[r * NP + i] : BW[r * NP + i];
+                acc += fma(A[r * NP + i], p.y[t], bw);
+                out[(size_t)ns * t + 1 + i * L + r] = zval(Zs, boff, t) + acc;
+            }
+        } else {
+            const int64_t te = t0 + L - 1;
+            double acc = te <= T - 1 ? p.LE[(size_t)i * T + te] + p.lambda[chunk_of(te)] : 0.0;
+            for (int r = r_hi; r >= r_lo; r--) {
+                const int64_t t = t0 + r;
+                out[(size_t)ns * t + 1 + i * L + r] = (ZT - zval(Zs, boff, t)) + acc;
+                acc += fma(A[r * NP + i], p.y[t], BW[r * NP + i]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// mode: 0 = full E/M step; 1 = forward quantities only; 2 = forward + backward quantities
 template <int N, int R>
-static void em_launch(EmParams &p, cudaStream_t st, hmm_info *info, Timer &ttop) {
+static void em_launch(EmParams &p, cudaStream_t st, hmm_info *info, Timer &ttop, int mode, double *alpha_out,
+                      double *beta_out, double *Zs, double *bsum) {
     constexpr int WPB = 4;
     const size_t mdl_d = (p.RL.hot + 1) & ~1;
     const size_t sm_fwd = sizeof(double) * (mdl_d + (size_t)WPB * EmWarpSmem<N, R>::DOUBLES);
@@ -801,18 +898,33 @@ static void em_launch(EmParams &p, cudaStream_t st, hmm_info *info, Timer &ttop)
     em_check<<<gchk, 128, 0, st>>>(p, 0);
     em_repair_fwd<N, R><<<1, 32, sm_frep, st>>>(p);
     em_offsets<N><<<1, 256, 0, st>>>(p, 0);
-    em_backward<N><<<gridc, 32 * WPB, sm_bwd, st>>>(p);
-    em_check<<<gchk, 128, 0, st>>>(p, 1);
-    em_repair_bwd<N><<<1, 32, sm_brep, st>>>(p);
-    em_offsets<N><<<1, 256, 0, st>>>(p, 1);
-    em_stats<N><<<p.nblk, 32 * WPB, sm_stats, st>>>(p);
-    HMM_CUDA(cudaFuncSetAttribute(em_finalize<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fin));
-    em_finalize<N><<<1, 1024, sm_fin, st>>>(p);
+    if (info) info->kernel_launches += 4;
+    if (mode != 1) {
+        em_backward<N><<<gridc, 32 * WPB, sm_bwd, st>>>(p);
+        em_check<<<gchk, 128, 0, st>>>(p, 1);
+        em_repair_bwd<N><<<1, 32, sm_brep, st>>>(p);
+        em_offsets<N><<<1, 256, 0, st>>>(p, 1);
+        if (info) info->kernel_launches += 4;
+    }
+    if (mode == 0) {
+        em_stats<N><<<p.nblk, 32 * WPB, sm_stats, st>>>(p);
+        HMM_CUDA(cudaFuncSetAttribute(em_finalize<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fin));
+        em_finalize<N><<<1, 1024, sm_fin, st>>>(p);
+        if (info) info->kernel_launches += 2;
+    } else {
+        const int nb = (int)((p.T + 256 * ZS_ITEMS - 1) / (256 * ZS_ITEMS));
+        fb_zscan<<<nb, 256, 0, st>>>(p, Zs, bsum);
+        fb_zscan_blocks<<<1, 32, 0, st>>>(bsum, nb);
+        const int64_t nthreads = p.T + p.RL.L - 1;
+        const int g = (int)((nthreads + 127) / 128);
+        if (alpha_out) fb_dense<N, false><<<g, 128, 0, st>>>(p, Zs, bsum, alpha_out);
+        if (beta_out) fb_dense<N, true><<<g, 128, 0, st>>>(p, Zs, bsum, beta_out);
+    }
     HMM_CUDA(cudaGetLastError());
-    if (info) info->kernel_launches += 10;
 }
 
-void ring_em_run(const double *X_dev, int64_t T, const HostModel &M, EmResult &out, cudaStream_t st, hmm_info *info) {
+static void ring_em_core(const double *X_dev, int64_t T, const HostModel &M, EmResult *outp, cudaStream_t st,
+                        hmm_info *info, int mode, double *alpha_out, double *beta_out) {
     Workspace &ws = workspace();
     const int N = M.N, L = M.K - 1, K = M.K, ns = M.nstates;
     const int R = (N <= 4) ? 8 : 4, SW = 32 * R;
@@ -894,17 +1006,28 @@ void ring_em_run(const double *X_dev, int64_t T, const HostModel &M, EmResult &o
     p.pstride = pstride;
     p.out = (double *)(base + o_out);
 
+    double *Zs = nullptr, *bsum = nullptr;
+    if (mode != 0) {
+        const size_t nb = (size_t)((T + 256 * ZS_ITEMS - 1) / (256 * ZS_ITEMS));
+        Zs = (double *)ws.get(Workspace::PSCORE, sizeof(double) * ((size_t)T + nb + 8));
+        bsum = Zs + T;
+    }
     Timer ttop(st);
     switch (N) {
-        case 1: em_launch<1, 8>(p, st, info, ttop); break;
-        case 2: em_launch<2, 8>(p, st, info, ttop); break;
-        case 3: em_launch<3, 8>(p, st, info, ttop); break;
-        case 4: em_launch<4, 8>(p, st, info, ttop); break;
-        case 5: em_launch<5, 4>(p, st, info, ttop); break;
-        case 6: em_launch<6, 4>(p, st, info, ttop); break;
-        case 7: em_launch<7, 4>(p, st, info, ttop); break;
+        case 1: em_launch<1, 8>(p, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
+        case 2: em_launch<2, 8>(p, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
+        case 3: em_launch<3, 8>(p, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
+        case 4: em_launch<4, 8>(p, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
+        case 5: em_launch<5, 4>(p, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
+        case 6: em_launch<6, 4>(p, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
+        case 7: em_launch<7, 4>(p, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
         default: fail(HMM_EUNSUPPORTED, "ring E/M engine supports 1..%d neurons", RING_MAX_N);
     }
+    if (mode != 0) {
+        HMM_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+    EmResult &out = *outp;
     std::vector<double> h(nout);
     int cnt[4] = {0, 0, 0, 0};
     HMM_CUDA(cudaMemcpyAsync(h.data(), p.out, sizeof(double) * nout, cudaMemcpyDeviceToHost, st));
@@ -921,6 +1044,15 @@ void ring_em_run(const double *X_dev, int64_t T, const HostModel &M, EmResult &o
         info->bwd_repaired = cnt[1];
         info->top_kernel_ms = ttop.ms();
     }
+}
+
+void ring_em_run(const double *X_dev, int64_t T, const HostModel &M, EmResult &out, cudaStream_t st, hmm_info *info) {
+    ring_em_core(X_dev, T, M, &out, st, info, 0, nullptr, nullptr);
+}
+
+void ring_fb_dense_run(const double *X_dev, int64_t T, const HostModel &M, double *alpha_dev, double *beta_dev,
+                       cudaStream_t st) {
+    ring_em_core(X_dev, T, M, nullptr, st, nullptr, beta_dev ? 2 : 1, alpha_dev, beta_dev);
 }
 
 }  // namespace hmm

@@ -1147,7 +1147,9 @@ static VitVariant pick_variant(int N, int LP, bool const_ok) {
     switch (N) {
         case 1: return pick_lp<1, 8>(LP, const_ok);
         case 2: return pick_lp<2, 8>(LP, const_ok);
-        case 3: return pick_lp<3, 8>(LP, const_ok);
+        case 3:
+            if (const_ok && LP == 64 && getenv("HMMCUDA_R4") && atoi(getenv("HMMCUDA_R4"))) return make_variant<3, 4, 60>();
+            return pick_lp<3, 8>(LP, const_ok);
         case 4: return pick_lp<4, 8>(LP, const_ok);
         case 5: return pick_lp<5, 4>(LP, const_ok);
         case 6: return make_variant<6, 4, 0>();

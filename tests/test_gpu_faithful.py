@@ -106,15 +106,24 @@ def test_viterbi_batch_faithful(hm, O, case_factory):
         assert np.array_equal(x[:, c], xo) and ll[c] == llo
 
 
-@pytest.mark.parametrize("N,K,T,seed", [(3, 60, 4000, 3), (2, 10, 1500, 1)])
+@pytest.mark.parametrize("N,K,T,seed", [(3, 60, 4000, 3), (2, 10, 1500, 1), (4, 48, 6000, 4), (3, 20, 3000, 5),
+                                        (5, 60, 2500, 6), (1, 97, 5000, 7)])
 def test_forward_backward_dense(hm, O, case_factory, N, K, T, seed):
-    S, lA, mu, sig = case_factory(N, K, T, seed)
+    """Dense alpha / beta (src/baumwelch.jl:25-51, 73-98).  Ring models with T >= 2048 are
+    materialised from the semi-Markov engine, everything else by the sequential kernel."""
+    S, lA, mu, sig = case_factory(N, K, T, seed, rate_scale=min(3.0, 60.0 / K))
+    mu = np.asfortranarray(0.8 * mu)  # a mis-specified model makes the posteriors less trivial
     a, b = hm.forward(S, lA, mu, sig), hm.backward(S, lA, mu, sig)
     ao, bo = O.forward(S, lA, mu, sig), O.backward(S, lA, mu, sig)
     assert a.shape == (lA.nstates, T) and a.flags.f_contiguous
-    assert np.allclose(a, ao, rtol=1e-12, atol=1e-10)
-    assert np.allclose(b, bo, rtol=1e-12, atol=1e-10)
+    assert np.allclose(a, ao, rtol=1e-12, atol=1e-9)
+    assert np.allclose(b, bo, rtol=1e-12, atol=1e-9)
     assert np.all(b[:, -1] == 0.0)
+    # update() fed with these dense arrays reproduces the oracle's update
+    lpo, ppo, muo, so = O.update(ao, bo, lA, mu, sig, S)
+    mu2 = mu.copy(order="F")
+    lA2, _, s2 = hm.update(a, b, lA, mu2, sig, S)
+    assert np.abs(mu2 - muo).max() < 1e-8 and abs(s2 - so) < 1e-9
 
 
 def test_reconstruct_and_unroll(hm, O, case_factory):
