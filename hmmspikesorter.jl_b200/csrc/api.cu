@@ -13,6 +13,8 @@
 
 using namespace hmm;
 
+static constexpr int64_t RING_Q_MIN = 128;  // the ring engine's look-back length
+
 static thread_local std::string g_err = "";
 static std::mutex g_entry;  // the library serialises concurrent entry (SURVEY 8b "Threading")
 
@@ -170,6 +172,182 @@ void viterbi_core(const double *y_dev, int64_t T, int C, BatchModels &B, int16_t
     if (ll_host) d2h(ll_host, ll_dev, sizeof(double) * C, st);
 }
 
+// traceback state codes carry a chain entry time (code = 8*t0 + neuron, -1 = noise)
+__global__ void shift_state_kernel(const long long *src, long long *dst, long long delta) {
+    long long v = *src;
+    *dst = v >= 0 ? v + delta : v;
+}
+
+// ---------------------------------------------------------------------------
+// Host-pointer decode as a software pipeline on one GPU: the recording is cut into
+// segments (time shards with ghost chunks, exactly the hmm_vshard_* mechanism); segment
+// k is decoded while segment k+1 is still crossing PCIe, and its part of x goes back
+// while later segments are decoded.  Boundaries are verified left to right (forward)
+// and against the right neighbour (traceback), so the result is the exact decode.
+// ---------------------------------------------------------------------------
+struct PipeSeg {
+    int64_t lb, le, mb, me;  // local span [lb, le) incl. ghosts, main span [mb, me)
+    int c_main0, c_main1;
+    std::unique_ptr<VitPlan> plan;
+    cudaEvent_t ev_copy = nullptr, ev_x = nullptr;
+};
+
+bool pipeline_wanted(const HostModel &M0, int64_t T, int C) {
+    if (getenv("HMMCUDA_NO_PIPELINE") && atoi(getenv("HMMCUDA_NO_PIPELINE"))) return false;
+    return C == 1 && T >= (int64_t)1 << 22 && ring_config().chunk_len == 0 && ring_config().warmup == 0 && M0.is_ring;
+}
+
+void viterbi_host_pipelined(const double *y, int64_t T, BatchModels &B, int16_t *x_out, double *ll_out, hmm_info *info) {
+    Workspace &ws = workspace();
+    cudaStream_t sc = main_stream(), sh = copy_stream(), sd = out_stream();
+    const HostModel &M0 = B.models[0];
+    const int L = M0.K - 1;
+    int S = 8;
+    if (const char *e = getenv("HMMCUDA_PIPE_SEGMENTS")) S = std::max(2, atoi(e));
+    int dev = 0, sms = 148;
+    HMM_CUDA(cudaGetDevice(&dev));
+    HMM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // one wave of chunks per segment; short warm-up (every boundary is verified anyway)
+    const int64_t W = 256;
+    int64_t Lc = (T / S + (int64_t)sms * 16 - 1) / ((int64_t)sms * 16);
+    Lc = ((Lc + 255) / 256) * 256;
+    if (Lc < 1024) Lc = 1024;
+    if (Lc < ((L + 32 + 255) / 256) * 256 + W) Lc = ((L + 32 + 255) / 256) * 256 + W;
+    const int64_t nchunks_tot = (T + Lc - 1) / Lc;
+    if (nchunks_tot < 2 * S) S = (int)std::max<int64_t>(1, nchunks_tot / 2);
+    std::vector<PipeSeg> seg(S);
+    {
+        int64_t q = nchunks_tot / S, r = nchunks_tot % S, c0 = 0;
+        for (int k = 0; k < S; k++) {
+            int64_t c1 = c0 + q + (k < r ? 1 : 0);
+            seg[k].mb = c0 * Lc;
+            seg[k].me = std::min<int64_t>(T, c1 * Lc);
+            seg[k].lb = std::max<int64_t>(0, seg[k].mb - Lc);
+            seg[k].le = std::min<int64_t>(T, seg[k].me + Lc);
+            c0 = c1;
+        }
+        // a last main span shorter than the engine's look-back joins the previous segment
+        if (S > 1 && T - seg[S - 1].mb < 2 * RING_Q_MIN) {
+            seg[S - 2].me = T;
+            seg[S - 2].le = T;
+            seg.pop_back();
+            S--;
+        }
+    }
+    double *y_dev = (double *)ws.get(Workspace::Y, sizeof(double) * (size_t)T);
+    int16_t *x_dev = (int16_t *)ws.get(Workspace::X, sizeof(int16_t) * (size_t)T);
+    size_t arena_cap = 1 << 20;
+    const int bvec = 1 + M0.N * L;
+    for (auto &g : seg) {
+        const size_t Tl = (size_t)(g.le - g.lb), nch = (size_t)((Tl + Lc - 1) / Lc);
+        arena_cap += Tl * 4 + Tl / 8 + 64 + nch * (2 * 8 * (size_t)bvec + 64) + (size_t)M0.nstates * (L + 1) * 10 + (256 << 10);
+    }
+    arena_cap += arena_cap / 8;
+    char *arena = (char *)ws.get(Workspace::TRACE, arena_cap);
+    double *ll_dev = (double *)ws.get(Workspace::SCRATCH, sizeof(double) * 1024);
+    size_t arena_off = 0;
+    for (auto &g : seg) {
+        HMM_CUDA(cudaEventCreateWithFlags(&g.ev_copy, cudaEventDisableTiming));
+        HMM_CUDA(cudaEventCreateWithFlags(&g.ev_x, cudaEventDisableTiming));
+    }
+    auto cleanup = [&] {
+        for (auto &g : seg) {
+            if (g.ev_copy) cudaEventDestroy(g.ev_copy);
+            if (g.ev_x) cudaEventDestroy(g.ev_x);
+        }
+    };
+    try {
+        // copy boundaries are shifted right by one chunk so that segment k's ghost arrives with it
+        auto copy_end = [&](int k) { return k == S - 1 ? T : std::min<int64_t>(T, seg[k].me + Lc); };
+        auto issue_copy = [&](int k) {
+            const int64_t a = k == 0 ? 0 : copy_end(k - 1), b = copy_end(k);
+            if (b > a) HMM_CUDA(cudaMemcpyAsync(y_dev + a, y + a, sizeof(double) * (size_t)(b - a), cudaMemcpyHostToDevice, sh));
+            HMM_CUDA(cudaEventRecord(seg[k].ev_copy, sh));
+        };
+        auto issue_x = [&](int k) {
+            HMM_CUDA(cudaStreamWaitEvent(sd, seg[k].ev_x, 0));
+            HMM_CUDA(cudaMemcpyAsync(x_out + seg[k].mb, x_dev + seg[k].mb, sizeof(int16_t) * (size_t)(seg[k].me - seg[k].mb),
+                                     cudaMemcpyDeviceToHost, sd));
+        };
+        auto link_trace = [&](int k) {  // own_start of segment k's first main chunk -> segment k-1's right ghost
+            shift_state_kernel<<<1, 1, 0, sc>>>(seg[k].plan->own_start_ptr(seg[k].c_main0),
+                                                seg[k - 1].plan->own_start_ptr(seg[k - 1].c_main1),
+                                                8 * (long long)(seg[k].lb - seg[k - 1].lb));
+            HMM_CUDA(cudaGetLastError());
+        };
+        issue_copy(0);
+        for (int k = 0; k < S; k++) {
+            PipeSeg &g = seg[k];
+            const bool first = k == 0, last = k == S - 1;
+            g.plan.reset(new VitPlan);
+            g.plan->use_arena(arena + arena_off, arena_cap - arena_off);
+            const int64_t Tl = g.le - g.lb;
+            g.plan->build(y_dev + g.lb, Tl, Tl, 1, B.models, B.layout, B.blob_dev, x_dev + g.lb, Tl, Lc, W, first, last, sc);
+            arena_off += (g.plan->arena_bytes_used() + 255) & ~size_t(255);
+            g.plan->set_x_window(g.mb - g.lb, g.me - g.lb);
+            g.c_main0 = (int)((g.mb - g.lb) / Lc);
+            g.c_main1 = last ? g.plan->nchunks() : (int)((g.me - g.lb) / Lc);
+            HMM_CUDA(cudaStreamWaitEvent(sc, g.ev_copy, 0));
+            g.plan->forward(sc, nullptr);
+            if (!first)  // the neighbour's true end vector replaces the left ghost chunk's speculative one
+                HMM_CUDA(cudaMemcpyAsync(g.plan->eb_ptr(g.c_main0 - 1), seg[k - 1].plan->eb_ptr(seg[k - 1].c_main1 - 1),
+                                         sizeof(double) * bvec, cudaMemcpyDeviceToDevice, sc));
+            g.plan->verify_fwd(sc);
+            g.plan->trace(sc);
+            if (!first) {
+                link_trace(k);
+                seg[k - 1].plan->verify_trace(sc);
+                HMM_CUDA(cudaEventRecord(seg[k - 1].ev_x, sc));
+            }
+            if (info) info->kernel_launches += first ? 8 : 9;
+            if (!last) issue_copy(k + 1);
+            if (!first) issue_x(k - 1);
+        }
+        seg[S - 1].plan->verify_trace(sc);
+        HMM_CUDA(cudaEventRecord(seg[S - 1].ev_x, sc));
+        issue_x(S - 1);
+        // traceback repairs inside a segment can, very rarely, move its own start state after the left
+        // neighbour was already verified against it: detect and redo the chain right to left
+        int tot_f = 0, tot_b = 0, nch = 0;
+        for (int k = 0; k < S; k++) {
+            int f = 0, b = 0;
+            seg[k].plan->read_counters(sc, &f, &b);
+            tot_f += f;
+            tot_b += b;
+            nch += seg[k].c_main1 - seg[k].c_main0;
+        }
+        if (tot_b > 0) {
+            HMM_CUDA(cudaStreamSynchronize(sd));
+            for (int k = S - 1; k >= 1; k--) {
+                link_trace(k);
+                seg[k - 1].plan->verify_trace(sc);
+            }
+            HMM_CUDA(cudaMemcpyAsync(x_out, x_dev, sizeof(int16_t) * (size_t)T, cudaMemcpyDeviceToHost, sc));
+        }
+        if (ll_out) {
+            ring_path_ll_run(y_dev, T, B.layout, B.blob_dev, M0, x_dev, ll_dev, ll_dev + 8, sc);
+            HMM_CUDA(cudaMemcpyAsync(ll_out, ll_dev, sizeof(double), cudaMemcpyDeviceToHost, sc));
+            if (info) info->kernel_launches += 2;
+        }
+        HMM_CUDA(cudaStreamSynchronize(sc));
+        HMM_CUDA(cudaStreamSynchronize(sd));
+        HMM_CUDA(cudaStreamSynchronize(sh));
+        if (info) {
+            info->engine = HMM_MODE_RING;
+            info->n_chunks = nch;
+            info->fwd_repaired = tot_f;
+            info->bwd_repaired = tot_b;
+        }
+    } catch (...) {
+        cudaStreamSynchronize(sc);
+        cudaStreamSynchronize(sd);
+        cudaStreamSynchronize(sh);
+        cleanup();
+        throw;
+    }
+    cleanup();
+}
+
 int viterbi_host(const double *y, int64_t T, int C, const int16_t *states, int states_shared, int N, int K,
                  int nstates, const hmm_trans *tr, int64_t ntrans, const double *mu, const double *sigma,
                  int16_t *x_out, double *ll_out, int16_t *T2_out, double *T1_out, int mode, hmm_info *info) {
@@ -185,6 +363,13 @@ int viterbi_host(const double *y, int64_t T, int C, const int16_t *states, int s
         tall.start();
         BatchModels B;
         build_models(C, states, states_shared, N, K, nstates, tr, ntrans, mu, sigma, B, st);
+        if (!T1_out && !T2_out && mode != HMM_MODE_FAITHFUL && ring_supported(B.models[0], T) &&
+            pipeline_wanted(B.models[0], T, C)) {
+            viterbi_host_pipelined(y, T, B, x_out, ll_out, info);
+            tall.stop();
+            if (info) info->device_ms = tall.ms();
+            return;
+        }
         double *y_dev = (double *)ws.get(Workspace::Y, sizeof(double) * (size_t)T * C);
         int16_t *x_dev = (int16_t *)ws.get(Workspace::X, sizeof(int16_t) * (size_t)T * C);
         double *T1_dev = T1_out ? (double *)ws.get(Workspace::T1, sizeof(double) * (size_t)T * nstates) : nullptr;
@@ -256,12 +441,6 @@ int hmm_viterbi_dev_f64(const double *y_dev, int64_t T, int32_t C, const int16_t
 // ---------------------------------------------------------------------------
 // time-sharded decode of one recording (config 5)
 // ---------------------------------------------------------------------------
-// traceback state codes carry a chain entry time (code = 8*t0 + neuron, -1 = noise)
-__global__ void shift_state_kernel(const long long *src, long long *dst, long long delta) {
-    long long v = *src;
-    *dst = v >= 0 ? v + delta : v;
-}
-
 struct hmm_vshard {
     VitPlan plan;
     std::vector<HostModel> models;

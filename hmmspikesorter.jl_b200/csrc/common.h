@@ -55,7 +55,8 @@ class Workspace {
 
 Workspace &workspace();      // per host thread
 cudaStream_t main_stream();  // per host thread, non-blocking stream
-cudaStream_t copy_stream();
+cudaStream_t copy_stream();  // host -> device copies of the pipelined decode
+cudaStream_t out_stream();   // device -> host copies of the pipelined decode
 void set_external_stream(cudaStream_t s, bool use);  // per host thread
 
 // ---------------------------------------------------------------------------

@@ -63,6 +63,10 @@ class VitPlan {
     double *eb_ptr(int chunk);              // device pointer: true end-boundary vector of `chunk` (channel 0)
     long long *own_start_ptr(int chunk);    // device pointer: traceback state at the start of `chunk`
     void *alloc(int slot, size_t bytes);
+    void use_arena(char *base, size_t cap);  // allocate everything out of this device buffer
+    size_t arena_bytes_used() const;
+    void set_x_window(int64_t lo, int64_t hi);  // local steps whose x may be written
+    int *counters_ptr();
 
   private:
     struct Impl;
@@ -75,7 +79,11 @@ class VitPlan {
     const char *blob_dev = nullptr;
     double *part = nullptr;
     int C = 1;
+    char *arena_base = nullptr;
+    size_t arena_cap = 0, arena_used = 0;
 };
+void ring_path_ll_run(const double *y_dev, int64_t T, const FaithfulLayout &FL, const char *blob_dev, const HostModel &M0,
+                      const int16_t *x_dev, double *ll_dev, double *part, cudaStream_t st);
 // Default chunk length / warm-up for a recording of T_total samples decoded on n_gpus GPUs.
 int ring_default_chunking(const HostModel &M0, int64_t T_total, int C, int n_gpus, int64_t *Lc_out, int64_t *W_out);
 

@@ -54,7 +54,7 @@ Workspace &workspace() {
 }
 
 struct Streams {
-    cudaStream_t main = nullptr, copy = nullptr;
+    cudaStream_t main = nullptr, copy = nullptr, out = nullptr;
     int dev = -1;
 };
 static thread_local cudaStream_t g_external = nullptr;
@@ -68,17 +68,19 @@ static Streams &streams() {
     int dev = 0;
     HMM_CUDA(cudaGetDevice(&dev));
     if (st.dev != dev) {
-        st.main = st.copy = nullptr;  // streams of another device are simply abandoned
+        st.main = st.copy = st.out = nullptr;  // streams of another device are simply abandoned
         st.dev = dev;
     }
     if (!st.main) {
         HMM_CUDA(cudaStreamCreateWithFlags(&st.main, cudaStreamNonBlocking));
         HMM_CUDA(cudaStreamCreateWithFlags(&st.copy, cudaStreamNonBlocking));
+        HMM_CUDA(cudaStreamCreateWithFlags(&st.out, cudaStreamNonBlocking));
     }
     return st;
 }
 cudaStream_t main_stream() { return g_use_external ? g_external : streams().main; }
 cudaStream_t copy_stream() { return streams().copy; }
+cudaStream_t out_stream() { return streams().out; }
 
 // ---------------------------------------------------------------------------
 // m[j] = sum_{l=1..N} mu[states[l,j], l] accumulated from 0.0 in neuron order

@@ -123,6 +123,7 @@ struct VitParams {
     int64_t x_stride;
     long long *own_start, *look_end;  // [C x nchunks] encoded states
     int *tr_flag;
+    int64_t x_lo, x_hi;    // x is written only for local steps in [x_lo, x_hi) (ghost chunks of a shard are not)
     int first_prologue;    // chunk 0 starts from the reference's initial condition (else: ghost chunk of a time shard)
     int last_true_end;     // the sequence really ends at T (else: ghost chunk; traceback starts speculatively)
     int debug_skip;        // debug: 1 = skip the recursion (time the FIR alone), 2 = skip the FIR
@@ -720,6 +721,8 @@ __device__ void trace_chunk(const VitParams &p, int ch, int c, int64_t tau_hi, l
         if (record_look && e <= b && e >= a) look = -1;
         if (s <= b && s >= a) own = -1;
         int64_t wa = a < s ? s : a, wb = b < e - 1 ? b : e - 1;
+        if (wa < p.x_lo) wa = p.x_lo;
+        if (wb > p.x_hi - 1) wb = p.x_hi - 1;
         for (int64_t t = wa + lane; t <= wb; t += 32) x[t] = 1;
     };
     auto emit_spike = [&](int64_t a, int64_t b, long long state) {
@@ -728,6 +731,8 @@ __device__ void trace_chunk(const VitParams &p, int ch, int c, int64_t tau_hi, l
         if (record_look && e <= b && e >= a) look = state;
         if (s <= b && s >= a) own = state;
         int64_t wa = a < s ? s : a, wb = b < e - 1 ? b : e - 1;
+        if (wa < p.x_lo) wa = p.x_lo;
+        if (wb > p.x_hi - 1) wb = p.x_hi - 1;
         for (int64_t t = wa + lane; t <= wb; t += 32) x[t] = (int16_t)(2 + i * L + (int)(t - t0));
     };
     while (cur >= lo) {
@@ -1174,6 +1179,12 @@ VitPlan::~VitPlan() {
 }
 
 void *VitPlan::alloc(int slot, size_t bytes) {
+    if (arena_base) {  // bump allocation out of a caller-provided device buffer
+        size_t o = (arena_used + 255) & ~size_t(255);
+        if (o + bytes > arena_cap) fail(HMM_ENOMEM, "decode arena too small (%zu + %zu > %zu)", o, bytes, arena_cap);
+        arena_used = o + bytes;
+        return arena_base + o;
+    }
     if (!own_memory) return workspace().get((Workspace::Slot)slot, bytes);
     void *q = nullptr;
     cudaError_t e = cudaMalloc(&q, bytes ? bytes : 16);
@@ -1288,6 +1299,8 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     p.look_end = (long long *)(base + o_look);
     p.tr_flag = (int *)(base + o_trflag);
     p.sm_slots = (int *)(base + o_slots);
+    p.x_lo = 0;
+    p.x_hi = T;
     p.first_prologue = first_prologue ? 1 : 0;
     p.last_true_end = last_true_end ? 1 : 0;
     part = (double *)(base + o_part);
@@ -1330,6 +1343,17 @@ void VitPlan::path_ll(cudaStream_t st, double *ll_dev, int64_t t_lo, int64_t t_h
     HMM_CUDA(cudaGetLastError());
 }
 
+void ring_path_ll_run(const double *y_dev, int64_t T, const FaithfulLayout &FL, const char *blob_dev, const HostModel &M0,
+                      const int16_t *x_dev, double *ll_dev, double *part /*>= 592 doubles*/, cudaStream_t st) {
+    const int nparts = 592;
+    const int ns = M0.nstates;
+    const size_t llsm = sizeof(double) * ((size_t)ns + M0.ntrans) + sizeof(int) * ((size_t)ns + 1 + M0.ntrans) + 16;
+    ring_path_ll_partial<<<dim3(nparts, 1), 256, llsm, st>>>(y_dev, T, T, blob_dev, FL.bytes, FL, ns, (int)M0.ntrans, x_dev,
+                                                             T, part, 0, T, 0, T);
+    ring_path_ll_final<<<1, 256, 0, st>>>(y_dev, T, T, blob_dev, FL.bytes, FL, x_dev, T, part, nparts, ll_dev, 1, T);
+    HMM_CUDA(cudaGetLastError());
+}
+
 void VitPlan::read_counters(cudaStream_t st, int *fwd_rep, int *bwd_rep) {
     VitParams &p = *p_;
     std::vector<int> cnt((size_t)C * 4);
@@ -1346,6 +1370,18 @@ void VitPlan::reset_counters(cudaStream_t st) {
     HMM_CUDA(cudaMemsetAsync(p_->counters, 0, sizeof(int) * (size_t)C * 4, st));
 }
 
+void VitPlan::use_arena(char *base, size_t cap) {
+    arena_base = base;
+    arena_cap = cap;
+    arena_used = 0;
+}
+size_t VitPlan::arena_bytes_used() const { return arena_used; }
+void VitPlan::set_x_window(int64_t lo, int64_t hi) {
+    p_->x_lo = lo;
+    p_->x_hi = hi;
+}
+
+int *VitPlan::counters_ptr() { return p_->counters; }
 int VitPlan::nchunks() const { return p_->nchunks; }
 int VitPlan::bvec() const { return p_->bvec; }
 double *VitPlan::eb_ptr(int chunk) { return p_->EB + (size_t)chunk * p_->bvec; }
