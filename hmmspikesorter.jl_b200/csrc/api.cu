@@ -372,6 +372,68 @@ int viterbi_host(const double *y, int64_t T, int C, const int16_t *states, int s
         }
         double *y_dev = (double *)ws.get(Workspace::Y, sizeof(double) * (size_t)T * C);
         int16_t *x_dev = (int16_t *)ws.get(Workspace::X, sizeof(int16_t) * (size_t)T * C);
+        {
+            // Many long channels (config 4): pipeline by channel -- channel c is decoded while channel
+            // c+1 crosses PCIe and channel c-1's x travels back.
+            bool all_ring = true;
+            for (auto &m : B.models) all_ring = all_ring && m.is_ring;
+            const bool no_pipe = getenv("HMMCUDA_NO_PIPELINE") && atoi(getenv("HMMCUDA_NO_PIPELINE"));
+            if (C > 1 && !T1_out && !T2_out && mode != HMM_MODE_FAITHFUL && all_ring && ring_supported(B.models[0], T) &&
+                T >= 262144 && !no_pipe) {
+                cudaStream_t sh = copy_stream(), sd = out_stream();
+                std::vector<cudaEvent_t> evc(C), evx(C);
+                for (int c = 0; c < C; c++) {
+                    HMM_CUDA(cudaEventCreateWithFlags(&evc[c], cudaEventDisableTiming));
+                    HMM_CUDA(cudaEventCreateWithFlags(&evx[c], cudaEventDisableTiming));
+                }
+                double *ll_dev = ll_out ? (double *)ws.get(Workspace::SCRATCH, sizeof(double) * C) : nullptr;
+                auto copy_in = [&](int c) {
+                    HMM_CUDA(cudaMemcpyAsync(y_dev + (size_t)c * T, y + (size_t)c * T, sizeof(double) * (size_t)T,
+                                             cudaMemcpyHostToDevice, sh));
+                    HMM_CUDA(cudaEventRecord(evc[c], sh));
+                };
+                auto copy_out = [&](int c) {
+                    HMM_CUDA(cudaStreamWaitEvent(sd, evx[c], 0));
+                    HMM_CUDA(cudaMemcpyAsync(x_out + (size_t)c * T, x_dev + (size_t)c * T, sizeof(int16_t) * (size_t)T,
+                                             cudaMemcpyDeviceToHost, sd));
+                };
+                try {
+                    copy_in(0);
+                    for (int c = 0; c < C; c++) {
+                        HMM_CUDA(cudaStreamWaitEvent(st, evc[c], 0));
+                        std::vector<HostModel> one(1, B.models[c]);
+                        ring_viterbi_run(y_dev + (size_t)c * T, T, T, 1, one, B.layout, B.blob_dev + (size_t)c * B.layout.bytes,
+                                         x_dev + (size_t)c * T, T, ll_dev ? ll_dev + c : nullptr, st, nullptr);
+                        HMM_CUDA(cudaEventRecord(evx[c], st));
+                        if (c + 1 < C) copy_in(c + 1);
+                        if (c >= 1) copy_out(c - 1);
+                    }
+                    copy_out(C - 1);
+                    if (ll_out) d2h(ll_out, ll_dev, sizeof(double) * C, st);
+                    tall.stop();
+                    HMM_CUDA(cudaStreamSynchronize(st));
+                    HMM_CUDA(cudaStreamSynchronize(sd));
+                    HMM_CUDA(cudaStreamSynchronize(sh));
+                } catch (...) {
+                    cudaDeviceSynchronize();
+                    for (int c = 0; c < C; c++) {
+                        cudaEventDestroy(evc[c]);
+                        cudaEventDestroy(evx[c]);
+                    }
+                    throw;
+                }
+                for (int c = 0; c < C; c++) {
+                    cudaEventDestroy(evc[c]);
+                    cudaEventDestroy(evx[c]);
+                }
+                if (info) {
+                    info->engine = HMM_MODE_RING;
+                    info->device_ms = tall.ms();
+                    info->kernel_launches = (int64_t)C * 10;
+                }
+                return;
+            }
+        }
         double *T1_dev = T1_out ? (double *)ws.get(Workspace::T1, sizeof(double) * (size_t)T * nstates) : nullptr;
         int16_t *T2_dev = T2_out ? (int16_t *)ws.get(Workspace::T2, sizeof(int16_t) * (size_t)T * nstates) : nullptr;
         h2d(y_dev, y, sizeof(double) * (size_t)T * C, st);

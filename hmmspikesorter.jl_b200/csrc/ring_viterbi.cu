@@ -126,10 +126,6 @@ struct VitParams {
     int64_t x_lo, x_hi;    // x is written only for local steps in [x_lo, x_hi) (ghost chunks of a shard are not)
     int first_prologue;    // chunk 0 starts from the reference's initial condition (else: ghost chunk of a time shard)
     int last_true_end;     // the sequence really ends at T (else: ghost chunk; traceback starts speculatively)
-    int debug_skip;        // debug: 1 = skip the recursion (time the FIR alone), 2 = skip the FIR
-    int *sm_slots;         // [256] per-SM CTA arrival counters (stagger)
-    int stagger_ns;        // start-up delay quantum that de-phases co-resident warps (FIR vs recursion)
-    int n_sm;
 };
 
 enum StartKind { START_PROLOGUE = 0, START_SPEC = 1, START_EXACT = 2 };
@@ -388,13 +384,10 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
 
     for (int64_t b = base0; b < e; b += G::SW) {
         // ---- stage y and run the FIR: F_i(b + t) for the whole super-window ----
-        if (p.debug_skip != 2) {
-            if constexpr (LPC > 0)
-                fir_superwindow_c<N, R, LPC>(y, T, b, coef, Bc, ytile, fbuf, lane);
-            else
-                fir_superwindow<N, R>(y, T, b, A, Bc, LP, ytile, fbuf, lane);
-        }
-        if (p.debug_skip == 1) continue;
+        if constexpr (LPC > 0)
+            fir_superwindow_c<N, R, LPC>(y, T, b, coef, Bc, ytile, fbuf, lane);
+        else
+            fir_superwindow<N, R>(y, T, b, A, Bc, LP, ytile, fbuf, lane);
         // ---- chunk 0: convert the faithful prologue (columns 0..L) into ring state ----
         if (kind == START_PROLOGUE && b == 0) {
             const double *sc = mdl + RL.scal;
@@ -607,19 +600,6 @@ __global__ void __launch_bounds__(128, (R == 8) ? 4 : 6)
     const int c = blockIdx.x * (blockDim.x >> 5) + warp;
     if (c >= p.nchunks) return;
     double *ws = smem_d + ((p.RL.hot + 1) & ~1) + (size_t)warp * WarpSmem<N, R>::DOUBLES;
-    if (p.stagger_ns > 0) {
-        // Co-resident CTAs start in lockstep and would alternate between an FP64-pipe-bound
-        // phase (FIR) and a latency-bound phase (recursion) together; offset them.
-        // arrival order of this CTA on its SM decides its phase offset
-        __shared__ int slot_s;
-        if (threadIdx.x == 0) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            slot_s = atomicAdd(p.sm_slots + (smid & 255), 1) & 3;
-        }
-        __syncthreads();
-        for (int q = 0; q < slot_s; q++) __nanosleep(p.stagger_ns);
-    }
     vit_process_chunk<N, R, LPC>(p, coef, ch, c, (c == 0 && p.first_prologue) ? START_PROLOGUE : START_SPEC, mdl, ws);
 }
 
@@ -1263,7 +1243,6 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     size_t o_look = carve(sizeof(long long) * (size_t)C * nchunks);
     size_t o_xend = carve(sizeof(int16_t) * C);
     size_t o_part = carve(sizeof(double) * (size_t)C * 1024);
-    size_t o_slots = carve(sizeof(int) * 256);
     char *base = (char *)alloc(Workspace::CHUNKS, off);
     // pageable source: the copy is staged before cudaMemcpyAsync returns, and hmdl outlives it anyway
     HMM_CUDA(cudaMemcpyAsync(base + o_model, hmdl.data(), sizeof(double) * hmdl.size(), cudaMemcpyHostToDevice, st));
@@ -1298,21 +1277,11 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     p.own_start = (long long *)(base + o_own);
     p.look_end = (long long *)(base + o_look);
     p.tr_flag = (int *)(base + o_trflag);
-    p.sm_slots = (int *)(base + o_slots);
     p.x_lo = 0;
     p.x_hi = T;
     p.first_prologue = first_prologue ? 1 : 0;
     p.last_true_end = last_true_end ? 1 : 0;
     part = (double *)(base + o_part);
-    {
-        const char *e = getenv("HMMCUDA_STAGGER_NS");
-        p.stagger_ns = e ? atoi(e) : 0;
-        const char *e2 = getenv("HMMCUDA_DEBUG_SKIP");
-        p.debug_skip = e2 ? atoi(e2) : 0;
-        int dev = 0;
-        HMM_CUDA(cudaGetDevice(&dev));
-        HMM_CUDA(cudaDeviceGetAttribute(&p.n_sm, cudaDevAttrMultiProcessorCount, dev));
-    }
 }
 
 void VitPlan::forward(cudaStream_t st, Timer *ttop) {
@@ -1321,7 +1290,6 @@ void VitPlan::forward(cudaStream_t st, Timer *ttop) {
     HMM_CUDA(cudaMemsetAsync(p.dec, 0, sizeof(uint32_t) * (size_t)C * p.T, st));
     HMM_CUDA(cudaMemsetAsync(p.nzmask, 0, sizeof(uint32_t) * (size_t)C * ((p.T + 31) / 32), st));
     HMM_CUDA(cudaMemsetAsync(p.counters, 0, sizeof(int) * (size_t)C * 4, st));
-    HMM_CUDA(cudaMemsetAsync(p.sm_slots, 0, sizeof(int) * 256, st));
     HMM_CUDA(cudaMemsetAsync(p.Pfin, 0, sizeof(double) * (size_t)C * p.RL.N * RING_Q, st));
     impl->variant.forward(p, hmdl.data(), C, st, ttop);
 }

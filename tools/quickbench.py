@@ -1,3 +1,4 @@
+import os; os.environ.setdefault("HMMCUDA_NO_PIPELINE", "1")  # kernel timing: keep the unpipelined single-launch path
 import sys, time, numpy as np
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as ge
