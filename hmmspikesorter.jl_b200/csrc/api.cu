@@ -722,6 +722,11 @@ int hmm_vshard_trace_verify(hmm_vshard *h, int32_t *n_repaired) {
 }
 
 int hmm_vshard_finish(hmm_vshard *h, int16_t *x_main_out, int32_t x_is_device, double *ll_partial_out) {
+    return hmm_vshard_finish_ex(h, x_main_out, x_is_device, ll_partial_out, nullptr, nullptr);
+}
+
+int hmm_vshard_finish_ex(hmm_vshard *h, int16_t *x_main_out, int32_t x_is_device, double *ll_partial_out,
+                         int32_t *fwd_repaired, int32_t *trace_repaired) {
     return guarded([&] {
         shard_dev(h);
         if (!x_main_out) fail(HMM_EINVAL, "null x_main_out");
@@ -734,7 +739,12 @@ int hmm_vshard_finish(hmm_vshard *h, int16_t *x_main_out, int32_t x_is_device, d
         }
         HMM_CUDA(cudaMemcpyAsync(x_main_out, h->x_loc + lo, sizeof(int16_t) * (size_t)(hi - lo),
                                  x_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        int cnt[4] = {0, 0, 0, 0};
+        if (fwd_repaired || trace_repaired)
+            HMM_CUDA(cudaMemcpyAsync(cnt, h->plan.counters_ptr(), sizeof cnt, cudaMemcpyDeviceToHost, st));
         HMM_CUDA(cudaStreamSynchronize(st));
+        if (fwd_repaired) *fwd_repaired = cnt[0];
+        if (trace_repaired) *trace_repaired = cnt[1];
     });
 }
 

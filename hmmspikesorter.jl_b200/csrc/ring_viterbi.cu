@@ -1130,8 +1130,8 @@ static VitVariant pick_lp(int LP, bool const_ok) {
 }
 static VitVariant pick_variant(int N, int LP, bool const_ok) {
     switch (N) {
-        case 1: return pick_lp<1, 8>(LP, const_ok);
-        case 2: return pick_lp<2, 8>(LP, const_ok);
+        case 1: return make_variant<1, 8, 0>();
+        case 2: return make_variant<2, 8, 0>();
         case 3:
             if (const_ok && LP == 64 && getenv("HMMCUDA_R4") && atoi(getenv("HMMCUDA_R4"))) return make_variant<3, 4, 60>();
             return pick_lp<3, 8>(LP, const_ok);

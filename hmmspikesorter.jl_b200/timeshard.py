@@ -153,6 +153,13 @@ class Shard:
             check(lib().hmm_vshard_finish(self._h, _p(x_out), i32(0), C.byref(ll) if want_ll else None))
         return ll.value
 
+    def finish_ex(self, x_ptr):
+        """finish into a device buffer; returns (ll_partial, fwd_repaired, trace_repaired) with one sync."""
+        self._dev()
+        ll, f, b = f64(0), i32(0), i32(0)
+        check(lib().hmm_vshard_finish_ex(self._h, C.c_void_p(x_ptr), i32(1), C.byref(ll), C.byref(f), C.byref(b)))
+        return ll.value, int(f.value), int(b.value)
+
     def close(self):
         if self._h:
             self._dev()

@@ -148,6 +148,9 @@ int hmm_vshard_trace_boundary_get(hmm_vshard *h, int64_t *out, int32_t out_is_de
 int hmm_vshard_trace_boundary_set(hmm_vshard *h, const int64_t *in, int32_t in_is_device); /* at main_end   <- rank r+1 */
 int hmm_vshard_trace_verify(hmm_vshard *h, int32_t *n_repaired);
 int hmm_vshard_finish(hmm_vshard *h, int16_t *x_main_out, int32_t x_is_device, double *ll_partial_out);
+/* finish + repair counters with a single synchronisation */
+int hmm_vshard_finish_ex(hmm_vshard *h, int16_t *x_main_out, int32_t x_is_device, double *ll_partial_out,
+                         int32_t *fwd_repaired, int32_t *trace_repaired);
 int hmm_vshard_repairs(hmm_vshard *h, int32_t *fwd_repaired, int32_t *trace_repaired); /* counters since forward */
 int hmm_vshard_destroy(hmm_vshard *h);
 
