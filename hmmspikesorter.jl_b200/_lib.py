@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libhmmcuda.so")
+SO_PATH = os.environ.get("LIBHMMCUDA", os.path.join(_HERE, "libhmmcuda.so"))  # same override as the Julia shim
 
 HMM_OK, HMM_EINVAL, HMM_ECUDA, HMM_ENOMEM, HMM_ENODEV, HMM_EUNSUPPORTED = range(6)
 MODE_AUTO, MODE_FAITHFUL, MODE_RING = 0, 1, 2

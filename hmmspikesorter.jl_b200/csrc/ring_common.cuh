@@ -85,26 +85,41 @@ struct FirGeom {
 // F_i(t0) = Bc[i] + sum_r A[r][i] * y[t0 + r], and leaves the results in `fbuf`
 // (element t0-b = R*l + j of neuron i at fbuf[i*FTILE + j*FS + l]).
 // `fbuf` may alias `ytile`.  A is the shared-memory copy [LP][NP] (zero padded).
+
+// FIR coefficients passed BY VALUE as a kernel parameter: they live in the
+// constant bank, and with the tap loop fully unrolled every DFMA takes its
+// coefficient as a c[0x0][imm] operand.  A DFMA with three distinct 64-bit
+// register operands is limited by register-file read bandwidth to one per 3
+// cycles per SM sub-partition; with a constant operand it issues at the FP64
+// pipe rate (one per 2 cycles) and the coefficient LDS traffic disappears.
+template <int N, int LPC>
+struct FirCoef {
+    double a[(LPC > 0 ? LPC : 1) * N];  // a[r*N + i]
+};
+
+// Issue the asynchronous staging of y[b, b + need) into a transposed tile (zero beyond T) and
+// commit it as one cp.async group; the caller waits for the group before the FIR reads it.
+template <int R>
+__device__ __forceinline__ void fir_stage(const double *__restrict__ y, int64_t T, int64_t b, int need, double *ytile,
+                                          int lane) {
+    using G = FirGeom<R>;
+    for (int k = lane; k < need; k += 32) {
+        int64_t g = b + k;
+        double *dst = ytile + (k & (R - 1)) * G::YS + (k >> G::LOGR);
+        if (g < T)
+            cp_async8(dst, y + g);
+        else
+            *dst = 0.0;
+    }
+    cp_async_commit();
+}
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+
 template <int N, int R>
-__device__ __forceinline__ void fir_superwindow(const double *__restrict__ y, int64_t T, int64_t b,
-                                                const double *A, const double *Bc, int LP, double *ytile,
-                                                double *fbuf, int lane) {
+__device__ __forceinline__ void fir_compute(const double *A, const double *Bc, int LP, const double *ytile,
+                                            double *fbuf, int lane) {
     using G = FirGeom<R>;
     constexpr int NP = (N + 1) & ~1;
-    {
-        const int need = G::SW + LP;
-        for (int k = lane; k < need; k += 32) {
-            int64_t g = b + k;
-            double *dst = ytile + (k & (R - 1)) * G::YS + (k >> G::LOGR);
-            if (g < T)
-                cp_async8(dst, y + g);
-            else
-                *dst = 0.0;
-        }
-        cp_async_commit();
-        cp_async_wait_all();
-        __syncwarp();
-    }
     double acc[N][R];
 #pragma unroll
     for (int i = 0; i < N; i++)
@@ -157,36 +172,21 @@ __device__ __forceinline__ void fir_superwindow(const double *__restrict__ y, in
     __syncwarp();
 }
 
-// FIR coefficients passed BY VALUE as a kernel parameter: they live in the
-// constant bank, and with the tap loop fully unrolled every DFMA takes its
-// coefficient as a c[0x0][imm] operand.  A DFMA with three distinct 64-bit
-// register operands is limited by register-file read bandwidth to one per 3
-// cycles per SM sub-partition; with a constant operand it issues at the FP64
-// pipe rate (one per 2 cycles) and the coefficient LDS traffic disappears.
-template <int N, int LPC>
-struct FirCoef {
-    double a[(LPC > 0 ? LPC : 1) * N];  // a[r*N + i]
-};
+template <int N, int R>
+__device__ __forceinline__ void fir_superwindow(const double *__restrict__ y, int64_t T, int64_t b,
+                                                const double *A, const double *Bc, int LP, double *ytile,
+                                                double *fbuf, int lane) {
+    fir_stage<R>(y, T, b, FirGeom<R>::SW + LP, ytile, lane);
+    cp_async_wait_all();
+    __syncwarp();
+    fir_compute<N, R>(A, Bc, LP, ytile, fbuf, lane);
+}
+
 
 template <int N, int R, int LPC>
-__device__ __forceinline__ void fir_superwindow_c(const double *__restrict__ y, int64_t T, int64_t b,
-                                                  const FirCoef<N, LPC> &coef, const double *Bc, double *ytile,
-                                                  double *fbuf, int lane) {
+__device__ __forceinline__ void fir_compute_c(const FirCoef<N, LPC> &coef, const double *Bc, const double *ytile,
+                                              double *fbuf, int lane) {
     using G = FirGeom<R>;
-    {
-        const int need = G::SW + LPC;
-        for (int k = lane; k < need; k += 32) {
-            int64_t g = b + k;
-            double *dst = ytile + (k & (R - 1)) * G::YS + (k >> G::LOGR);
-            if (g < T)
-                cp_async8(dst, y + g);
-            else
-                *dst = 0.0;
-        }
-        cp_async_commit();
-        cp_async_wait_all();
-        __syncwarp();
-    }
     double acc[N][R];
 #pragma unroll
     for (int i = 0; i < N; i++)
@@ -220,6 +220,40 @@ __device__ __forceinline__ void fir_superwindow_c(const double *__restrict__ y, 
 #pragma unroll
         for (int j = 0; j < R; j++) fbuf[i * G::FTILE + j * G::FS + lane] = acc[i][j];
     __syncwarp();
+}
+
+template <int N, int R, int LPC>
+__device__ __forceinline__ void fir_superwindow_c(const double *__restrict__ y, int64_t T, int64_t b,
+                                                  const FirCoef<N, LPC> &coef, const double *Bc, double *ytile,
+                                                  double *fbuf, int lane) {
+    fir_stage<R>(y, T, b, FirGeom<R>::SW + LPC, ytile, lane);
+    cp_async_wait_all();
+    __syncwarp();
+    fir_compute_c<N, R, LPC>(coef, Bc, ytile, fbuf, lane);
+}
+
+// ---- mbarrier helpers (producer / consumer hand-off between warps of one CTA) ----
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        " .reg .pred P1;\n"
+        "MBAR_WAIT:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        " @P1 bra MBAR_DONE;\n"
+        " bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"(a),
+        "r"(parity)
+        : "memory");
 }
 
 // F value of step (local index tl in the super-window) for the lane-per-step mapping

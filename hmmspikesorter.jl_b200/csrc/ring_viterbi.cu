@@ -103,6 +103,8 @@ struct VitParams {
     RingLayout RL;
     int64_t Lc, W;         // chunk length, warm-up / look-ahead (multiples of the super-window)
     int nchunks;           // per channel
+    int64_t Lc_t;          // traceback chunk length (Lc / tfac): the traceback is latency-bound per chunk, so it
+    int nchunks_t, tfac;   // uses shorter chunks than the forward pass; boundaries stay aligned
     int ns;                // nstates
     uint32_t *dec;         // [C x T]      packed decisions
     uint32_t *nzmask;      // [C x ceil(T/32)]
@@ -313,9 +315,25 @@ __global__ void __launch_bounds__(256) ring_vit_final(VitParams p) {
 // ---------------------------------------------------------------------------
 // One chunk, one warp.
 // ---------------------------------------------------------------------------
-template <int N, int R, int LPC>
+// ROLE_BOTH: one warp does the FIR and the recursion of its chunk in turn (repair kernel).
+// ROLE_FIR / ROLE_DP: a producer warp runs the FIR one super-window ahead into a double-buffered
+// F tile while a consumer warp of the same CTA runs the recursion; they hand the tiles over with
+// mbarriers, so the FP64-pipe-bound FIR and the latency-bound recursion overlap.
+enum { ROLE_BOTH = 0, ROLE_FIR = 1, ROLE_DP = 2 };
+
+template <int N, int R>
+struct SlotSmem {  // one chunk slot of the warp-specialised kernel, in doubles
+    using G = FirGeom<R>;
+    static constexpr int YT = 0;                                   // 2 y tiles
+    static constexpr int FT = 2 * G::YTILE;                        // 2 F tiles
+    static constexpr int RING = FT + 2 * N * G::FTILE;             // ring + prologue scratch
+    static constexpr int BAR = RING + N * RING_Q + 104;            // full[2], empty[2] mbarriers
+    static constexpr int DOUBLES = BAR + 4;
+};
+
+template <int N, int R, int LPC, int ROLE>
 __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coef, int ch, int c, int kind,
-                                  const double *mdl /*smem model*/, double *ws /*per-warp smem*/) {
+                                  const double *mdl /*smem model*/, double *ws /*per-warp or per-slot smem*/) {
     using G = FirGeom<R>;
     constexpr int NP = (N + 1) & ~1;
     const int lane = threadIdx.x & 31;
@@ -323,9 +341,12 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
     const int L = RL.L, LP = RL.LP;
     const double NEG = -INFINITY;
     double *ytile = ws;
-    double *fbuf = ws;  // aliases ytile (see WarpSmem)
-    double *ring = ws + WarpSmem<N, R>::TILE;
+    double *fbuf = ws;  // ROLE_BOTH: aliases ytile (see WarpSmem); specialised roles: set per super-window
+    double *ring = ws + (ROLE == ROLE_BOTH ? WarpSmem<N, R>::TILE : SlotSmem<N, R>::RING);
     double *zs = ring + N * RING_Q;  // [L+1] <= 97 doubles
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(ws + SlotSmem<N, R>::BAR), *bar_empty = bar_full + 2;
+    (void)bar_full;
+    (void)bar_empty;
     const double *A = mdl + RL.A;
     const double *Bc = mdl + RL.Bc, *eG = mdl + RL.eG, *eH = mdl + RL.eH, *eT = mdl + RL.eT;
     const double eTmax = mdl[RL.scal + 5], eHmin = mdl[RL.scal + 6];
@@ -339,7 +360,8 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
     int64_t base0;                                       // first super-window
     int64_t tau_first;                                   // first DP step
     double Gprev;
-    for (int k = lane; k < N * RING_Q; k += 32) ring[k] = NEG;
+    if (ROLE != ROLE_FIR)
+        for (int k = lane; k < N * RING_Q; k += 32) ring[k] = NEG;
     if (kind == START_PROLOGUE) {
         base0 = 0;
         tau_first = L + 1;
@@ -354,12 +376,38 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
         tau_first = s;
         const double *eb = p.EB + ((size_t)ch * p.nchunks + (c - 1)) * p.bvec;
         Gprev = eb[0];
-        for (int k = lane; k < L; k += 32) {
-            int64_t t0 = s - L + k;
-            for (int j = 0; j < N; j++) ring[j * RING_Q + (int)(t0 & (RING_Q - 1))] = eb[1 + j * L + k];
-        }
+        if (ROLE != ROLE_FIR)
+            for (int k = lane; k < L; k += 32) {
+                int64_t t0 = s - L + k;
+                for (int j = 0; j < N; j++) ring[j * RING_Q + (int)(t0 & (RING_Q - 1))] = eb[1 + j * L + k];
+            }
     }
     __syncwarp();
+    if (ROLE == ROLE_FIR) {
+        // ---- producer: stage tile k+1 while the FIR of tile k runs; hand F tiles to the consumer ----
+        const int need = G::SW + (LPC > 0 ? LPC : LP);
+        double *yt[2] = {ws + SlotSmem<N, R>::YT, ws + SlotSmem<N, R>::YT + G::YTILE};
+        double *ft[2] = {ws + SlotSmem<N, R>::FT, ws + SlotSmem<N, R>::FT + N * G::FTILE};
+        fir_stage<R>(y, T, base0, need, yt[0], lane);
+        int k = 0;
+        for (int64_t b = base0; b < e; b += G::SW, k++) {
+            const int buf = k & 1;
+            const bool more = b + G::SW < e;
+            if (more) fir_stage<R>(y, T, b + G::SW, need, yt[buf ^ 1], lane);
+            if (more)
+                cp_async_wait_but_one();
+            else
+                cp_async_wait_all();
+            __syncwarp();
+            mbar_wait(bar_empty + buf, ((k >> 1) & 1) ^ 1);  // the consumer is done with this F tile
+            if constexpr (LPC > 0)
+                fir_compute_c<N, R, LPC>(coef, Bc, yt[buf], ft[buf], lane);
+            else
+                fir_compute<N, R>(A, Bc, LP, yt[buf], ft[buf], lane);
+            if (lane == 0) mbar_arrive(bar_full + buf);   // fir_compute ends with __syncwarp()
+        }
+        return;
+    }
     uint32_t *dec = p.dec + (size_t)ch * T;
     uint32_t *nzm = p.nzmask + (size_t)ch * ((T + 31) / 32);
     const int Wd = L < 32 ? L : 32;
@@ -382,12 +430,29 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
     const int e_rel = (int)(e - base0);
     const int s_rel = (int)(s - base0);
 
-    for (int64_t b = base0; b < e; b += G::SW) {
-        // ---- stage y and run the FIR: F_i(b + t) for the whole super-window ----
-        if constexpr (LPC > 0)
-            fir_superwindow_c<N, R, LPC>(y, T, b, coef, Bc, ytile, fbuf, lane);
-        else
-            fir_superwindow<N, R>(y, T, b, A, Bc, LP, ytile, fbuf, lane);
+#ifdef HMM_PHASE_TIMING
+    long long tm_fir = 0, tm_dp = 0, tm_n = 0;
+#endif
+    int swk = 0;
+    for (int64_t b = base0; b < e; b += G::SW, swk++) {
+#ifdef HMM_PHASE_TIMING
+        const long long tm0 = clock64();
+#endif
+        if (ROLE == ROLE_DP) {
+            // ---- consumer: wait for the producer's F tile of this super-window ----
+            const int buf = swk & 1;
+            mbar_wait(bar_full + buf, (swk >> 1) & 1);
+            fbuf = ws + SlotSmem<N, R>::FT + buf * N * G::FTILE;
+        } else {
+            // ---- stage y and run the FIR: F_i(b + t) for the whole super-window ----
+            if constexpr (LPC > 0)
+                fir_superwindow_c<N, R, LPC>(y, T, b, coef, Bc, ytile, fbuf, lane);
+            else
+                fir_superwindow<N, R>(y, T, b, A, Bc, LP, ytile, fbuf, lane);
+        }
+#ifdef HMM_PHASE_TIMING
+        const long long tm1 = clock64();
+#endif
         // ---- chunk 0: convert the faithful prologue (columns 0..L) into ring state ----
         if (kind == START_PROLOGUE && b == 0) {
             const double *sc = mdl + RL.scal;
@@ -567,7 +632,24 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
                 if (lane == 0) nzm[tau0 >> 5] = nz;
             }
         }
+        if (ROLE == ROLE_DP) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + (swk & 1));
+        }
+#ifdef HMM_PHASE_TIMING
+        {
+            const long long tm2 = clock64();
+            tm_fir += tm1 - tm0;
+            tm_dp += tm2 - tm1;
+            tm_n++;
+        }
+#endif
     }
+#ifdef HMM_PHASE_TIMING
+    if (lane == 0 && kind == START_SPEC && (c % 293) == 1)
+        printf("chunk %d: %lld super-windows, FIR+staging %lld cyc/sw, recursion %lld cyc/sw\n", c, tm_n,
+               tm_fir / (tm_n ? tm_n : 1), tm_dp / (tm_n ? tm_n : 1));
+#endif
     // ---- end of chunk: true boundary vector for the next chunk, or final state ----
     if (!last) {
         double *eb = p.EB + ((size_t)ch * p.nchunks + c) * p.bvec;
@@ -589,18 +671,27 @@ __device__ void load_model_smem(const VitParams &p, int ch, double *mdl) {
     __syncthreads();
 }
 
+// Warp-specialised forward kernel: 8 warps = 4 chunk slots x {FIR producer, recursion consumer}.
 template <int N, int R, int LPC>
-__global__ void __launch_bounds__(128, (R == 8) ? 4 : 6)
-    ring_vit_forward(const __grid_constant__ VitParams p, const __grid_constant__ FirCoef<N, LPC> coef) {
+__global__ void __launch_bounds__(256, 2)
+    ring_vit_forward_ws(const __grid_constant__ VitParams p, const __grid_constant__ FirCoef<N, LPC> coef) {
     extern __shared__ __align__(16) double smem_d[];
     const int ch = blockIdx.y;
     double *mdl = smem_d;
-    load_model_smem<N, R>(p, ch, mdl);
-    const int warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int warp = threadIdx.x >> 5, slot = warp & 3;
+    double *ws = smem_d + ((p.RL.hot + 1) & ~1) + (size_t)slot * SlotSmem<N, R>::DOUBLES;
+    if ((threadIdx.x & 31) == 0 && warp < 4) {
+        uint64_t *bars = reinterpret_cast<uint64_t *>(ws + SlotSmem<N, R>::BAR);
+        for (int k = 0; k < 4; k++) mbar_init(bars + k, 1);
+    }
+    load_model_smem<N, R>(p, ch, mdl);  // ends with __syncthreads(): barriers initialised, model staged
+    const int c = blockIdx.x * 4 + slot;
     if (c >= p.nchunks) return;
-    double *ws = smem_d + ((p.RL.hot + 1) & ~1) + (size_t)warp * WarpSmem<N, R>::DOUBLES;
-    vit_process_chunk<N, R, LPC>(p, coef, ch, c, (c == 0 && p.first_prologue) ? START_PROLOGUE : START_SPEC, mdl, ws);
+    const int kind = (c == 0 && p.first_prologue) ? START_PROLOGUE : START_SPEC;
+    if (warp < 4)
+        vit_process_chunk<N, R, LPC, ROLE_FIR>(p, coef, ch, c, kind, mdl, ws);
+    else
+        vit_process_chunk<N, R, LPC, ROLE_DP>(p, coef, ch, c, kind, mdl, ws);
 }
 
 // Boundary check: speculative start vector of chunk c vs true end vector of c-1
@@ -658,7 +749,7 @@ __global__ void __launch_bounds__(32) ring_vit_repair_fwd(VitParams p) {
             need = !boundary_matches(sb, eb, p.bvec, lane);
         }
         if (need) {
-            vit_process_chunk<N, R, 0>(p, FirCoef<N, 0>{}, ch, c, START_EXACT, mdl, ws);
+            vit_process_chunk<N, R, 0, ROLE_BOTH>(p, FirCoef<N, 0>{}, ch, c, START_EXACT, mdl, ws);
             __threadfence();
             repaired++;
         }
@@ -683,9 +774,9 @@ __device__ void trace_chunk(const VitParams &p, int ch, int c, int64_t tau_hi, l
     const int lane = threadIdx.x & 31;
     const int L = p.RL.L;
     const int64_t T = p.T;
-    const int64_t s = (int64_t)c * p.Lc;
-    int64_t e = s + p.Lc;
-    if (c == p.nchunks - 1 || e > T) e = T;
+    const int64_t s = (int64_t)c * p.Lc_t;
+    int64_t e = s + p.Lc_t;
+    if (c == p.nchunks_t - 1 || e > T) e = T;
     const int64_t lo = (c == 0 && p.first_prologue) ? (int64_t)(L + 1) : s;
     const uint32_t *dec = p.dec + (size_t)ch * T;
     const uint32_t *nzm = p.nzmask + (size_t)ch * ((T + 31) / 32);
@@ -841,8 +932,8 @@ __device__ void trace_chunk(const VitParams &p, int ch, int c, int64_t tau_hi, l
         own = 0;  // nothing precedes chunk 0
     }
     if (lane == 0) {
-        p.own_start[(size_t)ch * p.nchunks + c] = own;
-        if (record_look) p.look_end[(size_t)ch * p.nchunks + c] = look;
+        p.own_start[(size_t)ch * p.nchunks_t + c] = own;
+        if (record_look) p.look_end[(size_t)ch * p.nchunks_t + c] = look;
     }
 }
 
@@ -866,11 +957,11 @@ __global__ void __launch_bounds__(128) ring_vit_trace(VitParams p) {
         for (int k = threadIdx.x; k < p.ns * (L + 1); k += blockDim.x) t2s_all[k] = g[k];
     }
     __syncthreads();
-    if (c >= p.nchunks) return;
+    if (c >= p.nchunks_t) return;
     const int64_t T = p.T;
-    const int64_t s = (int64_t)c * p.Lc;
-    int64_t e = s + p.Lc;
-    const bool last = (c == p.nchunks - 1);
+    const int64_t s = (int64_t)c * p.Lc_t;
+    int64_t e = s + p.Lc_t;
+    const bool last = (c == p.nchunks_t - 1);
     if (last || e > T) e = T;
     int64_t tau_hi = e + p.W - 1;
     long long st = -1;  // speculative: noise at tau_hi
@@ -884,8 +975,8 @@ __global__ void __launch_bounds__(128) ring_vit_trace(VitParams p) {
 __global__ void ring_vit_check_trace(VitParams p) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int ch = blockIdx.y;
-    if (c >= p.nchunks - 1) return;
-    size_t o = (size_t)ch * p.nchunks;
+    if (c >= p.nchunks_t - 1) return;
+    size_t o = (size_t)ch * p.nchunks_t;
     p.tr_flag[o + c] = (p.look_end[o + c] != p.own_start[o + c + 1]) ? 1 : 0;
 }
 
@@ -895,9 +986,9 @@ __global__ void __launch_bounds__(32) ring_vit_repair_trace(VitParams p) {
     uint32_t *tws = trsm;
     int16_t *t2s_all = reinterpret_cast<int16_t *>(trsm + TR_WARP_U32);
     const int ch = blockIdx.x, lane = threadIdx.x;
-    const size_t o = (size_t)ch * p.nchunks;
+    const size_t o = (size_t)ch * p.nchunks_t;
     int any = 0;
-    for (int c = lane; c < p.nchunks - 1; c += 32) any |= p.tr_flag[o + c];
+    for (int c = lane; c < p.nchunks_t - 1; c += 32) any |= p.tr_flag[o + c];
     if (!__any_sync(0xffffffffu, any)) return;
     const int L = p.RL.L;
     if (p.first_prologue) {
@@ -907,12 +998,12 @@ __global__ void __launch_bounds__(32) ring_vit_repair_trace(VitParams p) {
     __syncwarp();
     int repaired = 0;
     bool next_changed = false;
-    for (int c = p.nchunks - 2; c >= 0; c--) {
+    for (int c = p.nchunks_t - 2; c >= 0; c--) {
         bool need = p.tr_flag[o + c] != 0;
         if (!need && next_changed) need = p.look_end[o + c] != p.own_start[o + c + 1];
         if (need) {
             // true state at time e_c is the (final) start state of chunk c+1
-            int64_t e = (int64_t)(c + 1) * p.Lc;
+            int64_t e = (int64_t)(c + 1) * p.Lc_t;
             long long before = p.own_start[o + c];
             trace_chunk<N>(p, ch, c, e, p.own_start[o + c + 1], false, t2s_all, tws);
             __threadfence();
@@ -1038,19 +1129,17 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------
 template <int N, int R, int LPC>
 static size_t fwd_smem_bytes(const RingLayout &RL) {
-    constexpr int WPB = 4;
-    return sizeof(double) * (((RL.hot + 1) & ~1) + (size_t)WPB * WarpSmem<N, R>::DOUBLES);
+    return sizeof(double) * (((RL.hot + 1) & ~1) + (size_t)4 * SlotSmem<N, R>::DOUBLES);
 }
 
 // Resident warps per SM of the forward kernel (sets the one-wave chunk count).
 template <int N, int R, int LPC>
 static int fwd_warps_per_sm(const RingLayout &RL) {
-    constexpr int WPB = 4;
     const size_t sm_fwd = fwd_smem_bytes<N, R, LPC>(RL);
-    HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward<N, R, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+    HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws<N, R, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
     int nb = 0;
-    HMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ring_vit_forward<N, R, LPC>, 32 * WPB, sm_fwd));
-    return (nb > 0 ? nb : 1) * WPB;
+    HMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ring_vit_forward_ws<N, R, LPC>, 256, sm_fwd));
+    return (nb > 0 ? nb : 1) * 4;  // chunk slots (producer/consumer warp pairs) per SM
 }
 
 template <int N, int R, int LPC>
@@ -1058,7 +1147,7 @@ static void stage_forward(VitParams &p, const double *hmodel /*host ring model o
                           Timer *ttop) {
     constexpr int WPB = 4;
     const size_t sm_fwd = fwd_smem_bytes<N, R, LPC>(p.RL);
-    HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward<N, R, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+    HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws<N, R, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
     FirCoef<N, LPC> coef{};
     if (LPC > 0)
         for (int r = 0; r < LPC; r++)
@@ -1071,7 +1160,7 @@ static void stage_forward(VitParams &p, const double *hmodel /*host ring model o
         ring_vit_prologue<<<C, 1024, sm_pro, st>>>(p);
     }
     if (ttop) ttop->start();
-    ring_vit_forward<N, R, LPC><<<gridc, 32 * WPB, sm_fwd, st>>>(p, coef);
+    ring_vit_forward_ws<N, R, LPC><<<gridc, 256, sm_fwd, st>>>(p, coef);
     if (ttop) ttop->stop();
     HMM_CUDA(cudaGetLastError());
 }
@@ -1092,7 +1181,7 @@ static void stage_trace(VitParams &p, int C, cudaStream_t st) {
     const size_t sm_t2 = sizeof(int16_t) * (size_t)p.ns * (p.RL.L + 1) + 16;
     const size_t sm_tr = sm_t2 + sizeof(uint32_t) * (size_t)WPB * TR_WARP_U32;
     HMM_CUDA(cudaFuncSetAttribute(ring_vit_trace<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_tr));
-    dim3 gridc((p.nchunks + WPB - 1) / WPB, C);
+    dim3 gridc((p.nchunks_t + WPB - 1) / WPB, C);
     ring_vit_trace<N><<<gridc, 32 * WPB, sm_tr, st>>>(p);
     HMM_CUDA(cudaGetLastError());
 }
@@ -1102,7 +1191,7 @@ static void stage_verify_trace(VitParams &p, int C, cudaStream_t st) {
     const size_t sm_t2 = sizeof(int16_t) * (size_t)p.ns * (p.RL.L + 1) + 16;
     const size_t sm_trr = sm_t2 + sizeof(uint32_t) * (size_t)TR_WARP_U32;
     HMM_CUDA(cudaFuncSetAttribute(ring_vit_repair_trace<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_trr));
-    ring_vit_check_trace<<<dim3((p.nchunks + 127) / 128, C), 128, 0, st>>>(p);
+    ring_vit_check_trace<<<dim3((p.nchunks_t + 127) / 128, C), 128, 0, st>>>(p);
     ring_vit_repair_trace<N><<<C, 32, sm_trr, st>>>(p);
     HMM_CUDA(cudaGetLastError());
 }
@@ -1133,7 +1222,6 @@ static VitVariant pick_variant(int N, int LP, bool const_ok) {
         case 1: return make_variant<1, 8, 0>();
         case 2: return make_variant<2, 8, 0>();
         case 3:
-            if (const_ok && LP == 64 && getenv("HMMCUDA_R4") && atoi(getenv("HMMCUDA_R4"))) return make_variant<3, 4, 60>();
             return pick_lp<3, 8>(LP, const_ok);
         case 4: return pick_lp<4, 8>(LP, const_ok);
         case 5: return pick_lp<5, 4>(LP, const_ok);
@@ -1219,6 +1307,14 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     // the last chunk must be long enough to hold the final look-back of L steps
     if (nchunks > 1 && T - (int64_t)(nchunks - 1) * Lc < RING_Q) nchunks--;
 
+    int tfac = 1;
+    for (int f : {4, 2})
+        if (Lc % ((int64_t)f * 256) == 0 && Lc / f >= 2 * W && Lc / f >= 1024) {
+            tfac = f;
+            break;
+        }
+    const int64_t Lc_t = Lc / tfac;
+    const int nchunks_t = (int)((T + Lc_t - 1) / Lc_t);
     const int64_t pcols = L + 1;
     double *T1pro = (double *)alloc(Workspace::PROLOG, (sizeof(double) + sizeof(int16_t)) * (size_t)C * ns * pcols + 64);
     int16_t *T2pro = (int16_t *)(T1pro + (size_t)C * ns * pcols);
@@ -1237,10 +1333,10 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     size_t o_pfin = carve(sizeof(double) * (size_t)C * N * RING_Q);
     size_t o_gfin = carve(sizeof(double) * C);
     size_t o_flag = carve(sizeof(int) * (size_t)C * nchunks);
-    size_t o_trflag = carve(sizeof(int) * (size_t)C * nchunks);
+    size_t o_trflag = carve(sizeof(int) * (size_t)C * nchunks_t);
     size_t o_cnt = carve(sizeof(int) * (size_t)C * 4);
-    size_t o_own = carve(sizeof(long long) * (size_t)C * nchunks);
-    size_t o_look = carve(sizeof(long long) * (size_t)C * nchunks);
+    size_t o_own = carve(sizeof(long long) * (size_t)C * nchunks_t);
+    size_t o_look = carve(sizeof(long long) * (size_t)C * nchunks_t);
     size_t o_xend = carve(sizeof(int16_t) * C);
     size_t o_part = carve(sizeof(double) * (size_t)C * 1024);
     char *base = (char *)alloc(Workspace::CHUNKS, off);
@@ -1256,6 +1352,9 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     p.Lc = Lc;
     p.W = W;
     p.nchunks = nchunks;
+    p.Lc_t = Lc_t;
+    p.nchunks_t = nchunks_t;
+    p.tfac = tfac;
     p.ns = ns;
     p.dec = (uint32_t *)alloc(Workspace::DEC, sizeof(uint32_t) * (size_t)C * T);
     p.nzmask = (uint32_t *)alloc(Workspace::MASK, sizeof(uint32_t) * (size_t)C * ((T + 31) / 32));
@@ -1353,7 +1452,7 @@ int *VitPlan::counters_ptr() { return p_->counters; }
 int VitPlan::nchunks() const { return p_->nchunks; }
 int VitPlan::bvec() const { return p_->bvec; }
 double *VitPlan::eb_ptr(int chunk) { return p_->EB + (size_t)chunk * p_->bvec; }
-long long *VitPlan::own_start_ptr(int chunk) { return p_->own_start + chunk; }
+long long *VitPlan::own_start_ptr(int chunk) { return p_->own_start + (size_t)chunk * p_->tfac; }
 
 void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, const std::vector<HostModel> &models,
                       const FaithfulLayout &FL, const char *blob_dev, int16_t *x_dev, int64_t x_stride, double *ll_dev,
