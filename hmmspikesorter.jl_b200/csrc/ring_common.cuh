@@ -120,6 +120,9 @@ __device__ __forceinline__ void fir_compute(const double *A, const double *Bc, i
                                             double *fbuf, int lane) {
     using G = FirGeom<R>;
     constexpr int NP = (N + 1) & ~1;
+    __builtin_assume(__isShared(ytile));
+    __builtin_assume(__isShared(fbuf));
+    __builtin_assume(__isShared(A));
     double acc[N][R];
 #pragma unroll
     for (int i = 0; i < N; i++)
@@ -187,6 +190,8 @@ template <int N, int R, int LPC>
 __device__ __forceinline__ void fir_compute_c(const FirCoef<N, LPC> &coef, const double *Bc, const double *ytile,
                                               double *fbuf, int lane) {
     using G = FirGeom<R>;
+    __builtin_assume(__isShared(ytile));
+    __builtin_assume(__isShared(fbuf));
     double acc[N][R];
 #pragma unroll
     for (int i = 0; i < N; i++)
@@ -195,23 +200,27 @@ __device__ __forceinline__ void fir_compute_c(const FirCoef<N, LPC> &coef, const
     double w[R];
 #pragma unroll
     for (int j = 0; j < R; j++) w[j] = ytile[j * G::YS + lane];
-    // Fully unrolled so that every coefficient is a compile-time constant-bank offset (the
-    // compiler keeps them in uniform registers: LDCU + DFMA R, R, UR, R).  Measured at C2:
-    // full unroll 0.42 ms (28 KB of code; ncu shows stall_no_instruction), unroll-by-2 with
-    // vector-register coefficients 0.47 ms, shared-memory coefficients 0.52 ms.
+    // Fully unrolled over exactly LPC = L taps, so that every coefficient is a compile-time constant-bank offset
+    // (the compiler keeps them in uniform registers: LDCU.128 + DFMA R, R, UR, R -- no register-file or
+    // shared-memory traffic for them).  Measured at C2 (forward kernel, 18 M samples): full unroll 0.40 ms
+    // (28 KB of code: ncu shows a stall_no_instruction sample at every 128-byte line); the same loop rolled in
+    // groups of 8 taps (3.7 KB body, no instruction-fetch stalls, but register-indexed LDC coefficients and
+    // more dispatch stalls) 0.45 ms, with or without a coefficient prefetch queue; shared-memory coefficients 0.52 ms.
 #pragma unroll
     for (int r0 = 0; r0 < LPC; r0 += R) {
 #pragma unroll
         for (int u = 0; u < R; u++) {
             const int r = r0 + u;
-            const double ynew = ytile[u * G::YS + lane + 1 + (r0 >> G::LOGR)];
+            if (r < LPC) {
+                const double ynew = ytile[u * G::YS + lane + 1 + (r0 >> G::LOGR)];
 #pragma unroll
-            for (int j = 0; j < R; j++) {
-                const double yv = w[(u + j) % R];
+                for (int j = 0; j < R; j++) {
+                    const double yv = w[(u + j) % R];
 #pragma unroll
-                for (int i = 0; i < N; i++) acc[i][j] = fma(coef.a[r * N + i], yv, acc[i][j]);
+                    for (int i = 0; i < N; i++) acc[i][j] = fma(coef.a[r * N + i], yv, acc[i][j]);
+                }
+                w[u] = ynew;
             }
-            w[u] = ynew;
         }
     }
     __syncwarp();

@@ -340,6 +340,8 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
     const RingLayout &RL = p.RL;
     const int L = RL.L, LP = RL.LP;
     const double NEG = -INFINITY;
+    __builtin_assume(__isShared(ws));
+    __builtin_assume(__isShared(mdl));
     double *ytile = ws;
     double *fbuf = ws;  // ROLE_BOTH: aliases ytile (see WarpSmem); specialised roles: set per super-window
     double *ring = ws + (ROLE == ROLE_BOTH ? WarpSmem<N, R>::TILE : SlotSmem<N, R>::RING);
@@ -498,6 +500,10 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
             if (t0_rel + 32 <= tf_rel) {  // before the first recursion step: pre-loaded entries only
                 lq4 = lq3; lq3 = lq2; lq2 = lq1;
                 lq1 = (kind == START_SPEC) ? 0u : 0xffffffffu;
+                if (t0_rel >= s_rel) {  // (prologue columns: the traceback takes them from T2pro)
+                    dec[base0 + t0_rel + lane] = 0u;
+                    if (lane == 0) nzm[(base0 + t0_rel) >> 5] = 0u;
+                }
                 continue;
             }
             if (t0_rel >= e_rel) break;
@@ -510,8 +516,8 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
             for (int i = 0; i < N; i++) Fv[i] = fbuf[i * G::FTILE + (tl & (R - 1)) * G::FS + (tl >> G::LOGR)];
             // Quiet-window fast path: if none of the pending chain scores that arrive in this
             // window was live when it was created, no tail can win any decision here: G stays,
-            // every head is entered from noise and all backpointers are 0 (the decision arrays
-            // are pre-zeroed) -- the tails are not even read.
+            // every head is entered from noise and all backpointers are 0 -- the tails are not
+            // even read.
             if (L >= 32 && t0_rel >= tf_rel && t0_rel + 32 <= e_rel) {
                 const uint32_t lo = qq == 1 ? lq1 : qq == 2 ? lq2 : qq == 3 ? lq3 : lq4;
                 const uint32_t hi = qq == 1 ? 0u : qq == 2 ? lq1 : qq == 3 ? lq2 : lq3;
@@ -528,6 +534,10 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
                     }
                     lq4 = lq3; lq3 = lq2; lq2 = lq1;
                     lq1 = __ballot_sync(0xffffffffu, live);
+                    if (t0_rel >= s_rel) {  // all-noise decisions: one coalesced 128-byte store
+                        dec[base0 + t0_rel + lane] = 0u;
+                        if (lane == 0) nzm[(base0 + t0_rel) >> 5] = 0u;
+                    }
                     __syncwarp();
                     continue;
                 }
@@ -1212,19 +1222,19 @@ static VitVariant make_variant() {
                       &stage_trace<N, R, LPC>, &stage_verify_trace<N, R, LPC>};
 }
 template <int N, int R>
-static VitVariant pick_lp(int LP, bool const_ok) {
-    if (const_ok && LP == 64) return make_variant<N, R, 64>();
-    if (const_ok && LP == 48) return make_variant<N, R, 48>();
+static VitVariant pick_lp(int L, bool const_ok) {
+    if (const_ok && L == 59) return make_variant<N, R, 59>();  // K = 60 templates
+    if (const_ok && L == 47) return make_variant<N, R, 47>();  // K = 48 templates
     return make_variant<N, R, 0>();
 }
-static VitVariant pick_variant(int N, int LP, bool const_ok) {
+static VitVariant pick_variant(int N, int L, bool const_ok) {
     switch (N) {
         case 1: return make_variant<1, 8, 0>();
         case 2: return make_variant<2, 8, 0>();
         case 3:
-            return pick_lp<3, 8>(LP, const_ok);
-        case 4: return pick_lp<4, 8>(LP, const_ok);
-        case 5: return pick_lp<5, 4>(LP, const_ok);
+            return pick_lp<3, 8>(L, const_ok);
+        case 4: return pick_lp<4, 8>(L, const_ok);
+        case 5: return pick_lp<5, 4>(L, const_ok);
         case 6: return make_variant<6, 4, 0>();
         case 7: return make_variant<7, 4, 0>();
     }
@@ -1269,7 +1279,7 @@ int ring_default_chunking(const HostModel &M0, int64_t T_total, int C, int n_gpu
     const int R = (N <= 4) ? 8 : 4, SW = 32 * R;
     RingLayout RL = ring_layout(N, L);
     const bool no_const = getenv("HMMCUDA_NO_CONST_FIR") && atoi(getenv("HMMCUDA_NO_CONST_FIR")) != 0;
-    const VitVariant variant = pick_variant(N, RL.LP, C == 1 && !no_const);
+    const VitVariant variant = pick_variant(N, RL.L, C == 1 && !no_const);
     int64_t W = ring_config().warmup > 0 ? ring_config().warmup : 512;
     W = ((W + SW - 1) / SW) * SW;
     if (W < ((L + 32 + SW - 1) / SW) * SW) W = ((L + 32 + SW - 1) / SW) * SW;
@@ -1302,7 +1312,7 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     const int N = M0.N, L = M0.K - 1, ns = M0.nstates;
     RingLayout RL = ring_layout(N, L);
     const bool no_const = getenv("HMMCUDA_NO_CONST_FIR") && atoi(getenv("HMMCUDA_NO_CONST_FIR")) != 0;
-    impl->variant = pick_variant(N, RL.LP, C == 1 && !no_const);
+    impl->variant = pick_variant(N, RL.L, C == 1 && !no_const);
     int nchunks = (int)((T + Lc - 1) / Lc);
     // the last chunk must be long enough to hold the final look-back of L steps
     if (nchunks > 1 && T - (int64_t)(nchunks - 1) * Lc < RING_Q) nchunks--;
@@ -1386,8 +1396,8 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
 void VitPlan::forward(cudaStream_t st, Timer *ttop) {
     VitParams &p = *p_;
     // a plan can be run repeatedly: everything the kernels accumulate into is re-zeroed here
-    HMM_CUDA(cudaMemsetAsync(p.dec, 0, sizeof(uint32_t) * (size_t)C * p.T, st));
-    HMM_CUDA(cudaMemsetAsync(p.nzmask, 0, sizeof(uint32_t) * (size_t)C * ((p.T + 31) / 32), st));
+    // (the decision words and the non-zero masks are written for every step of every chunk's main range by the
+    // forward kernel, so they need no clearing)
     HMM_CUDA(cudaMemsetAsync(p.counters, 0, sizeof(int) * (size_t)C * 4, st));
     HMM_CUDA(cudaMemsetAsync(p.Pfin, 0, sizeof(double) * (size_t)C * p.RL.N * RING_Q, st));
     impl->variant.forward(p, hmdl.data(), C, st, ttop);
