@@ -788,47 +788,65 @@ __device__ void trace_chunk(const VitParams &p, int ch, int c, int64_t tau_hi, l
     int64_t e = s + p.Lc_t;
     if (c == p.nchunks_t - 1 || e > T) e = T;
     const int64_t lo = (c == 0 && p.first_prologue) ? (int64_t)(L + 1) : s;
-    const uint32_t *dec = p.dec + (size_t)ch * T;
-    const uint32_t *nzm = p.nzmask + (size_t)ch * ((T + 31) / 32);
+    // Everything below is in 32-bit coordinates relative to the chunk start s (a multiple of 256):
+    // the walk covers [lo, tau_hi], at most Lc_t + W steps, and a chain entered before lo lies at most L below 0.
+    const uint32_t *dec_s = p.dec + (size_t)ch * T + s;
+    const uint32_t *nzm_s = p.nzmask + (size_t)ch * ((T + 31) / 32) + (s >> 5);
     int16_t *x = p.x + (size_t)ch * p.x_stride;
+    int16_t *xs = x + s;
+    const int e_r = (int)(e - s), lo_r = (int)(lo - s);
+    const int dmin_r = s >= L ? -(1 << 30) : (int)(L - s);  // steps below it have no decision word L steps earlier
+    int xlo_r, xhi_r;                                        // the part of [s, e) this plan writes x for
+    {
+        int64_t a = p.x_lo - s, b = p.x_hi - s;
+        xlo_r = (int)(a < 0 ? 0 : (a > e_r ? e_r : a));
+        xhi_r = (int)(b < 0 ? 0 : (b > e_r ? e_r : b));
+    }
     uint32_t *mw = tws, *pre = mw + TR_TILE_W, *ent = pre + TR_TILE_W;
     uint16_t *pos = reinterpret_cast<uint16_t *>(ent + 2 * TR_CAP);
     long long own = -2, look = -2;
-    int64_t cur = tau_hi;
-    int64_t tile_wlo = 0, tile_whi = -1;  // invalid
-    const int64_t wlo = lo >> 5;
-    // segment [a, b] is decoded as `state`: remember what the chunk boundaries see, write x
-    auto emit_noise = [&](int64_t a, int64_t b) {
-        if (record_look && e <= b && e >= a) look = -1;
-        if (s <= b && s >= a) own = -1;
-        int64_t wa = a < s ? s : a, wb = b < e - 1 ? b : e - 1;
-        if (wa < p.x_lo) wa = p.x_lo;
-        if (wb > p.x_hi - 1) wb = p.x_hi - 1;
-        for (int64_t t = wa + lane; t <= wb; t += 32) x[t] = 1;
+    int cur = (int)(tau_hi - s);
+    int tile_wlo = 0, tile_whi = -1;  // invalid
+    const int wlo = lo_r >> 5;
+    // ---- noise everywhere first (16-byte stores); the spikes are painted over it ----
+    if (xhi_r > xlo_r) {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(xs + xlo_r);
+        int head = (int)(((16 - (addr & 15)) & 15) >> 1);
+        if (head > xhi_r - xlo_r) head = xhi_r - xlo_r;
+        if (lane < head) xs[xlo_r + lane] = 1;
+        const int a2 = xlo_r + head;
+        const int nvec = (xhi_r - a2) >> 3;
+        uint4 *vp = reinterpret_cast<uint4 *>(xs + a2);
+        const uint4 ones = make_uint4(0x00010001u, 0x00010001u, 0x00010001u, 0x00010001u);
+        for (int k = lane; k < nvec; k += 32) vp[k] = ones;
+        const int a3 = a2 + 8 * nvec;
+        if (a3 + lane < xhi_r) xs[a3 + lane] = 1;
+    }
+    __syncwarp();
+    // segment [a, b] is decoded as `state`: remember what the chunk boundaries see
+    auto see = [&](int a, int b, long long state) {
+        if (record_look && e_r <= b && e_r >= a) look = state;
+        if (0 <= b && 0 >= a) own = state;
     };
-    auto emit_spike = [&](int64_t a, int64_t b, long long state) {
-        const int i = (int)(state & 7);
-        const int64_t t0 = state >> 3;
-        if (record_look && e <= b && e >= a) look = state;
-        if (s <= b && s >= a) own = state;
-        int64_t wa = a < s ? s : a, wb = b < e - 1 ? b : e - 1;
-        if (wa < p.x_lo) wa = p.x_lo;
-        if (wb > p.x_hi - 1) wb = p.x_hi - 1;
-        for (int64_t t = wa + lane; t <= wb; t += 32) x[t] = (int16_t)(2 + i * L + (int)(t - t0));
+    auto emit_spike = [&](int a, int b, long long state, int t0_r) {
+        see(a, b, state);
+        const int wa = a < xlo_r ? xlo_r : a, wb = b < xhi_r - 1 ? b : xhi_r - 1;
+        const int base = 2 + (int)(state & 7) * L - t0_r;
+        for (int t = wa + lane; t <= wb; t += 32) xs[t] = (int16_t)(base + t);
     };
-    while (cur >= lo) {
+    while (cur >= lo_r) {
         if (st < 0) {
             // ---- make sure the tile holding `cur` is staged: mask words, ranks, decision entries ----
-            const int64_t wc = cur >> 5;
+            const int wc = cur >> 5;
             if (wc > tile_whi || wc < tile_wlo) {
                 tile_whi = wc;
                 tile_wlo = wc - (TR_TILE_W - 1);
                 if (tile_wlo < wlo) tile_wlo = wlo;
-                const int nW = (int)(tile_whi - tile_wlo + 1);
+                const int nW = tile_whi - tile_wlo + 1;
                 __syncwarp();
                 for (int k = lane; k < TR_TILE_W; k += 32) {
-                    uint32_t word = k < nW ? nzm[tile_wlo + k] : 0u;
-                    if (tile_wlo + k == wlo) word &= ~((1u << (lo & 31)) - 1u);
+                    uint32_t word = k < nW ? nzm_s[tile_wlo + k] : 0u;
+                    if (tile_wlo + k == wlo) word &= ~((1u << (lo_r & 31)) - 1u);
                     mw[k] = word;
                 }
                 __syncwarp();
@@ -857,76 +875,75 @@ __device__ void trace_chunk(const VitParams &p, int ch, int c, int64_t tau_hi, l
                 __syncwarp();
                 const int n = total < TR_CAP ? total : TR_CAP;
                 for (int q = lane; q < n; q += 32) {
-                    const int64_t tp = (tile_wlo << 5) + pos[q];
-                    ent[2 * q] = dec[tp];
-                    ent[2 * q + 1] = tp >= L ? dec[tp - L] : 0u;
+                    const int tp = (tile_wlo << 5) + pos[q];
+                    ent[2 * q] = dec_s[tp];
+                    ent[2 * q + 1] = tp >= dmin_r ? dec_s[tp - L] : 0u;
                 }
                 __syncwarp();
             }
             // ---- latest step tp <= cur in this tile where noise was entered from a tail ----
-            int64_t tp = -1;
-            uint32_t wsel = 0;
-            for (int64_t whi = wc; whi >= tile_wlo; whi -= 32) {
-                const int64_t wi = whi - lane;
+            int tp = -(1 << 30);
+            for (int whi = wc; whi >= tile_wlo; whi -= 32) {
+                const int wi = whi - lane;
                 uint32_t word = 0;
                 if (wi >= tile_wlo) {
                     word = mw[wi - tile_wlo];
                     if (wi == wc) {
-                        const int hb = (int)(cur & 31);
+                        const int hb = cur & 31;
                         if (hb < 31) word &= (2u << hb) - 1u;
                     }
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, word != 0);
                 if (bal) {
                     const int src = __ffs(bal) - 1;
-                    wsel = __shfl_sync(0xffffffffu, word, src);
+                    const uint32_t wsel = __shfl_sync(0xffffffffu, word, src);
                     tp = ((whi - src) << 5) + (31 - __clz(wsel));
                     break;
                 }
             }
-            if (tp < 0) {  // noise all the way down to the bottom of the tile
-                const int64_t bottom = (tile_wlo << 5) < lo ? lo : (tile_wlo << 5);
-                emit_noise(bottom, cur);
+            if (tp == -(1 << 30)) {  // noise all the way down to the bottom of the tile
+                const int bottom = (tile_wlo << 5) < lo_r ? lo_r : (tile_wlo << 5);
+                see(bottom, cur, -1);
                 cur = bottom - 1;
                 continue;  // reaches lo -> loop ends; otherwise the next tile is staged
             }
-            emit_noise(tp, cur);  // (tp, cur] and tp itself are noise
+            see(tp, cur, -1);  // (tp, cur] and tp itself are noise
             uint32_t d1, d2;
             {
-                const int widx = (int)((tp >> 5) - tile_wlo);
+                const int widx = (tp >> 5) - tile_wlo;
                 const int rank = (int)pre[widx] + __popc(mw[widx] & ((1u << (tp & 31)) - 1u));
                 if (rank < TR_CAP) {
                     d1 = ent[2 * rank];
                     d2 = ent[2 * rank + 1];
                 } else {
-                    d1 = dec[tp];
-                    d2 = tp >= L ? dec[tp - L] : 0u;
+                    d1 = dec_s[tp];
+                    d2 = tp >= dmin_r ? dec_s[tp - L] : 0u;
                 }
             }
             const int j = (int)(d1 & 15u);  // 1..N: noise at tp was entered from tail_j at tp-1
-            const int64_t t0 = tp - L;      // that chain was entered at t0 and occupies [t0, tp-1]
-            const long long sp = enc_spike(t0, j - 1);
-            emit_spike(t0 < lo ? lo : t0, tp - 1, sp);
-            if (t0 < lo) {
+            const int t0 = tp - L;          // that chain was entered at t0 and occupies [t0, tp-1]
+            const long long sp = enc_spike(s + t0, j - 1);
+            emit_spike(t0 < lo_r ? lo_r : t0, tp - 1, sp, t0);
+            if (t0 < lo_r) {
                 st = sp;
-                cur = lo - 1;
+                cur = lo_r - 1;
                 break;
             }
             const int k = (int)((d2 >> (4 * j)) & 15u);
             cur = t0 - 1;
-            st = (k == 0) ? -1 : enc_spike(t0 - L, k - 1);
+            st = (k == 0) ? -1 : enc_spike(s + t0 - L, k - 1);
         } else {
             // chain state at cur (start state, or chains entered directly from another chain's tail)
             const int i = (int)(st & 7);
-            const int64_t t0 = st >> 3;
-            emit_spike(t0 < lo ? lo : t0, cur, st);
-            if (t0 < lo) {
-                cur = lo - 1;
+            const int t0 = (int)((st >> 3) - s);
+            emit_spike(t0 < lo_r ? lo_r : t0, cur, st, t0);
+            if (t0 < lo_r) {
+                cur = lo_r - 1;
                 break;
             }
-            const int k = (int)((dec[t0] >> (4 * (i + 1))) & 15u);
+            const int k = (int)((dec_s[t0] >> (4 * (i + 1))) & 15u);
             cur = t0 - 1;
-            st = (k == 0) ? -1 : enc_spike(t0 - L, k - 1);
+            st = (k == 0) ? -1 : enc_spike(s + t0 - L, k - 1);
         }
     }
     if (c == 0 && p.first_prologue) {
