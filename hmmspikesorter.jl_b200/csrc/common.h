@@ -44,12 +44,18 @@ class Workspace {
         ALPHA, BETA, SCRATCH, NSLOTS
     };
     void *get(Slot s, size_t bytes);
+    // Grow-only pinned, device-mapped host buffers (two slots): staging for small per-call uploads and a
+    // landing zone kernels can write results into directly.  *dev_ptr receives the device-side alias.
+    void *pinned(int slot, size_t bytes, void **dev_ptr = nullptr);
     void release();
     ~Workspace() { release(); }
 
   private:
+    void bind_device();
     void *ptr_[NSLOTS] = {};
     size_t cap_[NSLOTS] = {};
+    void *hptr_[2] = {};
+    size_t hcap_[2] = {};
     int dev_ = -1;
 };
 

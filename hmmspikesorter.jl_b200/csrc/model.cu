@@ -10,13 +10,17 @@
 namespace hmm {
 
 // ---------------------------------------------------------------------------
-void *Workspace::get(Slot s, size_t bytes) {
+void Workspace::bind_device() {  // buffers belong to one device: switching devices drops them
     int dev = 0;
     HMM_CUDA(cudaGetDevice(&dev));
     if (dev != dev_) {
         release();
         dev_ = dev;
     }
+}
+
+void *Workspace::get(Slot s, size_t bytes) {
+    bind_device();
     if (bytes == 0) bytes = 16;
     if (cap_[s] < bytes) {
         if (ptr_[s]) {
@@ -40,11 +44,33 @@ void *Workspace::get(Slot s, size_t bytes) {
     return ptr_[s];
 }
 
+void *Workspace::pinned(int slot, size_t bytes, void **dev_ptr) {
+    bind_device();
+    if (bytes == 0) bytes = 16;
+    if (hcap_[slot] < bytes) {
+        if (hptr_[slot]) {
+            HMM_CUDA(cudaFreeHost(hptr_[slot]));
+            hptr_[slot] = nullptr;
+            hcap_[slot] = 0;
+        }
+        const size_t want = bytes + bytes / 4 + 4096;
+        HMM_CUDA(cudaHostAlloc(&hptr_[slot], want, cudaHostAllocMapped | cudaHostAllocPortable));
+        hcap_[slot] = want;
+    }
+    if (dev_ptr) HMM_CUDA(cudaHostGetDevicePointer(dev_ptr, hptr_[slot], 0));
+    return hptr_[slot];
+}
+
 void Workspace::release() {
     for (int i = 0; i < NSLOTS; i++) {
         if (ptr_[i]) cudaFree(ptr_[i]);
         ptr_[i] = nullptr;
         cap_[i] = 0;
+    }
+    for (int i = 0; i < 2; i++) {
+        if (hptr_[i]) cudaFreeHost(hptr_[i]);
+        hptr_[i] = nullptr;
+        hcap_[i] = 0;
     }
 }
 

@@ -26,7 +26,7 @@ constexpr int RING_Q = 128;      // ring-buffer length (>= L + 32), power of two
 // Per-channel ring model, a flat array of doubles on the device.
 struct RingLayout {
     int N, L, LP, NP;            // LP = L rounded up to 8; NP = N rounded up to even
-    int A, BW, B0, BWsuf, Bc, eG, eH, eT, scal, cL, hot, total;  // offsets in doubles
+    int A, BW, B0, BWsuf, Bc, eG, eH, eT, scal, cL, xG, xH, xT, hot, total;  // offsets in doubles
 };
 // scal[]: 0 w_nn, 1 c_emit, 2 two_s2, 3 m0, 4 sigma
 __host__ __device__ inline RingLayout ring_layout(int N, int L) {
@@ -44,6 +44,9 @@ __host__ __device__ inline RingLayout ring_layout(int N, int L) {
     R.eT = o; o += N * R.NP;      // eT[j*NP + i]
     R.scal = o; o += 8;
     R.cL = o; o += R.NP;          // liveness margin per neuron (ring_viterbi.cu)
+    R.xG = o; o += R.NP;          // exp(eG), exp(eH), exp(eT): linear-domain weights (ring_em.cu)
+    R.xH = o; o += R.NP;
+    R.xT = o; o += N * R.NP;
     R.hot = o;
     // cold part (boundary handling only; read from global memory)
     R.BW = o; o += R.LP * R.NP;   // BW[r*NP + i] = b[i][r] + (r>0 ? w_c[i][r-1]-w_nn : 0)

@@ -43,6 +43,7 @@ struct EmParams {
     double *lS;                       // [1] log of the normalised total likelihood
     int *counters;                    // [0] fwd repaired [1] bwd repaired
     double *part;                     // [nblk][PSTRIDE] statistic partials
+    double *tot;                      // [PSTRIDE] their column sums (em_reduce)
     int nblk, pstride;
     double *out;                      // finalize output
 };
@@ -90,6 +91,17 @@ __device__ void em_fwd_chunk(const EmParams &p, int c, int kind, const double *m
         for (int i = 0; i < N; i++)
             if (i != j) c = fmax(c, lC[j * NP + i] - lH[i]);
         cF[j] = c;
+    }
+    // linear-domain copies of the weights, and cM[j] = the largest weight a tail of neuron j is multiplied by
+    const double *xA = mdl + RL.xG, *xH = mdl + RL.xH, *xC = mdl + RL.xT;
+    double cM[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        double c = lA[j];
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            if (i != j) c = fmax(c, lC[j * NP + i]);
+        cM[j] = c;
     }
     const double *cold = p.model;
     const double *y = p.y;
@@ -205,25 +217,75 @@ __device__ void em_fwd_chunk(const EmParams &p, int c, int kind, const double *m
                         continue;
                     }
                 }
-                double lX = NEG;
+                // Live window.  The sums are formed in the linear domain, relative to the largest term of
+                // the window (ref), so that a step costs N exp + 1 log instead of ~N^2 + 5 log-sum-exps:
+                //   g_t = g_{t-1} + sum_j u_j(t) xA_j   (a prefix sum over the lanes),   lg_t = ref + log g_t
+                double mx = NEG;
 #pragma unroll
-                for (int j = 0; j < N; j++) lX = lse2(lX, lt[j] + lA[j]);
-                const double lCs = lse_scan(lX, lane);
-                const double lg = lse2(lgprev, lCs);
-                double lgm1 = shfl_up_d(lg, 1);
-                if (lane == 0) lgm1 = lgprev;
-                if (active) {
+                for (int j = 0; j < N; j++) mx = fmax(mx, lt[j] + cM[j]);
 #pragma unroll
-                    for (int i = 0; i < N; i++) {
-                        double lp = lgm1 + lH[i];
+                for (int d = 16; d >= 1; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+                const double ref = fmax(lgprev, mx);
+                double lg, lgm1;
+                if (ref - lgprev < 600.0) {
+                    double u[N];
 #pragma unroll
-                        for (int j = 0; j < N; j++)
-                            if (j != i) lp = lse2(lp, lt[j] + lC[j * NP + i]);
-                        const double lq = lp + Fv[i];
-                        ring[i * RING_Q + slot_w] = lq;
-                        if (t0_rel >= s_rel) p.LQ[(size_t)i * T + tau] = lq;
+                    for (int j = 0; j < N; j++) u[j] = exp(lt[j] - ref);  // exp(-inf) = 0 for idle lanes
+                    const double g0 = exp(lgprev - ref);
+                    double cs = 0.0;
+#pragma unroll
+                    for (int j = 0; j < N; j++) cs = fma(u[j], xA[j], cs);
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const double o = shfl_up_d(cs, d);
+                        if (lane >= d) cs += o;
                     }
-                    if (t0_rel >= s_rel) p.LG[tau] = lg;
+                    const double g = g0 + cs;
+                    lg = ref + log(g);
+                    double gm1 = shfl_up_d(g, 1);
+                    lgm1 = shfl_up_d(lg, 1);
+                    if (lane == 0) {
+                        gm1 = g0;
+                        lgm1 = lgprev;
+                    }
+                    if (active) {
+#pragma unroll
+                        for (int i = 0; i < N; i++) {
+                            double cross = 0.0;
+#pragma unroll
+                            for (int j = 0; j < N; j++)
+                                if (j != i) cross = fma(u[j], xC[j * NP + i], cross);
+                            const double nz = gm1 * xH[i];
+                            double lp = lgm1 + lH[i];
+                            if (cross > nz * 0x1p-60) lp = ref + log(nz + cross);  // a tail feeds head i directly
+                            const double lq = lp + Fv[i];
+                            ring[i * RING_Q + slot_w] = lq;
+                            if (t0_rel >= s_rel) p.LQ[(size_t)i * T + tau] = lq;
+                        }
+                        if (t0_rel >= s_rel) p.LG[tau] = lg;
+                    }
+                } else {
+                    // a single window spans more than e^600: stay in the log domain
+                    double lX = NEG;
+#pragma unroll
+                    for (int j = 0; j < N; j++) lX = lse2(lX, lt[j] + lA[j]);
+                    const double lCs = lse_scan(lX, lane);
+                    lg = lse2(lgprev, lCs);
+                    lgm1 = shfl_up_d(lg, 1);
+                    if (lane == 0) lgm1 = lgprev;
+                    if (active) {
+#pragma unroll
+                        for (int i = 0; i < N; i++) {
+                            double lp = lgm1 + lH[i];
+#pragma unroll
+                            for (int j = 0; j < N; j++)
+                                if (j != i) lp = lse2(lp, lt[j] + lC[j * NP + i]);
+                            const double lq = lp + Fv[i];
+                            ring[i * RING_Q + slot_w] = lq;
+                            if (t0_rel >= s_rel) p.LQ[(size_t)i * T + tau] = lq;
+                        }
+                        if (t0_rel >= s_rel) p.LG[tau] = lg;
+                    }
                 }
                 lgprev = shfl_d(lg, 31);
                 __syncwarp();
@@ -242,7 +304,7 @@ __device__ void em_fwd_chunk(const EmParams &p, int c, int kind, const double *m
 }
 
 template <int N, int R>
-__global__ void __launch_bounds__(128) em_forward(EmParams p) {
+__global__ void __launch_bounds__(128, 4) em_forward(EmParams p) {
     extern __shared__ __align__(16) double smem_d[];
     double *mdl = smem_d;
     for (int k = threadIdx.x; k < p.RL.hot; k += blockDim.x) mdl[k] = p.model[k];
@@ -275,9 +337,12 @@ __device__ __forceinline__ bool em_boundary_matches(const double *sb, const doub
     return !__any_sync(0xffffffffu, bad);
 }
 
-__global__ void em_check(EmParams p, int backward) {
+// dirs: bit 0 = forward boundaries, bit 1 = backward boundaries (blockIdx.y selects the direction)
+__global__ void em_check(EmParams p, int dirs) {
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int backward = blockIdx.y;
+    if (!((dirs >> backward) & 1)) return;
     if (!backward) {
         if (gw >= p.nchunks || gw == 0) return;
         bool ok = em_boundary_matches(p.SBf + (size_t)gw * p.bvec, p.EBf + (size_t)(gw - 1) * p.bvec, p.bvec, lane);
@@ -308,6 +373,16 @@ __device__ void em_bwd_chunk(const EmParams &p, int c, int kind, const double *m
         for (int i = 0; i < N; i++)
             if (i != j) c2 = fmax(c2, lC[i * NP + j] - lA[i]);
         cB[j] = c2;
+    }
+    const double *xA = mdl + RL.xG, *xH = mdl + RL.xH, *xC = mdl + RL.xT;
+    double cM[N];  // the largest weight an entry into chain j is multiplied by
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        double c2 = lH[j];
+#pragma unroll
+        for (int i = 0; i < N; i++)
+            if (i != j) c2 = fmax(c2, lC[i * NP + j]);
+        cM[j] = c2;
     }
     const int64_t T = p.T;
     const int64_t s = (int64_t)c * p.Lc;
@@ -375,24 +450,70 @@ __device__ void em_bwd_chunk(const EmParams &p, int c, int kind, const double *m
                     continue;
                 }
             }
-            double lY = -INFINITY;
+            // Live window: linear domain relative to the window's largest term (see em_fwd_chunk).
+            double mx = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < N; j++) lY = lse2(lY, lH[j] + lr[j]);
-            const double sc = lse_scan(lY, lane);
-            const double lh = lse2(lhprev, sc);
-            double lhp1 = shfl_up_d(lh, 1);  // lh_{t+1}
-            if (lane == 0) lhp1 = lhprev;
-            if (active) {
+            for (int j = 0; j < N; j++) mx = fmax(mx, lr[j] + cM[j]);
 #pragma unroll
-                for (int i = 0; i < N; i++) {
-                    double le = lA[i] + lhp1;
+            for (int d = 16; d >= 1; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+            const double ref = fmax(lhprev, mx);
+            double lh, lhp1;
+            if (ref - lhprev < 600.0) {
+                double v[N];
 #pragma unroll
-                    for (int j = 0; j < N; j++)
-                        if (j != i) le = lse2(le, lC[i * NP + j] + lr[j]);
-                    ring[i * RING_Q + (int)(t & (RING_Q - 1))] = le;
-                    if (t < e) p.LE[(size_t)i * T + t] = le;
+                for (int j = 0; j < N; j++) v[j] = exp(lr[j] - ref);
+                const double h0 = exp(lhprev - ref);
+                double cs = 0.0;
+#pragma unroll
+                for (int j = 0; j < N; j++) cs = fma(v[j], xH[j], cs);
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const double o = shfl_up_d(cs, d);
+                    if (lane >= d) cs += o;
                 }
-                if (t < e) p.LH[t] = lh;
+                const double h = h0 + cs;
+                lh = ref + log(h);
+                double hp1 = shfl_up_d(h, 1);
+                lhp1 = shfl_up_d(lh, 1);  // lh_{t+1}
+                if (lane == 0) {
+                    hp1 = h0;
+                    lhp1 = lhprev;
+                }
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < N; i++) {
+                        double cross = 0.0;
+#pragma unroll
+                        for (int j = 0; j < N; j++)
+                            if (j != i) cross = fma(v[j], xC[i * NP + j], cross);
+                        const double nz = hp1 * xA[i];
+                        double le = lA[i] + lhp1;
+                        if (cross > nz * 0x1p-60) le = ref + log(nz + cross);
+                        ring[i * RING_Q + (int)(t & (RING_Q - 1))] = le;
+                        if (t < e) p.LE[(size_t)i * T + t] = le;
+                    }
+                    if (t < e) p.LH[t] = lh;
+                }
+            } else {
+                double lY = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < N; j++) lY = lse2(lY, lH[j] + lr[j]);
+                const double sc = lse_scan(lY, lane);
+                lh = lse2(lhprev, sc);
+                lhp1 = shfl_up_d(lh, 1);  // lh_{t+1}
+                if (lane == 0) lhp1 = lhprev;
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < N; i++) {
+                        double le = lA[i] + lhp1;
+#pragma unroll
+                        for (int j = 0; j < N; j++)
+                            if (j != i) le = lse2(le, lC[i * NP + j] + lr[j]);
+                        ring[i * RING_Q + (int)(t & (RING_Q - 1))] = le;
+                        if (t < e) p.LE[(size_t)i * T + t] = le;
+                    }
+                    if (t < e) p.LH[t] = lh;
+                }
             }
             lhprev = shfl_d(lh, 31);
             __syncwarp();
@@ -432,64 +553,60 @@ __global__ void __launch_bounds__(128) em_backward(EmParams p) {
 // sequential repair + per-chunk log offsets (one warp)
 // ---------------------------------------------------------------------------
 template <int N, int R>
-__global__ void __launch_bounds__(32) em_repair_fwd(EmParams p) {
+__global__ void __launch_bounds__(64) em_repair(EmParams p, int dirs, int fwd_doubles /*smem doubles of the forward half*/) {
     extern __shared__ __align__(16) double smem_d[];
-    const int lane = threadIdx.x;
-    int any = 0;
-    for (int c = 1 + lane; c < p.nchunks; c += 32) any |= p.flag_f[c];
+    const int lane = threadIdx.x & 31;
+    const int backward = threadIdx.x >> 5;  // warp 0 repairs the forward pass, warp 1 the backward pass
+    if (!((dirs >> backward) & 1)) return;
+    double *mdl = smem_d + (backward ? fwd_doubles : 0);
+    double *ws = mdl + ((p.RL.hot + 1) & ~1);
     int repaired = 0;
-    if (__any_sync(0xffffffffu, any)) {
-        double *mdl = smem_d;
-        for (int k = lane; k < p.RL.hot; k += 32) mdl[k] = p.model[k];
-        __syncwarp();
-        double *ws = smem_d + ((p.RL.hot + 1) & ~1);
-        bool prev = false;
-        for (int c = 1; c < p.nchunks; c++) {
-            bool need = p.flag_f[c] != 0;
-            if (!need && prev)
-                need = !em_boundary_matches(p.SBf + (size_t)c * p.bvec, p.EBf + (size_t)(c - 1) * p.bvec, p.bvec, lane);
-            if (need) {
-                em_fwd_chunk<N, R>(p, c, EM_EXACT, mdl, ws);
-                // an exactly restarted chunk continues chunk c-1's normalisation
-                if (lane == 0) p.SBf[(size_t)c * p.bvec] = p.EBf[(size_t)(c - 1) * p.bvec];
-                __threadfence();
-                __syncwarp();
-                repaired++;
+    if (!backward) {
+        int any = 0;
+        for (int c = 1 + lane; c < p.nchunks; c += 32) any |= p.flag_f[c];
+        if (__any_sync(0xffffffffu, any)) {
+            for (int k = lane; k < p.RL.hot; k += 32) mdl[k] = p.model[k];
+            __syncwarp();
+            bool prev = false;
+            for (int c = 1; c < p.nchunks; c++) {
+                bool need = p.flag_f[c] != 0;
+                if (!need && prev)
+                    need = !em_boundary_matches(p.SBf + (size_t)c * p.bvec, p.EBf + (size_t)(c - 1) * p.bvec, p.bvec, lane);
+                if (need) {
+                    em_fwd_chunk<N, R>(p, c, EM_EXACT, mdl, ws);
+                    // an exactly restarted chunk continues chunk c-1's normalisation
+                    if (lane == 0) p.SBf[(size_t)c * p.bvec] = p.EBf[(size_t)(c - 1) * p.bvec];
+                    __threadfence();
+                    __syncwarp();
+                    repaired++;
+                }
+                prev = need;
             }
-            prev = need;
         }
-    }
-    if (lane == 0) p.counters[0] = repaired;
-}
-
-template <int N>
-__global__ void __launch_bounds__(32) em_repair_bwd(EmParams p) {
-    extern __shared__ __align__(16) double smem_d[];
-    const int lane = threadIdx.x;
-    int any = 0;
-    for (int c = lane; c < p.nchunks - 1; c += 32) any |= p.flag_b[c];
-    int repaired = 0;
-    if (__any_sync(0xffffffffu, any)) {
-        double *mdl = smem_d;
-        for (int k = lane; k < p.RL.hot; k += 32) mdl[k] = p.model[k];
-        __syncwarp();
-        double *ring = smem_d + ((p.RL.hot + 1) & ~1);
-        bool prev = false;
-        for (int c = p.nchunks - 2; c >= 0; c--) {
-            bool need = p.flag_b[c] != 0;
-            if (!need && prev)
-                need = !em_boundary_matches(p.SBb + (size_t)c * p.bvec, p.EBb + (size_t)(c + 1) * p.bvec, p.bvec, lane);
-            if (need) {
-                em_bwd_chunk<N>(p, c, EM_EXACT, mdl, ring);
-                if (lane == 0) p.SBb[(size_t)c * p.bvec] = p.EBb[(size_t)(c + 1) * p.bvec];
-                __threadfence();
-                __syncwarp();
-                repaired++;
+        if (lane == 0) p.counters[0] = repaired;
+    } else {
+        int any = 0;
+        for (int c = lane; c < p.nchunks - 1; c += 32) any |= p.flag_b[c];
+        if (__any_sync(0xffffffffu, any)) {
+            for (int k = lane; k < p.RL.hot; k += 32) mdl[k] = p.model[k];
+            __syncwarp();
+            bool prev = false;
+            for (int c = p.nchunks - 2; c >= 0; c--) {
+                bool need = p.flag_b[c] != 0;
+                if (!need && prev)
+                    need = !em_boundary_matches(p.SBb + (size_t)c * p.bvec, p.EBb + (size_t)(c + 1) * p.bvec, p.bvec, lane);
+                if (need) {
+                    em_bwd_chunk<N>(p, c, EM_EXACT, mdl, ws);
+                    if (lane == 0) p.SBb[(size_t)c * p.bvec] = p.EBb[(size_t)(c + 1) * p.bvec];
+                    __threadfence();
+                    __syncwarp();
+                    repaired++;
+                }
+                prev = need;
             }
-            prev = need;
         }
+        if (lane == 0) p.counters[1] = repaired;
     }
-    if (lane == 0) p.counters[1] = repaired;
 }
 
 // kappa_c = sum_{k<=c} (EBf[k-1].lg - SBf[k].lg);  lambda_c = sum_{k>=c} (EBb[k+1].lh - SBb[k].lh)
@@ -502,29 +619,36 @@ __device__ __forceinline__ double block_scan_256(double v, double *wsum) {
         double o = shfl_up_d(v, d);
         if (lane >= d) v += o;
     }
-    if (lane == 31) wsum[warp] = v;
+    if (lane == 31 && warp < 8) wsum[warp] = v;
     __syncthreads();
     double base = 0.0;
-    for (int w = 0; w < warp; w++) base += wsum[w];
+    for (int w = 0; w < warp && w < 8; w++) base += wsum[w];
     __syncthreads();
-    return v + base;
+    return v + base;  // (threads beyond the first 256 may take part in the barriers; their result is unused)
 }
 
 template <int N>
-__global__ void __launch_bounds__(256) em_offsets(EmParams p, int backward) {
+__global__ void __launch_bounds__(1024) em_offsets(EmParams p, int dirs) {
     __shared__ double wsum[8];
+    const int backward = blockIdx.x;  // block 0: kappa and lS, block 1: lambda
+    if (!((dirs >> backward) & 1)) return;
     const int n = p.nchunks;
     const int per = (n + 255) / 256;  // contiguous chunks per thread
-    const int c0 = threadIdx.x * per;
+    const int c0 = threadIdx.x < 256 ? threadIdx.x * per : n;  // the scan itself runs on the first 256 threads
+    // The per-chunk differences are first gathered with independent loads (the boundary vectors are bvec
+    // doubles apart) into kappa[] / lambda[] themselves, then scanned in place in a fixed order.
     if (!backward) {
         // kappa_c = sum_{k<=c} d_k,  d_k = EBf[k-1].lg - SBf[k].lg  (d_0 = 0)
+        for (int c = threadIdx.x; c < n; c += blockDim.x)
+            p.kappa[c] = c >= 1 ? p.EBf[(size_t)(c - 1) * p.bvec] - p.SBf[(size_t)c * p.bvec] : 0.0;
+        __syncthreads();
         double loc = 0.0;
         for (int c = c0; c < c0 + per && c < n; c++)
-            if (c >= 1) loc += p.EBf[(size_t)(c - 1) * p.bvec] - p.SBf[(size_t)c * p.bvec];
+            if (c >= 1) loc += p.kappa[c];
         const double incl = block_scan_256(loc, wsum);
         double run = incl - loc;
         for (int c = c0; c < c0 + per && c < n; c++) {
-            if (c >= 1) run += p.EBf[(size_t)(c - 1) * p.bvec] - p.SBf[(size_t)c * p.bvec];
+            if (c >= 1) run += p.kappa[c];
             p.kappa[c] = run;
         }
         __syncthreads();
@@ -542,16 +666,19 @@ __global__ void __launch_bounds__(256) em_offsets(EmParams p, int backward) {
         }
     } else {
         // lambda_c = sum_{k>=c} d_k,  d_k = EBb[k+1].lh - SBb[k].lh  (d_{n-1} = 0): scan the reversed order
+        for (int c = threadIdx.x; c < n; c += blockDim.x)
+            p.lambda[c] = c < n - 1 ? p.EBb[(size_t)(c + 1) * p.bvec] - p.SBb[(size_t)c * p.bvec] : 0.0;
+        __syncthreads();
         double loc = 0.0;
         for (int r = c0; r < c0 + per && r < n; r++) {
             const int c = n - 1 - r;
-            if (c < n - 1) loc += p.EBb[(size_t)(c + 1) * p.bvec] - p.SBb[(size_t)c * p.bvec];
+            if (c < n - 1) loc += p.lambda[c];
         }
         const double incl = block_scan_256(loc, wsum);
         double run = incl - loc;
         for (int r = c0; r < c0 + per && r < n; r++) {
             const int c = n - 1 - r;
-            if (c < n - 1) run += p.EBb[(size_t)(c + 1) * p.bvec] - p.SBb[(size_t)c * p.bvec];
+            if (c < n - 1) run += p.lambda[c];
             p.lambda[c] = run;
         }
     }
@@ -584,57 +711,79 @@ __global__ void __launch_bounds__(128) em_stats(EmParams p) {
     }
     const int64_t nwin = (T + 31) / 32;
     const int64_t gw = (int64_t)blockIdx.x * WPB + warp, nw = (int64_t)gridDim.x * WPB;
-    for (int64_t w = gw; w < nwin; w += nw) {
+    // Everything one window reads from global memory.  The loads of window w + nw are issued before window w
+    // is processed (the pass is otherwise bound by one exposed memory round trip per window).
+    struct WinLoads {
+        double kap, lam, lame, lamx, vLG, vLH, vLQ[N], vLEe[N], vLEx[N], vFn[N], yk[4];
+    };
+    auto issue = [&](int64_t w, WinLoads &o) {
         const int64_t t = w * 32 + lane;
-        const bool ok = t < T;
         // chunk indices without per-lane 64-bit divisions: Lc is a multiple of 256, so the whole
         // window lies in one chunk; t+L-1 and t+L are at most one chunk further (L < Lc)
         int c = (int)((w * 32) / p.Lc);
         if (c >= p.nchunks) c = p.nchunks - 1;
         const int64_t cend = (c == p.nchunks - 1) ? T : (int64_t)(c + 1) * p.Lc;
-        const int64_t tc = ok ? t : T - 1;
+        const int64_t tc = t < T ? t : T - 1;
         const int64_t te = tc + L - 1;  // the chain entered at t ends here
         const int64_t tx = tc + L;      // for xi: the chain entered at t+1 ends here
         const int ce = (te >= cend) ? c + 1 : c, cx = (tx >= cend) ? c + 1 : c;
         const bool e_in = te <= T - 1, x_in = tx <= T - 1, has_next = tc <= T - 2;
-        // ---- issue every global load of the window up front (independent, clamped indices) ----
-        const double kap = p.kappa[c], lam = p.lambda[c];
-        const double lame = p.lambda[e_in ? ce : c], lamx = p.lambda[x_in ? cx : c];
-        const double vLG = p.LG[tc], vLH = p.LH[tc];
-        double vLQ[N], vLEe[N], vLEx[N], vFn[N];
+        o.kap = p.kappa[c];
+        o.lam = p.lambda[c];
+        o.lame = p.lambda[e_in ? ce : c];
+        o.lamx = p.lambda[x_in ? cx : c];
+        o.vLG = p.LG[tc];
+        o.vLH = p.LH[tc];
 #pragma unroll
         for (int i = 0; i < N; i++) {
-            vLQ[i] = p.LQ[(size_t)i * T + tc];
-            vLEe[i] = p.LE[(size_t)i * T + (e_in ? te : T - 1)];
-            vLEx[i] = p.LE[(size_t)i * T + (x_in ? tx : T - 1)];
-            vFn[i] = p.Fg[(size_t)i * T + (has_next ? tc + 1 : T - 1)];
+            o.vLQ[i] = p.LQ[(size_t)i * T + tc];
+            o.vLEe[i] = p.LE[(size_t)i * T + (e_in ? te : T - 1)];
+            o.vLEx[i] = p.LE[(size_t)i * T + (x_in ? tx : T - 1)];
+            o.vFn[i] = p.Fg[(size_t)i * T + (has_next ? tc + 1 : T - 1)];
         }
-        double yv = 0.0;
-        for (int k = lane; k < 32 + L; k += 32) {
-            int64_t g = w * 32 + k;
-            double v = g < T ? p.y[g] : 0.0;
-            ysm[k] = v;
-            if (k == lane) yv = v;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = lane + 32 * q;
+            const int64_t g = w * 32 + k;
+            o.yk[q] = (k < 32 + L && g < T) ? p.y[g] : 0.0;
         }
+    };
+    WinLoads cur, nxt;
+    if (gw < nwin) issue(gw, cur);
+    for (int64_t w = gw; w < nwin; w += nw) {
+        if (w + nw < nwin) issue(w + nw, nxt);
+        const int64_t t = w * 32 + lane;
+        const bool ok = t < T;
+        const int64_t tc = ok ? t : T - 1;
+        const bool e_in = tc + L - 1 <= T - 1, x_in = tc + L <= T - 1, has_next = tc <= T - 2;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (lane + 32 * q < 32 + L) ysm[lane + 32 * q] = cur.yk[q];
+        const double yv = cur.yk[0];
         double pi[N];
         double pmax = 0.0;
         if (ok) {
-            const double g0 = exp(vLG + kap + vLH + lam - lS);
+            // posteriors below e^-75 (< 1e-32) cannot change sums that are >= ~1: skip their exp
+            const double base = cur.kap - lS;
+            const double g0 = exp(cur.vLG + cur.kap + cur.vLH + cur.lam - lS);
             a_g0all += g0;
             if (has_next) a_g0 += g0;
             a_y += yv;
             a_y2 += yv * yv;
 #pragma unroll
             for (int i = 0; i < N; i++) {
-                const double le = e_in ? vLEe[i] + lame : 0.0;
-                pi[i] = exp(vLQ[i] + kap + le - lS);
+                const double le = e_in ? cur.vLEe[i] + cur.lame : 0.0;
+                const double ap = cur.vLQ[i] + cur.kap + le - lS;
+                pi[i] = ap > -75.0 ? exp(ap) : 0.0;
                 a_s0[i] += pi[i];
                 pmax = fmax(pmax, pi[i]);
                 if (has_next) {
-                    const double lex = x_in ? vLEx[i] + lamx : 0.0;
-                    a_xi[i] += exp(vLG + kap + lH[i] + vFn[i] + lex - lS);
+                    const double lex = x_in ? cur.vLEx[i] + cur.lamx : 0.0;
+                    const double ax = cur.vLG + cur.kap + lH[i] + cur.vFn[i] + lex - lS;
+                    if (ax > -75.0) a_xi[i] += exp(ax);
                 }
             }
+            (void)base;
         } else {
 #pragma unroll
             for (int i = 0; i < N; i++) pi[i] = 0.0;
@@ -658,6 +807,7 @@ __global__ void __launch_bounds__(128) em_stats(EmParams p) {
             }
         }
         __syncwarp();
+        cur = nxt;
     }
     // block reduction (fixed order -> deterministic)
     __syncthreads();
@@ -693,6 +843,26 @@ __global__ void __launch_bounds__(128) em_stats(EmParams p) {
     }
 }
 
+// Column sums of the per-CTA statistic partials in a fixed order: 32 columns x 32 row groups per CTA.
+__global__ void __launch_bounds__(1024) em_reduce(EmParams p) {
+    __shared__ double red[32][33];
+    const int col = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int k = blockIdx.x * 32 + col;
+    const int rows = (p.nblk + 31) / 32;
+    double v = 0.0;
+    if (k < p.pstride) {
+        const int b1 = (g + 1) * rows < p.nblk ? (g + 1) * rows : p.nblk;
+        for (int b = g * rows; b < b1; b++) v += p.part[(size_t)b * p.pstride + k];
+    }
+    red[g][col] = v;
+    __syncthreads();
+    if (g == 0 && k < p.pstride) {
+        double t = 0.0;
+        for (int q = 0; q < 32; q++) t += red[q][col];
+        p.tot[k] = t;
+    }
+}
+
 // out layout: [0] sigma [1] loglik [2..2+N) lp  then mu [K*N] then pp [ns]
 template <int N>
 __global__ void __launch_bounds__(1024) em_finalize(EmParams p) {
@@ -702,23 +872,8 @@ __global__ void __launch_bounds__(1024) em_finalize(EmParams p) {
     const int64_t T = p.T;
     double *tot = sm;
     double *S0 = sm + p.pstride;
-    {
-        // column sums of the per-CTA partials: 4 row groups per column, combined in a fixed order
-        double *grp = S0;  // scratch [4][pstride] (S0 is filled later); sized by the host
-        const int ngrp = 4;
-        const int rows = (p.nblk + ngrp - 1) / ngrp;
-        for (int idx = threadIdx.x; idx < ngrp * p.pstride; idx += blockDim.x) {
-            const int g = idx / p.pstride, k = idx - g * p.pstride;
-            double v = 0.0;
-            const int b1 = (g + 1) * rows < p.nblk ? (g + 1) * rows : p.nblk;
-            for (int b = g * rows; b < b1; b++) v += p.part[(size_t)b * p.pstride + k];
-            grp[idx] = v;
-        }
-        __syncthreads();
-        for (int k = threadIdx.x; k < p.pstride; k += blockDim.x)
-            tot[k] = ((grp[k] + grp[p.pstride + k]) + grp[2 * p.pstride + k]) + grp[3 * p.pstride + k];
-        __syncthreads();
-    }
+    for (int k = threadIdx.x; k < p.pstride; k += blockDim.x) tot[k] = p.tot[k];
+    __syncthreads();
     const double lS = p.lS[0];
     const double lam0 = p.lambda[0];
     const double kapl = p.kappa[p.nchunks - 1];
@@ -760,14 +915,20 @@ __global__ void __launch_bounds__(1024) em_finalize(EmParams p) {
         pp[1 + i * L + sph] = p.LQneg[i * L + sph] + p.LE[(size_t)i * T + (L - 1 - sph)] + lam0 - lS;
     }
     if (threadIdx.x < N) mu[(size_t)K * threadIdx.x] = 0.0;  // row 1 stays 0 (src/baumwelch.jl:268)
+    // S1^2 / S0 per template sample (the divisions in parallel; summed in a fixed order below)
+    double *qterm = S0 + (size_t)N * S1_LAGS;  // piv is no longer needed
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < N * L; idx += blockDim.x) {
+        const int i = idx / L, sph = idx % L;
+        const double s1 = S1[i * S1_LAGS + sph];
+        qterm[i * S1_LAGS + sph] = s1 * s1 / S0[i * S1_LAGS + sph];
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         pp[0] = p.LG[0] + p.LH[0] + lam0 - lS;
         double q = 0.0;
         for (int i = 0; i < N; i++)
-            for (int sph = 0; sph < L; sph++) {
-                double s1 = S1[i * S1_LAGS + sph];
-                q += s1 * s1 / S0[i * S1_LAGS + sph];
-            }
+            for (int sph = 0; sph < L; sph++) q += qterm[i * S1_LAGS + sph];
         // sigma^2 = sum_t sum_j gamma (y - m_j_new)^2 / sum gamma, with m_noise_new = 0 and
         // m_(i,s)_new = S1/S0  =>  (sum y^2 - sum S1^2/S0) / T      (src/baumwelch.jl:288-307)
         out[0] = sqrt((tot[2] - q) / (double)T);
@@ -776,6 +937,9 @@ __global__ void __launch_bounds__(1024) em_finalize(EmParams p) {
         const double ssq = tot[2] - 2.0 * m0 * tot[1] + (double)T * m0 * m0;
         out[1] = (double)T * c_emit - ssq / two_s2 + (double)(T - 1) * w_nn + lS;
         for (int i = 0; i < N; i++) out[2 + i] = log(tot[4 + i]) - log(tot[0]);  // xb[2:end], :254-265
+        double *cnt_out = pp + p.ns;
+        cnt_out[0] = (double)p.counters[0];
+        cnt_out[1] = (double)p.counters[1];
     }
 }
 
@@ -876,6 +1040,22 @@ __global__ void __launch_bounds__(128) fb_dense(EmParams p, const double *Zs, co
 
 // ---------------------------------------------------------------------------
 // mode: 0 = full E/M step; 1 = forward quantities only; 2 = forward + backward quantities
+// Warps of the forward and of the backward kernel that are co-resident on one SM (the smaller of the two):
+// the chunk count is matched to it so that each pass runs as exactly one wave.
+template <int N, int R>
+static int em_warps_per_sm(const RingLayout &RL) {
+    constexpr int WPB = 4;
+    const size_t mdl_d = (RL.hot + 1) & ~1;
+    const size_t sm_fwd = sizeof(double) * (mdl_d + (size_t)WPB * EmWarpSmem<N, R>::DOUBLES);
+    const size_t sm_bwd = sizeof(double) * (mdl_d + (size_t)WPB * N * RING_Q);
+    HMM_CUDA(cudaFuncSetAttribute(em_forward<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+    int nf = 0, nb = 0;
+    HMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nf, em_forward<N, R>, 32 * WPB, sm_fwd));
+    HMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, em_backward<N>, 32 * WPB, sm_bwd));
+    const int n = nf < nb ? nf : nb;
+    return (n > 0 ? n : 1) * WPB;
+}
+
 template <int N, int R>
 static void em_launch(EmParams &p, cudaStream_t st, hmm_info *info, Timer &ttop, int mode, double *alpha_out,
                       double *beta_out, double *Zs, double *bsum) {
@@ -888,29 +1068,29 @@ static void em_launch(EmParams &p, cudaStream_t st, hmm_info *info, Timer &ttop,
     const size_t sm_stats = sizeof(double) * std::max<size_t>((size_t)WPB * (160 + N * 32), (size_t)WPB * p.pstride);
     const size_t sm_fin = sizeof(double) * ((size_t)p.pstride + std::max<size_t>(3 * (size_t)N * S1_LAGS, 4 * (size_t)p.pstride));
     HMM_CUDA(cudaFuncSetAttribute(em_forward<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
-    HMM_CUDA(cudaFuncSetAttribute(em_repair_fwd<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_frep));
     HMM_CUDA(cudaFuncSetAttribute(em_stats<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stats));
     const int gridc = (p.nchunks + WPB - 1) / WPB;
     const int gchk = (p.nchunks * 32 + 127) / 128;
+    const int dirs = mode != 1 ? 3 : 1;  // bit 0 forward, bit 1 backward
+    const int fwd_doubles = (int)(mdl_d + EmWarpSmem<N, R>::DOUBLES);
+    const size_t sm_rep = sizeof(double) * ((size_t)fwd_doubles + mdl_d + (size_t)N * RING_Q);
+    HMM_CUDA(cudaFuncSetAttribute(em_repair<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rep));
+    // The backward pass needs only the F scores the forward kernel stored, not its verification, so both
+    // passes run first and are then verified, repaired and normalised by one launch each.
     ttop.start();
     em_forward<N, R><<<gridc, 32 * WPB, sm_fwd, st>>>(p);
     ttop.stop();
-    em_check<<<gchk, 128, 0, st>>>(p, 0);
-    em_repair_fwd<N, R><<<1, 32, sm_frep, st>>>(p);
-    em_offsets<N><<<1, 256, 0, st>>>(p, 0);
-    if (info) info->kernel_launches += 4;
-    if (mode != 1) {
-        em_backward<N><<<gridc, 32 * WPB, sm_bwd, st>>>(p);
-        em_check<<<gchk, 128, 0, st>>>(p, 1);
-        em_repair_bwd<N><<<1, 32, sm_brep, st>>>(p);
-        em_offsets<N><<<1, 256, 0, st>>>(p, 1);
-        if (info) info->kernel_launches += 4;
-    }
+    if (mode != 1) em_backward<N><<<gridc, 32 * WPB, sm_bwd, st>>>(p);
+    em_check<<<dim3(gchk, 2), 128, 0, st>>>(p, dirs);
+    em_repair<N, R><<<1, 64, sm_rep, st>>>(p, dirs, fwd_doubles);
+    em_offsets<N><<<2, 1024, 0, st>>>(p, dirs);
+    if (info) info->kernel_launches += (mode != 1 ? 5 : 4);
     if (mode == 0) {
         em_stats<N><<<p.nblk, 32 * WPB, sm_stats, st>>>(p);
         HMM_CUDA(cudaFuncSetAttribute(em_finalize<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fin));
+        em_reduce<<<(p.pstride + 31) / 32, 1024, 0, st>>>(p);
         em_finalize<N><<<1, 1024, sm_fin, st>>>(p);
-        if (info) info->kernel_launches += 2;
+        if (info) info->kernel_launches += 3;
     } else {
         const int nb = (int)((p.T + 256 * ZS_ITEMS - 1) / (256 * ZS_ITEMS));
         fb_zscan<<<nb, 256, 0, st>>>(p, Zs, bsum);
@@ -939,7 +1119,18 @@ static void ring_em_core(const double *X_dev, int64_t T, const HostModel &M, EmR
         int dev = 0, sms = 148;
         HMM_CUDA(cudaGetDevice(&dev));
         HMM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        Lc = (T + (int64_t)sms * 16 - 1) / ((int64_t)sms * 16);
+        int wps = 16;
+        switch (N) {
+            case 1: wps = em_warps_per_sm<1, 8>(RL); break;
+            case 2: wps = em_warps_per_sm<2, 8>(RL); break;
+            case 3: wps = em_warps_per_sm<3, 8>(RL); break;
+            case 4: wps = em_warps_per_sm<4, 8>(RL); break;
+            case 5: wps = em_warps_per_sm<5, 4>(RL); break;
+            case 6: wps = em_warps_per_sm<6, 4>(RL); break;
+            case 7: wps = em_warps_per_sm<7, 4>(RL); break;
+            default: break;
+        }
+        Lc = (T + (int64_t)sms * wps - 1) / ((int64_t)sms * wps);
         if (Lc < 3 * W) Lc = 3 * W;
     }
     Lc = ((Lc + SW - 1) / SW) * SW;
@@ -948,19 +1139,19 @@ static void ring_em_core(const double *X_dev, int64_t T, const HostModel &M, EmR
     int nchunks = (int)((T + Lc - 1) / Lc);
     if (nchunks > 1 && T - (int64_t)(nchunks - 1) * Lc < RING_Q) nchunks--;
 
-    std::vector<double> hmdl(RL.total);
-    ring_pack(M, RL, hmdl.data());
+    double *hmdl = (double *)ws.pinned(0, sizeof(double) * RL.total);  // pinned: the upload below is truly async
+    ring_pack(M, RL, hmdl);
     const int bvec = 1 + N * L;
     const int pstride = 4 + 2 * N + N * S1_LAGS;
     const int nblk = 148 * 6;
-    const int nout = 2 + N + K * N + ns;
+    const int nout = 2 + N + K * N + ns + 2;  // ... + the two repair counters
     size_t off = 0;
     auto carve = [&](size_t bytes) {
         size_t r = off;
         off += (bytes + 255) & ~size_t(255);
         return r;
     };
-    size_t o_model = carve(sizeof(double) * hmdl.size());
+    size_t o_model = carve(sizeof(double) * RL.total);
     size_t o_neg = carve(sizeof(double) * N * L);
     size_t o_b = carve(sizeof(double) * 4 * (size_t)nchunks * bvec);
     size_t o_flag = carve(sizeof(int) * 2 * (size_t)nchunks);
@@ -968,11 +1159,11 @@ static void ring_em_core(const double *X_dev, int64_t T, const HostModel &M, EmR
     size_t o_ls = carve(sizeof(double) * 2);
     size_t o_cnt = carve(sizeof(int) * 4);
     size_t o_part = carve(sizeof(double) * (size_t)nblk * pstride);
+    size_t o_tot = carve(sizeof(double) * pstride);
     size_t o_out = carve(sizeof(double) * nout);
     char *base = (char *)ws.get(Workspace::CHUNKS, off);
     double *steps = (double *)ws.get(Workspace::FWDQ, sizeof(double) * (size_t)T * (3 * N + 2));
-    HMM_CUDA(cudaMemcpyAsync(base + o_model, hmdl.data(), sizeof(double) * hmdl.size(), cudaMemcpyHostToDevice, st));
-    HMM_CUDA(cudaStreamSynchronize(st));
+    HMM_CUDA(cudaMemcpyAsync(base + o_model, hmdl, sizeof(double) * RL.total, cudaMemcpyHostToDevice, st));
     HMM_CUDA(cudaMemsetAsync(base + o_cnt, 0, sizeof(int) * 4, st));
 
     EmParams p{};
@@ -1002,9 +1193,15 @@ static void ring_em_core(const double *X_dev, int64_t T, const HostModel &M, EmR
     p.lS = (double *)(base + o_ls);
     p.counters = (int *)(base + o_cnt);
     p.part = (double *)(base + o_part);
+    p.tot = (double *)(base + o_tot);
     p.nblk = nblk;
     p.pstride = pstride;
-    p.out = (double *)(base + o_out);
+    // em_finalize writes its few hundred doubles straight into mapped pinned host memory: no device-to-host
+    // copy, one stream synchronisation per E/M step
+    void *out_dev = nullptr;
+    double *out_host = (double *)ws.pinned(1, sizeof(double) * nout, &out_dev);
+    p.out = (double *)out_dev;
+    (void)o_out;
 
     double *Zs = nullptr, *bsum = nullptr;
     if (mode != 0) {
@@ -1028,16 +1225,14 @@ static void ring_em_core(const double *X_dev, int64_t T, const HostModel &M, EmR
         return;
     }
     EmResult &out = *outp;
-    std::vector<double> h(nout);
-    int cnt[4] = {0, 0, 0, 0};
-    HMM_CUDA(cudaMemcpyAsync(h.data(), p.out, sizeof(double) * nout, cudaMemcpyDeviceToHost, st));
-    HMM_CUDA(cudaMemcpyAsync(cnt, p.counters, sizeof(cnt), cudaMemcpyDeviceToHost, st));
     HMM_CUDA(cudaStreamSynchronize(st));
+    const double *h = out_host;
+    const int cnt[2] = {(int)h[nout - 2], (int)h[nout - 1]};
     out.sigma = h[0];
     out.loglik = h[1];
-    out.lp.assign(h.begin() + 2, h.begin() + 2 + N);
-    out.mu.assign(h.begin() + 2 + N, h.begin() + 2 + N + (size_t)K * N);
-    out.pp.assign(h.begin() + 2 + N + (size_t)K * N, h.end());
+    out.lp.assign(h + 2, h + 2 + N);
+    out.mu.assign(h + 2 + N, h + 2 + N + (size_t)K * N);
+    out.pp.assign(h + 2 + N + (size_t)K * N, h + 2 + N + (size_t)K * N + ns);
     if (info) {
         info->n_chunks = nchunks;
         info->fwd_repaired = cnt[0];

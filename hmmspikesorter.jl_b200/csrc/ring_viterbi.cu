@@ -93,6 +93,11 @@ void ring_pack(const HostModel &M, const RingLayout &R, double *dst) {
             if (i != j) c = std::max(c, dst[R.eT + j * R.NP + i] - dst[R.eH + i]);
         dst[R.cL + j] = c + 1e-9;
     }
+    for (int i = 0; i < N; i++) {
+        dst[R.xG + i] = std::exp(dst[R.eG + i]);
+        dst[R.xH + i] = std::exp(dst[R.eH + i]);
+        for (int j = 0; j < N; j++) dst[R.xT + j * R.NP + i] = (i == j) ? 0.0 : std::exp(dst[R.eT + j * R.NP + i]);
+    }
 }
 
 // ---------------------------------------------------------------------------
