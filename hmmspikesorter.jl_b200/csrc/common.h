@@ -64,6 +64,7 @@ cudaStream_t main_stream();  // per host thread, non-blocking stream
 cudaStream_t copy_stream();  // host -> device copies of the pipelined decode
 cudaStream_t out_stream();   // device -> host copies of the pipelined decode
 void set_external_stream(cudaStream_t s, bool use);  // per host thread
+cudaEvent_t sync_event(int k);  // k = 0..3: per host thread, timing disabled (fork/join between the streams)
 
 // ---------------------------------------------------------------------------
 // Host-side analysis of one StateMatrix + templates (one channel).

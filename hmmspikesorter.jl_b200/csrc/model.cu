@@ -81,6 +81,7 @@ Workspace &workspace() {
 
 struct Streams {
     cudaStream_t main = nullptr, copy = nullptr, out = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int dev = -1;
 };
 static thread_local cudaStream_t g_external = nullptr;
@@ -95,6 +96,7 @@ static Streams &streams() {
     HMM_CUDA(cudaGetDevice(&dev));
     if (st.dev != dev) {
         st.main = st.copy = st.out = nullptr;  // streams of another device are simply abandoned
+        for (auto &e : st.ev) e = nullptr;
         st.dev = dev;
     }
     if (!st.main) {
@@ -107,6 +109,11 @@ static Streams &streams() {
 cudaStream_t main_stream() { return g_use_external ? g_external : streams().main; }
 cudaStream_t copy_stream() { return streams().copy; }
 cudaStream_t out_stream() { return streams().out; }
+cudaEvent_t sync_event(int k) {
+    Streams &st = streams();
+    if (!st.ev[k]) HMM_CUDA(cudaEventCreateWithFlags(&st.ev[k], cudaEventDisableTiming));
+    return st.ev[k];
+}
 
 // ---------------------------------------------------------------------------
 // m[j] = sum_{l=1..N} mu[states[l,j], l] accumulated from 0.0 in neuron order

@@ -41,21 +41,24 @@ struct EmParams {
     int *flag_f, *flag_b;
     double *kappa, *lambda;           // per-chunk log offsets (forward / backward)
     double *lS;                       // [1] log of the normalised total likelihood
-    int *counters;                    // [0] fwd repaired [1] bwd repaired
+    int *counters;                    // [0] fwd repaired [1] bwd repaired [2] any fwd flag [3] any bwd flag
+    double *dk;                       // [2][nchunks] boundary differences in scan order (em_check)
     double *part;                     // [nblk][PSTRIDE] statistic partials
     double *tot;                      // [PSTRIDE] their column sums (em_reduce)
     int nblk, pstride;
     double *out;                      // finalize output
+    int dbg;                          // debug switch (HMMCUDA_EM_DBG): 1 = log-domain live windows
 };
 
 enum { EM_INIT = 0, EM_SPEC = 1, EM_EXACT = 2 };
 constexpr int S1_LAGS = 96;  // == RING_MAX_L
 
+
 template <int N, int R>
 struct EmWarpSmem {
     using G = FirGeom<R>;
-    static constexpr int TILE = (G::YTILE > N * G::FTILE) ? G::YTILE : N * G::FTILE;
-    static constexpr int DOUBLES = TILE + N * RING_Q;
+    static constexpr int TILE = (G::YTILE > N * G::FTILE) ? G::YTILE : N * G::FTILE;  // em_fir: y tile / F tile
+    static constexpr int DOUBLES = N * RING_Q;                                        // recursions: the ring
 };
 
 // Inclusive log-sum-exp scan over the lanes of a warp (lane 0 first).
@@ -79,9 +82,8 @@ __device__ void em_fwd_chunk(const EmParams &p, int c, int kind, const double *m
     const RingLayout &RL = p.RL;
     const int L = RL.L, LP = RL.LP;
     const double NEG = -INFINITY;
-    double *ytile = ws, *fbuf = ws;
-    double *ring = ws + EmWarpSmem<N, R>::TILE;
-    const double *A = mdl + RL.A, *Bc = mdl + RL.Bc, *lA = mdl + RL.eG, *lH = mdl + RL.eH, *lC = mdl + RL.eT;
+    double *ring = ws;
+    const double *lA = mdl + RL.eG, *lH = mdl + RL.eH, *lC = mdl + RL.eT;
     // cF[j] = max(lA_j, max_i(lC_ji - lH_i)): how much a tail of neuron j can gain on the noise term
     double cF[N];
 #pragma unroll
@@ -149,8 +151,12 @@ __device__ void em_fwd_chunk(const EmParams &p, int c, int kind, const double *m
     const int mysub = lane / Wd;
     const int tf_rel = (int)(tau_first - base0), e_rel = (int)(e - base0), s_rel = (int)(s - base0);
 
+    // F_i(tau) comes from the FIR pass (em_fir; end-of-recording terms already dropped).  The loads of the
+    // next window are issued before the current one is processed.
+    double Fnx[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) Fnx[i] = base0 + lane < T ? p.Fg[(size_t)i * T + base0 + lane] : 0.0;
     for (int64_t b = base0; b < e; b += G::SW) {
-        fir_superwindow<N, R>(y, T, b, A, Bc, LP, ytile, fbuf, lane);
         if (kind == EM_SPEC && b == s) {
             double *sb = p.SBf + (size_t)c * p.bvec;
             if (lane == 0) sb[0] = lgprev;
@@ -163,20 +169,13 @@ __device__ void em_fwd_chunk(const EmParams &p, int c, int kind, const double *m
         for (int wdw = 0; wdw < R; wdw++) {
             const int t0_rel = b_rel + 32 * wdw;
             if (t0_rel >= e_rel) break;
-            const int tl = 32 * wdw + lane;
             const int t_rel = t0_rel + lane;
             const int64_t tau = base0 + t_rel;
             double Fv[N];
 #pragma unroll
             for (int i = 0; i < N; i++) {
-                double f = fbuf[i * G::FTILE + fbuf_index<R>(tl)];
-                // chains that run past the end of the recording: drop the terms beyond T-1
-                if (tau > T - L && tau < T) f -= cold[RL.BWsuf + (int)(T - tau) * NP + i];
-                Fv[i] = f;
-            }
-            if (t0_rel >= s_rel && tau < e) {
-#pragma unroll
-                for (int i = 0; i < N; i++) p.Fg[(size_t)i * T + tau] = Fv[i];
+                Fv[i] = Fnx[i];
+                Fnx[i] = (t0_rel + 32 < e_rel && tau + 32 < T) ? p.Fg[(size_t)i * T + tau + 32] : 0.0;
             }
             const bool in_range = t_rel >= tf_rel && t_rel < e_rel;
             const int slot_w = t_rel & (RING_Q - 1);
@@ -227,7 +226,7 @@ __device__ void em_fwd_chunk(const EmParams &p, int c, int kind, const double *m
                 for (int d = 16; d >= 1; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
                 const double ref = fmax(lgprev, mx);
                 double lg, lgm1;
-                if (ref - lgprev < 600.0) {
+                if (ref - lgprev < 600.0 && !(p.dbg & 1)) {
                     double u[N];
 #pragma unroll
                     for (int j = 0; j < N; j++) u[j] = exp(lt[j] - ref);  // exp(-inf) = 0 for idle lanes
@@ -303,6 +302,46 @@ __device__ void em_fwd_chunk(const EmParams &p, int c, int kind, const double *m
     __syncwarp();
 }
 
+// ---------------------------------------------------------------------------
+// FIR pass: F_i(t0) = Bc_i + sum_r a[i][r] y[t0 + r] for every t0, one super-window per warp, stored to
+// Fg[N][T].  Chains that would run past the end of the recording have the terms beyond T-1 dropped here.
+// LPC > 0: coefficients as constant-bank operands (ring_common.cuh), else from shared memory.
+// ---------------------------------------------------------------------------
+template <int N, int R, int LPC>
+__global__ void __launch_bounds__(128) em_fir(EmParams p, const __grid_constant__ FirCoef<N, LPC> coef) {
+    using G = FirGeom<R>;
+    constexpr int NP = (N + 1) & ~1;
+    extern __shared__ __align__(16) double smem_d[];
+    double *mdl = smem_d;
+    for (int k = threadIdx.x; k < p.RL.hot; k += blockDim.x) mdl[k] = p.model[k];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const RingLayout &RL = p.RL;
+    const int L = RL.L;
+    const int64_t T = p.T;
+    const int64_t b = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * G::SW;
+    if (b >= T) return;
+    double *tile = smem_d + ((RL.hot + 1) & ~1) + (size_t)warp * EmWarpSmem<N, R>::TILE;
+    if constexpr (LPC > 0)
+        fir_superwindow_c<N, R, LPC>(p.y, T, b, coef, mdl + RL.Bc, tile, tile, lane);
+    else
+        fir_superwindow<N, R>(p.y, T, b, mdl + RL.A, mdl + RL.Bc, RL.LP, tile, tile, lane);
+    const double *BWsuf = p.model + RL.BWsuf;
+#pragma unroll
+    for (int wdw = 0; wdw < R; wdw++) {
+        const int tl = 32 * wdw + lane;
+        const int64_t tau = b + tl;
+        if (tau < T) {
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                double f = tile[i * G::FTILE + fbuf_index<R>(tl)];
+                if (tau > T - L) f -= BWsuf[(int)(T - tau) * NP + i];
+                p.Fg[(size_t)i * T + tau] = f;
+            }
+        }
+    }
+}
+
 template <int N, int R>
 __global__ void __launch_bounds__(128, 4) em_forward(EmParams p) {
     extern __shared__ __align__(16) double smem_d[];
@@ -343,14 +382,34 @@ __global__ void em_check(EmParams p, int dirs) {
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int backward = blockIdx.y;
     if (!((dirs >> backward) & 1)) return;
+    const int n = p.nchunks;
+    if (gw >= n) return;
+    // also leaves the difference of the two normalisations in scan order for em_fixup (valid when nothing is
+    // repaired) and raises counters[2 + direction] when any boundary failed
     if (!backward) {
-        if (gw >= p.nchunks || gw == 0) return;
-        bool ok = em_boundary_matches(p.SBf + (size_t)gw * p.bvec, p.EBf + (size_t)(gw - 1) * p.bvec, p.bvec, lane);
-        if (lane == 0) p.flag_f[gw] = ok ? 0 : 1;
+        if (gw == 0) {
+            if (lane == 0) p.dk[0] = 0.0;
+            return;
+        }
+        const double *sb = p.SBf + (size_t)gw * p.bvec, *eb = p.EBf + (size_t)(gw - 1) * p.bvec;
+        bool ok = em_boundary_matches(sb, eb, p.bvec, lane);
+        if (lane == 0) {
+            p.flag_f[gw] = ok ? 0 : 1;
+            p.dk[gw] = eb[0] - sb[0];
+            if (!ok) atomicOr(&p.counters[2], 1);
+        }
     } else {
-        if (gw >= p.nchunks - 1) return;
-        bool ok = em_boundary_matches(p.SBb + (size_t)gw * p.bvec, p.EBb + (size_t)(gw + 1) * p.bvec, p.bvec, lane);
-        if (lane == 0) p.flag_b[gw] = ok ? 0 : 1;
+        if (gw == n - 1) {
+            if (lane == 0) p.dk[n] = 0.0;  // r = n-1-c = 0
+            return;
+        }
+        const double *sb = p.SBb + (size_t)gw * p.bvec, *eb = p.EBb + (size_t)(gw + 1) * p.bvec;
+        bool ok = em_boundary_matches(sb, eb, p.bvec, lane);
+        if (lane == 0) {
+            p.flag_b[gw] = ok ? 0 : 1;
+            p.dk[n + (n - 1 - gw)] = eb[0] - sb[0];
+            if (!ok) atomicOr(&p.counters[3], 1);
+        }
     }
 }
 
@@ -417,12 +476,22 @@ __device__ void em_bwd_chunk(const EmParams &p, int c, int kind, const double *m
     const int nsub = (32 + Wd - 1) / Wd;
     const int mysub = lane / Wd;
     // windows of 32 steps, descending; lane 0 is the latest step of the window
+    double Fnx[N];  // F of the next (earlier) window, loaded one window ahead
+    {
+        const int64_t t = ((hi - 1) | 31) - lane;
+#pragma unroll
+        for (int i = 0; i < N; i++) Fnx[i] = (t <= hi - 1 && t >= s) ? p.Fg[(size_t)i * T + t + 1] : 0.0;
+    }
     for (int64_t wtop = ((hi - 1) | 31); wtop >= s; wtop -= 32) {
         const int64_t t = wtop - lane;
         const bool in_range = t <= hi - 1 && t >= s;
         double Fn[N];
 #pragma unroll
-        for (int i = 0; i < N; i++) Fn[i] = (in_range) ? p.Fg[(size_t)i * T + t + 1] : 0.0;
+        for (int i = 0; i < N; i++) {
+            Fn[i] = Fnx[i];
+            const int64_t tn = t - 32;
+            Fnx[i] = (tn <= hi - 1 && tn >= s) ? p.Fg[(size_t)i * T + tn + 1] : 0.0;
+        }
         // F of the warm-up region belongs to the next chunk and is complete: the forward pass has finished
         for (int sub = 0; sub < nsub; sub++) {
             const bool active = in_range && (mysub == sub);
@@ -458,7 +527,7 @@ __device__ void em_bwd_chunk(const EmParams &p, int c, int kind, const double *m
             for (int d = 16; d >= 1; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
             const double ref = fmax(lhprev, mx);
             double lh, lhp1;
-            if (ref - lhprev < 600.0) {
+            if (ref - lhprev < 600.0 && !(p.dbg & 1)) {
                 double v[N];
 #pragma unroll
                 for (int j = 0; j < N; j++) v[j] = exp(lr[j] - ref);
@@ -537,7 +606,7 @@ __device__ void em_bwd_chunk(const EmParams &p, int c, int kind, const double *m
 }
 
 template <int N>
-__global__ void __launch_bounds__(128) em_backward(EmParams p) {
+__global__ void __launch_bounds__(128, 4) em_backward(EmParams p) {
     extern __shared__ __align__(16) double smem_d[];
     double *mdl = smem_d;
     for (int k = threadIdx.x; k < p.RL.hot; k += blockDim.x) mdl[k] = p.model[k];
@@ -552,66 +621,8 @@ __global__ void __launch_bounds__(128) em_backward(EmParams p) {
 // ---------------------------------------------------------------------------
 // sequential repair + per-chunk log offsets (one warp)
 // ---------------------------------------------------------------------------
-template <int N, int R>
-__global__ void __launch_bounds__(64) em_repair(EmParams p, int dirs, int fwd_doubles /*smem doubles of the forward half*/) {
-    extern __shared__ __align__(16) double smem_d[];
-    const int lane = threadIdx.x & 31;
-    const int backward = threadIdx.x >> 5;  // warp 0 repairs the forward pass, warp 1 the backward pass
-    if (!((dirs >> backward) & 1)) return;
-    double *mdl = smem_d + (backward ? fwd_doubles : 0);
-    double *ws = mdl + ((p.RL.hot + 1) & ~1);
-    int repaired = 0;
-    if (!backward) {
-        int any = 0;
-        for (int c = 1 + lane; c < p.nchunks; c += 32) any |= p.flag_f[c];
-        if (__any_sync(0xffffffffu, any)) {
-            for (int k = lane; k < p.RL.hot; k += 32) mdl[k] = p.model[k];
-            __syncwarp();
-            bool prev = false;
-            for (int c = 1; c < p.nchunks; c++) {
-                bool need = p.flag_f[c] != 0;
-                if (!need && prev)
-                    need = !em_boundary_matches(p.SBf + (size_t)c * p.bvec, p.EBf + (size_t)(c - 1) * p.bvec, p.bvec, lane);
-                if (need) {
-                    em_fwd_chunk<N, R>(p, c, EM_EXACT, mdl, ws);
-                    // an exactly restarted chunk continues chunk c-1's normalisation
-                    if (lane == 0) p.SBf[(size_t)c * p.bvec] = p.EBf[(size_t)(c - 1) * p.bvec];
-                    __threadfence();
-                    __syncwarp();
-                    repaired++;
-                }
-                prev = need;
-            }
-        }
-        if (lane == 0) p.counters[0] = repaired;
-    } else {
-        int any = 0;
-        for (int c = lane; c < p.nchunks - 1; c += 32) any |= p.flag_b[c];
-        if (__any_sync(0xffffffffu, any)) {
-            for (int k = lane; k < p.RL.hot; k += 32) mdl[k] = p.model[k];
-            __syncwarp();
-            bool prev = false;
-            for (int c = p.nchunks - 2; c >= 0; c--) {
-                bool need = p.flag_b[c] != 0;
-                if (!need && prev)
-                    need = !em_boundary_matches(p.SBb + (size_t)c * p.bvec, p.EBb + (size_t)(c + 1) * p.bvec, p.bvec, lane);
-                if (need) {
-                    em_bwd_chunk<N>(p, c, EM_EXACT, mdl, ws);
-                    if (lane == 0) p.SBb[(size_t)c * p.bvec] = p.EBb[(size_t)(c + 1) * p.bvec];
-                    __threadfence();
-                    __syncwarp();
-                    repaired++;
-                }
-                prev = need;
-            }
-        }
-        if (lane == 0) p.counters[1] = repaired;
-    }
-}
-
-// kappa_c = sum_{k<=c} (EBf[k-1].lg - SBf[k].lg);  lambda_c = sum_{k>=c} (EBb[k+1].lh - SBb[k].lh)
-// plus lS = kappa_last + LSE(alpha-hat at T-1).  Single block.
-// Block-wide inclusive scan of one double per thread (256 threads), fixed order.
+// Block-wide inclusive scan of one double per thread over the first 256 threads, fixed order.  (Threads
+// beyond the first 256 may take part in the barriers; their result is unused.)
 __device__ __forceinline__ double block_scan_256(double v, double *wsum) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -624,63 +635,145 @@ __device__ __forceinline__ double block_scan_256(double v, double *wsum) {
     double base = 0.0;
     for (int w = 0; w < warp && w < 8; w++) base += wsum[w];
     __syncthreads();
-    return v + base;  // (threads beyond the first 256 may take part in the barriers; their result is unused)
+    return v + base;
 }
 
-template <int N>
-__global__ void __launch_bounds__(1024) em_offsets(EmParams p, int dirs) {
+constexpr int EM_SCAN_SMEM = 4096;  // chunk differences scanned in shared memory up to this many chunks
+
+// One launch per E/M step, one CTA per direction (block 0 forward, block 1 backward):
+//  1. sequential repair by warp 0: re-run flagged chunks from the true boundary vector; a re-run changes the
+//     chunk's end vector, so its successor is re-checked against it;
+//  2. per-chunk log offsets  kappa_c = sum_{k<=c} (EBf[k-1].lg - SBf[k].lg),
+//                            lambda_c = sum_{k>=c} (EBb[k+1].lh - SBb[k].lh),
+//     and lS = kappa_last + LSE(alpha-hat at T-1).
+template <int N, int R>
+__global__ void __launch_bounds__(1024) em_fixup(EmParams p, int dirs) {
+    extern __shared__ __align__(16) double smem_d[];
     __shared__ double wsum[8];
-    const int backward = blockIdx.x;  // block 0: kappa and lS, block 1: lambda
+    const int backward = blockIdx.x;
     if (!((dirs >> backward) & 1)) return;
     const int n = p.nchunks;
+    double *mdl = smem_d;
+    double *ws = mdl + ((p.RL.hot + 1) & ~1);
+    double *dsm = ws + N * RING_Q;  // [EM_SCAN_SMEM]
+    const int any = p.counters[2 + backward];  // raised by em_check when some boundary failed
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int repaired = 0;
+        if (any) {
+            for (int k = lane; k < p.RL.hot; k += 32) mdl[k] = p.model[k];
+            __syncwarp();
+            bool prev = false;
+            if (!backward) {
+                for (int c = 1; c < n; c++) {
+                    bool need = p.flag_f[c] != 0;
+                    if (!need && prev)
+                        need = !em_boundary_matches(p.SBf + (size_t)c * p.bvec, p.EBf + (size_t)(c - 1) * p.bvec, p.bvec, lane);
+                    if (need) {
+                        em_fwd_chunk<N, R>(p, c, EM_EXACT, mdl, ws);
+                        // an exactly restarted chunk continues chunk c-1's normalisation
+                        if (lane == 0) p.SBf[(size_t)c * p.bvec] = p.EBf[(size_t)(c - 1) * p.bvec];
+                        __threadfence();
+                        __syncwarp();
+                        repaired++;
+                    }
+                    prev = need;
+                }
+            } else {
+                for (int c = n - 2; c >= 0; c--) {
+                    bool need = p.flag_b[c] != 0;
+                    if (!need && prev)
+                        need = !em_boundary_matches(p.SBb + (size_t)c * p.bvec, p.EBb + (size_t)(c + 1) * p.bvec, p.bvec, lane);
+                    if (need) {
+                        em_bwd_chunk<N>(p, c, EM_EXACT, mdl, ws);
+                        if (lane == 0) p.SBb[(size_t)c * p.bvec] = p.EBb[(size_t)(c + 1) * p.bvec];
+                        __threadfence();
+                        __syncwarp();
+                        repaired++;
+                    }
+                    prev = need;
+                }
+            }
+        }
+        if (lane == 0) p.counters[backward] = repaired;
+    }
+    __syncthreads();
+    // ---- offsets: gather the per-chunk differences with independent loads (the boundary vectors are bvec
+    // doubles apart), then scan them in a fixed order on the first 256 threads ----
     const int per = (n + 255) / 256;  // contiguous chunks per thread
-    const int c0 = threadIdx.x < 256 ? threadIdx.x * per : n;  // the scan itself runs on the first 256 threads
-    // The per-chunk differences are first gathered with independent loads (the boundary vectors are bvec
-    // doubles apart) into kappa[] / lambda[] themselves, then scanned in place in a fixed order.
-    if (!backward) {
-        // kappa_c = sum_{k<=c} d_k,  d_k = EBf[k-1].lg - SBf[k].lg  (d_0 = 0)
+    const int c0 = threadIdx.x < 256 ? threadIdx.x * per : n;
+    double *res = backward ? p.lambda : p.kappa;
+    double *d = n <= EM_SCAN_SMEM ? dsm : res;  // staging of the differences (in place when too many for smem)
+    if (!any) {  // nothing was repaired: em_check's differences stand
+        for (int r = threadIdx.x; r < n; r += blockDim.x) d[r] = p.dk[(size_t)backward * n + r];
+    } else if (!backward) {
         for (int c = threadIdx.x; c < n; c += blockDim.x)
-            p.kappa[c] = c >= 1 ? p.EBf[(size_t)(c - 1) * p.bvec] - p.SBf[(size_t)c * p.bvec] : 0.0;
-        __syncthreads();
-        double loc = 0.0;
-        for (int c = c0; c < c0 + per && c < n; c++)
-            if (c >= 1) loc += p.kappa[c];
-        const double incl = block_scan_256(loc, wsum);
-        double run = incl - loc;
-        for (int c = c0; c < c0 + per && c < n; c++) {
-            if (c >= 1) run += p.kappa[c];
-            p.kappa[c] = run;
+            d[c] = c >= 1 ? p.EBf[(size_t)(c - 1) * p.bvec] - p.SBf[(size_t)c * p.bvec] : 0.0;
+    } else {  // reversed order: r = n-1-c
+        for (int r = threadIdx.x; r < n; r += blockDim.x) {
+            const int c = n - 1 - r;
+            d[r] = c < n - 1 ? p.EBb[(size_t)(c + 1) * p.bvec] - p.SBb[(size_t)c * p.bvec] : 0.0;
+        }
+    }
+    // meanwhile warp 8: log-sum-exp of alpha-hat at T-1 (all loads first, then one max / exp / sum pass)
+    __shared__ double ls_tail;
+    if (!backward && (threadIdx.x >> 5) == 8) {
+        const int lane = threadIdx.x & 31, L = p.RL.L;
+        const int64_t T = p.T;
+        constexpr int PER = (N * RING_MAX_L + 31) / 32;
+        double v[PER];
+        double m = lane == 0 ? p.LG[T - 1] : -INFINITY;
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const int idx = lane + 32 * q;
+            v[q] = -INFINITY;
+            if (idx < N * L) {
+                const int i = idx / L, k = idx % L;  // t0 = T - L + k
+                v[q] = p.LQ[(size_t)i * T + (T - L + k)];
+            }
+        }
+        const double v0 = m;
+#pragma unroll
+        for (int q = 0; q < PER; q++) m = fmax(m, v[q]);
+        for (int d2 = 16; d2 >= 1; d2 >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, d2));
+        double sum = v0 == -INFINITY ? 0.0 : exp(v0 - m);
+#pragma unroll
+        for (int q = 0; q < PER; q++)
+            if (v[q] != -INFINITY) sum += exp(v[q] - m);
+        for (int d2 = 16; d2 >= 1; d2 >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d2);
+        if (lane == 0) ls_tail = m + log(sum);
+    }
+    __syncthreads();
+    double loc = 0.0;
+    for (int r = c0; r < c0 + per && r < n; r++) loc += d[r];
+    const double incl = block_scan_256(loc, wsum);
+    double run = incl - loc;
+    if (!backward) {
+        for (int r = c0; r < c0 + per && r < n; r++) {
+            run += d[r];
+            res[r] = run;
+        }
+    } else if (d == res) {
+        // in place and reversed: lambda[c] lives at index n-1-r, which another thread may still read as d[..]
+        for (int r = c0; r < c0 + per && r < n; r++) {
+            run += d[r];
+            d[r] = run;
         }
         __syncthreads();
-        if (threadIdx.x < 32) {
-            const int lane = threadIdx.x, L = p.RL.L;
-            const int64_t T = p.T;
-            double v = -INFINITY;
-            for (int idx = lane; idx < N * L; idx += 32) {
-                int i = idx / L, k = idx % L;  // t0 = T - L + k
-                v = lse2(v, p.LQ[(size_t)i * T + (T - L + k)]);
-            }
-            if (lane == 0) v = lse2(v, p.LG[T - 1]);
-            for (int d = 16; d >= 1; d >>= 1) v = lse2(v, __shfl_xor_sync(0xffffffffu, v, d));
-            if (lane == 0) p.lS[0] = v + p.kappa[n - 1];
+        for (int r = threadIdx.x; r < n / 2; r += blockDim.x) {
+            const double a2 = d[r], b2 = d[n - 1 - r];
+            d[r] = b2;
+            d[n - 1 - r] = a2;
         }
     } else {
-        // lambda_c = sum_{k>=c} d_k,  d_k = EBb[k+1].lh - SBb[k].lh  (d_{n-1} = 0): scan the reversed order
-        for (int c = threadIdx.x; c < n; c += blockDim.x)
-            p.lambda[c] = c < n - 1 ? p.EBb[(size_t)(c + 1) * p.bvec] - p.SBb[(size_t)c * p.bvec] : 0.0;
+        for (int r = c0; r < c0 + per && r < n; r++) {
+            run += d[r];
+            res[n - 1 - r] = run;
+        }
+    }
+    if (!backward) {
         __syncthreads();
-        double loc = 0.0;
-        for (int r = c0; r < c0 + per && r < n; r++) {
-            const int c = n - 1 - r;
-            if (c < n - 1) loc += p.lambda[c];
-        }
-        const double incl = block_scan_256(loc, wsum);
-        double run = incl - loc;
-        for (int r = c0; r < c0 + per && r < n; r++) {
-            const int c = n - 1 - r;
-            if (c < n - 1) run += p.lambda[c];
-            p.lambda[c] = run;
-        }
+        if (threadIdx.x == 0) p.lS[0] = ls_tail + p.kappa[n - 1];
     }
 }
 
@@ -763,8 +856,9 @@ __global__ void __launch_bounds__(128) em_stats(EmParams p) {
         double pi[N];
         double pmax = 0.0;
         if (ok) {
-            // posteriors below e^-75 (< 1e-32) cannot change sums that are >= ~1: skip their exp
-            const double base = cur.kap - lS;
+            // exp underflows to zero below -745.2: skip it there (a nearly silent neuron's statistics are sums
+            // of very small terms whose RELATIVE accuracy matters -- lp = log(xi / gamma0) -- so nothing larger
+            // may be dropped)
             const double g0 = exp(cur.vLG + cur.kap + cur.vLH + cur.lam - lS);
             a_g0all += g0;
             if (has_next) a_g0 += g0;
@@ -774,16 +868,15 @@ __global__ void __launch_bounds__(128) em_stats(EmParams p) {
             for (int i = 0; i < N; i++) {
                 const double le = e_in ? cur.vLEe[i] + cur.lame : 0.0;
                 const double ap = cur.vLQ[i] + cur.kap + le - lS;
-                pi[i] = ap > -75.0 ? exp(ap) : 0.0;
+                pi[i] = ap > -745.5 ? exp(ap) : 0.0;
                 a_s0[i] += pi[i];
                 pmax = fmax(pmax, pi[i]);
                 if (has_next) {
                     const double lex = x_in ? cur.vLEx[i] + cur.lamx : 0.0;
                     const double ax = cur.vLG + cur.kap + lH[i] + cur.vFn[i] + lex - lS;
-                    if (ax > -75.0) a_xi[i] += exp(ax);
+                    if (ax > -745.5) a_xi[i] += exp(ax);
                 }
             }
-            (void)base;
         } else {
 #pragma unroll
             for (int i = 0; i < N; i++) pi[i] = 0.0;
@@ -1056,15 +1149,56 @@ static int em_warps_per_sm(const RingLayout &RL) {
     return (n > 0 ? n : 1) * WPB;
 }
 
+template <int N, int R, int LPC>
+static void em_fir_launch(EmParams &p, const double *hmdl, cudaStream_t st) {
+    constexpr int WPB = 4;
+    const size_t sm = sizeof(double) * (((p.RL.hot + 1) & ~1) + (size_t)WPB * EmWarpSmem<N, R>::TILE);
+    HMM_CUDA(cudaFuncSetAttribute(em_fir<N, R, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    FirCoef<N, LPC> coef{};
+    if (LPC > 0)
+        for (int r = 0; r < LPC; r++)
+            for (int i = 0; i < N; i++) coef.a[r * N + i] = hmdl[p.RL.A + r * p.RL.NP + i];
+    const int64_t nsw = (p.T + 32 * R - 1) / (32 * R);
+    em_fir<N, R, LPC><<<(unsigned)((nsw + WPB - 1) / WPB), 32 * WPB, sm, st>>>(p, coef);
+}
+
+// Optional per-stage device timing (HMMCUDA_EM_TIMING=1): events between the launches, printed after the step.
+struct EmStageTimes {
+    static constexpr int MAXE = 10;
+    cudaEvent_t ev[MAXE] = {};
+    const char *name[MAXE] = {};
+    int n = 0;
+    bool on = false;
+    void mark(const char *what, cudaStream_t st) {
+        if (!on || n >= MAXE) return;
+        if (!ev[n]) cudaEventCreate(&ev[n]);
+        cudaEventRecord(ev[n], st);
+        name[n++] = what;
+    }
+    void report() {
+        if (!on || n < 2) return;
+        cudaEventSynchronize(ev[n - 1]);
+        for (int k = 1; k < n; k++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[k - 1], ev[k]);
+            fprintf(stderr, "%s %.1f us%s", name[k], 1e3 * ms, k == n - 1 ? "\n" : " | ");
+        }
+        n = 0;
+    }
+};
+static thread_local EmStageTimes g_em_times;
+
 template <int N, int R>
-static void em_launch(EmParams &p, cudaStream_t st, hmm_info *info, Timer &ttop, int mode, double *alpha_out,
-                      double *beta_out, double *Zs, double *bsum) {
+static void em_launch(EmParams &p, const double *hmdl, cudaStream_t st, hmm_info *info, Timer &ttop, int mode,
+                      double *alpha_out, double *beta_out, double *Zs, double *bsum) {
+    EmStageTimes &tm = g_em_times;
+    tm.on = getenv("HMMCUDA_EM_TIMING") != nullptr;
+    tm.n = 0;
+    tm.mark("start", st);
     constexpr int WPB = 4;
     const size_t mdl_d = (p.RL.hot + 1) & ~1;
     const size_t sm_fwd = sizeof(double) * (mdl_d + (size_t)WPB * EmWarpSmem<N, R>::DOUBLES);
-    const size_t sm_frep = sizeof(double) * (mdl_d + EmWarpSmem<N, R>::DOUBLES);
     const size_t sm_bwd = sizeof(double) * (mdl_d + (size_t)WPB * N * RING_Q);
-    const size_t sm_brep = sizeof(double) * (mdl_d + (size_t)N * RING_Q);
     const size_t sm_stats = sizeof(double) * std::max<size_t>((size_t)WPB * (160 + N * 32), (size_t)WPB * p.pstride);
     const size_t sm_fin = sizeof(double) * ((size_t)p.pstride + std::max<size_t>(3 * (size_t)N * S1_LAGS, 4 * (size_t)p.pstride));
     HMM_CUDA(cudaFuncSetAttribute(em_forward<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
@@ -1072,24 +1206,37 @@ static void em_launch(EmParams &p, cudaStream_t st, hmm_info *info, Timer &ttop,
     const int gridc = (p.nchunks + WPB - 1) / WPB;
     const int gchk = (p.nchunks * 32 + 127) / 128;
     const int dirs = mode != 1 ? 3 : 1;  // bit 0 forward, bit 1 backward
-    const int fwd_doubles = (int)(mdl_d + EmWarpSmem<N, R>::DOUBLES);
-    const size_t sm_rep = sizeof(double) * ((size_t)fwd_doubles + mdl_d + (size_t)N * RING_Q);
-    HMM_CUDA(cudaFuncSetAttribute(em_repair<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rep));
-    // The backward pass needs only the F scores the forward kernel stored, not its verification, so both
-    // passes run first and are then verified, repaired and normalised by one launch each.
+    const size_t sm_rep = sizeof(double) * (mdl_d + (size_t)N * RING_Q + EM_SCAN_SMEM);
+    HMM_CUDA(cudaFuncSetAttribute(em_fixup<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rep));
+    // FIR pass first: F_i(t0) for every sample, consumed by both recursions and by the statistics pass
+    if (N >= 3 && N <= 5 && p.RL.L == 59)
+        em_fir_launch<N, R, (N >= 3 && N <= 5) ? 59 : 0>(p, hmdl, st);
+    else if (N >= 3 && N <= 5 && p.RL.L == 47)
+        em_fir_launch<N, R, (N >= 3 && N <= 5) ? 47 : 0>(p, hmdl, st);
+    else
+        em_fir_launch<N, R, 0>(p, hmdl, st);
+    tm.mark("fir", st);
     ttop.start();
     em_forward<N, R><<<gridc, 32 * WPB, sm_fwd, st>>>(p);
     ttop.stop();
+    tm.mark("forward", st);
+    // (the backward pass needs only the F scores, not the forward results: measured on a second stream it did
+    // not overlap -- each pass already fills every SM with one wave of chunks -- so it simply follows)
     if (mode != 1) em_backward<N><<<gridc, 32 * WPB, sm_bwd, st>>>(p);
+    tm.mark("backward", st);
     em_check<<<dim3(gchk, 2), 128, 0, st>>>(p, dirs);
-    em_repair<N, R><<<1, 64, sm_rep, st>>>(p, dirs, fwd_doubles);
-    em_offsets<N><<<2, 1024, 0, st>>>(p, dirs);
+    tm.mark("check", st);
+    em_fixup<N, R><<<2, 1024, sm_rep, st>>>(p, dirs);
+    tm.mark("fixup", st);
     if (info) info->kernel_launches += (mode != 1 ? 5 : 4);
     if (mode == 0) {
         em_stats<N><<<p.nblk, 32 * WPB, sm_stats, st>>>(p);
+        tm.mark("stats", st);
         HMM_CUDA(cudaFuncSetAttribute(em_finalize<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fin));
         em_reduce<<<(p.pstride + 31) / 32, 1024, 0, st>>>(p);
+        tm.mark("reduce", st);
         em_finalize<N><<<1, 1024, sm_fin, st>>>(p);
+        tm.mark("finalize", st);
         if (info) info->kernel_launches += 3;
     } else {
         const int nb = (int)((p.T + 256 * ZS_ITEMS - 1) / (256 * ZS_ITEMS));
@@ -1156,6 +1303,7 @@ static void ring_em_core(const double *X_dev, int64_t T, const HostModel &M, EmR
     size_t o_b = carve(sizeof(double) * 4 * (size_t)nchunks * bvec);
     size_t o_flag = carve(sizeof(int) * 2 * (size_t)nchunks);
     size_t o_kl = carve(sizeof(double) * 2 * (size_t)nchunks);
+    size_t o_dk = carve(sizeof(double) * 2 * (size_t)nchunks);
     size_t o_ls = carve(sizeof(double) * 2);
     size_t o_cnt = carve(sizeof(int) * 4);
     size_t o_part = carve(sizeof(double) * (size_t)nblk * pstride);
@@ -1190,6 +1338,7 @@ static void ring_em_core(const double *X_dev, int64_t T, const HostModel &M, EmR
     p.flag_b = p.flag_f + nchunks;
     p.kappa = (double *)(base + o_kl);
     p.lambda = p.kappa + nchunks;
+    p.dk = (double *)(base + o_dk);
     p.lS = (double *)(base + o_ls);
     p.counters = (int *)(base + o_cnt);
     p.part = (double *)(base + o_part);
@@ -1201,6 +1350,7 @@ static void ring_em_core(const double *X_dev, int64_t T, const HostModel &M, EmR
     void *out_dev = nullptr;
     double *out_host = (double *)ws.pinned(1, sizeof(double) * nout, &out_dev);
     p.out = (double *)out_dev;
+    p.dbg = getenv("HMMCUDA_EM_DBG") ? atoi(getenv("HMMCUDA_EM_DBG")) : 0;
     (void)o_out;
 
     double *Zs = nullptr, *bsum = nullptr;
@@ -1211,13 +1361,13 @@ static void ring_em_core(const double *X_dev, int64_t T, const HostModel &M, EmR
     }
     Timer ttop(st);
     switch (N) {
-        case 1: em_launch<1, 8>(p, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
-        case 2: em_launch<2, 8>(p, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
-        case 3: em_launch<3, 8>(p, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
-        case 4: em_launch<4, 8>(p, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
-        case 5: em_launch<5, 4>(p, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
-        case 6: em_launch<6, 4>(p, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
-        case 7: em_launch<7, 4>(p, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
+        case 1: em_launch<1, 8>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
+        case 2: em_launch<2, 8>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
+        case 3: em_launch<3, 8>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
+        case 4: em_launch<4, 8>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
+        case 5: em_launch<5, 4>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
+        case 6: em_launch<6, 4>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
+        case 7: em_launch<7, 4>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
         default: fail(HMM_EUNSUPPORTED, "ring E/M engine supports 1..%d neurons", RING_MAX_N);
     }
     if (mode != 0) {
@@ -1226,6 +1376,7 @@ static void ring_em_core(const double *X_dev, int64_t T, const HostModel &M, EmR
     }
     EmResult &out = *outp;
     HMM_CUDA(cudaStreamSynchronize(st));
+    g_em_times.report();
     const double *h = out_host;
     const int cnt[2] = {(int)h[nout - 2], (int)h[nout - 1]};
     out.sigma = h[0];
