@@ -334,7 +334,12 @@ def run_c5(args):
 
     # everything below is stream-ordered on torch's current stream: the library's kernels, the
     # boundary copies and the NCCL point-to-point messages -- no host synchronisation in between
-    hm._lib.check(L.hmm_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    # (a dedicated stream: torch's default stream is the legacy NULL stream, whose handle 0 means "private
+    # stream" to hmm_set_stream)
+    work = torch.cuda.Stream(device=dev)
+    work.wait_stream(torch.cuda.current_stream())
+    torch.cuda.set_stream(work)
+    hm._lib.check(L.hmm_set_stream(C.c_void_p(work.cuda_stream)))
 
     def p2p(send_t, recv_t, send_to, recv_from):
         ops = []
@@ -368,16 +373,29 @@ def run_c5(args):
             dist.all_reduce(cnt)
         return int(cnt.item())
 
+    res = torch.zeros(2, dtype=torch.float64, device=dev)  # verdict: [total ll, inconsistent shard boundaries]
+    summ = torch.zeros(sh.summary_len, dtype=torch.float64, device=dev)
+    gath = torch.zeros(world * sh.summary_len, dtype=torch.float64, device=dev)
+
     def step():
-        # optimistic single round: one message per neighbour and direction
+        # Optimistic, one collective: every shard decodes its span completely on its own, trusting its ghost
+        # chunks (verified like any chunk boundary inside one GPU); the shards' boundary summaries (2 x 297 + 4
+        # doubles each) are all-gathered and EVERY rank checks EVERY shard boundary, so all ranks reach the same
+        # verdict without another collective.  The host synchronises once, to read the verdict.
         sh.forward()
-        fwd_round(False)
+        sh.fwd_verify(count=False)
         sh.trace()
-        trace_round(False)
-        ll, f, b = sh.finish_ex(x_main.data_ptr())  # the step's only host synchronisation
+        sh.trace_verify(count=False)
+        sh.summary_dev(x_main.data_ptr(), summ.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(gath, summ)
+        else:
+            gath.copy_(summ)
+        sh.judge_dev(gath.data_ptr(), world, res.data_ptr())
+        ll, bad = res.tolist()  # the step's only host synchronisation
         stats["fwd_rounds"] += 1
         stats["trace_rounds"] += 1
-        if all_sum(f + b) == 0:
+        if bad == 0:
             return ll
         # some shard repaired a chunk: its outgoing boundary may have changed -> iterate to a fixed point
         stats["repaired"] += 1
@@ -390,21 +408,52 @@ def run_c5(args):
             stats["trace_rounds"] += 1
             if all_sum(trace_round(True)) == 0:
                 break
-        return sh.finish(x_ptr=x_main.data_ptr())
+        part = torch.tensor([sh.finish(x_ptr=x_main.data_ptr())], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(part)
+        return float(part.item())
 
     for _ in range(max(3, args.warmup)):
         step()
     dist.barrier(device_ids=[local])
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()  # the library's kernels, the copies and NCCL all run on (or are ordered with) this stream
     for _ in range(args.steps):
         ll_part = step()
+    ev1.record()
     dist.barrier(device_ids=[local])
     torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dt = torch.tensor([ev0.elapsed_time(ev1) * 1e-3], dtype=torch.float64, device=dev)
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    llt = torch.tensor([ll_part], dtype=torch.float64, device=dev)
-    dist.all_reduce(llt)
+    if os.environ.get("HMM_C5_PHASES"):
+        # where a step's time goes: the same phases with a host synchronisation after each (rank 0, stderr)
+        names = ["forward+verify", "trace+verify", "path ll + summary + x copy", "all_gather", "judge+read"]
+        acc = [[] for _ in names]
+        for _ in range(5):
+            dist.barrier(device_ids=[local])
+            torch.cuda.synchronize()
+            marks = [time.perf_counter()]
+
+            def mark():
+                torch.cuda.synchronize()
+                marks.append(time.perf_counter())
+
+            sh.forward(); sh.fwd_verify(count=False); mark()
+            sh.trace(); sh.trace_verify(count=False); mark()
+            sh.summary_dev(x_main.data_ptr(), summ.data_ptr()); mark()
+            if world > 1:
+                dist.all_gather_into_tensor(gath, summ)
+            else:
+                gath.copy_(summ)
+            mark()
+            sh.judge_dev(gath.data_ptr(), world, res.data_ptr()); res.tolist(); mark()
+            for k in range(len(names)):
+                acc[k].append(1e3 * (marks[k + 1] - marks[k]))
+        if rank == 0:
+            print("c5 phases (ms, median of 5, host-synchronised): "
+                  + ", ".join(f"{n} {sorted(a)[2]:.3f}" for n, a in zip(names, acc)), file=sys.stderr)
+    llt = torch.tensor([ll_part], dtype=torch.float64, device=dev)  # step() returns the all-reduced ll
     # checksum of the stitched path: per-rank sums gathered on rank 0
     chk = torch.tensor([int(x_main.to(torch.int64).sum().item())], dtype=torch.int64, device=dev)
     dist.all_reduce(chk)
@@ -419,7 +468,7 @@ def run_c5(args):
                                    "time-chunked Viterbi across GPUs with NCCL boundary exchange"
                                    + ("" if T == 108_000_000 else f" [T={T}]"),
                        "chunk_len": chunk_len, "warmup": warm, "boundary_bytes": 8 * sh.bvec + 8,
-                       "exchange_rounds_per_step": [stats["fwd_rounds"] / (args.steps + max(3, args.warmup)),
+                       "protocol": "one all-gather of shard summaries per decode, every rank judges every boundary", "exchange_rounds_per_step": [stats["fwd_rounds"] / (args.steps + max(3, args.warmup)),
                                                     stats["trace_rounds"] / (args.steps + max(3, args.warmup))],
                        "chunks_repaired": stats["repaired"], "ll": float(llt.item()), "x_checksum": int(chk.item()),
                        "l2": "inputs larger than L2 (>= 108 MB of y per GPU)"}}))

@@ -748,6 +748,57 @@ int hmm_vshard_finish_ex(hmm_vshard *h, int16_t *x_main_out, int32_t x_is_device
     });
 }
 
+// summary layout (doubles): [0, bvec) forward vector at main_end | [bvec, 2 bvec) speculative start vector at
+// main_begin | trace state at main_begin (own, global time) | trace state assumed at main_end | partial ll | 0
+__global__ void shard_summary_kernel(const double *eb_last, const double *sb_first, const long long *own_first,
+                                     const long long *own_ghost, const double *ll, long long shift, int bvec,
+                                     double *out) {
+    for (int k = threadIdx.x; k < bvec; k += blockDim.x) {
+        out[k] = eb_last ? eb_last[k] : 0.0;
+        out[bvec + k] = sb_first ? sb_first[k] : 0.0;
+    }
+    if (threadIdx.x == 0) {
+        auto glob = [&](const long long *q) {
+            if (!q) return -2.0;
+            const long long v = *q;
+            return (double)(v >= 0 ? v + shift : v);  // < 2^53: exact
+        };
+        out[2 * bvec + 0] = glob(own_first);
+        out[2 * bvec + 1] = glob(own_ghost);
+        out[2 * bvec + 2] = ll[0];
+        out[2 * bvec + 3] = 0.0;
+    }
+}
+
+int hmm_vshard_summary_len(const hmm_vshard *h) { return h ? 2 * h->plan.bvec() + 4 : 0; }
+
+int hmm_vshard_summary_dev(hmm_vshard *h, int16_t *x_main_dev, double *summary_dev) {
+    return guarded([&] {
+        shard_dev(h);
+        if (!summary_dev) fail(HMM_EINVAL, "null summary_dev");
+        cudaStream_t st = main_stream();
+        const int64_t lo = h->main_begin - h->local_begin, hi = h->main_end - h->local_begin;
+        h->plan.path_ll(st, h->ll_dev, lo, hi, h->local_begin, h->T_global, h->first);
+        shard_summary_kernel<<<1, 256, 0, st>>>(h->last ? nullptr : h->plan.eb_ptr(h->c_main1 - 1),
+                                                h->first ? nullptr : h->plan.sb_ptr(h->c_main0),
+                                                h->first ? nullptr : h->plan.own_start_ptr(h->c_main0),
+                                                h->last ? nullptr : h->plan.own_start_ptr(h->c_main1), h->ll_dev,
+                                                8 * (long long)h->local_begin, h->plan.bvec(), summary_dev);
+        if (x_main_dev)
+            HMM_CUDA(cudaMemcpyAsync(x_main_dev, h->x_loc + lo, sizeof(int16_t) * (size_t)(hi - lo),
+                                     cudaMemcpyDeviceToDevice, st));
+        HMM_CUDA(cudaGetLastError());
+    });
+}
+
+int hmm_vshard_judge_dev(hmm_vshard *h, const double *gathered_dev, int32_t n_ranks, double *out_dev) {
+    return guarded([&] {
+        shard_dev(h);
+        if (!gathered_dev || !out_dev || n_ranks < 1) fail(HMM_EINVAL, "bad judge arguments");
+        vshard_judge_run(gathered_dev, n_ranks, h->plan.bvec(), out_dev, main_stream());
+    });
+}
+
 int hmm_vshard_repairs(hmm_vshard *h, int32_t *fwd_repaired, int32_t *trace_repaired) {
     return guarded([&] {
         shard_dev(h);

@@ -67,6 +67,7 @@ class VitPlan {
     size_t arena_bytes_used() const;
     void set_x_window(int64_t lo, int64_t hi);  // local steps whose x may be written
     int *counters_ptr();
+    double *sb_ptr(int chunk);  // speculative start vector of a chunk
 
   private:
     struct Impl;
@@ -82,6 +83,7 @@ class VitPlan {
     char *arena_base = nullptr;
     size_t arena_cap = 0, arena_used = 0;
 };
+void vshard_judge_run(const double *gathered_dev, int n_ranks, int bvec, double *out_dev, cudaStream_t st);
 void ring_path_ll_run(const double *y_dev, int64_t T, const FaithfulLayout &FL, const char *blob_dev, const HostModel &M0,
                       const int16_t *x_dev, double *ll_dev, double *part, cudaStream_t st);
 // Default chunk length / warm-up for a recording of T_total samples decoded on n_gpus GPUs.

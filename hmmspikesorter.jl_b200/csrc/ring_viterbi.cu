@@ -739,6 +739,36 @@ __global__ void ring_vit_check_fwd(VitParams p) {
     if (lane == 0) p.fwd_flag[(size_t)ch * p.nchunks + gw] = ok ? 0 : 1;
 }
 
+// Time-sharded decode, one-collective protocol: every rank checks every shard boundary of the all-gathered
+// summaries (layout: api.cu shard_summary_kernel).  One warp per boundary r | r+1, then a fixed-order sum of ll.
+__global__ void vshard_judge_kernel(const double *g, int n, int bvec, double *out) {
+    __shared__ int bad[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int len = 2 * bvec + 4;
+    if (lane == 0) bad[w] = 0;
+    __syncwarp();
+    for (int r = w; r < n - 1; r += (blockDim.x >> 5)) {
+        const double *left = g + (size_t)r * len, *right = g + (size_t)(r + 1) * len;
+        const bool okf = boundary_matches(right + bvec, left, bvec, lane);          // start vector of r+1 vs end vector of r
+        const bool okt = left[2 * bvec + 1] == right[2 * bvec + 0];                  // state assumed by r vs state of r+1
+        if (lane == 0 && !(okf && okt)) bad[w]++;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ll = 0.0;
+        int nb = 0;
+        for (int r = 0; r < n; r++) ll += g[(size_t)r * len + 2 * bvec + 2];
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) nb += bad[k];
+        out[0] = ll;
+        out[1] = (double)nb;
+    }
+}
+
+void vshard_judge_run(const double *gathered_dev, int n_ranks, int bvec, double *out_dev, cudaStream_t st) {
+    vshard_judge_kernel<<<1, 256, 0, st>>>(gathered_dev, n_ranks, bvec, out_dev);
+    HMM_CUDA(cudaGetLastError());
+}
+
 // Sequential repair (one warp per channel): re-run flagged chunks from the true
 // boundary vector; a re-run changes EB[c], so chunk c+1 is re-checked against it.
 template <int N, int R>
@@ -750,7 +780,10 @@ __global__ void __launch_bounds__(32) ring_vit_repair_fwd(VitParams p) {
     // fast exit when nothing is flagged
     int any = 0;
     for (int c = 1 + lane; c < p.nchunks; c += 32) any |= flag[c];
-    if (!__any_sync(0xffffffffu, any)) return;
+    if (!__any_sync(0xffffffffu, any)) {
+        if (lane == 0) p.counters[ch * 4 + 0] = 0;  // the counter always describes the LAST verification
+        return;
+    }
     double *mdl = smem_d;
     load_model_smem<N, R>(p, ch, mdl);
     double *ws = smem_d + ((p.RL.hot + 1) & ~1);
@@ -1021,7 +1054,10 @@ __global__ void __launch_bounds__(32) ring_vit_repair_trace(VitParams p) {
     const size_t o = (size_t)ch * p.nchunks_t;
     int any = 0;
     for (int c = lane; c < p.nchunks_t - 1; c += 32) any |= p.tr_flag[o + c];
-    if (!__any_sync(0xffffffffu, any)) return;
+    if (!__any_sync(0xffffffffu, any)) {
+        if (lane == 0) p.counters[ch * 4 + 1] = 0;
+        return;
+    }
     const int L = p.RL.L;
     if (p.first_prologue) {
         const int16_t *g = p.T2pro + (size_t)ch * p.ns * (L + 1);
@@ -1484,6 +1520,7 @@ int *VitPlan::counters_ptr() { return p_->counters; }
 int VitPlan::nchunks() const { return p_->nchunks; }
 int VitPlan::bvec() const { return p_->bvec; }
 double *VitPlan::eb_ptr(int chunk) { return p_->EB + (size_t)chunk * p_->bvec; }
+double *VitPlan::sb_ptr(int chunk) { return p_->SB + (size_t)chunk * p_->bvec; }
 long long *VitPlan::own_start_ptr(int chunk) { return p_->own_start + (size_t)chunk * p_->tfac; }
 
 void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, const std::vector<HostModel> &models,

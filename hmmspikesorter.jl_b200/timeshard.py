@@ -160,6 +160,21 @@ class Shard:
         check(lib().hmm_vshard_finish_ex(self._h, C.c_void_p(x_ptr), i32(1), C.byref(ll), C.byref(f), C.byref(b)))
         return ll.value, int(f.value), int(b.value)
 
+    @property
+    def summary_len(self) -> int:
+        return int(lib().hmm_vshard_summary_len(self._h))
+
+    def summary_dev(self, x_ptr, summary_ptr):
+        """One-collective protocol, step 1: x of the main span into device buffer `x_ptr` (0 = skip) and this
+        shard's boundary summary (summary_len doubles) into device buffer `summary_ptr`; asynchronous."""
+        self._dev()
+        check(lib().hmm_vshard_summary_dev(self._h, C.c_void_p(x_ptr) if x_ptr else None, C.c_void_p(summary_ptr)))
+
+    def judge_dev(self, gathered_ptr, n_ranks, out_ptr):
+        """Step 2, after the all-gather: [total ll, inconsistent shard boundaries] into device buffer `out_ptr`."""
+        self._dev()
+        check(lib().hmm_vshard_judge_dev(self._h, C.c_void_p(gathered_ptr), i32(n_ranks), C.c_void_p(out_ptr)))
+
     def close(self):
         if self._h:
             self._dev()

@@ -66,7 +66,8 @@ int hmm_set_device(int device);     /* device used by subsequent calls from this
 int hmm_get_device(void);
 /* Run the calling thread's subsequent work on `cuda_stream` (a cudaStream_t owned by the caller, e.g.
  * torch.cuda.current_stream().cuda_stream) so that it is stream-ordered with the caller's own kernels
- * and NCCL collectives; NULL restores the library's private stream. */
+ * and NCCL collectives; NULL restores the library's private stream (so the legacy default stream, whose
+ * handle is 0, cannot be selected: use a created stream). */
 int hmm_set_stream(void *cuda_stream);
 
 /* Tunables of the ring engine (0 keeps the default): chunk length and
@@ -151,7 +152,21 @@ int hmm_vshard_finish(hmm_vshard *h, int16_t *x_main_out, int32_t x_is_device, d
 /* finish + repair counters with a single synchronisation */
 int hmm_vshard_finish_ex(hmm_vshard *h, int16_t *x_main_out, int32_t x_is_device, double *ll_partial_out,
                          int32_t *fwd_repaired, int32_t *trace_repaired);
-int hmm_vshard_repairs(hmm_vshard *h, int32_t *fwd_repaired, int32_t *trace_repaired); /* counters since forward */
+/* One-collective protocol (no host synchronisation until the verdict is read).  After forward ->
+ * fwd_verify -> trace -> trace_verify, run purely locally on the ghost chunks' results:
+ *   summary_dev : x of the main span into x_main_dev (may be NULL) and, into summary_dev
+ *                 (hmm_vshard_summary_len() doubles): the true forward vector at main_end, the speculative one
+ *                 this shard started from at main_begin, the traceback states at main_begin (own) and at
+ *                 main_end (assumed), and the partial ll -- all on the library's stream;
+ *   [caller: ONE all-gather of the summaries over the ranks, rank order]
+ *   judge_dev   : every rank checks EVERY shard boundary of the gathered summaries (same arithmetic as the
+ *                 chunk boundaries inside one GPU), so all ranks reach the same verdict without another
+ *                 collective: out_dev[0] = total ll, out_dev[1] = number of inconsistent shard boundaries.
+ * A non-zero verdict means some ghost chunk guessed wrong: fall back to the exchange / verify rounds above. */
+int hmm_vshard_summary_len(const hmm_vshard *h);
+int hmm_vshard_summary_dev(hmm_vshard *h, int16_t *x_main_dev, double *summary_dev);
+int hmm_vshard_judge_dev(hmm_vshard *h, const double *gathered_dev, int32_t n_ranks, double *out_dev);
+int hmm_vshard_repairs(hmm_vshard *h, int32_t *fwd_repaired, int32_t *trace_repaired); /* of the last fwd_verify / trace_verify */
 int hmm_vshard_destroy(hmm_vshard *h);
 
 /* ---- Baum-Welch ---------------------------------------------------------- */

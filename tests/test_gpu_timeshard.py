@@ -34,3 +34,55 @@ def test_time_sharded_dense_spiking_repairs_across_shards(hm, O, case_factory):
     x_ref, ll_ref = O.viterbi(S, lA, mu, sig)
     x, ll, info = hm.viterbi_time_sharded(S, lA, mu, sig, 5, chunk_len=1024, warmup=256, return_info=True)
     assert np.array_equal(x, x_ref) and abs(ll - ll_ref) <= 1e-9 * abs(ll_ref)
+
+
+def test_one_collective_protocol_summaries_and_judge(hm, O, case_factory):
+    """hmm_vshard_summary_dev / hmm_vshard_judge_dev (bench.py --workload c5): every shard decodes on its own,
+    the boundary summaries are gathered (here: concatenated) and one kernel checks every shard boundary.  The
+    stitched result must equal the oracle's; a corrupted summary must be detected."""
+    import torch
+
+    ts = hm.timeshard
+    T, n = 400_000, 4
+    S, lA, mu, sig = case_factory(3, 60, T, 64)
+    x_ref, ll_ref = O.viterbi(S, lA, mu, sig)
+    dev = torch.device("cuda", 0)
+    spans = ts.shard_plan(T, n, 4096)
+    xs, summaries, shards = [], [], []
+    for span in spans:
+        y_loc = torch.from_numpy(np.ascontiguousarray(S[span[0]:span[1]])).to(dev)
+        sh = ts.Shard(y_loc.data_ptr(), False, span, T, 4096, 512, lA, mu, sig)
+        x_main = torch.empty(span[3] - span[2], dtype=torch.int16, device=dev)
+        summ = torch.zeros(sh.summary_len, dtype=torch.float64, device=dev)
+        sh.forward()
+        sh.fwd_verify(count=False)
+        sh.trace()
+        sh.trace_verify(count=False)
+        sh.summary_dev(x_main.data_ptr(), summ.data_ptr())
+        torch.cuda.synchronize()
+        xs.append(x_main.cpu().numpy())
+        summaries.append(summ)
+        shards.append((sh, y_loc))
+    gath = torch.cat(summaries).contiguous()
+    res = torch.zeros(2, dtype=torch.float64, device=dev)
+    shards[0][0].judge_dev(gath.data_ptr(), n, res.data_ptr())
+    torch.cuda.synchronize()
+    ll, bad = res.tolist()
+    assert bad == 0
+    assert np.array_equal(np.concatenate(xs), x_ref)
+    assert abs(ll - ll_ref) <= 1e-9 * abs(ll_ref)
+    # a wrong traceback state at a shard boundary, and a wrong forward vector, are both caught
+    slen = shards[0][0].summary_len
+    bvec = shards[0][0].bvec
+    g2 = gath.clone()
+    g2[1 * slen + 2 * bvec + 0] += 8.0
+    shards[0][0].judge_dev(g2.data_ptr(), n, res.data_ptr())
+    torch.cuda.synchronize()
+    assert res.tolist()[1] == 1
+    g3 = gath.clone()
+    g3[2 * slen + 5] += 1e-3  # end vector of shard 2 (entry 5 of the forward vector)
+    shards[0][0].judge_dev(g3.data_ptr(), n, res.data_ptr())
+    torch.cuda.synchronize()
+    assert res.tolist()[1] == 1
+    for sh, _ in shards:
+        sh.close()
