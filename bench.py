@@ -42,7 +42,7 @@ import __graft_entry__ as ge  # noqa: E402
 T_C2 = 18_000_000
 T_C3 = 1_800_000
 BYTES_PER_SAMPLE = 10  # 8 B read of S + 2 B write of x
-NCU_TRAFFIC_BYTES = 169545216  # ring_vit_forward<3,8,64>: dram read + write per launch (profiles/r01_ring_vit_forward_ncu.md)
+NCU_TRAFFIC_BYTES = 199488256  # ring_vit_forward_ws<3,8,59>: dram read + write per launch (profiles/r01_ring_vit_forward_ws_ncu.md)
 FP64_PEAK_GDFMA = 18421.7  # measured FP64 FMA issue rate, profiles/r01_fp64_peak.jsonl
 
 
@@ -181,6 +181,11 @@ def run_ours(args):
                                             C.c_void_p(x_dev.data_ptr()), C.byref(ll), i32(hm.MODES["ring"]),
                                             C.byref(info)))
 
+    # The library issues its work on this (created) torch stream, so the torch CUDA events below bracket it.
+    work = torch.cuda.Stream(device=dev)
+    work.wait_stream(torch.cuda.current_stream())
+    torch.cuda.set_stream(work)
+    hm._lib.check(L.hmm_set_stream(C.c_void_p(work.cuda_stream)))
     for _ in range(args.warmup):
         step_dev()
     sampler = ClockSampler(local)
@@ -188,15 +193,18 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     top_ms, kern_ms, launches = [], [], 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    ev0.record()
     for _ in range(args.steps):
         step_dev()
         top_ms.append(info.top_kernel_ms)
         kern_ms.append(info.kernel_ms)
         launches += info.kernel_launches
+    ev1.record()
     barrier()
-    dt = time.perf_counter() - t0
-    dt = max_over_ranks(dt)
+    wall = max_over_ranks(time.perf_counter() - t0)
+    dt = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)  # device time of the K steps (CUDA events), max over ranks
     ms_per_step = dt / args.steps * 1e3
     value = world * T / (dt / args.steps) / 1e6
     chunks, rep_f, rep_b = info.n_chunks, info.fwd_repaired, info.bwd_repaired
@@ -219,17 +227,19 @@ def run_ours(args):
     for _ in range(max(3, args.warmup // 2)):
         step_e2e()
     barrier()
-    t0 = time.perf_counter()
+    ev0.record()
     for _ in range(args.steps):
         step_e2e()
         launches += info.kernel_launches
+    ev1.record()
     barrier()
-    dt_e = max_over_ranks(time.perf_counter() - t0)
+    dt_e = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
     e2e_val = world * T / (dt_e / args.steps) / 1e6
     clocks = sampler.stop() if rank == 0 else None
     same = bool(np.array_equal(x_first, x_pin)) and ll.value == ll2.value
     L.hmm_host_free(yh)
     L.hmm_host_free(xh)
+    L.hmm_set_stream(None)
 
     # ---- Baum-Welch half of the metric (config 3), rank-local, resident X --------
     bw = None
@@ -247,11 +257,12 @@ def run_ours(args):
         peak, peak_src = measured_peak_hbm()
         top = float(np.mean(top_ms))
         achieved = BYTES_PER_SAMPLE * T / (top * 1e-3) / 1e9
-        dfma = (T + chunks * 512.0) * lA.N * 64  # LP = 64 taps for K = 60; 512-sample warm-up per chunk
+        dfma = (T + chunks * 512.0) * lA.N * (lA.K - 1)  # L = K - 1 = 59 taps; 512-sample warm-up per chunk
         out = {
             "metric": "Viterbi Msamples/s (N=3,K=60; Baum-Welch iters/s in `baum_welch`)",
             "value": round(value, 2), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
+            "wall_ms_per_step": round(wall / args.steps * 1e3, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "BASELINE config 2: single-channel 30 kHz x 10 min (18M samples), N=3 x K=60, "
                                    "Viterbi decode only, fixed lA/mu/sigma" + ("" if T == T_C2 else f" [T={T}]"),
@@ -264,7 +275,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": 2 * T + 8, "host_memory": "pinned", "same_result_as_resident": same},
             "gpu_launches": int(launches),
             "kernel_ms_per_step": round(float(np.mean(kern_ms)), 4),
-            "roofline": {"bound": "hbm", "kernel": "ring_vit_forward<3,8,64>", "achieved": round(achieved, 1),
+            "roofline": {"bound": "hbm", "kernel": "ring_vit_forward_ws<3,8,59>", "achieved": round(achieved, 1),
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": NCU_TRAFFIC_BYTES, "kernel_ms": round(top, 4),
                          "note": "algorithmic 10 B/sample; traffic = dram read+write per launch from the ncu --set "
@@ -273,7 +284,7 @@ def run_ours(args):
                            "frac": round(dfma / (top * 1e-3) / 1e9 / FP64_PEAK_GDFMA, 4),
                            "peak_source": "measured with tools/fp64_peak.cu on this pool's B200 "
                                           "(profiles/r01_fp64_peak.jsonl)",
-                           "work": "FIR: (samples + chunks*warmup) x N x LP fused multiply-adds"},
+                           "work": "FIR: (samples + chunks*warmup) x N x L fused multiply-adds, L = K-1 = 59 taps"},
             "cpu_baseline": cpu,
             "baum_welch": bw,
             "clocks": clocks,

@@ -196,15 +196,29 @@ __global__ void __launch_bounds__(1024) ring_vit_prologue(VitParams p) {
     __syncthreads();
     double *prev = c0, *cur = c1;
     const bool one_state = blockDim.x >= (unsigned)ns;  // thread j owns state j: keep its first edge in registers
-    int my_deg = 0, my_src = 0, my_e0 = 0;
-    double my_w = 0.0;
+    // the sequential sweep needs one thread per state: the warps beyond that leave, which makes its L barriers
+    // (one per column) several times cheaper than with all 32 warps of the emission phase
+    if (one_state && threadIdx.x >= (unsigned)((ns + 31) & ~31)) return;
+    // thread j keeps the incoming edges of state j in registers (ring models: at most N + 1 <= 8 of them; the
+    // rare longer lists continue from global memory), so a column costs no global load
+    constexpr int PRO_DEG = 8;
+    int my_deg = 0, my_e0 = 0;
+    int my_src[PRO_DEG];
+    double my_w[PRO_DEG];
+#pragma unroll
+    for (int e = 0; e < PRO_DEG; e++) {
+        my_src[e] = 0;
+        my_w[e] = 0.0;
+    }
     if (one_state && threadIdx.x < (unsigned)ns) {
         my_e0 = gp[threadIdx.x];
         my_deg = gp[threadIdx.x + 1] - my_e0;
-        if (my_deg > 0) {
-            my_src = gs[my_e0];
-            my_w = glp[my_e0];
-        }
+#pragma unroll
+        for (int e = 0; e < PRO_DEG; e++)
+            if (e < my_deg) {
+                my_src[e] = gs[my_e0 + e];
+                my_w[e] = glp[my_e0 + e];
+            }
     }
     for (int t = 1; t <= L; t++) {
         if (one_state) {
@@ -212,19 +226,21 @@ __global__ void __launch_bounds__(1024) ring_vit_prologue(VitParams p) {
             if (j < ns) {
                 double best = -INFINITY;
                 int bp = 0;
-                if (my_deg > 0) {
-                    const double tt = __dadd_rn(prev[my_src], my_w);
-                    if (tt > best) {
-                        best = tt;
-                        bp = my_src;
-                    }
-                    for (int e = my_e0 + 1; e < my_e0 + my_deg; e++) {
-                        const int k2 = gs[e];
-                        const double t3 = __dadd_rn(prev[k2], glp[e]);
-                        if (t3 > best) {  // strict: first candidate in list order wins ties
-                            best = t3;
-                            bp = k2;
+#pragma unroll
+                for (int e = 0; e < PRO_DEG; e++)
+                    if (e < my_deg) {
+                        const double tt = __dadd_rn(prev[my_src[e]], my_w[e]);
+                        if (tt > best) {  // strict: first candidate in list order wins ties
+                            best = tt;
+                            bp = my_src[e];
                         }
+                    }
+                for (int e = my_e0 + PRO_DEG; e < my_e0 + my_deg; e++) {
+                    const int k2 = gs[e];
+                    const double t3 = __dadd_rn(prev[k2], glp[e]);
+                    if (t3 > best) {
+                        best = t3;
+                        bp = k2;
                     }
                 }
                 const double v = __dadd_rn(best, q[(size_t)t * ns + j]);

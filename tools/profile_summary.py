@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turn ncu exports brought back in gpurun_out/ into the tracked summaries under profiles/.
 
-  python tools/profile_summary.py launches gpurun_out/launches.csv profiles/r01_launches_c2.md
+  python tools/profile_summary.py launches gpurun_out/launches.csv profiles/r01_launches_c2.md [first-K-launches-per-kernel]
   python tools/profile_summary.py kernel   gpurun_out/prof_fwd2.ncu-rep profiles/r01_ring_vit_forward.md
 """
 import collections
@@ -10,13 +10,17 @@ import subprocess
 import sys
 
 
-def launches(src, dst):
+def launches(src, dst, first=0):
+    """first > 0: only the first `first` launches of every kernel (bench.py runs its device-resident steps first;
+    the later launches of the same kernels belong to the pipelined host-pointer decode, which works on segments)."""
     lines = [l for l in open(src) if not l.startswith("==")]
     agg = collections.OrderedDict()
     for row in csv.DictReader(lines):
         if row.get("Metric Name") != "gpu__time_duration.sum":
             continue
-        agg.setdefault(row["Kernel Name"], []).append(float(row["Metric Value"].replace(",", "")))
+        v = agg.setdefault(row["Kernel Name"], [])
+        if first <= 0 or len(v) < first:
+            v.append(float(row["Metric Value"].replace(",", "")))
     tot = sum(sum(v) / len(v) for v in agg.values())
     with open(dst, "w") as f:
         f.write("# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare SHARES)\n\n")
@@ -57,4 +61,7 @@ def kernel(rep, dst):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 0)
+    else:
+        kernel(sys.argv[2], sys.argv[3])
