@@ -488,6 +488,151 @@ def run_c5(args):
     dist.destroy_process_group()
 
 
+def run_c4(args):
+    """BASELINE config 4: a 128-channel probe x 10 min at 30 kHz, independent per-channel HMMs (N=4, K=48),
+    channels sharded over the GPUs (strong scaling: 128 channels in total, no collective on the data path).
+    `value`: all of a rank's channels decoded from HBM by one hmm_viterbi_dev_f64 call per step; `e2e`: the
+    same channels through the host-pointer batch API from pinned host memory, in groups of 16 channels."""
+    import torch
+    import torch.distributed as dist
+
+    hm = ge.load_package()
+    L = hm.lib()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    hm._lib.check(L.hmm_set_device(i32(local)))
+    C_total, N, K = 128, 4, 48
+    T = args.samples
+    Cn = C_total // world
+    # 4 distinct synthetic channels per rank (different templates / rates / noise), tiled to the rank's share
+    rng = np.random.default_rng(1000 + rank)
+    base, sts, trs, mus, sig = [], [], [], [], []
+    for c in range(4):
+        prm = [(rng.uniform(2, 4), rng.uniform(0.3, 0.9), rng.uniform(0.1, 0.3)) for _ in range(N)]
+        temps = np.stack([hm.create_spike_template(K, *q) for q in prm], axis=1)
+        pp = rng.uniform(0.0005, 0.004, size=N)
+        base.append(hm.create_signal(T, 0.3, pp, temps, hm.make_rng(1000 + 16 * rank + c)))
+        mu = np.asfortranarray(temps.copy())
+        mu[0, :] = 0
+        lA = hm.StateMatrix(N, K, np.log(pp), False)
+        sts.append(np.asfortranarray(lA.states).ravel(order="F"))
+        trs.append(lA.transitions)
+        mus.append(mu.ravel(order="F"))
+        sig.append(0.3)
+    pick = [c % 4 for c in range(Cn)]
+    st = np.ascontiguousarray(np.concatenate([sts[k] for k in pick]))
+    tr = np.ascontiguousarray(np.concatenate([trs[k] for k in pick]))
+    mu = np.ascontiguousarray(np.concatenate([mus[k] for k in pick]))
+    sg = np.asarray([sig[k] for k in pick])
+    ntr = trs[0].size
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    info = hm.HmmInfo()
+    y_dev = torch.empty((Cn, T), dtype=torch.float64, device=dev)  # channel-major == [T x C] column-major
+    for c in range(Cn):
+        y_dev[c].copy_(torch.from_numpy(base[pick[c]]))
+    x_dev = torch.empty((Cn, T), dtype=torch.int16, device=dev)
+    ll = np.zeros(Cn)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    work = torch.cuda.Stream(device=dev)
+    work.wait_stream(torch.cuda.current_stream())
+    torch.cuda.set_stream(work)
+    hm._lib.check(L.hmm_set_stream(C.c_void_p(work.cuda_stream)))
+
+    def step_dev():
+        hm._lib.check(L.hmm_viterbi_dev_f64(C.c_void_p(y_dev.data_ptr()), i64(T), i32(Cn), p(st), i32(0), i32(N), i32(K),
+                                            i32(lA.nstates), p(tr), i64(ntr), p(mu), p(sg),
+                                            C.c_void_p(x_dev.data_ptr()), p(ll), i32(hm.MODES["ring"]), C.byref(info)))
+
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    launches = 0
+    for _ in range(args.steps):
+        step_dev()
+        launches += info.kernel_launches
+    ev1.record()
+    barrier()
+    dt = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
+    value = C_total * T / (dt / args.steps) / 1e6
+    chk = int(x_dev.to(torch.int32).sum(dtype=torch.int64).item())
+    # ---- end to end: groups of 16 channels through the batch host-pointer API, pinned host memory ----
+    G = min(16, Cn)
+    yh, xh = C.c_void_p(), C.c_void_p()
+    hm._lib.check(L.hmm_host_alloc(C.byref(yh), C.c_uint64(8 * T * G)))
+    hm._lib.check(L.hmm_host_alloc(C.byref(xh), C.c_uint64(2 * T * G)))
+    Y = np.ctypeslib.as_array(C.cast(yh, C.POINTER(C.c_double)), shape=(G, T))
+    for c in range(G):
+        Y[c] = base[pick[c]]
+    gsel = slice(0, G)
+    stg = np.ascontiguousarray(np.concatenate([sts[k] for k in pick[gsel]]))
+    trg = np.ascontiguousarray(np.concatenate([trs[k] for k in pick[gsel]]))
+    mug = np.ascontiguousarray(np.concatenate([mus[k] for k in pick[gsel]]))
+    sgg = np.asarray([sig[k] for k in pick[gsel]])
+    llg = np.zeros(G)
+
+    def step_e2e():
+        for _ in range(Cn // G):
+            hm._lib.check(L.hmm_viterbi_batch_f64(yh, i64(T), i32(G), p(stg), i32(0), i32(N), i32(K), i32(lA.nstates),
+                                                  p(trg), i64(ntr), p(mug), p(sgg), xh, p(llg), i32(hm.MODES["ring"]),
+                                                  C.byref(info)))
+
+    step_e2e()
+    barrier()
+    ev0.record()
+    e_steps = max(1, min(3, args.steps))
+    for _ in range(e_steps):
+        step_e2e()
+    ev1.record()
+    barrier()
+    dt_e = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
+    e2e_val = C_total * T / (dt_e / e_steps) / 1e6
+    L.hmm_host_free(yh)
+    L.hmm_host_free(xh)
+    L.hmm_set_stream(None)
+    if world > 1:
+        t = torch.tensor([chk], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        chk = int(t.item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "Viterbi Msamples/s, 128-channel probe, independent per-channel HMMs (config 4)",
+            "value": round(value, 2), "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": round(dt / args.steps * 1e3, 4), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE config 4: 128-channel probe x 10 min at 30 kHz, independent per-channel "
+                                   "HMMs (N=4, K=48), channels sharded over the GPUs" + ("" if T == T_C2 else f" [T={T}]"),
+                       "channels_per_gpu": Cn, "samples_per_channel": T,
+                       "data_note": "4 distinct synthetic channels per rank tiled to the rank's share",
+                       "parallelism": f"channel-sharded x{world}, no collective", "x_checksum": chk,
+                       "l2": "inputs larger than L2"},
+            "e2e": {"value": round(e2e_val, 2), "unit": "Msamples/s", "h2d_bytes_per_step": 8 * T * Cn,
+                    "d2h_bytes_per_step": (2 * T + 8) * Cn, "host_memory": "pinned",
+                    "note": f"groups of {G} channels per hmm_viterbi_batch_f64 call"},
+            "gpu_launches": int(launches)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def bench_bw(hm, args, rank):
     """Config 3: T = 1.8 M, N=3 x K=60, E/M iterations from mu0 = 0.7 truth."""
     T = min(T_C3, args.samples)
@@ -601,8 +746,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-bw", action="store_true")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
                     help="c2 (default, the driver's contract line): one 18M-sample channel per GPU; "
+                         "c4: 128 channels (N=4, K=48) sharded by channel; "
                          "c5: one 108M-sample recording time-sharded over the GPUs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -611,6 +757,8 @@ def main():
         run_reference(args)
     elif args.workload == "c5":
         run_c5(args)
+    elif args.workload == "c4":
+        run_c4(args)
     else:
         run_ours(args)
 
