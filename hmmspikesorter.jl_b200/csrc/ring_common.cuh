@@ -58,6 +58,11 @@ __host__ __device__ inline RingLayout ring_layout(int N, int L) {
 
 void ring_pack(const HostModel &M, const RingLayout &R, double *dst);
 
+// Warp index broadcast from lane 0: the value is the same as threadIdx.x >> 5, but the compiler now KNOWS it is
+// warp-uniform, so the chunk index, the role and every loop bound derived from it can live in uniform
+// registers and loop control runs on the uniform datapath (e.g. UR-indexed LDCU in a rolled FIR tap loop).
+__device__ __forceinline__ int warp_index_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ double shfl_down_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
@@ -205,11 +210,17 @@ __device__ __forceinline__ void fir_compute_c(const FirCoef<N, LPC> &coef, const
     for (int j = 0; j < R; j++) w[j] = ytile[j * G::YS + lane];
     // Fully unrolled over exactly LPC = L taps, so that every coefficient is a compile-time constant-bank offset
     // (the compiler keeps them in uniform registers: LDCU.128 + DFMA R, R, UR, R -- no register-file or
-    // shared-memory traffic for them).  Measured at C2 (forward kernel, 18 M samples): full unroll 0.40 ms
-    // (28 KB of code: ncu shows a stall_no_instruction sample at every 128-byte line); the same loop rolled in
-    // groups of 8 taps (3.7 KB body, no instruction-fetch stalls, but register-indexed LDC coefficients and
-    // more dispatch stalls) 0.45 ms, with or without a coefficient prefetch queue; shared-memory coefficients 0.52 ms.
+    // shared-memory traffic for them).  Measured at C2 (forward kernel, 18 M samples): full unroll 0.36 ms
+    // (25 KB of code: ncu shows a stall_no_instruction sample at every 128-byte line).  -DHMM_FIR_ROLLED rolls
+    // the loop in groups of 8 taps (3.7 KB body, no instruction-fetch stalls): with the warp index known to be
+    // uniform (warp_index_uniform) the compiler indexes the coefficients through uniform registers
+    // (LDCU.64 c[0x0][UR+imm]) and the kernel takes 0.38 ms; before that it used register-indexed LDC and took
+    // 0.45 ms.  Shared-memory coefficients: 0.52 ms.
+#ifdef HMM_FIR_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int r0 = 0; r0 < LPC; r0 += R) {
 #pragma unroll
         for (int u = 0; u < R; u++) {

@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(128) em_fir(EmParams p, const __grid_constant_
     double *mdl = smem_d;
     for (int k = threadIdx.x; k < p.RL.hot; k += blockDim.x) mdl[k] = p.model[k];
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = warp_index_uniform();
     const RingLayout &RL = p.RL;
     const int L = RL.L;
     const int64_t T = p.T;
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(128, 4) em_forward(EmParams p) {
     double *mdl = smem_d;
     for (int k = threadIdx.x; k < p.RL.hot; k += blockDim.x) mdl[k] = p.model[k];
     __syncthreads();
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_index_uniform();
     const int c = blockIdx.x * (blockDim.x >> 5) + warp;
     if (c >= p.nchunks) return;
     double *ws = smem_d + ((p.RL.hot + 1) & ~1) + (size_t)warp * EmWarpSmem<N, R>::DOUBLES;
@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(128, 4) em_backward(EmParams p) {
     double *mdl = smem_d;
     for (int k = threadIdx.x; k < p.RL.hot; k += blockDim.x) mdl[k] = p.model[k];
     __syncthreads();
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_index_uniform();
     const int c = blockIdx.x * (blockDim.x >> 5) + warp;
     if (c >= p.nchunks) return;
     double *ring = smem_d + ((p.RL.hot + 1) & ~1) + (size_t)warp * N * RING_Q;
@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(128, 4) em_backward(EmParams p) {
 // Block-wide inclusive scan of one double per thread over the first 256 threads, fixed order.  (Threads
 // beyond the first 256 may take part in the barriers; their result is unused.)
 __device__ __forceinline__ double block_scan_256(double v, double *wsum) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = warp_index_uniform();
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         double o = shfl_up_d(v, d);
@@ -786,7 +786,7 @@ template <int N>
 __global__ void __launch_bounds__(128) em_stats(EmParams p) {
     extern __shared__ __align__(16) double smem_d[];
     constexpr int WPB = 4;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = warp_index_uniform();
     const RingLayout &RL = p.RL;
     const int L = RL.L;
     const int64_t T = p.T;

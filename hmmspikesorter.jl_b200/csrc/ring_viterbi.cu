@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(256, 2)
     extern __shared__ __align__(16) double smem_d[];
     const int ch = blockIdx.y;
     double *mdl = smem_d;
-    const int warp = threadIdx.x >> 5, slot = warp & 3;
+    const int warp = warp_index_uniform(), slot = warp & 3;
     double *ws = smem_d + ((p.RL.hot + 1) & ~1) + (size_t)slot * SlotSmem<N, R>::DOUBLES;
     if ((threadIdx.x & 31) == 0 && warp < 4) {
         uint64_t *bars = reinterpret_cast<uint64_t *>(ws + SlotSmem<N, R>::BAR);
@@ -1028,7 +1028,7 @@ template <int N>
 __global__ void __launch_bounds__(128) ring_vit_trace(VitParams p) {
     extern __shared__ __align__(16) uint32_t trsm[];
     const int ch = blockIdx.y;
-    const int warp = threadIdx.x >> 5;
+    const int warp = warp_index_uniform();
     uint32_t *tws = trsm + (size_t)warp * TR_WARP_U32;
     int16_t *t2s_all = reinterpret_cast<int16_t *>(trsm + (size_t)(blockDim.x >> 5) * TR_WARP_U32);
     const int c = blockIdx.x * (blockDim.x >> 5) + warp;
