@@ -413,22 +413,45 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
         double *ft[2] = {ws + SlotSmem<N, R>::FT, ws + SlotSmem<N, R>::FT + N * G::FTILE};
         fir_stage<R>(y, T, base0, need, yt[0], lane);
         int k = 0;
+#ifdef HMM_PHASE_TIMING
+        long long pt_stage = 0, pt_wait = 0, pt_fir = 0;
+#endif
         for (int64_t b = base0; b < e; b += G::SW, k++) {
             const int buf = k & 1;
             const bool more = b + G::SW < e;
+#ifdef HMM_PHASE_TIMING
+            const long long q0 = clock64();
+#endif
             if (more) fir_stage<R>(y, T, b + G::SW, need, yt[buf ^ 1], lane);
             if (more)
                 cp_async_wait_but_one();
             else
                 cp_async_wait_all();
             __syncwarp();
+#ifdef HMM_PHASE_TIMING
+            const long long q1 = clock64();
+#endif
             mbar_wait(bar_empty + buf, ((k >> 1) & 1) ^ 1);  // the consumer is done with this F tile
+#ifdef HMM_PHASE_TIMING
+            const long long q2 = clock64();
+#endif
             if constexpr (LPC > 0)
                 fir_compute_c<N, R, LPC>(coef, Bc, yt[buf], ft[buf], lane);
             else
                 fir_compute<N, R>(A, Bc, LP, yt[buf], ft[buf], lane);
             if (lane == 0) mbar_arrive(bar_full + buf);   // fir_compute ends with __syncwarp()
+#ifdef HMM_PHASE_TIMING
+            const long long q3 = clock64();
+            pt_stage += q1 - q0;
+            pt_wait += q2 - q1;
+            pt_fir += q3 - q2;
+#endif
         }
+#ifdef HMM_PHASE_TIMING
+        if (lane == 0 && kind == START_SPEC && (c % 293) == 1)
+            printf("producer %d: %d super-windows, staging %lld, wait-for-empty %lld, FIR %lld cyc/sw\n", c, k,
+                   pt_stage / (k ? k : 1), pt_wait / (k ? k : 1), pt_fir / (k ? k : 1));
+#endif
         return;
     }
     uint32_t *dec = p.dec + (size_t)ch * T;

@@ -108,3 +108,34 @@ def test_one_step_train_model_in_place(hm, O, case_factory):
     smo = O.OracleStateMatrix(2, 30, o[0], False)
     assert np.abs(lA2.transitions["lp"] - smo.transitions["lp"]).max() < 1e-9
     assert np.allclose(lA2.pi[np.isfinite(o[1])], o[1][np.isfinite(o[1])], atol=1e-6)
+
+
+def test_em_silent_neuron_and_high_snr(hm, O, case_factory, monkeypatch):
+    """Two numerically awkward corners of the E/M step:
+    (a) a neuron whose prior is 2^-90 (the reference's initial lp, src/baumwelch.jl:311): its statistics are sums of
+        terms around e^-100 whose RELATIVE accuracy sets the new lp -- nothing representable may be dropped;
+    (b) sigma ten times smaller than the data's (a spike gains thousands of nats): a single 32-step window spans
+        more than e^600 and the live windows fall back from the linear to the log domain.
+    Both against the oracle, and the linear-domain live windows against the log-domain ones (HMMCUDA_EM_DBG=1)."""
+    N, K, T = 3, 60, 24000
+    S, lA_true, mu_true, sig = case_factory(N, K, T, 21, rate_scale=2.0)
+    mu0 = np.asfortranarray(0.7 * mu_true)
+    # (a)
+    lp0 = np.log(np.array([0.01, 2.0 ** -90, 0.003]))
+    lA = hm.StateMatrix(N, K, lp0, False)
+    r = hm.em_step(S, lA, mu0.copy(order="F"), float(np.std(S)), mode="ring", return_info=True)
+    o = O.em_step(S, O.OracleStateMatrix(N, K, lp0, False), mu0.copy(order="F"), float(np.std(S)))
+    _compare(r, o, tol=1e-8)
+    assert r[0][1] < -15  # the silent neuron stays rare (p < 1e-6), and its lp is still accurate to 1e-8
+    # (b)
+    lA = hm.StateMatrix(N, K, np.log(np.full(N, 0.01)), False)
+    s_small = 0.1 * sig
+    r_lin = hm.em_step(S, lA, mu_true.copy(order="F"), s_small, mode="ring", return_info=True)
+    o = O.em_step(S, O.OracleStateMatrix(N, K, np.log(np.full(N, 0.01)), False), mu_true.copy(order="F"), s_small)
+    _compare(r_lin, o, tol=1e-8)
+    monkeypatch.setenv("HMMCUDA_EM_DBG", "1")  # log-domain live windows everywhere
+    r_log = hm.em_step(S, lA, mu_true.copy(order="F"), s_small, mode="ring", return_info=True)
+    monkeypatch.delenv("HMMCUDA_EM_DBG")
+    _compare(r_log, o, tol=1e-8)
+    assert abs(r_lin[4] - r_log[4]) <= 1e-12 * abs(r_log[4])
+    assert np.abs(r_lin[2] - r_log[2]).max() < 1e-10
