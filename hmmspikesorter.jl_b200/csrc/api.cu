@@ -137,12 +137,14 @@ void build_models(int C, const int16_t *states, int states_shared, int N, int K,
             fail(HMM_EINVAL, "channel %d has a different transition topology than channel 0", c);
     }
     B.layout = faithful_layout(nstates, ntrans);
-    std::vector<char> host((size_t)C * B.layout.bytes, 0);
-    for (int c = 0; c < C; c++) faithful_pack(B.models[c], B.layout, host.data() + (size_t)c * B.layout.bytes);
-    B.blob_dev = (char *)workspace().get(Workspace::MODEL, host.size());
-    // small pageable copy: synchronous w.r.t. the host buffer, so `host` may die afterwards
-    HMM_CUDA(cudaMemcpyAsync(B.blob_dev, host.data(), host.size(), cudaMemcpyHostToDevice, st));
-    HMM_CUDA(cudaStreamSynchronize(st));
+    // packed into a pinned staging buffer (slot 2; every entry point synchronises before it returns, so the
+    // buffer is free again by the next call): the upload is asynchronous and the kernels simply follow it
+    const size_t bytes = (size_t)C * B.layout.bytes;
+    char *host = (char *)workspace().pinned(2, bytes);
+    memset(host, 0, bytes);
+    for (int c = 0; c < C; c++) faithful_pack(B.models[c], B.layout, host + (size_t)c * B.layout.bytes);
+    B.blob_dev = (char *)workspace().get(Workspace::MODEL, bytes);
+    HMM_CUDA(cudaMemcpyAsync(B.blob_dev, host, bytes, cudaMemcpyHostToDevice, st));
 }
 
 // Core decode on device-resident y / x.
