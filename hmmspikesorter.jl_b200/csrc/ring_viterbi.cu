@@ -454,8 +454,9 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
 #endif
         return;
     }
-    uint32_t *dec = p.dec + (size_t)ch * T;
-    uint32_t *nzm = p.nzmask + (size_t)ch * ((T + 31) / 32);
+    // decision words / mask words of this chunk's first super-window: indexed with 32-bit relative steps below
+    uint32_t *decb = p.dec + (size_t)ch * T + base0;
+    uint32_t *nzb = p.nzmask + (size_t)ch * ((T + 31) / 32) + (base0 >> 5);
     const int Wd = L < 32 ? L : 32;
     const int nsub = (32 + Wd - 1) / Wd;
     const int mysub = lane / Wd;
@@ -470,8 +471,13 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
     // may still win a decision when it arrives L steps later); see the quiet-window fast path
     uint32_t lq1, lq2, lq3, lq4;
     lq1 = lq2 = lq3 = lq4 = (kind == START_SPEC) ? 0u : 0xffffffffu;
-    const int qq = (L >> 5) + ((L & 31) ? 1 : 0);  // windows back to the first word holding step t-L
-    const int lsh = (32 - (L & 31)) & 31;
+    double Gq = NAN, ghq[N], thq[N];  // quiet-window constants, valid for G == Gq
+#pragma unroll
+    for (int i = 0; i < N; i++) ghq[i] = thq[i] = 0.0;
+    // (compile-time for the constant-coefficient variants, where L = LPC: the selects below fold away)
+    const int Lq = LPC > 0 ? LPC : L;
+    const int qq = (Lq >> 5) + ((Lq & 31) ? 1 : 0);  // windows back to the first word holding step t-L
+    const int lsh = (32 - (Lq & 31)) & 31;
     const int tf_rel = (int)(tau_first - base0);  // steps are tracked relative to base0 in 32 bits
     const int e_rel = (int)(e - base0);
     const int s_rel = (int)(s - base0);
@@ -545,8 +551,8 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
                 lq4 = lq3; lq3 = lq2; lq2 = lq1;
                 lq1 = (kind == START_SPEC) ? 0u : 0xffffffffu;
                 if (t0_rel >= s_rel) {  // (prologue columns: the traceback takes them from T2pro)
-                    dec[base0 + t0_rel + lane] = 0u;
-                    if (lane == 0) nzm[(base0 + t0_rel) >> 5] = 0u;
+                    decb[t0_rel + lane] = 0u;
+                    if (lane == 0) nzb[t0_rel >> 5] = 0u;
                 }
                 continue;
             }
@@ -566,21 +572,31 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
                 const uint32_t lo = qq == 1 ? lq1 : qq == 2 ? lq2 : qq == 3 ? lq3 : lq4;
                 const uint32_t hi = qq == 1 ? 0u : qq == 2 ? lq1 : qq == 3 ? lq2 : lq3;
                 if (__funnelshift_r(lo, hi, lsh) == 0u) {
-                    const double marg = 1e-13 * fabs(Gprev);
+                    if (Gq != Gprev) {  // G moves only where a chain ends: G + eH and the liveness thresholds
+                        Gq = Gprev;     // are recomputed then, not once per window
+                        const double marg = 1e-13 * fabs(Gprev);
+#pragma unroll
+                        for (int i = 0; i < N; i++) {
+                            ghq[i] = Gprev + eHr[i];
+                            thq[i] = (Gprev - cLr[i]) - marg;  // live <=> q + cL + marg > G (margins >> rounding)
+                        }
+                    }
                     bool live = false;
 #pragma unroll
                     for (int i = 0; i < N; i++) {
-                        const double gh = Gprev + eHr[i];
-                        const double q = gh + Fv[i];
+                        const double q = ghq[i] + Fv[i];
                         ring[i * RING_Q + slot_w] = q;
-                        if (last) p.Pfin[((size_t)ch * N + i) * RING_Q + slot_w] = gh;
-                        live = live || (q + cLr[i] + marg > Gprev);
+                        live = live || (q > thq[i]);
+                    }
+                    if (last) {
+#pragma unroll
+                        for (int i = 0; i < N; i++) p.Pfin[((size_t)ch * N + i) * RING_Q + slot_w] = ghq[i];
                     }
                     lq4 = lq3; lq3 = lq2; lq2 = lq1;
                     lq1 = __ballot_sync(0xffffffffu, live);
                     if (t0_rel >= s_rel) {  // all-noise decisions: one coalesced 128-byte store
-                        dec[base0 + t0_rel + lane] = 0u;
-                        if (lane == 0) nzm[(base0 + t0_rel) >> 5] = 0u;
+                        decb[t0_rel + lane] = 0u;
+                        if (lane == 0) nzb[t0_rel >> 5] = 0u;
                     }
                     __syncwarp();
                     continue;
@@ -681,9 +697,8 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
             lq4 = lq3; lq3 = lq2; lq2 = lq1;
             lq1 = lvw;
             if (t0_rel >= s_rel) {  // main range only (warm-up decisions belong to the previous chunk)
-                const int64_t tau0 = base0 + t0_rel;
-                if (t_rel < e_rel) dec[tau0 + lane] = myword;
-                if (lane == 0) nzm[tau0 >> 5] = nz;
+                if (t_rel < e_rel) decb[t_rel] = myword;
+                if (lane == 0) nzb[t0_rel >> 5] = nz;
             }
         }
         if (ROLE == ROLE_DP) {
