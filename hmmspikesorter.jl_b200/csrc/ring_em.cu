@@ -153,9 +153,23 @@ __device__ void em_fwd_chunk(const EmParams &p, int c, int kind, const double *m
 
     // F_i(tau) comes from the FIR pass (em_fir; end-of-recording terms already dropped).  The loads of the
     // next window are issued before the current one is processed.
+    // per-neuron row pointers at base0 (steps are 32-bit offsets from it below)
+    const double *fgp[N];
+    double *lqp[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        fgp[i] = p.Fg + (size_t)i * T + base0;
+        lqp[i] = p.LQ + (size_t)i * T + base0;
+    }
+    double *lgp = p.LG + base0;
+    const int T_rel = (int)((T - base0) < (int64_t)1 << 30 ? (T - base0) : (int64_t)1 << 30);
     double Fnx[N];
 #pragma unroll
-    for (int i = 0; i < N; i++) Fnx[i] = base0 + lane < T ? p.Fg[(size_t)i * T + base0 + lane] : 0.0;
+    for (int i = 0; i < N; i++) Fnx[i] = lane < T_rel ? fgp[i][lane] : 0.0;
+    // dead-window constants, valid while lg == lgq (lg moves only where a chain ends)
+    double lgq = NAN, lhq[N], thq[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) lhq[i] = thq[i] = 0.0;
     for (int64_t b = base0; b < e; b += G::SW) {
         if (kind == EM_SPEC && b == s) {
             double *sb = p.SBf + (size_t)c * p.bvec;
@@ -175,7 +189,7 @@ __device__ void em_fwd_chunk(const EmParams &p, int c, int kind, const double *m
 #pragma unroll
             for (int i = 0; i < N; i++) {
                 Fv[i] = Fnx[i];
-                Fnx[i] = (t0_rel + 32 < e_rel && tau + 32 < T) ? p.Fg[(size_t)i * T + tau + 32] : 0.0;
+                Fnx[i] = (t0_rel + 32 < e_rel && t_rel + 32 < T_rel) ? fgp[i][t_rel + 32] : 0.0;
             }
             const bool in_range = t_rel >= tf_rel && t_rel < e_rel;
             const int slot_w = t_rel & (RING_Q - 1);
@@ -199,18 +213,26 @@ __device__ void em_fwd_chunk(const EmParams &p, int c, int kind, const double *m
                 // half an ulp" shortcut (32 lanes x N terms of e^-43 still sum to < e^-37.5), so
                 // lg stays and lp_i = lg + lH_i exactly -- no transcendental, no scan.
                 {
+                    if (lgq != lgprev) {
+                        lgq = lgprev;
+#pragma unroll
+                        for (int i = 0; i < N; i++) {
+                            lhq[i] = lgprev + lH[i];
+                            thq[i] = (lgprev - 43.0) - cF[i];  // alive <=> lt_j + cF_j > lg - 43
+                        }
+                    }
                     bool alive = false;
 #pragma unroll
-                    for (int j = 0; j < N; j++) alive = alive || (lt[j] + cF[j] > lgprev - 43.0);
+                    for (int j = 0; j < N; j++) alive = alive || (lt[j] > thq[j]);
                     if (!__any_sync(0xffffffffu, active && alive)) {
                         if (active) {
 #pragma unroll
                             for (int i = 0; i < N; i++) {
-                                const double lq = (lgprev + lH[i]) + Fv[i];
+                                const double lq = lhq[i] + Fv[i];
                                 ring[i * RING_Q + slot_w] = lq;
-                                if (t0_rel >= s_rel) p.LQ[(size_t)i * T + tau] = lq;
+                                if (t0_rel >= s_rel) lqp[i][t_rel] = lq;
                             }
-                            if (t0_rel >= s_rel) p.LG[tau] = lgprev;
+                            if (t0_rel >= s_rel) lgp[t_rel] = lgprev;
                         }
                         __syncwarp();
                         continue;
@@ -259,9 +281,9 @@ __device__ void em_fwd_chunk(const EmParams &p, int c, int kind, const double *m
                             if (cross > nz * 0x1p-60) lp = ref + log(nz + cross);  // a tail feeds head i directly
                             const double lq = lp + Fv[i];
                             ring[i * RING_Q + slot_w] = lq;
-                            if (t0_rel >= s_rel) p.LQ[(size_t)i * T + tau] = lq;
+                            if (t0_rel >= s_rel) lqp[i][t_rel] = lq;
                         }
-                        if (t0_rel >= s_rel) p.LG[tau] = lg;
+                        if (t0_rel >= s_rel) lgp[t_rel] = lg;
                     }
                 } else {
                     // a single window spans more than e^600: stay in the log domain
@@ -281,9 +303,9 @@ __device__ void em_fwd_chunk(const EmParams &p, int c, int kind, const double *m
                                 if (j != i) lp = lse2(lp, lt[j] + lC[j * NP + i]);
                             const double lq = lp + Fv[i];
                             ring[i * RING_Q + slot_w] = lq;
-                            if (t0_rel >= s_rel) p.LQ[(size_t)i * T + tau] = lq;
+                            if (t0_rel >= s_rel) lqp[i][t_rel] = lq;
                         }
-                        if (t0_rel >= s_rel) p.LG[tau] = lg;
+                        if (t0_rel >= s_rel) lgp[t_rel] = lg;
                     }
                 }
                 lgprev = shfl_d(lg, 31);
@@ -476,12 +498,24 @@ __device__ void em_bwd_chunk(const EmParams &p, int c, int kind, const double *m
     const int nsub = (32 + Wd - 1) / Wd;
     const int mysub = lane / Wd;
     // windows of 32 steps, descending; lane 0 is the latest step of the window
+    // per-neuron row pointers (F shifted by one step: the recursion at t uses F(t+1))
+    const double *fgp[N];
+    double *lep[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        fgp[i] = p.Fg + (size_t)i * T + 1;
+        lep[i] = p.LE + (size_t)i * T;
+    }
     double Fnx[N];  // F of the next (earlier) window, loaded one window ahead
     {
         const int64_t t = ((hi - 1) | 31) - lane;
 #pragma unroll
-        for (int i = 0; i < N; i++) Fnx[i] = (t <= hi - 1 && t >= s) ? p.Fg[(size_t)i * T + t + 1] : 0.0;
+        for (int i = 0; i < N; i++) Fnx[i] = (t <= hi - 1 && t >= s) ? fgp[i][t] : 0.0;
     }
+    // dead-window constants, valid while lh == lhq
+    double lhq = NAN, leq[N], thq[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) leq[i] = thq[i] = 0.0;
     for (int64_t wtop = ((hi - 1) | 31); wtop >= s; wtop -= 32) {
         const int64_t t = wtop - lane;
         const bool in_range = t <= hi - 1 && t >= s;
@@ -490,7 +524,7 @@ __device__ void em_bwd_chunk(const EmParams &p, int c, int kind, const double *m
         for (int i = 0; i < N; i++) {
             Fn[i] = Fnx[i];
             const int64_t tn = t - 32;
-            Fnx[i] = (tn <= hi - 1 && tn >= s) ? p.Fg[(size_t)i * T + tn + 1] : 0.0;
+            Fnx[i] = (tn <= hi - 1 && tn >= s) ? fgp[i][tn] : 0.0;
         }
         // F of the warm-up region belongs to the next chunk and is complete: the forward pass has finished
         for (int sub = 0; sub < nsub; sub++) {
@@ -502,16 +536,23 @@ __device__ void em_bwd_chunk(const EmParams &p, int c, int kind, const double *m
             // Dead-window fast path (see em_fwd_chunk): every entry term is more than e^-43 below
             // the noise continuation, so lh stays and le_i = lA_i + lh exactly.
             {
+                if (lhq != lhprev) {
+                    lhq = lhprev;
+#pragma unroll
+                    for (int i = 0; i < N; i++) {
+                        leq[i] = lA[i] + lhprev;
+                        thq[i] = (lhprev - 43.0) - cB[i];  // alive <=> lr_j + cB_j > lh - 43
+                    }
+                }
                 bool alive = false;
 #pragma unroll
-                for (int j = 0; j < N; j++) alive = alive || (lr[j] + cB[j] > lhprev - 43.0);
+                for (int j = 0; j < N; j++) alive = alive || (lr[j] > thq[j]);
                 if (!__any_sync(0xffffffffu, active && alive)) {
                     if (active) {
 #pragma unroll
                         for (int i = 0; i < N; i++) {
-                            const double le = lA[i] + lhprev;
-                            ring[i * RING_Q + (int)(t & (RING_Q - 1))] = le;
-                            if (t < e) p.LE[(size_t)i * T + t] = le;
+                            ring[i * RING_Q + (int)(t & (RING_Q - 1))] = leq[i];
+                            if (t < e) lep[i][t] = leq[i];
                         }
                         if (t < e) p.LH[t] = lhprev;
                     }
@@ -559,7 +600,7 @@ __device__ void em_bwd_chunk(const EmParams &p, int c, int kind, const double *m
                         double le = lA[i] + lhp1;
                         if (cross > nz * 0x1p-60) le = ref + log(nz + cross);
                         ring[i * RING_Q + (int)(t & (RING_Q - 1))] = le;
-                        if (t < e) p.LE[(size_t)i * T + t] = le;
+                        if (t < e) lep[i][t] = le;
                     }
                     if (t < e) p.LH[t] = lh;
                 }
@@ -579,7 +620,7 @@ __device__ void em_bwd_chunk(const EmParams &p, int c, int kind, const double *m
                         for (int j = 0; j < N; j++)
                             if (j != i) le = lse2(le, lC[i * NP + j] + lr[j]);
                         ring[i * RING_Q + (int)(t & (RING_Q - 1))] = le;
-                        if (t < e) p.LE[(size_t)i * T + t] = le;
+                        if (t < e) lep[i][t] = le;
                     }
                     if (t < e) p.LH[t] = lh;
                 }
