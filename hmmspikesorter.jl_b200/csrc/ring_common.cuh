@@ -111,13 +111,24 @@ template <int R>
 __device__ __forceinline__ void fir_stage(const double *__restrict__ y, int64_t T, int64_t b, int need, double *ytile,
                                           int lane) {
     using G = FirGeom<R>;
-    for (int k = lane; k < need; k += 32) {
-        int64_t g = b + k;
-        double *dst = ytile + (k & (R - 1)) * G::YS + (k >> G::LOGR);
-        if (g < T)
-            cp_async8(dst, y + g);
-        else
-            *dst = 0.0;
+    if (b + need <= T) {
+        // interior: element k = lane + 32 m goes to row lane % R, column lane / R + (32 / R) m -- one pointer pair
+        // per lane and immediate offsets, no per-element bounds test
+        const double *src = y + b + lane;
+        double *dst = ytile + (lane & (R - 1)) * G::YS + (lane >> G::LOGR);
+        constexpr int MAXM = (G::SW + RING_MAX_L + 31) / 32;
+#pragma unroll
+        for (int m = 0; m < MAXM; m++)
+            if (lane + 32 * m < need) cp_async8(dst + (32 / R) * m, src + 32 * m);
+    } else {
+        for (int k = lane; k < need; k += 32) {
+            int64_t g = b + k;
+            double *dst = ytile + (k & (R - 1)) * G::YS + (k >> G::LOGR);
+            if (g < T)
+                cp_async8(dst, y + g);
+            else
+                *dst = 0.0;
+        }
     }
     cp_async_commit();
 }
