@@ -42,7 +42,7 @@ import __graft_entry__ as ge  # noqa: E402
 T_C2 = 18_000_000
 T_C3 = 1_800_000
 BYTES_PER_SAMPLE = 10  # 8 B read of S + 2 B write of x
-NCU_TRAFFIC_BYTES = 199488256  # ring_vit_forward_ws<3,8,59>: dram read + write per launch (profiles/r01_ring_vit_forward_ws_ncu.md)
+NCU_TRAFFIC_BYTES = 198057728  # ring_vit_forward_ws<3,8,59>: dram read + write per launch (profiles/r01_ring_vit_forward_ws_ncu.md)
 FP64_PEAK_GDFMA = 18421.7  # measured FP64 FMA issue rate, profiles/r01_fp64_peak.jsonl
 
 
