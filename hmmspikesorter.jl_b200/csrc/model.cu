@@ -141,7 +141,6 @@ static bool detect_ring(const int16_t *states, const hmm_trans *tr, int64_t ntra
                 if (states[l + (size_t)N * j] != (l == i ? s + 1 : 1)) return false;
         }
     auto head = [&](int i) { return 1 + i * L; };      // 0-based
-    auto tail = [&](int i) { return (i + 1) * L; };    // 0-based
     const double NEG = -std::numeric_limits<double>::infinity();
     RingParams &R = M.ring;
     R.N = N;
@@ -196,7 +195,6 @@ static bool detect_ring(const int16_t *states, const hmm_trans *tr, int64_t ntra
     for (int d = 0; d < ns; d++)
         for (int e = M.in_ptr[d] + 1; e < M.in_ptr[d + 1]; e++)
             if (M.in_src[e] <= M.in_src[e - 1]) return false;
-    (void)tail;
     return true;
 }
 

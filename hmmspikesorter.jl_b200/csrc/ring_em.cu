@@ -80,7 +80,7 @@ __device__ void em_fwd_chunk(const EmParams &p, int c, int kind, const double *m
     constexpr int NP = (N + 1) & ~1;
     const int lane = threadIdx.x & 31;
     const RingLayout &RL = p.RL;
-    const int L = RL.L, LP = RL.LP;
+    const int L = RL.L;
     const double NEG = -INFINITY;
     double *ring = ws;
     const double *lA = mdl + RL.eG, *lH = mdl + RL.eH, *lC = mdl + RL.eT;
