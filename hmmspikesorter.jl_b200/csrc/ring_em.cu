@@ -1331,7 +1331,7 @@ static void ring_em_core(const double *X_dev, int64_t T, const HostModel &M, EmR
     ring_pack(M, RL, hmdl);
     const int bvec = 1 + N * L;
     const int pstride = 4 + 2 * N + N * S1_LAGS;
-    const int nblk = 148 * 6;
+    const int nblk = 148 * 3;  // one resident wave of the statistics pass (165 registers: 3 CTAs per SM)
     const int nout = 2 + N + K * N + ns + 2;  // ... + the two repair counters
     size_t off = 0;
     auto carve = [&](size_t bytes) {
