@@ -6,8 +6,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <memory>
 #include <mutex>
+#include <thread>
 
 #include "engines.h"
 
@@ -194,6 +196,65 @@ struct PipeSeg {
     cudaEvent_t ev_copy = nullptr, ev_x = nullptr;
 };
 
+// ---- pageable callers (a Julia Array, a plain numpy array) -------------------------------------------------
+// cudaMemcpyAsync from pageable memory is staged by the driver on the calling thread at ~10 GB/s and does not
+// overlap with anything.  The pipelined decode therefore copies a pageable recording into its own pinned staging
+// buffer with a few host threads, block by block in time order, while earlier blocks are already on their way to
+// the device; x travels back through pinned staging the same way.
+static bool host_is_pinned(const void *q) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, q) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static int staging_threads() {
+    unsigned hc = std::thread::hardware_concurrency();
+    int n = hc ? (int)(hc / 2) : 4;
+    return n < 2 ? 2 : (n > 8 ? 8 : n);
+}
+
+struct HostStager {  // parallel, in-order memcpy of src[0, n) bytes into dst, in blocks
+    std::vector<std::thread> th;
+    std::unique_ptr<std::atomic<unsigned char>[]> done;
+    std::atomic<int64_t> next{0};
+    int64_t nb = 0, blk = 0, n = 0;
+    const char *src = nullptr;
+    char *dst = nullptr;
+    void start(const void *s, void *d, int64_t bytes, int64_t block_bytes, int nthreads) {
+        src = (const char *)s;
+        dst = (char *)d;
+        n = bytes;
+        blk = block_bytes;
+        nb = (bytes + blk - 1) / blk;
+        done.reset(new std::atomic<unsigned char>[(size_t)(nb > 0 ? nb : 1)]);
+        for (int64_t j = 0; j < nb; j++) done[(size_t)j].store(0, std::memory_order_relaxed);
+        for (int t = 0; t < nthreads; t++)
+            th.emplace_back([this] {
+                for (;;) {
+                    const int64_t j = next.fetch_add(1);
+                    if (j >= nb) return;
+                    const int64_t o = j * blk, len = std::min<int64_t>(blk, n - o);
+                    memcpy(dst + o, src + o, (size_t)len);
+                    done[(size_t)j].store(1, std::memory_order_release);
+                }
+            });
+    }
+    void wait_bytes(int64_t upto) {  // until [0, upto) has been copied
+        const int64_t jb = std::min<int64_t>(nb, (upto + blk - 1) / blk);
+        for (int64_t j = 0; j < jb; j++)
+            while (!done[(size_t)j].load(std::memory_order_acquire)) std::this_thread::yield();
+    }
+    void join() {
+        for (auto &t : th)
+            if (t.joinable()) t.join();
+        th.clear();
+    }
+    ~HostStager() { join(); }
+};
+
 bool pipeline_wanted(const HostModel &M0, int64_t T, int C) {
     if (getenv("HMMCUDA_NO_PIPELINE") && atoi(getenv("HMMCUDA_NO_PIPELINE"))) return false;
     return C == 1 && T >= (int64_t)1 << 22 && ring_config().chunk_len == 0 && ring_config().warmup == 0 && M0.is_ring;
@@ -238,6 +299,17 @@ void viterbi_host_pipelined(const double *y, int64_t T, BatchModels &B, int16_t 
     }
     double *y_dev = (double *)ws.get(Workspace::Y, sizeof(double) * (size_t)T);
     int16_t *x_dev = (int16_t *)ws.get(Workspace::X, sizeof(int16_t) * (size_t)T);
+    const bool no_staging = getenv("HMMCUDA_NO_STAGING") && atoi(getenv("HMMCUDA_NO_STAGING"));
+    const bool y_pageable = !no_staging && !host_is_pinned(y), x_pageable = !no_staging && !host_is_pinned(x_out);
+    const double *y_src = y;
+    int16_t *x_dst = x_out;
+    HostStager stager;
+    if (y_pageable) {
+        double *ys = (double *)ws.pinned(4, sizeof(double) * (size_t)T);
+        stager.start(y, ys, (int64_t)sizeof(double) * T, (int64_t)8 << 20, staging_threads());
+        y_src = ys;
+    }
+    if (x_pageable) x_dst = (int16_t *)ws.pinned(5, sizeof(int16_t) * (size_t)T);
     size_t arena_cap = 1 << 20;
     const int bvec = 1 + M0.N * L;
     for (auto &g : seg) {
@@ -263,12 +335,13 @@ void viterbi_host_pipelined(const double *y, int64_t T, BatchModels &B, int16_t 
         auto copy_end = [&](int k) { return k == S - 1 ? T : std::min<int64_t>(T, seg[k].me + Lc); };
         auto issue_copy = [&](int k) {
             const int64_t a = k == 0 ? 0 : copy_end(k - 1), b = copy_end(k);
-            if (b > a) HMM_CUDA(cudaMemcpyAsync(y_dev + a, y + a, sizeof(double) * (size_t)(b - a), cudaMemcpyHostToDevice, sh));
+            if (y_pageable) stager.wait_bytes((int64_t)sizeof(double) * b);
+            if (b > a) HMM_CUDA(cudaMemcpyAsync(y_dev + a, y_src + a, sizeof(double) * (size_t)(b - a), cudaMemcpyHostToDevice, sh));
             HMM_CUDA(cudaEventRecord(seg[k].ev_copy, sh));
         };
         auto issue_x = [&](int k) {
             HMM_CUDA(cudaStreamWaitEvent(sd, seg[k].ev_x, 0));
-            HMM_CUDA(cudaMemcpyAsync(x_out + seg[k].mb, x_dev + seg[k].mb, sizeof(int16_t) * (size_t)(seg[k].me - seg[k].mb),
+            HMM_CUDA(cudaMemcpyAsync(x_dst + seg[k].mb, x_dev + seg[k].mb, sizeof(int16_t) * (size_t)(seg[k].me - seg[k].mb),
                                      cudaMemcpyDeviceToHost, sd));
         };
         auto link_trace = [&](int k) {  // own_start of segment k's first main chunk -> segment k-1's right ghost
@@ -324,7 +397,7 @@ void viterbi_host_pipelined(const double *y, int64_t T, BatchModels &B, int16_t 
                 link_trace(k);
                 seg[k - 1].plan->verify_trace(sc);
             }
-            HMM_CUDA(cudaMemcpyAsync(x_out, x_dev, sizeof(int16_t) * (size_t)T, cudaMemcpyDeviceToHost, sc));
+            HMM_CUDA(cudaMemcpyAsync(x_dst, x_dev, sizeof(int16_t) * (size_t)T, cudaMemcpyDeviceToHost, sc));
         }
         if (ll_out) {
             ring_path_ll_run(y_dev, T, B.layout, B.blob_dev, M0, x_dev, ll_dev, ll_dev + 8, sc);
@@ -334,6 +407,12 @@ void viterbi_host_pipelined(const double *y, int64_t T, BatchModels &B, int16_t 
         HMM_CUDA(cudaStreamSynchronize(sc));
         HMM_CUDA(cudaStreamSynchronize(sd));
         HMM_CUDA(cudaStreamSynchronize(sh));
+        stager.join();
+        if (x_pageable) {  // pinned staging -> the caller's pageable x, in parallel
+            HostStager back;
+            back.start(x_dst, x_out, (int64_t)sizeof(int16_t) * T, (int64_t)4 << 20, staging_threads());
+            back.join();
+        }
         if (info) {
             info->engine = HMM_MODE_RING;
             info->n_chunks = nch;

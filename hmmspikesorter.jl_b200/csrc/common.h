@@ -44,7 +44,7 @@ class Workspace {
         ALPHA, BETA, SCRATCH, NSLOTS
     };
     void *get(Slot s, size_t bytes);
-    // Grow-only pinned, device-mapped host buffers (four slots): staging for small per-call uploads and a
+    // Grow-only pinned, device-mapped host buffers (six slots): staging for per-call uploads / pageable callers and a
     // landing zone kernels can write results into directly.  *dev_ptr receives the device-side alias.
     void *pinned(int slot, size_t bytes, void **dev_ptr = nullptr);
     void release();
@@ -54,8 +54,8 @@ class Workspace {
     void bind_device();
     void *ptr_[NSLOTS] = {};
     size_t cap_[NSLOTS] = {};
-    void *hptr_[4] = {};
-    size_t hcap_[4] = {};
+    void *hptr_[6] = {};
+    size_t hcap_[6] = {};
     int dev_ = -1;
 };
 

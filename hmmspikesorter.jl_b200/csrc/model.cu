@@ -67,7 +67,7 @@ void Workspace::release() {
         ptr_[i] = nullptr;
         cap_[i] = 0;
     }
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < 6; i++) {
         if (hptr_[i]) cudaFreeHost(hptr_[i]);
         hptr_[i] = nullptr;
         hcap_[i] = 0;
