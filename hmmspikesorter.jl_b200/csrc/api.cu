@@ -193,7 +193,7 @@ struct PipeSeg {
     int64_t lb, le, mb, me;  // local span [lb, le) incl. ghosts, main span [mb, me)
     int c_main0, c_main1;
     std::unique_ptr<VitPlan> plan;
-    cudaEvent_t ev_copy = nullptr, ev_x = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_x = nullptr, ev_xd = nullptr;  // y arrived / x final on device / x on host
 };
 
 // ---- pageable callers (a Julia Array, a plain numpy array) -------------------------------------------------
@@ -304,6 +304,8 @@ void viterbi_host_pipelined(const double *y, int64_t T, BatchModels &B, int16_t 
     const double *y_src = y;
     int16_t *x_dst = x_out;
     HostStager stager;
+    std::thread drainer;
+    std::atomic<int> x_issued{0}, drain_abort{0};
     if (y_pageable) {
         double *ys = (double *)ws.pinned(4, sizeof(double) * (size_t)T);
         stager.start(y, ys, (int64_t)sizeof(double) * T, (int64_t)8 << 20, staging_threads());
@@ -323,11 +325,13 @@ void viterbi_host_pipelined(const double *y, int64_t T, BatchModels &B, int16_t 
     for (auto &g : seg) {
         HMM_CUDA(cudaEventCreateWithFlags(&g.ev_copy, cudaEventDisableTiming));
         HMM_CUDA(cudaEventCreateWithFlags(&g.ev_x, cudaEventDisableTiming));
+        HMM_CUDA(cudaEventCreateWithFlags(&g.ev_xd, cudaEventDisableTiming));
     }
     auto cleanup = [&] {
         for (auto &g : seg) {
             if (g.ev_copy) cudaEventDestroy(g.ev_copy);
             if (g.ev_x) cudaEventDestroy(g.ev_x);
+            if (g.ev_xd) cudaEventDestroy(g.ev_xd);
         }
     };
     try {
@@ -343,6 +347,8 @@ void viterbi_host_pipelined(const double *y, int64_t T, BatchModels &B, int16_t 
             HMM_CUDA(cudaStreamWaitEvent(sd, seg[k].ev_x, 0));
             HMM_CUDA(cudaMemcpyAsync(x_dst + seg[k].mb, x_dev + seg[k].mb, sizeof(int16_t) * (size_t)(seg[k].me - seg[k].mb),
                                      cudaMemcpyDeviceToHost, sd));
+            HMM_CUDA(cudaEventRecord(seg[k].ev_xd, sd));
+            x_issued.store(k + 1, std::memory_order_release);
         };
         auto link_trace = [&](int k) {  // own_start of segment k's first main chunk -> segment k-1's right ghost
             shift_state_kernel<<<1, 1, 0, sc>>>(seg[k].plan->own_start_ptr(seg[k].c_main0),
@@ -350,6 +356,22 @@ void viterbi_host_pipelined(const double *y, int64_t T, BatchModels &B, int16_t 
                                                 8 * (long long)(seg[k].lb - seg[k - 1].lb));
             HMM_CUDA(cudaGetLastError());
         };
+        if (x_pageable) {
+            // a drainer thread moves each segment's x from pinned staging to the caller's array as soon as it landed
+            int dev_id = 0;
+            HMM_CUDA(cudaGetDevice(&dev_id));
+            drainer = std::thread([&, dev_id] {
+                cudaSetDevice(dev_id);
+                for (int k = 0; k < S; k++) {
+                    while (x_issued.load(std::memory_order_acquire) <= k) {
+                        if (drain_abort.load(std::memory_order_acquire)) return;
+                        std::this_thread::yield();
+                    }
+                    if (cudaEventSynchronize(seg[k].ev_xd) != cudaSuccess) return;
+                    memcpy(x_out + seg[k].mb, x_dst + seg[k].mb, sizeof(int16_t) * (size_t)(seg[k].me - seg[k].mb));
+                }
+            });
+        }
         issue_copy(0);
         for (int k = 0; k < S; k++) {
             PipeSeg &g = seg[k];
@@ -408,7 +430,8 @@ void viterbi_host_pipelined(const double *y, int64_t T, BatchModels &B, int16_t 
         HMM_CUDA(cudaStreamSynchronize(sd));
         HMM_CUDA(cudaStreamSynchronize(sh));
         stager.join();
-        if (x_pageable) {  // pinned staging -> the caller's pageable x, in parallel
+        if (drainer.joinable()) drainer.join();
+        if (x_pageable && tot_b > 0) {  // the traceback was redone after the segments had been drained: copy x again
             HostStager back;
             back.start(x_dst, x_out, (int64_t)sizeof(int16_t) * T, (int64_t)4 << 20, staging_threads());
             back.join();
@@ -420,9 +443,12 @@ void viterbi_host_pipelined(const double *y, int64_t T, BatchModels &B, int16_t 
             info->bwd_repaired = tot_b;
         }
     } catch (...) {
+        drain_abort.store(1);
         cudaStreamSynchronize(sc);
         cudaStreamSynchronize(sd);
         cudaStreamSynchronize(sh);
+        if (drainer.joinable()) drainer.join();
+        stager.join();
         cleanup();
         throw;
     }
