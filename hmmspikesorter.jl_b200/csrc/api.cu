@@ -308,7 +308,7 @@ void viterbi_host_pipelined(const double *y, int64_t T, BatchModels &B, int16_t 
     std::atomic<int> x_issued{0}, drain_abort{0};
     if (y_pageable) {
         double *ys = (double *)ws.pinned(4, sizeof(double) * (size_t)T);
-        stager.start(y, ys, (int64_t)sizeof(double) * T, (int64_t)8 << 20, staging_threads());
+        stager.start(y, ys, (int64_t)sizeof(double) * T, (int64_t)1 << 20, staging_threads());
         y_src = ys;
     }
     if (x_pageable) x_dst = (int16_t *)ws.pinned(5, sizeof(int16_t) * (size_t)T);
