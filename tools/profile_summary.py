@@ -2,7 +2,7 @@
 """Turn ncu exports brought back in gpurun_out/ into the tracked summaries under profiles/.
 
   python tools/profile_summary.py launches gpurun_out/launches.csv profiles/r01_launches_c2.md [first-K-launches-per-kernel]
-  python tools/profile_summary.py kernel   gpurun_out/prof_fwd2.ncu-rep profiles/r01_ring_vit_forward.md
+  python tools/profile_summary.py kernel   gpurun_out/prof_fwd9.ncu-rep profiles/r01_ring_vit_forward_ws_ncu.md
 """
 import collections
 import csv
