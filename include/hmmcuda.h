@@ -79,7 +79,9 @@ int hmm_set_ring_params(int64_t chunk_len, int64_t warmup);
  * viterbi(y, lA::StateMatrix, mu, sigma) -> (x, ll)       src/viterbi.jl:44-98
  * T2_out / T1_out: nullable [nstates x T]; when given, the dense trellis of
  * src/viterbi.jl:52-53 is materialised (the `(x, T2, T1)` form of
- * README.md:34).  Host pointers.
+ * README.md:34).  Host pointers, pageable or pinned (hmm_host_alloc): long ring-model
+ * decodes overlap the upload, the decode and the download segment by segment, pageable
+ * buffers going through the library's own pinned staging; the result is the same decode.
  */
 int hmm_viterbi_f64(const double *y, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
                     const hmm_trans *tr, int64_t ntrans, const double *mu, double sigma, int16_t *x_out,
