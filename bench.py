@@ -356,94 +356,15 @@ def run_c5(args):
     span = ts.shard_plan(T, world, chunk_len)[rank]
     y_loc = torch.from_numpy(S[span[0]:span[1]]).to(dev)
     x_main = torch.empty(span[3] - span[2], dtype=torch.int16, device=dev)
-    sh = ts.Shard(y_loc.data_ptr(), False, span, T, chunk_len, warm, lA, mu, sigma)
-    vec_out = torch.empty(sh.bvec, dtype=torch.float64, device=dev)
-    vec_in = torch.empty(sh.bvec, dtype=torch.float64, device=dev)
-    s_out = torch.zeros(1, dtype=torch.int64, device=dev)
-    s_in = torch.zeros(1, dtype=torch.int64, device=dev)
-    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
-    stats = {"fwd_rounds": 0, "trace_rounds": 0, "repaired": 0}
-
-    # everything below is stream-ordered on torch's current stream: the library's kernels, the
-    # boundary copies and the NCCL point-to-point messages -- no host synchronisation in between
-    # (a dedicated stream: torch's default stream is the legacy NULL stream, whose handle 0 means "private
-    # stream" to hmm_set_stream)
+    # everything below is stream-ordered on one created torch stream: the library's kernels, the copies and the
+    # NCCL collective -- no host synchronisation until the verdict is read (torch's default stream is the legacy
+    # NULL stream, whose handle 0 means "private stream" to hmm_set_stream)
     work = torch.cuda.Stream(device=dev)
     work.wait_stream(torch.cuda.current_stream())
     torch.cuda.set_stream(work)
-    hm._lib.check(L.hmm_set_stream(C.c_void_p(work.cuda_stream)))
-
-    def p2p(send_t, recv_t, send_to, recv_from):
-        ops = []
-        if send_to is not None:
-            ops.append(dist.P2POp(dist.isend, send_t, send_to))
-        if recv_from is not None:
-            ops.append(dist.P2POp(dist.irecv, recv_t, recv_from))
-        if ops:
-            for r in dist.batch_isend_irecv(ops):
-                r.wait()  # makes the current stream wait, not the host
-
-    def fwd_round(count):
-        if not sh.last:
-            sh.fwd_get(out_ptr=vec_out.data_ptr())
-        p2p(vec_out, vec_in, None if sh.last else rank + 1, None if sh.first else rank - 1)
-        if not sh.first:
-            sh.fwd_set(in_ptr=vec_in.data_ptr())
-        return sh.fwd_verify(count=count)
-
-    def trace_round(count):
-        if not sh.first:
-            sh.trace_get(out_ptr=s_out.data_ptr())
-        p2p(s_out, s_in, None if sh.first else rank - 1, None if sh.last else rank + 1)
-        if not sh.last:
-            sh.trace_set(in_ptr=s_in.data_ptr())
-        return sh.trace_verify(count=count)
-
-    def all_sum(v):
-        cnt[0] = v
-        if world > 1:
-            dist.all_reduce(cnt)
-        return int(cnt.item())
-
-    res = torch.zeros(2, dtype=torch.float64, device=dev)  # verdict: [total ll, inconsistent shard boundaries]
-    summ = torch.zeros(sh.summary_len, dtype=torch.float64, device=dev)
-    gath = torch.zeros(world * sh.summary_len, dtype=torch.float64, device=dev)
-
-    def step():
-        # Optimistic, one collective: every shard decodes its span completely on its own, trusting its ghost
-        # chunks (verified like any chunk boundary inside one GPU); the shards' boundary summaries (2 x 297 + 4
-        # doubles each) are all-gathered and EVERY rank checks EVERY shard boundary, so all ranks reach the same
-        # verdict without another collective.  The host synchronises once, to read the verdict.
-        sh.forward()
-        sh.fwd_verify(count=False)
-        sh.trace()
-        sh.trace_verify(count=False)
-        sh.summary_dev(x_main.data_ptr(), summ.data_ptr())
-        if world > 1:
-            dist.all_gather_into_tensor(gath, summ)
-        else:
-            gath.copy_(summ)
-        sh.judge_dev(gath.data_ptr(), world, res.data_ptr())
-        ll, bad = res.tolist()  # the step's only host synchronisation
-        stats["fwd_rounds"] += 1
-        stats["trace_rounds"] += 1
-        if bad == 0:
-            return ll
-        # some shard repaired a chunk: its outgoing boundary may have changed -> iterate to a fixed point
-        stats["repaired"] += 1
-        for _ in range(world + 1):
-            stats["fwd_rounds"] += 1
-            if all_sum(fwd_round(True)) == 0:
-                break
-        sh.trace()
-        for _ in range(world + 1):
-            stats["trace_rounds"] += 1
-            if all_sum(trace_round(True)) == 0:
-                break
-        part = torch.tensor([sh.finish(x_ptr=x_main.data_ptr())], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(part)
-        return float(part.item())
+    dec = ts.DistDecoder(y_loc.data_ptr(), span, T, chunk_len, warm, lA, mu, sigma, x_main.data_ptr(), dev)
+    sh, stats = dec.sh, dec.stats
+    step = dec.decode  # one decode of the whole recording (hmmspikesorter.jl_b200/timeshard.py: DistDecoder)
 
     for _ in range(max(3, args.warmup)):
         step()
@@ -462,6 +383,7 @@ def run_c5(args):
         # where a step's time goes: the same phases with a host synchronisation after each (rank 0, stderr)
         names = ["forward+verify", "trace+verify", "path ll + summary + x copy", "all_gather", "judge+read"]
         acc = [[] for _ in names]
+        hm._lib.check(L.hmm_set_stream(C.c_void_p(work.cuda_stream)))
         for _ in range(5):
             dist.barrier(device_ids=[local])
             torch.cuda.synchronize()
@@ -473,15 +395,16 @@ def run_c5(args):
 
             sh.forward(); sh.fwd_verify(count=False); mark()
             sh.trace(); sh.trace_verify(count=False); mark()
-            sh.summary_dev(x_main.data_ptr(), summ.data_ptr()); mark()
+            sh.summary_dev(x_main.data_ptr(), dec.summ.data_ptr()); mark()
             if world > 1:
-                dist.all_gather_into_tensor(gath, summ)
+                dist.all_gather_into_tensor(dec.gath, dec.summ)
             else:
-                gath.copy_(summ)
+                dec.gath.copy_(dec.summ)
             mark()
-            sh.judge_dev(gath.data_ptr(), world, res.data_ptr()); res.tolist(); mark()
+            sh.judge_dev(dec.gath.data_ptr(), world, dec.res.data_ptr()); dec.res.tolist(); mark()
             for k in range(len(names)):
                 acc[k].append(1e3 * (marks[k + 1] - marks[k]))
+        L.hmm_set_stream(None)
         if rank == 0:
             print("c5 phases (ms, median of 5, host-synchronised): "
                   + ", ".join(f"{n} {sorted(a)[2]:.3f}" for n, a in zip(names, acc)), file=sys.stderr)
@@ -502,9 +425,9 @@ def run_c5(args):
                        "chunk_len": chunk_len, "warmup": warm, "boundary_bytes": 8 * sh.bvec + 8,
                        "protocol": "one all-gather of shard summaries per decode, every rank judges every boundary", "exchange_rounds_per_step": [stats["fwd_rounds"] / (args.steps + max(3, args.warmup)),
                                                     stats["trace_rounds"] / (args.steps + max(3, args.warmup))],
-                       "chunks_repaired": stats["repaired"], "ll": float(llt.item()), "x_checksum": int(chk.item()),
+                       "fallbacks": stats["fallbacks"], "ll": float(llt.item()), "x_checksum": int(chk.item()),
                        "l2": "inputs larger than L2 (>= 108 MB of y per GPU)"}}))
-    sh.close()
+    dec.close()
     L.hmm_set_stream(None)
     dist.destroy_process_group()
 

@@ -234,67 +234,149 @@ def viterbi_time_sharded(y, lA, mu, sigma, n_shards: int, *, devices: Optional[S
     return (x, ll, info) if return_info else (x, ll)
 
 
-def viterbi_time_sharded_dist(y_local_dev_ptr: int, span, T: int, chunk_len: int, warmup: int, lA, mu, sigma,
-                              x_main_dev_ptr: int, device):
-    """One shard per torch.distributed rank.  `y_local_dev_ptr` points at this rank's samples
-    [span[0], span[1]) in HBM, `x_main_dev_ptr` receives x for [span[2], span[3]).  Boundary
-    messages are point-to-point sends of device tensors (NCCL over NVLink on a GPU box).
-    Returns (ll summed over ranks, info)."""
-    import torch
-    import torch.distributed as dist
+class DistDecoder:
+    """One shard per torch.distributed rank (NCCL on a GPU box).  `y_local_dev_ptr` points at this rank's samples
+    [span[0], span[1]) in HBM, `x_main_dev_ptr` receives x for [span[2], span[3]).
 
-    rank, world = dist.get_rank(), dist.get_world_size()
-    sh = Shard(y_local_dev_ptr, False, span, T, chunk_len, warmup, lA, mu, sigma)
-    info = {"fwd_rounds": 0, "trace_rounds": 0, "fwd_repaired": 0, "trace_repaired": 0}
-    try:
+    decode() runs the one-collective protocol: every rank decodes its span completely on its own (the ghost chunks
+    play the neighbours), the ranks all-gather their boundary summaries (a few KB) and every rank checks every
+    shard boundary, so all ranks reach the same verdict without a second collective; the host synchronises once,
+    to read [total ll, inconsistent boundaries].  Only a non-zero verdict falls back to the iterative protocol
+    (boundary vector to the right / traceback state to the left, point-to-point, verify rounds until nothing is
+    repaired).  Everything is stream-ordered on torch's current stream (a created stream: the legacy default
+    stream cannot carry the library's work, so one is created when needed)."""
+
+    def __init__(self, y_local_dev_ptr: int, span, T: int, chunk_len: int, warmup: int, lA, mu, sigma,
+                 x_main_dev_ptr: int, device):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.device = device
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.x_ptr = x_main_dev_ptr
+        self.sh = Shard(y_local_dev_ptr, False, span, T, chunk_len, warmup, lA, mu, sigma)
+        f8, i8 = torch.float64, torch.int64
+        self.summ = torch.zeros(self.sh.summary_len, dtype=f8, device=device)
+        self.gath = torch.zeros(self.world * self.sh.summary_len, dtype=f8, device=device)
+        self.res = torch.zeros(2, dtype=f8, device=device)
+        self.vec_out = torch.empty(self.sh.bvec, dtype=f8, device=device)
+        self.vec_in = torch.empty(self.sh.bvec, dtype=f8, device=device)
+        self.s_out = torch.zeros(1, dtype=i8, device=device)
+        self.s_in = torch.zeros(1, dtype=i8, device=device)
+        self.cnt = torch.zeros(1, dtype=i8, device=device)
+        self._own_stream = None
+        self.stats = {"decodes": 0, "fwd_rounds": 0, "trace_rounds": 0, "fallbacks": 0}
+
+    # -- stream plumbing -------------------------------------------------------------------------------------
+    def _enter_stream(self):
+        torch = self.torch
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream != 0:
+            check(lib().hmm_set_stream(C.c_void_p(cur.cuda_stream)))
+            return None
+        if self._own_stream is None:
+            self._own_stream = torch.cuda.Stream(device=self.device)
+        self._own_stream.wait_stream(cur)
+        ctx = torch.cuda.stream(self._own_stream)
+        ctx.__enter__()
+        check(lib().hmm_set_stream(C.c_void_p(self._own_stream.cuda_stream)))
+        return (ctx, cur)
+
+    def _leave_stream(self, tok):
+        lib().hmm_set_stream(None)
+        if tok is not None:
+            ctx, cur = tok
+            ctx.__exit__(None, None, None)
+            cur.wait_stream(self._own_stream)
+
+    # -- building blocks (also used by bench.py's phase timing) ----------------------------------------------
+    def local_decode(self):
+        sh = self.sh
         sh.forward()
-        vec_out = torch.empty(sh.bvec, dtype=torch.float64, device=device)
-        vec_in = torch.empty(sh.bvec, dtype=torch.float64, device=device)
-        cnt = torch.zeros(1, dtype=torch.int64, device=device)
-        while True:
-            ops = []
+        sh.fwd_verify(count=False)
+        sh.trace()
+        sh.trace_verify(count=False)
+
+    def gather_and_judge(self):
+        sh = self.sh
+        sh.summary_dev(self.x_ptr, self.summ.data_ptr())
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(self.gath, self.summ)
+        else:
+            self.gath.copy_(self.summ)
+        sh.judge_dev(self.gath.data_ptr(), self.world, self.res.data_ptr())
+
+    def _p2p(self, send_t, recv_t, send_to, recv_from):
+        dist = self.dist
+        ops = []
+        if send_to is not None:
+            ops.append(dist.P2POp(dist.isend, send_t, send_to))
+        if recv_from is not None:
+            ops.append(dist.P2POp(dist.irecv, recv_t, recv_from))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()  # makes the current stream wait, not the host
+
+    def _all_sum(self, v: int) -> int:
+        self.cnt[0] = v
+        if self.world > 1:
+            self.dist.all_reduce(self.cnt)
+        return int(self.cnt.item())
+
+    def _fallback(self) -> float:
+        sh, rank, world = self.sh, self.rank, self.world
+        self.stats["fallbacks"] += 1
+        for _ in range(world + 1):
+            self.stats["fwd_rounds"] += 1
             if not sh.last:
-                sh.fwd_get(out_ptr=vec_out.data_ptr())
-                ops.append(dist.P2POp(dist.isend, vec_out, rank + 1))
+                sh.fwd_get(out_ptr=self.vec_out.data_ptr())
+            self._p2p(self.vec_out, self.vec_in, None if sh.last else rank + 1, None if sh.first else rank - 1)
             if not sh.first:
-                ops.append(dist.P2POp(dist.irecv, vec_in, rank - 1))
-            if ops:
-                for r in dist.batch_isend_irecv(ops):
-                    r.wait()
-                torch.cuda.synchronize(device) if torch.cuda.is_available() else None
-            if not sh.first:
-                sh.fwd_set(in_ptr=vec_in.data_ptr())
-            cnt[0] = sh.fwd_verify()
-            dist.all_reduce(cnt)
-            info["fwd_rounds"] += 1
-            info["fwd_repaired"] += int(cnt.item())
-            if int(cnt.item()) == 0 or info["fwd_rounds"] > world:
+                sh.fwd_set(in_ptr=self.vec_in.data_ptr())
+            if self._all_sum(sh.fwd_verify(count=True)) == 0:
                 break
         sh.trace()
-        s_out = torch.zeros(1, dtype=torch.int64, device=device)
-        s_in = torch.zeros(1, dtype=torch.int64, device=device)
-        while True:
-            ops = []
+        for _ in range(world + 1):
+            self.stats["trace_rounds"] += 1
             if not sh.first:
-                sh.trace_get(out_ptr=s_out.data_ptr())
-                ops.append(dist.P2POp(dist.isend, s_out, rank - 1))
+                sh.trace_get(out_ptr=self.s_out.data_ptr())
+            self._p2p(self.s_out, self.s_in, None if sh.first else rank - 1, None if sh.last else rank + 1)
             if not sh.last:
-                ops.append(dist.P2POp(dist.irecv, s_in, rank + 1))
-            if ops:
-                for r in dist.batch_isend_irecv(ops):
-                    r.wait()
-                torch.cuda.synchronize(device) if torch.cuda.is_available() else None
-            if not sh.last:
-                sh.trace_set(in_ptr=s_in.data_ptr())
-            cnt[0] = sh.trace_verify()
-            dist.all_reduce(cnt)
-            info["trace_rounds"] += 1
-            info["trace_repaired"] += int(cnt.item())
-            if int(cnt.item()) == 0 or info["trace_rounds"] > world:
+                sh.trace_set(in_ptr=self.s_in.data_ptr())
+            if self._all_sum(sh.trace_verify(count=True)) == 0:
                 break
-        ll = sh.finish(x_ptr=x_main_dev_ptr)
-        t = torch.tensor([ll], dtype=torch.float64, device=device)
-        dist.all_reduce(t)
-        return float(t.item()), info
+        part = self.torch.tensor([sh.finish(x_ptr=self.x_ptr)], dtype=self.torch.float64, device=self.device)
+        if world > 1:
+            self.dist.all_reduce(part)
+        return float(part.item())
+
+    def decode(self) -> float:
+        """One decode of the whole recording; returns the total ll (identical on every rank)."""
+        tok = self._enter_stream()
+        try:
+            self.local_decode()
+            self.gather_and_judge()
+            ll, bad = self.res.tolist()  # the decode's only host synchronisation
+            self.stats["decodes"] += 1
+            self.stats["fwd_rounds"] += 1
+            self.stats["trace_rounds"] += 1
+            if bad != 0:
+                ll = self._fallback()
+            return ll
+        finally:
+            self._leave_stream(tok)
+
+    def close(self):
+        self.sh.close()
+
+
+def viterbi_time_sharded_dist(y_local_dev_ptr: int, span, T: int, chunk_len: int, warmup: int, lA, mu, sigma,
+                              x_main_dev_ptr: int, device):
+    """One shard per torch.distributed rank: see DistDecoder.  Returns (total ll, stats)."""
+    d = DistDecoder(y_local_dev_ptr, span, T, chunk_len, warmup, lA, mu, sigma, x_main_dev_ptr, device)
+    try:
+        return d.decode(), dict(d.stats)
     finally:
-        sh.close()
+        d.close()

@@ -86,3 +86,30 @@ def test_one_collective_protocol_summaries_and_judge(hm, O, case_factory):
     assert res.tolist()[1] == 1
     for sh, _ in shards:
         sh.close()
+
+
+def test_dist_decoder_single_rank(hm, O, case_factory):
+    """DistDecoder (the torch.distributed driver of bench.py --workload c5) with one rank and no process group:
+    the whole one-collective path -- local decode, summary, judge, single read -- against the oracle, twice (a
+    decoder is re-run per recording), on torch's default stream (the decoder then creates its own)."""
+    import torch
+
+    ts = hm.timeshard
+    T = 300_000
+    S, lA, mu, sig = case_factory(5, 60, T, 65)
+    x_ref, ll_ref = O.viterbi(S, lA, mu, sig)
+    dev = torch.device("cuda", 0)
+    span = ts.shard_plan(T, 1, 4096)[0]
+    y_loc = torch.from_numpy(np.ascontiguousarray(S[span[0]:span[1]])).to(dev)
+    x_main = torch.zeros(span[3] - span[2], dtype=torch.int16, device=dev)
+    dec = ts.DistDecoder(y_loc.data_ptr(), span, T, 4096, 512, lA, mu, sig, x_main.data_ptr(), dev)
+    try:
+        for _ in range(2):
+            x_main.zero_()
+            ll = dec.decode()
+            torch.cuda.synchronize()
+            assert np.array_equal(x_main.cpu().numpy(), x_ref)
+            assert abs(ll - ll_ref) <= 1e-9 * abs(ll_ref)
+        assert dec.stats["fallbacks"] == 0 and dec.stats["decodes"] == 2
+    finally:
+        dec.close()
