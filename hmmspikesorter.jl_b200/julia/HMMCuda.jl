@@ -129,3 +129,41 @@ function reconstruct_signal(x::Array{T,1}, lA::StateMatrix, μ::Array{Float64,2}
     end
     Y
 end
+
+# ---- optional: keep X resident in HBM across the E/M iterations -----------------------------------------
+# train_model(X, sm, μ, σ, nsteps, callback) (src/baumwelch.jl:324-354) uploads X on every iteration when it
+# calls the one-step method above.  `with_resident(X) do step ... end` uploads it once; `step(lA, μ, σ)` is then
+# a drop-in for the one-step train_model(X, lA, μ, σ) inside the unchanged loop body.
+function with_resident(f::Function, X::Array{Float64,1})
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve X _check(ccall((:hmm_train_create, libhmmcuda), Cint, (Ptr{Float64}, Int64, Ref{Ptr{Cvoid}}),
+                                X, length(X), ctx))
+    step = function (lA::StateMatrix, μ::Array{Float64,2}, σ::Float64)
+        lp = Vector{Float64}(undef, max(_nxi(lA) - 1, 1)); pp = Vector{Float64}(undef, lA.nstates)
+        s = Ref{Float64}(σ); ll = Ref{Float64}(0.0); tr = lA.transitions
+        GC.@preserve lA μ lp pp begin
+            _check(ccall((:hmm_train_em_step, libhmmcuda), Cint,
+                (Ptr{Cvoid}, Ptr{Int16}, Int32, Int32, Int32, Ptr{Cvoid}, Int64,
+                 Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ptr{Cvoid}),
+                ctx[], lA.states, lA.N, lA.K, lA.nstates, pointer(tr), length(tr), μ, s, lp, pp, ll, C_NULL))
+        end
+        lA_new = StateMatrix(lA.states .- one(Int16), pp, lA.K, lp[1:_nxi(lA)-1]; allow_overlaps=lA.resolve_overlaps)
+        lA_new, μ, s[]
+    end
+    try
+        return f(step)
+    finally
+        ccall((:hmm_train_destroy, libhmmcuda), Cint, (Ptr{Cvoid},), ctx[])
+    end
+end
+
+# ---- optional: pinned host arrays ------------------------------------------------------------------------
+# A Julia Array is pageable: long decodes then go through the library's pinned staging threads (≈2.9 Gsamples/s).
+# Recordings that live in a pinned buffer reach the PCIe rate (≈5.6 Gsamples/s).  `pinned_vector(Float64, T)`
+# returns an ordinary Vector backed by hmm_host_alloc memory; release it with `free_pinned(v)` when done.
+function pinned_vector(::Type{T}, n::Integer) where T
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    _check(ccall((:hmm_host_alloc, libhmmcuda), Cint, (Ref{Ptr{Cvoid}}, UInt64), p, UInt64(n) * sizeof(T)))
+    unsafe_wrap(Array, convert(Ptr{T}, p[]), n; own=false)
+end
+free_pinned(v::Array) = (ccall((:hmm_host_free, libhmmcuda), Cint, (Ptr{Cvoid},), pointer(v)); nothing)
