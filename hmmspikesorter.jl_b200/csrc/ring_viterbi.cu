@@ -1429,18 +1429,17 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     // the last chunk must be long enough to hold the final look-back of L steps
     if (nchunks > 1 && T - (int64_t)(nchunks - 1) * Lc < RING_Q) nchunks--;
 
-    // Traceback chunks: the longest divisor of the forward chunk that is a multiple of 32 steps (mask-word
-    // alignment), at most 4096 steps and at least max(1024, 2 W) -- the walk is latency-bound per warp, so it
+    // Traceback chunks: a divisor of the forward chunk that is a multiple of 32 steps (mask-word alignment) and
+    // at least max(1024, 2 W) -- the longest one of at most 4096 steps, else the shortest admissible one -- the walk is latency-bound per warp, so it
     // wants several times more chunks than the forward pass has.
     int tfac = 1;
-    for (int64_t f = (Lc + 4095) / 4096; f <= 64; f++) {
+    for (int64_t f = 2; f <= 64; f++) {  // f ascending = sub-chunk length descending
         if (Lc % f) continue;
         const int64_t lt = Lc / f;
         if (lt < 1024 || lt < 2 * W) break;
-        if (lt % 32 == 0) {
-            tfac = (int)f;
-            break;
-        }
+        if (lt % 32) continue;
+        tfac = (int)f;             // the finest admissible split so far ...
+        if (lt <= 4096) break;     // ... and fine enough
     }
     const int64_t Lc_t = Lc / tfac;
     const int nchunks_t = (int)((T + Lc_t - 1) / Lc_t);
