@@ -213,3 +213,68 @@ def test_reconstruct_and_chunked(hm, O, case_factory):
     assert ml.size == S.size and (ml != x).mean() < 0.05
     with pytest.raises(ValueError):
         O.reconstruct_signal(np.array([0], dtype=np.int16), lA, mu)
+
+
+@pytest.mark.parametrize("N,K,T,seed", [(2, 5, 70, 31), (1, 6, 90, 32), (3, 4, 50, 33)])
+def test_em_step_against_50_digit_arithmetic(hm, O, N, K, T, seed):
+    """An independent statement of src/baumwelch.jl:25-51, 73-98, 205-309 in the LINEAR domain with mpmath at 50
+    digits (plain sum-product, no log-sum-exp, no operation-order assumptions): alpha, beta, gamma, xi, then the
+    M-step formulas.  The oracle's one-step train_model must agree to ~1e-12 -- this pins the oracle's E/M
+    arithmetic beyond its own invariants."""
+    import mpmath as mp
+
+    mp.mp.dps = 50
+    temps = np.stack([hm.create_spike_template(K, 2.0 + i, 0.7 - 0.1 * i, 0.25) for i in range(N)], axis=1)
+    p = np.array([0.05, 0.03, 0.04][:N])
+    S = hm.create_signal(T, 0.4, p, temps, hm.make_rng(seed))
+    sm = O.OracleStateMatrix(N, K, np.log(np.full(N, 0.04)), False)
+    mu0 = np.asfortranarray(0.8 * temps)
+    mu0[0, :] = 0.0
+    s0 = 0.5
+    lp, pp, mu1, s1, llk = O.em_step(S, sm, mu0.copy(order="F"), s0)
+
+    ns, states, tr = sm.nstates, np.asarray(sm.states), sm.transitions
+    m = [mp.fsum(mp.mpf(float(mu0[states[l, j] - 1, l])) for l in range(N)) for j in range(ns)]
+    sig = mp.mpf(s0)
+    y = [mp.mpf(float(v)) for v in S]
+
+    def b(j, t):  # funcl, src/utils.jl:3-4
+        d = y[t] - m[j]
+        return mp.exp(-mp.log(2 * mp.pi) / 2 - mp.log(sig) - d * d / (2 * sig * sig))
+
+    edges = [(int(e["src"]) - 1, int(e["dst"]) - 1, mp.exp(mp.mpf(float(e["lp"])))) for e in tr]
+    al = [[mp.mpf(0)] * ns for _ in range(T)]
+    be = [[mp.mpf(0)] * ns for _ in range(T)]
+    for j in range(ns):
+        al[0][j] = b(j, 0)  # no prior, noise not forced (src/baumwelch.jl:30-37)
+        be[T - 1][j] = mp.mpf(1)
+    for t in range(1, T):
+        for (k, j, a) in edges:
+            al[t][j] += al[t - 1][k] * a * b(j, t)
+    for t in range(T - 2, -1, -1):
+        for (k, j, a) in edges:
+            be[t][k] += a * b(j, t + 1) * be[t + 1][j]
+    Z = mp.fsum(al[T - 1])
+    assert abs(mp.log(Z) - llk) <= 1e-12 * abs(llk)
+    gam = [[al[t][j] * be[t][j] / Z for j in range(ns)] for t in range(T)]
+    # transition posteriors out of the noise state, list order (src/baumwelch.jl:226-253)
+    from_noise = [(j, a) for (k, j, a) in edges if k == 0]
+    xx = [mp.fsum(al[t][0] * a * b(j, t + 1) * be[t + 1][j] / Z for t in range(T - 1)) for (j, a) in from_noise]
+    bb = mp.fsum(gam[t][0] for t in range(T - 1))
+    lp_ref = [mp.log(x / bb) for x in xx][1:]
+    assert max(abs(float(a2) - b2) for a2, b2 in zip(lp_ref, lp)) < 1e-11
+    # templates: states with exactly one active neuron (src/baumwelch.jl:266-287)
+    mu_ref = np.zeros_like(mu0)
+    for l in range(N):
+        for s_ in range(2, K + 1):
+            js = [j for j in range(ns) if states[l, j] == s_ and all(states[q, j] == 1 for q in range(N) if q != l)]
+            num = mp.fsum(y[t] * gam[t][j] for t in range(T) for j in js)
+            den = mp.fsum(gam[t][j] for t in range(T) for j in js)
+            mu_ref[s_ - 1, l] = float(num / den)
+    assert np.abs(mu_ref - mu1).max() < 1e-11
+    # sigma with the NEW means over all states (src/baumwelch.jl:288-307)
+    m1 = [mp.fsum(mp.mpf(float(mu_ref[states[l, j] - 1, l])) for l in range(N)) for j in range(ns)]
+    num = mp.fsum((y[t] - m1[j]) ** 2 * gam[t][j] for t in range(T) for j in range(ns))
+    den = mp.fsum(gam[t][j] for t in range(T) for j in range(ns))
+    assert abs(float(mp.sqrt(num / den)) - s1) < 1e-12
+    assert max(abs(float(mp.log(gam[0][j])) - pp[j]) for j in range(ns) if gam[0][j] > mp.mpf("1e-250")) < 1e-9
