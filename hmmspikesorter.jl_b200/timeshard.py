@@ -247,7 +247,7 @@ class DistDecoder:
     stream cannot carry the library's work, so one is created when needed)."""
 
     def __init__(self, y_local_dev_ptr: int, span, T: int, chunk_len: int, warmup: int, lA, mu, sigma,
-                 x_main_dev_ptr: int, device):
+                 x_main_dev_ptr: int, device, shard=None):
         import torch
         import torch.distributed as dist
 
@@ -256,7 +256,9 @@ class DistDecoder:
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.x_ptr = x_main_dev_ptr
-        self.sh = Shard(y_local_dev_ptr, False, span, T, chunk_len, warmup, lA, mu, sigma)
+        # `shard`: an object with Shard's interface (the CPU tests drive the message protocol with a stand-in)
+        self.sh = shard if shard is not None else Shard(y_local_dev_ptr, False, span, T, chunk_len, warmup, lA, mu,
+                                                        sigma)
         f8, i8 = torch.float64, torch.int64
         self.summ = torch.zeros(self.sh.summary_len, dtype=f8, device=device)
         self.gath = torch.zeros(self.world * self.sh.summary_len, dtype=f8, device=device)
@@ -272,6 +274,8 @@ class DistDecoder:
     # -- stream plumbing -------------------------------------------------------------------------------------
     def _enter_stream(self):
         torch = self.torch
+        if getattr(self.device, "type", "cuda") != "cuda":
+            return None  # CPU stand-in (tests): nothing to order
         cur = torch.cuda.current_stream(self.device)
         if cur.cuda_stream != 0:
             check(lib().hmm_set_stream(C.c_void_p(cur.cuda_stream)))
@@ -285,6 +289,8 @@ class DistDecoder:
         return (ctx, cur)
 
     def _leave_stream(self, tok):
+        if getattr(self.device, "type", "cuda") != "cuda":
+            return
         lib().hmm_set_stream(None)
         if tok is not None:
             ctx, cur = tok

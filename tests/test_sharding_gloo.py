@@ -99,3 +99,91 @@ def test_channel_sharding_world2_gloo(hm, O, tmp_path):
     assert all(o["ok"] for o in outs)
     assert all(o["tmax"] == 2.0 for o in outs)
     assert sorted(tuple(o["span"]) for o in outs) == [(0, 3), (3, 5)]
+
+
+DIST_WORKER = textwrap.dedent("""
+    import os, sys, json, ctypes
+    import numpy as np
+    sys.path.insert(0, {root!r})
+    import torch, torch.distributed as dist
+    import __graft_entry__ as ge
+    hm = ge.load_package()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + os.environ["MASTER_PORT"], rank=rank, world_size=world)
+
+    def view(ptr, n, ct):   # the decoder passes raw addresses, as it does to the C ABI
+        return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ct)), shape=(n,))
+
+    class FakeShard:
+        # Stand-in with hmm_vshard's interface: "decodes" nothing, but produces and consumes the protocol's
+        # messages so that their routing, ordering and termination can be checked on CPU.
+        bvec, summary_len = 7, 2 * 7 + 4
+        def __init__(self):
+            self.first, self.last = rank == 0, rank == world - 1
+            self.calls, self.fwd_in, self.trace_in = [], None, None
+            self.force_bad, self.fwd_repairs_left = False, 0
+        def forward(self): self.calls.append("forward")
+        def trace(self): self.calls.append("trace")
+        def fwd_verify(self, count=True):
+            self.calls.append("fwd_verify")
+            if count and self.fwd_repairs_left > 0:
+                self.fwd_repairs_left -= 1
+                return 1
+            return 0
+        def trace_verify(self, count=True):
+            self.calls.append("trace_verify")
+            return 0
+        def summary_dev(self, x_ptr, summ_ptr):
+            s = view(summ_ptr, self.summary_len, ctypes.c_double)
+            s[:] = 0.0
+            s[2 * self.bvec + 2] = 10.0 + rank          # partial ll
+        def judge_dev(self, gath_ptr, n, out_ptr):
+            g = view(gath_ptr, n * self.summary_len, ctypes.c_double).reshape(n, self.summary_len)
+            out = view(out_ptr, 2, ctypes.c_double)
+            out[0] = g[:, 2 * self.bvec + 2].sum()
+            out[1] = 1.0 if self.force_bad else 0.0
+        def fwd_get(self, out_ptr): view(out_ptr, self.bvec, ctypes.c_double)[:] = 100.0 + rank
+        def fwd_set(self, in_ptr): self.fwd_in = float(view(in_ptr, self.bvec, ctypes.c_double)[0])
+        def trace_get(self, out_ptr): view(out_ptr, 1, ctypes.c_int64)[0] = 1000 + rank
+        def trace_set(self, in_ptr): self.trace_in = int(view(in_ptr, 1, ctypes.c_int64)[0])
+        def finish(self, x_ptr=None): return 10.0 + rank
+        def close(self): pass
+
+    sh = FakeShard()
+    dec = hm.timeshard.DistDecoder(0, (0, 0, 0, 0), 0, 0, 0, None, None, 0.0, 0, torch.device("cpu"), shard=sh)
+    want = sum(10.0 + r for r in range(world))
+    ll_fast = dec.decode()                       # fast path: one all-gather, verdict 0
+    fast_calls = list(sh.calls)
+    sh.calls.clear()
+    sh.force_bad = True                          # verdict != 0 on every rank -> iterative fallback
+    sh.fwd_repairs_left = 1 if rank == 1 else 0  # rank 1 repairs once: everyone must go a second forward round
+    ll_slow = dec.decode()
+    ok = ll_fast == want and ll_slow == want and dec.stats["fallbacks"] == 1
+    ok = ok and fast_calls == ["forward", "fwd_verify", "trace", "trace_verify"]
+    ok = ok and sh.calls.count("fwd_verify") == 1 + 2 and sh.calls.count("trace_verify") == 1 + 1
+    ok = ok and (sh.first or sh.fwd_in == 100.0 + rank - 1) and (sh.last or sh.trace_in == 1000 + rank + 1)
+    print(json.dumps({{"rank": rank, "ok": bool(ok), "calls": sh.calls, "stats": dec.stats}}))
+    dist.destroy_process_group()
+""")
+
+
+def test_dist_decoder_protocol_world3_gloo(hm, tmp_path):
+    """DistDecoder's two protocols over a real (gloo) process group of three ranks, with a stand-in shard: the fast
+    path is one all-gather and no point-to-point traffic; a non-zero verdict runs the iterative fallback, whose
+    boundary vectors travel right and traceback states left, and whose rounds end on all ranks together."""
+    script = tmp_path / "dist_worker.py"
+    script.write_text(DIST_WORKER.format(root=ROOT))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for rank in range(3):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="3", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    import json
+    for p in procs:
+        out, err = p.communicate(timeout=240)
+        assert p.returncode == 0, err[-3000:]
+        o = json.loads(out.strip().splitlines()[-1])
+        assert o["ok"], o
