@@ -96,10 +96,15 @@ int hmm_set_stream(void *cuda_stream) {
 }
 
 int hmm_set_ring_params(int64_t chunk_len, int64_t warmup) {
-    if (chunk_len < 0 || warmup < 0) return set_err(HMM_EINVAL, "negative ring parameter");
-    ring_config().chunk_len = chunk_len;
-    ring_config().warmup = warmup;
-    return HMM_OK;
+    return guarded([&] {  // under the entry lock: a decode on another thread never sees half an update
+        if (chunk_len < 0 || warmup < 0) fail(HMM_EINVAL, "negative ring parameter");
+        ring_config().chunk_len = chunk_len;
+        ring_config().warmup = warmup;
+    });
+}
+
+int hmm_release_workspace(void) {
+    return guarded([&] { workspace().release(); });
 }
 
 int hmm_host_alloc(void **ptr_out, uint64_t bytes) {

@@ -53,7 +53,7 @@ def get_valid_transitions(states0: np.ndarray, K: int, lp: np.ndarray, row_block
     impossible neuron transition makes the whole sum -Inf (the `break`)."""
     N, n = states0.shape
     lp = np.asarray(lp, dtype=np.float64)
-    lpz = lpz_of(lp[:N])
+    lpz = lpz_of(lp)  # the WHOLE vector (src/types.jl:96): overlap models pass N + N(N-1)/2 entries, only lp[1:N] are indexed
     out = []
     s = states0.astype(np.int32)
     for r0 in range(0, n, row_block):
@@ -108,7 +108,7 @@ def transitions_fast(states0: np.ndarray, K: int, lp, allow_overlaps: bool) -> n
     src, dst, codes = _topology(states0, K, allow_overlaps)
     lp = np.asarray(lp, dtype=np.float64)
     N = states0.shape[0]
-    lpz = lpz_of(lp[:N])
+    lpz = lpz_of(lp)  # the WHOLE vector (src/types.jl:96): overlap models pass N + N(N-1)/2 entries, only lp[1:N] are indexed
     lpt = np.zeros(src.size, dtype=np.float64)
     for i in range(N):
         c = codes[:, i]

@@ -29,20 +29,26 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def shard_plan(T: int, n_shards: int, chunk_len: int) -> List[Tuple[int, int, int, int]]:
+def shard_plan(T: int, n_shards: int, chunk_len: int, warmup: Optional[int] = None) -> List[Tuple[int, int, int, int]]:
     """(local_begin, local_end, main_begin, main_end) per shard: main spans are whole chunks,
-    balanced over the shards; one ghost chunk on either side."""
+    balanced over the shards; one ghost chunk on either side.  A final partial chunk shorter than the
+    look-ahead a right ghost must hold (warmup + 128 samples; `warmup` unknown: any partial chunk) joins the
+    chunk before it, as the single-GPU pipeline does (api.cu viterbi_host_pipelined) -- otherwise the previous
+    shard's right ghost would be clipped at T and hmm_vshard_create would reject it."""
     nchunks = -(-T // chunk_len)
+    tail = T - (nchunks - 1) * chunk_len
+    min_tail = (chunk_len if warmup is None else warmup) + 128
+    if nchunks > 1 and tail < min(min_tail, chunk_len):
+        nchunks -= 1
     if n_shards > nchunks:
         raise ValueError("more shards than chunks")
     q, r = divmod(nchunks, n_shards)
     out, c0 = [], 0
     for s in range(n_shards):
         c1 = c0 + q + (1 if s < r else 0)
-        mb, me = c0 * chunk_len, min(T, c1 * chunk_len)
+        mb, me = c0 * chunk_len, (T if s == n_shards - 1 else c1 * chunk_len)
         out.append((max(0, mb - chunk_len), min(T, me + chunk_len), mb, me))
         c0 = c1
-    # a final main span shorter than the engine's look-back is merged into its neighbour's ghost
     return out
 
 

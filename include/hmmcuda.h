@@ -74,6 +74,10 @@ int hmm_set_stream(void *cuda_stream);
  * speculative warm-up / look-ahead, in samples (rounded to multiples of 256). */
 int hmm_set_ring_params(int64_t chunk_len, int64_t warmup);
 
+/* Frees the calling thread's grow-only device workspace and pinned staging buffers (they are otherwise kept
+ * for the next call; a pageable-host decode of T samples leaves 10 T bytes of pinned staging behind). */
+int hmm_release_workspace(void);
+
 /* ---- Viterbi ------------------------------------------------------------- */
 /*
  * viterbi(y, lA::StateMatrix, mu, sigma) -> (x, ll)       src/viterbi.jl:44-98

@@ -142,8 +142,11 @@ double orc_lpz(const double *lp, int64_t N) {
  * dst inner) -> list sorted by (src, dst).  Returns count; if tr == NULL
  * only counts. */
 int64_t orc_get_valid_transitions(const int16_t *states0, int64_t N, int64_t nstates, int64_t K, const double *lp,
-                                  orc_trans *tr, int64_t cap) {
-    double lpz = orc_lpz(lp, N);
+                                  int64_t nlp, orc_trans *tr, int64_t cap) {
+    /* sum(lp) runs over the WHOLE vector (nlp >= N entries: update() hands xb[2:end], which for overlap
+     * models has one entry per transition out of the silent state, src/baumwelch.jl:226,265), while
+     * isvalid_transition only indexes lp[i], i < N. */
+    double lpz = orc_lpz(lp, nlp < N ? N : nlp);
     int64_t n = 0;
     for (int64_t i = 0; i < nstates; i++)
         for (int64_t j = 0; j < nstates; j++) {
@@ -269,6 +272,92 @@ int orc_viterbi(const double *y, int64_t T, const int16_t *states1, int64_t N, i
     }
     *ll_out = ll;
     free(m); free(q); free(ckpt); free(b1); free(b2); free(colA); free(colB);
+    return ORC_OK;
+}
+
+/*
+ * Near-tie screen (SURVEY 8d "inputs screened for decision margins"): one forward sweep in the reference's
+ * own arithmetic (src/viterbi.jl:65-88) that records, for every destination state with two or more finite
+ * candidates at every column i >= from_col (0-based; the structural exact ties of SURVEY H3 sit at column 1),
+ * the margin best - second best of `T1[k,i-1] + lp`, and the margin of the final argmax (:90).
+ * out[0] = smallest absolute margin, out[1] = smallest margin relative to |T1[j,i]|,
+ * out[2] = number of decisions with relative margin < rel_a, out[3] = same for rel_b,
+ * out[4] = column of the smallest relative margin, out[5] = number of decisions examined.
+ * A decision whose margin is below a few dozen ulp of the score is decided by the reference's own rounding
+ * noise; bit-exact agreement of x is only meaningful for inputs without such decisions.
+ */
+int orc_viterbi_screen(const double *y, int64_t T, const int16_t *states1, int64_t N, int64_t K, int64_t nstates,
+                       const orc_trans *tr, int64_t ntrans, const double *mu, double sigma, int64_t from_col,
+                       double rel_a, double rel_b, double *out /* [6] */) {
+    if (T < 1 || nstates < 1) return ORC_EARG;
+    double lsig = log(sigma);
+    double *m = malloc(sizeof(double) * nstates), *q = malloc(sizeof(double) * nstates);
+    double *colA = malloc(sizeof(double) * nstates), *colB = malloc(sizeof(double) * nstates);
+    double *sec = malloc(sizeof(double) * nstates);
+    if (!m || !q || !colA || !colB || !sec) return ORC_ENOMEM;
+    state_means(states1, N, nstates, mu, K, m);
+    for (int64_t j = 0; j < nstates; j++) colA[j] = funcl4(y[0], m[j], sigma, lsig);
+    colA[0] = 0;
+    double min_abs = INFINITY, min_rel = INFINITY, na = 0, nb = 0, argcol = -1, nexam = 0;
+    double *prev = colA, *cur = colB;
+    for (int64_t i = 1; i < T; i++) {
+        for (int64_t j = 0; j < nstates; j++) {
+            q[j] = funcl4(y[i], m[j], sigma, lsig);
+            cur[j] = -INFINITY;
+            sec[j] = -INFINITY;
+        }
+        for (int64_t e = 0; e < ntrans; e++) {
+            int64_t k = tr[e].src - 1, j = tr[e].dst - 1;
+            double t = prev[k] + tr[e].lp;
+            if (t > cur[j]) {
+                sec[j] = cur[j];
+                cur[j] = t;
+            } else if (t > sec[j])
+                sec[j] = t;
+        }
+        for (int64_t j = 0; j < nstates; j++) {
+            const double best = cur[j];
+            cur[j] += q[j];
+            if (i >= from_col && isfinite(sec[j]) && isfinite(best)) {
+                double mg = best - sec[j], sc = fabs(cur[j]);
+                double rel = sc > 0 ? mg / sc : INFINITY;
+                nexam += 1;
+                if (mg < min_abs) min_abs = mg;
+                if (rel < min_rel) {
+                    min_rel = rel;
+                    argcol = (double)i;
+                }
+                if (rel < rel_a) na += 1;
+                if (rel < rel_b) nb += 1;
+            }
+        }
+        double *tmp = prev;
+        prev = cur;
+        cur = tmp;
+    }
+    {   /* final argmax, :90 */
+        double b1 = -INFINITY, b2 = -INFINITY;
+        for (int64_t j = 0; j < nstates; j++) {
+            if (prev[j] > b1) {
+                b2 = b1;
+                b1 = prev[j];
+            } else if (prev[j] > b2)
+                b2 = prev[j];
+        }
+        if (isfinite(b2) && T - 1 >= from_col) {
+            double mg = b1 - b2, rel = fabs(b1) > 0 ? mg / fabs(b1) : INFINITY;
+            nexam += 1;
+            if (mg < min_abs) min_abs = mg;
+            if (rel < min_rel) {
+                min_rel = rel;
+                argcol = (double)(T - 1);
+            }
+            if (rel < rel_a) na += 1;
+            if (rel < rel_b) nb += 1;
+        }
+    }
+    out[0] = min_abs; out[1] = min_rel; out[2] = na; out[3] = nb; out[4] = argcol; out[5] = nexam;
+    free(m); free(q); free(colA); free(colB); free(sec);
     return ORC_OK;
 }
 

@@ -65,9 +65,9 @@ class OracleStateMatrix:
             L.orc_generate_states(i64(N), i64(K), C.c_int(int(allow_overlaps)), _p(states0))
         ns = states0.shape[1]
         N = states0.shape[0]
-        n = L.orc_get_valid_transitions(_p(states0), i64(N), i64(ns), i64(K), _p(lp), None, i64(0))
+        n = L.orc_get_valid_transitions(_p(states0), i64(N), i64(ns), i64(K), _p(lp), i64(lp.size), None, i64(0))
         tr = np.empty(n, dtype=TRANS_DTYPE)
-        n2 = L.orc_get_valid_transitions(_p(states0), i64(N), i64(ns), i64(K), _p(lp), _p(tr), i64(n))
+        n2 = L.orc_get_valid_transitions(_p(states0), i64(N), i64(ns), i64(K), _p(lp), i64(lp.size), _p(tr), i64(n))
         assert n2 == n
         self.states = np.asfortranarray(states0 + np.int16(1))
         self.transitions = tr
@@ -99,6 +99,21 @@ def viterbi(y, lA, mu, sigma, trellis=False):
     if rc:
         raise RuntimeError(f"orc_viterbi rc={rc}")
     return (x, ll.value, T2, T1) if trellis else (x, ll.value)
+
+
+def viterbi_screen(y, lA, mu, sigma, from_col=2, rel_a=1e-9, rel_b=64 * 2.220446049250313e-16):
+    """Near-tie screen in the reference's arithmetic: dict with the smallest absolute / relative decision margin
+    at columns >= from_col (0-based) and the number of decisions with relative margin below rel_a / rel_b."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    st, tr, mu = _margs(lA, mu)
+    out = np.zeros(6)
+    rc = lib().orc_viterbi_screen(_p(y), i64(y.size), _p(st), i64(lA.N), i64(lA.K), i64(lA.nstates), _p(tr),
+                                  i64(tr.size), _p(mu), f64(sigma), i64(from_col), f64(rel_a), f64(rel_b), _p(out))
+    if rc:
+        raise RuntimeError(f"orc_viterbi_screen rc={rc}")
+    return {"min_abs_margin": float(out[0]), "min_rel_margin": float(out[1]), "n_below_rel_a": int(out[2]),
+            "n_below_rel_b": int(out[3]), "rel_a": rel_a, "rel_b": rel_b, "argmin_col": int(out[4]),
+            "decisions": int(out[5]), "from_col": from_col}
 
 
 def forward(V, lA, mu, sigma):

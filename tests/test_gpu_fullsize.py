@@ -1,15 +1,23 @@
-"""BASELINE.json full-size configurations through the C ABI.  The CPU oracle cannot
-decode these in seconds, so parity is carried by size-independent properties:
-  * chunk-geometry invariance: two different time-chunkings give the bit-identical x
-    (every chunk boundary is a speculative start that must reproduce the sequential answer);
-  * every step of x is a valid transition of the StateMatrix and the chain structure holds;
-  * ll recomputed independently from (x, y) in numpy matches the reported ll to 1e-9;
-  * a 2 M-sample prefix equals the faithful (reference-order) engine away from the cut;
-plus config 1 (README example) end to end against the oracle."""
+"""BASELINE.json full-size configurations through the C ABI, against the CPU oracle AT the BASELINE sizes:
+  * config 2: the whole 18 M-sample decode, x bit-exact and ll to 1e-9, plus the near-tie screen of the input;
+  * config 4: two full 18 M-sample channels of a batched (N=4, K=48) decode;
+  * config 5: a 20 M-sample prefix of the N=5 recording decoded by both, and the full 108 M-sample decode
+    against that prefix away from the cut;
+  * config 3: one E/M iteration at T = 1.8 M and 20 iterations at T = 200 k, fits within 1e-6;
+  * config 1 (README example) end to end.
+The oracle takes tens of seconds per case at these sizes (it is the reference's sequential algorithm); independent
+oracle calls run on host threads.  Size-independent properties (chunk-geometry invariance, path structure, an
+independent numpy recomputation of ll) are kept as well."""
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-9     # north_star: T1 / log-likelihoods within 1e-9 relative (FP64)
+FIT_ATOL = 1e-6    # north_star: fitted mu / sigma / lA within 1e-6
+EPS64 = 64 * 2.220446049250313e-16
 
 
 def _c2(hm, T, seed):
@@ -50,12 +58,27 @@ def _check_structure(x, lA):
     assert starts_ok.all()
 
 
-def test_config2_full_size_properties(hm):
+def _same_path(x, xo, what):
+    bad = np.nonzero(x != xo)[0]
+    assert bad.size == 0, f"{what}: {bad.size} of {x.size} states differ from the oracle, first at {bad[:5]}"
+
+
+def test_config2_full_size_vs_oracle(hm, O):
+    """The BASELINE config-2 decode (18 M samples, N=3, K=60) against the oracle's decode of the SAME 18 M samples."""
     T = 18_000_000
     S, lA, mu, sig = _c2(hm, T, 2)
     hm.set_ring_params(0, 0)
-    x, ll, info = hm.viterbi(S, lA, mu, sig, mode="ring", return_info=True)
+    with ThreadPoolExecutor(2) as ex:  # the oracle runs on host threads while the GPU decodes
+        f_dec = ex.submit(O.viterbi, S, lA, mu, sig)
+        f_scr = ex.submit(O.viterbi_screen, S, lA, mu, sig)
+        x, ll, info = hm.viterbi(S, lA, mu, sig, mode="ring", return_info=True)
+        xo, llo = f_dec.result()
+        scr = f_scr.result()
     assert info["engine"] == 2 and x.shape == (T,)
+    # the input has no decision that the reference's own rounding noise would decide (SURVEY 8d screen)
+    assert scr["n_below_rel_b"] == 0 and scr["min_rel_margin"] > EPS64, scr
+    _same_path(x, xo, "config 2")
+    assert abs(ll - llo) <= LL_RTOL * abs(llo), (ll, llo)
     try:
         hm.set_ring_params(12288, 1024)
         x2, ll2, info2 = hm.viterbi(S, lA, mu, sig, mode="ring", return_info=True)
@@ -74,7 +97,7 @@ def test_config2_full_size_properties(hm):
     assert 0.5 < 1 - np.std(Y - S) / np.std(S) < 0.7
 
 
-def test_config5_long_sequence_properties(hm):
+def test_config5_long_sequence_vs_oracle(hm, O):
     """Config 5: single channel, 1 h at 30 kHz (108 M samples), N=5 x K=60."""
     T, N, K = 108_000_000, 5, 60
     params = [(3.0, 0.8, 0.2), (4.0, 0.3, 0.2), (2.0, 0.5, 0.3), (2.5, 0.6, 0.25), (3.5, 0.4, 0.15)]
@@ -93,9 +116,90 @@ def test_config5_long_sequence_properties(hm):
     assert np.array_equal(x, x2)
     del x2
     _check_structure(x, lA)
-    Tq = 20_000_000  # ll check on a slice of the path keeps host memory modest
-    xq, llq = hm.viterbi(S[:Tq], lA, mu, 0.3, mode="ring")
+    # a 20 M-sample prefix decoded by the oracle and by the GPU; the full decode agrees with it away from the cut
+    Tq = 20_000_000
+    with ThreadPoolExecutor(2) as ex:
+        f_dec = ex.submit(O.viterbi, S[:Tq], lA, mu, 0.3)
+        f_scr = ex.submit(O.viterbi_screen, S[:Tq], lA, mu, 0.3)
+        xq, llq = hm.viterbi(S[:Tq], lA, mu, 0.3, mode="ring")
+        xo, llo = f_dec.result()
+        scr = f_scr.result()
+    assert scr["n_below_rel_b"] == 0, scr
+    _same_path(xq, xo, "config 5 prefix")
+    assert abs(llq - llo) <= LL_RTOL * abs(llo), (llq, llo)
+    assert np.array_equal(x[:Tq - 8192], xo[:Tq - 8192])
     assert abs(llq - _ll_numpy(S[:Tq], xq, lA, mu, 0.3)) <= 1e-9 * abs(llq)
+
+
+def _c4_channels(hm, C, T, seed0=1000):
+    N, K = 4, 48
+    rng = np.random.default_rng(seed0)
+    models, cols = [], []
+    for c in range(C):
+        prm = [(rng.uniform(2, 4), rng.uniform(0.3, 0.9), rng.uniform(0.1, 0.3)) for _ in range(N)]
+        temps = np.stack([hm.create_spike_template(K, *q) for q in prm], axis=1)
+        pp = rng.uniform(0.0005, 0.004, size=N)
+        cols.append(hm.create_signal(T, 0.3, pp, temps, hm.make_rng(seed0 + c)))
+        mu = np.asfortranarray(temps.copy())
+        mu[0, :] = 0.0
+        models.append((hm.StateMatrix(N, K, np.log(pp), False), mu, 0.3))
+    return np.asfortranarray(np.stack(cols, axis=1)), models
+
+
+def test_config4_two_full_size_channels_vs_oracle(hm, O):
+    """Config 4 at the BASELINE length: two independent 18 M-sample channels (N=4, K=48, own templates and
+    rates) through the batch entry point, each against the oracle's decode of the same 18 M samples."""
+    T = 18_000_000
+    Y, models = _c4_channels(hm, 2, T)
+    with ThreadPoolExecutor(2) as ex:
+        fo = [ex.submit(O.viterbi, Y[:, c], *models[c]) for c in range(2)]
+        x, ll, info = hm.viterbi_batch(Y, models, mode="ring", return_info=True)
+        ref = [f.result() for f in fo]
+    assert info["engine"] == 2
+    for c in range(2):
+        _same_path(x[:, c], ref[c][0], f"config 4 channel {c}")
+        assert abs(ll[c] - ref[c][1]) <= LL_RTOL * abs(ref[c][1])
+
+
+def test_config3_one_iteration_full_size_vs_oracle(hm, O):
+    """Config 3 at the BASELINE length: one E/M step on T = 1.8 M samples (the oracle materialises alpha, beta
+    and gamma: 7.7 GB of host memory, about a minute)."""
+    T, N, K = 1_800_000, 3, 60
+    S, _, mu_true, _ = _c2(hm, T, 3)
+    lp0 = np.log(np.full(N, 0.01))
+    mu0 = np.asfortranarray(0.7 * mu_true)
+    s0 = float(np.std(S))
+    with ThreadPoolExecutor(1) as ex:
+        fo = ex.submit(O.em_step, S, O.OracleStateMatrix(N, K, lp0, False), mu0.copy(order="F"), s0)
+        lp, pp, mu1, s1, ll, info = hm.em_step(S, hm.StateMatrix(N, K, lp0, False), mu0.copy(order="F"), s0,
+                                               mode="ring", return_info=True)
+        lpo, ppo, muo, so, llo = fo.result()
+    assert info["engine"] == 2
+    assert np.abs(mu1 - muo).max() < FIT_ATOL and abs(s1 - so) < FIT_ATOL and np.abs(lp - lpo).max() < FIT_ATOL
+    assert abs(ll - llo) <= LL_RTOL * abs(llo), (ll, llo)
+    fin = np.isfinite(ppo)
+    assert np.array_equal(np.isfinite(pp), fin) and np.abs(pp[fin] - ppo[fin]).max() < FIT_ATOL
+
+
+def test_config3_twenty_iterations_vs_oracle(hm, O):
+    """BASELINE config 3's 20 Baum-Welch iterations (on T = 200 k so that the oracle finishes in about a minute):
+    every iteration's fit is compared, not only the last one."""
+    T, N, K = 200_000, 3, 60
+    S, _, mu_true, _ = _c2(hm, T, 3)
+    lp0 = np.log(np.full(N, 0.01))
+    mu0 = np.asfortranarray(0.7 * mu_true)
+    s0 = float(np.std(S))
+    seen = []
+    mu = mu0.copy(order="F")
+    lA_fit, mu_fit, s_fit = hm.train_model(S, hm.StateMatrix(N, K, lp0, False), mu, s0, 20,
+                                           lambda m: seen.append(m.copy()))
+    smo, muo, so = O.OracleStateMatrix(N, K, lp0, False), mu0.copy(order="F"), s0
+    for it in range(20):
+        assert np.abs(seen[it] - muo).max() < FIT_ATOL, it
+        lpo, ppo, muo, so, llo = O.em_step(S, smo, muo, so)
+        smo = O.OracleStateMatrix(N, K, lpo, False)
+    assert np.abs(mu_fit - muo).max() < FIT_ATOL and abs(s_fit - so) < FIT_ATOL
+    assert np.abs(lA_fit.transitions["lp"] - smo.transitions["lp"]).max() < FIT_ATOL
 
 
 def test_config4_channel_batch(hm, O):

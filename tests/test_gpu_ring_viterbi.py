@@ -49,7 +49,50 @@ def test_ring_viterbi_dense_spiking_forces_repairs(hm, O, case_factory):
         info = _check(hm, O, S, lA, mu, sig)
     finally:
         hm.set_ring_params(0, 0)
-    assert info["fwd_repaired"] >= 0 and info["bwd_repaired"] >= 0
+    assert info["n_chunks"] > 50
+
+
+@pytest.mark.parametrize("N,K,seed", [(3, 60, 61), (5, 60, 62), (2, 12, 63)])
+def test_ring_viterbi_wrong_speculation_is_detected_and_repaired(hm, O, case_factory, monkeypatch, N, K, seed):
+    """The exactness argument IS the verify/repair path, so it must be seen to run: with the warm-up / look-ahead
+    forced to 0 (HMMCUDA_DEBUG_WARMUP) every chunk starts from an empty state and every traceback chunk ends in
+    an assumed noise state -- wrong wherever a spike straddles a boundary.  Verification has to catch each of
+    them and the sequential repair has to restore the oracle's path."""
+    S, lA, mu, sig = case_factory(N, K, 150000, seed, rate_scale=3.0)
+    monkeypatch.setenv("HMMCUDA_DEBUG_WARMUP", "0")
+    try:
+        hm.set_ring_params(2048, 256)
+        info = _check(hm, O, S, lA, mu, sig)
+    finally:
+        hm.set_ring_params(0, 0)
+    assert info["n_chunks"] >= 70
+    assert info["fwd_repaired"] > 0 and info["bwd_repaired"] > 0, info
+
+
+def test_ring_viterbi_forced_flags_exercise_partial_repair(hm, O, case_factory, monkeypatch):
+    """HMMCUDA_DEBUG_FLAG_EVERY=3: the boundary checks also flag every third chunk, so repaired (exact-start) and
+    accepted (speculative) chunks alternate; the decode must not change."""
+    S, lA, mu, sig = case_factory(3, 60, 200000, 71)
+    monkeypatch.setenv("HMMCUDA_DEBUG_FLAG_EVERY", "3")
+    try:
+        hm.set_ring_params(4096, 512)
+        info = _check(hm, O, S, lA, mu, sig)
+    finally:
+        hm.set_ring_params(0, 0)
+    assert info["fwd_repaired"] >= info["n_chunks"] // 3 - 1 and info["bwd_repaired"] > 0, info
+
+
+def test_pipelined_host_decode_repairs(hm, O, case_factory, monkeypatch):
+    """The host-pointer pipeline (segments = time shards with ghost chunks, api.cu viterbi_host_pipelined) with forced
+    flags: repairs inside the segments and the right-to-left traceback re-link must give the oracle's path."""
+    S, lA, mu, sig = case_factory(3, 60, (1 << 22) + 12345, 81)
+    hm.set_ring_params(0, 0)
+    monkeypatch.setenv("HMMCUDA_DEBUG_FLAG_EVERY", "5")
+    x, ll, info = hm.viterbi(S, lA, mu, sig, mode="ring", return_info=True)
+    monkeypatch.delenv("HMMCUDA_DEBUG_FLAG_EVERY")
+    assert info["fwd_repaired"] > 0 and info["bwd_repaired"] > 0, info
+    xo, llo = O.viterbi(S, lA, mu, sig)
+    assert np.array_equal(x, xo) and abs(ll - llo) <= LL_RTOL * abs(llo)
 
 
 def test_ring_viterbi_fitted_like_model(hm, O, case_factory):

@@ -113,3 +113,67 @@ def test_dist_decoder_single_rank(hm, O, case_factory):
         assert dec.stats["fallbacks"] == 0 and dec.stats["decodes"] == 2
     finally:
         dec.close()
+
+
+def test_judge_sees_what_a_locally_repaired_chunk_was_started_from(hm, O, case_factory):
+    """A shard whose first main chunk was REPAIRED locally from a wrong ghost-chunk end vector must not pass the
+    judge on the strength of its stale speculative start vector (which may well equal the neighbour's true end
+    vector): after an exact re-run the start vector on record is the one the chunk was really computed from.
+    Here the ghost's end vector of shard 1 is overwritten with a perturbed copy before verification."""
+    import torch
+
+    ts = hm.timeshard
+    T, n = 300_000, 3
+    S, lA, mu, sig = case_factory(3, 60, T, 66)
+    dev = torch.device("cuda", 0)
+    spans = ts.shard_plan(T, n, 4096)
+    summaries, shards = [], []
+    for r, span in enumerate(spans):
+        y_loc = torch.from_numpy(np.ascontiguousarray(S[span[0]:span[1]])).to(dev)
+        sh = ts.Shard(y_loc.data_ptr(), False, span, T, 4096, 512, lA, mu, sig)
+        summ = torch.zeros(sh.summary_len, dtype=torch.float64, device=dev)
+        sh.forward()
+        if r == 1:
+            # what the left neighbour would send, but wrong: shard 0's true end vector with one entry moved
+            v = shards[0][0].fwd_get()
+            v[1 + 7] += 0.5
+            sh.fwd_set(v)
+            assert sh.fwd_verify(count=True) >= 1  # the first main chunk is re-run from the wrong vector
+        else:
+            sh.fwd_verify(count=False)
+        sh.trace()
+        sh.trace_verify(count=False)
+        sh.summary_dev(0, summ.data_ptr())
+        summaries.append(summ)
+        shards.append((sh, y_loc))
+    gath = torch.cat(summaries).contiguous()
+    res = torch.zeros(2, dtype=torch.float64, device=dev)
+    shards[0][0].judge_dev(gath.data_ptr(), n, res.data_ptr())
+    torch.cuda.synchronize()
+    assert res.tolist()[1] >= 1, "the judge accepted a shard that was started from a wrong boundary vector"
+    for sh, _ in shards:
+        sh.close()
+
+
+def test_time_sharded_forced_repairs(hm, O, case_factory, monkeypatch):
+    """Exchange/verify rounds with every chunk of every shard flagged (HMMCUDA_DEBUG_FLAG_EVERY=1): the first main
+    chunk of each shard is first repaired from its ghost chunk, then again from the neighbour's true vector."""
+    S, lA, mu, sig = case_factory(3, 60, 250_000, 67, rate_scale=2.0)
+    x_ref, ll_ref = O.viterbi(S, lA, mu, sig)
+    monkeypatch.setenv("HMMCUDA_DEBUG_FLAG_EVERY", "1")
+    x, ll, info = hm.viterbi_time_sharded(S, lA, mu, sig, 4, chunk_len=4096, warmup=512, return_info=True)
+    assert np.array_equal(x, x_ref) and abs(ll - ll_ref) <= 1e-9 * abs(ll_ref)
+    assert info["fwd_repaired"] > 0 and info["trace_repaired"] > 0, info
+
+
+def test_shard_plan_short_tail_is_merged(hm, O, case_factory):
+    """T = k * chunk_len + a remainder shorter than the look-back: the short final span joins the previous shard
+    instead of becoming a shard of its own (hmm_vshard_create would reject its neighbour's ghost)."""
+    ts = hm.timeshard
+    T = 10 * 4096 + 100
+    plan = ts.shard_plan(T, 10, 4096)
+    assert plan[-1][3] == T and all(p[3] - p[2] >= 4096 for p in plan)
+    S, lA, mu, sig = case_factory(3, 60, T, 68)
+    x_ref, ll_ref = O.viterbi(S, lA, mu, sig)
+    x, ll = hm.viterbi_time_sharded(S, lA, mu, sig, 10, chunk_len=4096, warmup=512)
+    assert np.array_equal(x, x_ref) and abs(ll - ll_ref) <= 1e-9 * abs(ll_ref)

@@ -278,3 +278,50 @@ def test_em_step_against_50_digit_arithmetic(hm, O, N, K, T, seed):
     den = mp.fsum(gam[t][j] for t in range(T) for j in range(ns))
     assert abs(float(mp.sqrt(num / den)) - s1) < 1e-12
     assert max(abs(float(mp.log(gam[0][j])) - pp[j]) for j in range(ns) if gam[0][j] > mp.mpf("1e-250")) < 1e-9
+
+
+def _isvalid_transition_literal(states0, K, lp, j1, j2):
+    """src/types.jl:94-113, line for line (0-based j1/j2): sum(lp) runs over the WHOLE vector."""
+    lpt = 0.0
+    s = 0.0
+    for v in lp:
+        s += float(v)
+    lpz = float(np.log1p(-np.exp(s)))
+    for i in range(states0.shape[0]):
+        s1, s2 = int(states0[i, j1]), int(states0[i, j2])
+        if s1 == 0 and s2 == 0:
+            lpt += lpz
+        elif s1 == 0 and s2 == 1:
+            lpt += float(lp[i])
+        elif (s2 - s1 == 1) or (s1 == K - 1 and s2 == 0):
+            lpt += 0.0
+        else:
+            return -np.inf
+    return lpt
+
+
+def test_overlap_rebuild_uses_the_full_lp_vector(hm, O):
+    """update() rebuilds an overlap StateMatrix from xb[2:end], which has one entry per transition out of the
+    silent state (N + N(N-1)/2 = 3 for N = 2), not N (src/baumwelch.jl:226,264-265); sum(lp) at
+    src/types.jl:96 covers all of them.  Both mirrors must follow the literal restatement."""
+    N, K = 2, 4
+    base = hm.StateMatrix(N, K, np.log([0.01, 0.02]), True)
+    assert int((base.transitions["src"] == 1).sum()) - 1 == 3
+    lp3 = np.log([0.011, 0.019, 0.0004])
+    s0 = np.asarray(base.states, dtype=np.int16) - 1
+    expect = []
+    for i in range(base.nstates):
+        for j in range(base.nstates):
+            a = _isvalid_transition_literal(s0, K, lp3, i, j)
+            if np.isfinite(a):
+                expect.append((i + 1, j + 1, a))
+    pp = np.full(base.nstates, -np.log(base.nstates))
+    got_h = hm.StateMatrix.from_states(base.states, pp, K, lp3, True).transitions
+    got_o = O.OracleStateMatrix(N, K, lp3, True, states0=np.asfortranarray(s0)).transitions
+    for got in (got_h, got_o):
+        assert got.size == len(expect)
+        assert [(int(r["src"]), int(r["dst"])) for r in got] == [(a, b) for a, b, _ in expect]
+        assert np.array_equal(got["lp"], np.array([w for _, _, w in expect]))
+    # the truncated sum (first N entries only) gives different noise->noise weights: the test can tell
+    trunc = np.log1p(-np.exp(lp3[:N].sum()))
+    assert got_h["lp"][0] != N * trunc
