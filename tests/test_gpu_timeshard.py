@@ -171,9 +171,9 @@ def test_shard_plan_short_tail_is_merged(hm, O, case_factory):
     instead of becoming a shard of its own (hmm_vshard_create would reject its neighbour's ghost)."""
     ts = hm.timeshard
     T = 10 * 4096 + 100
-    plan = ts.shard_plan(T, 10, 4096)
-    assert plan[-1][3] == T and all(p[3] - p[2] >= 4096 for p in plan)
+    plan = ts.shard_plan(T, 5, 4096)
+    assert plan[-1][3] == T and plan[-1][3] - plan[-1][2] == 2 * 4096 + 100 and all(p[3] - p[2] >= 4096 for p in plan)
     S, lA, mu, sig = case_factory(3, 60, T, 68)
     x_ref, ll_ref = O.viterbi(S, lA, mu, sig)
-    x, ll = hm.viterbi_time_sharded(S, lA, mu, sig, 10, chunk_len=4096, warmup=512)
+    x, ll = hm.viterbi_time_sharded(S, lA, mu, sig, 5, chunk_len=4096, warmup=512)
     assert np.array_equal(x, x_ref) and abs(ll - ll_ref) <= 1e-9 * abs(ll_ref)
