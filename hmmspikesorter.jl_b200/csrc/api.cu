@@ -25,11 +25,14 @@ static int set_err(int code, const std::string &m) {
     return code;
 }
 
+static void begin_call();  // advances the cache epochs (entries used by the running call are never evicted)
+
 template <class F>
 static int guarded(F &&f) {
     std::lock_guard<std::mutex> lk(g_entry);
     try {
         g_err.clear();
+        begin_call();
         f();
         return HMM_OK;
     } catch (const Error &e) {
@@ -60,9 +63,11 @@ static void d2h(void *dst, const void *src, size_t bytes, cudaStream_t st) {
     HMM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
 }
 
+static void drop_caches();
+
 extern "C" {
 
-int hmm_version(void) { return 100; /* 0.1.0 */ }
+int hmm_version(void) { return 200; /* 0.2.0 */ }
 const char *hmm_last_error(void) { return g_err.c_str(); }
 
 int hmm_device_count(void) {
@@ -104,7 +109,15 @@ int hmm_set_ring_params(int64_t chunk_len, int64_t warmup) {
 }
 
 int hmm_release_workspace(void) {
-    return guarded([&] { workspace().release(); });
+    return guarded([&] {
+        cudaDeviceSynchronize();
+        drop_caches();
+        workspace().release();
+    });
+}
+
+int hmm_set_profiling(int on) {
+    return guarded([&] { ring_config().profile = on ? 1 : 0; });
 }
 
 int hmm_host_alloc(void **ptr_out, uint64_t bytes) {
@@ -130,29 +143,125 @@ namespace {
 struct BatchModels {
     std::vector<HostModel> models;
     FaithfulLayout layout;
-    char *blob_dev = nullptr;
+    char *blob_dev = nullptr;  // owned (cudaMalloc): stable for as long as the entry lives, graphs may refer to it
+    uint64_t id = 0;           // identity for the decode-program cache
+    uint64_t hash = 0, epoch = 0;
+    int dev = 0, C = 0, shared = 0, N = 0, K = 0, nstates = 0;
+    int64_t ntrans = 0;
+    std::vector<char> raw;     // copy of the caller's arrays: a hit is confirmed byte for byte
+    ~BatchModels() {
+        if (blob_dev) cudaFree(blob_dev);
+    }
 };
 
-void build_models(int C, const int16_t *states, int states_shared, int N, int K, int nstates, const hmm_trans *tr,
-                  int64_t ntrans, const double *mu, const double *sigma, BatchModels &B, cudaStream_t st) {
-    B.models.resize(C);
+// ---- model cache -------------------------------------------------------------------------------------------
+// Validating a StateMatrix, building its CSR forms, packing and uploading them costs tens of microseconds per
+// channel; callers decode many recordings (or one recording many times) with the same model.  Entries are keyed by
+// the bytes of the arrays that crossed the ABI (hash first, then compared byte for byte).
+std::vector<std::unique_ptr<BatchModels>> g_models;
+uint64_t g_model_seq = 0, g_call_epoch = 0;
+constexpr size_t MAX_MODELS = 48;
+
+inline uint64_t mix64(uint64_t h, const void *data, size_t n) {
+    const unsigned char *q = (const unsigned char *)data;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t w;
+        memcpy(&w, q + i, 8);
+        h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29;
+    }
+    uint64_t w = 0;
+    if (i < n) memcpy(&w, q + i, n - i);
+    h = (h ^ w ^ (uint64_t)n) * 0xBF58476D1CE4E5B9ull;
+    return h ^ (h >> 32);
+}
+
+BatchModels &get_models(int C, const int16_t *states, int states_shared, int N, int K, int nstates, const hmm_trans *tr,
+                        int64_t ntrans, const double *mu, const double *sigma, cudaStream_t st) {
+    if (!states || !tr || !mu || !sigma) fail(HMM_EINVAL, "null model array");
+    if (C < 1 || N < 1 || K < 1 || nstates < 1 || ntrans < 1) fail(HMM_EINVAL, "bad model sizes");
+    int dev = 0;
+    HMM_CUDA(cudaGetDevice(&dev));
+    const size_t b_st = sizeof(int16_t) * (size_t)N * nstates * (states_shared ? 1 : C);
+    const size_t b_tr = sizeof(hmm_trans) * (size_t)ntrans * C, b_mu = sizeof(double) * (size_t)K * N * C;
+    const size_t b_sg = sizeof(double) * (size_t)C;
+    uint64_t h = 0x1234567ull + (uint64_t)dev;
+    h = mix64(h, states, b_st);
+    h = mix64(h, tr, b_tr);
+    h = mix64(h, mu, b_mu);
+    h = mix64(h, sigma, b_sg);
+    for (auto &q : g_models) {
+        if (q->hash != h || q->dev != dev || q->C != C || q->shared != states_shared || q->N != N || q->K != K ||
+            q->nstates != nstates || q->ntrans != ntrans || q->raw.size() != b_st + b_tr + b_mu + b_sg)
+            continue;
+        const char *r = q->raw.data();
+        if (memcmp(r, states, b_st) || memcmp(r + b_st, tr, b_tr) || memcmp(r + b_st + b_tr, mu, b_mu) ||
+            memcmp(r + b_st + b_tr + b_mu, sigma, b_sg))
+            continue;
+        q->epoch = g_call_epoch;
+        return *q;
+    }
+    std::unique_ptr<BatchModels> B(new BatchModels);
+    B->models.resize(C);
     for (int c = 0; c < C; c++) {
         const int16_t *stc = states_shared ? states : states + (size_t)c * N * nstates;
         analyse_model(stc, N, K, nstates, tr + (size_t)c * ntrans, ntrans, mu + (size_t)c * K * N, sigma[c],
-                      B.models[c]);
-        if (c > 0 && (B.models[c].in_ptr != B.models[0].in_ptr || B.models[c].in_src != B.models[0].in_src))
+                      B->models[c]);
+        if (c > 0 && (B->models[c].in_ptr != B->models[0].in_ptr || B->models[c].in_src != B->models[0].in_src))
             fail(HMM_EINVAL, "channel %d has a different transition topology than channel 0", c);
     }
-    B.layout = faithful_layout(nstates, ntrans);
-    // packed into a pinned staging buffer (slot 2; every entry point synchronises before it returns, so the
-    // buffer is free again by the next call): the upload is asynchronous and the kernels simply follow it
-    const size_t bytes = (size_t)C * B.layout.bytes;
+    B->layout = faithful_layout(nstates, ntrans);
+    // packed into a pinned staging buffer (slot 2) so that the upload is asynchronous; the stream is synchronised
+    // before the staging buffer can be reused (every entry point synchronises before it returns)
+    const size_t bytes = (size_t)C * B->layout.bytes;
     char *host = (char *)workspace().pinned(2, bytes);
     memset(host, 0, bytes);
-    for (int c = 0; c < C; c++) faithful_pack(B.models[c], B.layout, host + (size_t)c * B.layout.bytes);
-    B.blob_dev = (char *)workspace().get(Workspace::MODEL, bytes);
-    HMM_CUDA(cudaMemcpyAsync(B.blob_dev, host, bytes, cudaMemcpyHostToDevice, st));
+    for (int c = 0; c < C; c++) faithful_pack(B->models[c], B->layout, host + (size_t)c * B->layout.bytes);
+    cudaError_t e = cudaMalloc((void **)&B->blob_dev, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        B->blob_dev = nullptr;
+        fail(HMM_ENOMEM, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    HMM_CUDA(cudaMemcpyAsync(B->blob_dev, host, bytes, cudaMemcpyHostToDevice, st));
+    HMM_CUDA(cudaStreamSynchronize(st));  // once per model: the staging buffer is free again
+    B->raw.resize(b_st + b_tr + b_mu + b_sg);
+    memcpy(B->raw.data(), states, b_st);
+    memcpy(B->raw.data() + b_st, tr, b_tr);
+    memcpy(B->raw.data() + b_st + b_tr, mu, b_mu);
+    memcpy(B->raw.data() + b_st + b_tr + b_mu, sigma, b_sg);
+    B->hash = h; B->dev = dev; B->C = C; B->shared = states_shared; B->N = N; B->K = K; B->nstates = nstates;
+    B->ntrans = ntrans;
+    B->id = ++g_model_seq;
+    B->epoch = g_call_epoch;
+    if (g_models.size() >= MAX_MODELS) {  // least recently used entry of an earlier call (none of its work is in flight)
+        size_t victim = g_models.size();
+        for (size_t k = 0; k < g_models.size(); k++)
+            if (g_models[k]->epoch < g_call_epoch && (victim == g_models.size() || g_models[k]->epoch < g_models[victim]->epoch))
+                victim = k;
+        if (victim < g_models.size()) {
+            // decode programs refer to the model's device blob: they go with it
+            ring_drop_programs();
+            g_models.erase(g_models.begin() + victim);
+        }
+    }
+    g_models.push_back(std::move(B));
+    return *g_models.back();
 }
+
+}  // namespace
+
+static void begin_call() {
+    g_call_epoch++;
+    ring_new_epoch();
+}
+static void drop_caches() {
+    ring_drop_programs();
+    g_models.clear();
+}
+
+namespace {
 
 // Core decode on device-resident y / x.
 void viterbi_core(const double *y_dev, int64_t T, int C, BatchModels &B, int16_t *x_dev, double *ll_host,
@@ -170,15 +279,15 @@ void viterbi_core(const double *y_dev, int64_t T, int C, BatchModels &B, int16_t
         engine = HMM_MODE_RING;
     } else
         engine = (all_ring && ring_supported(M0, T) && T >= 32768) ? HMM_MODE_RING : HMM_MODE_FAITHFUL;
-    double *ll_dev = nullptr;
-    if (ll_host) ll_dev = (double *)workspace().get(Workspace::SCRATCH, sizeof(double) * C);
     if (info) info->engine = engine;
-    if (engine == HMM_MODE_FAITHFUL)
+    if (engine == HMM_MODE_FAITHFUL) {
+        double *ll_dev = nullptr;
+        if (ll_host) ll_dev = (double *)workspace().get(Workspace::SCRATCH, sizeof(double) * C);
         faithful_viterbi_run(y_dev, T, T, C, B.layout, B.blob_dev, M0, x_dev, T, ll_dev, T1_dev, T2_dev,
                              want_trellis ? T : 0, false, nullptr, st, info);
-    else
-        ring_viterbi_run(y_dev, T, T, C, B.models, B.layout, B.blob_dev, x_dev, T, ll_dev, st, info);
-    if (ll_host) d2h(ll_host, ll_dev, sizeof(double) * C, st);
+        if (ll_host) d2h(ll_host, ll_dev, sizeof(double) * C, st);
+    } else  // synchronises the stream once and leaves ll / the repair counts in ll_host / info
+        ring_viterbi_run(y_dev, T, T, C, B.models, B.layout, B.blob_dev, B.id, x_dev, T, ll_host, st, info, nullptr);
 }
 
 // traceback state codes carry a chain entry time (code = 8*t0 + neuron, -1 = noise)
@@ -325,7 +434,7 @@ void viterbi_host_pipelined(const double *y, int64_t T, BatchModels &B, int16_t 
     }
     arena_cap += arena_cap / 8;
     char *arena = (char *)ws.get(Workspace::TRACE, arena_cap);
-    double *ll_dev = (double *)ws.get(Workspace::SCRATCH, sizeof(double) * 1024);
+    double *ll_dev = (double *)ws.get(Workspace::SCRATCH, sizeof(double) * 1024);  // [0] ll, [8..600) partials, then counters
     size_t arena_off = 0;
     for (auto &g : seg) {
         HMM_CUDA(cudaEventCreateWithFlags(&g.ev_copy, cudaEventDisableTiming));
@@ -473,8 +582,7 @@ int viterbi_host(const double *y, int64_t T, int C, const int16_t *states, int s
         Workspace &ws = workspace();
         Timer tall(st);
         tall.start();
-        BatchModels B;
-        build_models(C, states, states_shared, N, K, nstates, tr, ntrans, mu, sigma, B, st);
+        BatchModels &B = get_models(C, states, states_shared, N, K, nstates, tr, ntrans, mu, sigma, st);
         if (!T1_out && !T2_out && mode != HMM_MODE_FAITHFUL && ring_supported(B.models[0], T) &&
             pipeline_wanted(B.models[0], T, C)) {
             viterbi_host_pipelined(y, T, B, x_out, ll_out, info);
@@ -498,7 +606,7 @@ int viterbi_host(const double *y, int64_t T, int C, const int16_t *states, int s
                     HMM_CUDA(cudaEventCreateWithFlags(&evc[c], cudaEventDisableTiming));
                     HMM_CUDA(cudaEventCreateWithFlags(&evx[c], cudaEventDisableTiming));
                 }
-                double *ll_dev = ll_out ? (double *)ws.get(Workspace::SCRATCH, sizeof(double) * C) : nullptr;
+                std::vector<RingPending> pend;
                 auto copy_in = [&](int c) {
                     HMM_CUDA(cudaMemcpyAsync(y_dev + (size_t)c * T, y + (size_t)c * T, sizeof(double) * (size_t)T,
                                              cudaMemcpyHostToDevice, sh));
@@ -515,17 +623,17 @@ int viterbi_host(const double *y, int64_t T, int C, const int16_t *states, int s
                         HMM_CUDA(cudaStreamWaitEvent(st, evc[c], 0));
                         std::vector<HostModel> one(1, B.models[c]);
                         ring_viterbi_run(y_dev + (size_t)c * T, T, T, 1, one, B.layout, B.blob_dev + (size_t)c * B.layout.bytes,
-                                         x_dev + (size_t)c * T, T, ll_dev ? ll_dev + c : nullptr, st, nullptr);
+                                         B.id, x_dev + (size_t)c * T, T, ll_out ? ll_out + c : nullptr, st, nullptr, &pend);
                         HMM_CUDA(cudaEventRecord(evx[c], st));
                         if (c + 1 < C) copy_in(c + 1);
                         if (c >= 1) copy_out(c - 1);
                     }
                     copy_out(C - 1);
-                    if (ll_out) d2h(ll_out, ll_dev, sizeof(double) * C, st);
                     tall.stop();
                     HMM_CUDA(cudaStreamSynchronize(st));
                     HMM_CUDA(cudaStreamSynchronize(sd));
                     HMM_CUDA(cudaStreamSynchronize(sh));
+                    ring_collect(pend);
                 } catch (...) {
                     cudaDeviceSynchronize();
                     for (int c = 0; c < C; c++) {
@@ -541,7 +649,7 @@ int viterbi_host(const double *y, int64_t T, int C, const int16_t *states, int s
                 if (info) {
                     info->engine = HMM_MODE_RING;
                     info->device_ms = tall.ms();
-                    info->kernel_launches = (int64_t)C * 10;
+                    info->kernel_launches = (int64_t)C * (ll_out ? 6 : 5);
                 }
                 return;
             }
@@ -601,8 +709,7 @@ int hmm_viterbi_dev_f64(const double *y_dev, int64_t T, int32_t C, const int16_t
         if (T < 1 || C < 1) fail(HMM_EINVAL, "T and C must be positive");
         require_device();
         cudaStream_t st = main_stream();
-        BatchModels B;
-        build_models(C, states, states_shared, N, K, nstates, tr, ntrans, mu, sigma, B, st);
+        BatchModels &B = get_models(C, states, states_shared, N, K, nstates, tr, ntrans, mu, sigma, st);
         Timer tk(st);
         tk.start();
         viterbi_core(y_dev, T, C, B, x_dev, ll_out, nullptr, nullptr, mode, st, info);
@@ -941,8 +1048,7 @@ static int fb_host(bool backward, const double *V, int64_t T, const int16_t *sta
         require_device();
         cudaStream_t st = main_stream();
         Workspace &ws = workspace();
-        BatchModels B;
-        build_models(1, states, 1, N, K, nstates, tr, ntrans, mu, &sigma, B, st);
+        BatchModels &B = get_models(1, states, 1, N, K, nstates, tr, ntrans, mu, &sigma, st);
         double *V_dev = (double *)ws.get(Workspace::Y, sizeof(double) * (size_t)T);
         double *o_dev = (double *)ws.get(backward ? Workspace::BETA : Workspace::ALPHA,
                                          sizeof(double) * (size_t)T * nstates);

@@ -31,13 +31,30 @@ void faithful_fb_run(bool backward, const double *V_dev, int64_t T, const Faithf
 struct RingConfig {
     int64_t chunk_len = 0;  // 0 = auto
     int64_t warmup = 0;     // 0 = default
+    int profile = 0;        // hmm_set_profiling: eager launches with per-kernel event timers instead of a CUDA graph
 };
 RingConfig &ring_config();
 bool ring_supported(const HostModel &M, int64_t T);
-// models[C] must share topology (N, K).  Leaves x in x_dev; ll via path scoring.
+// Results of a decode that has been launched but not yet synchronised with: ll and the repair counts sit in
+// mapped pinned memory (res_h: [C x 4] doubles) and are handed to the caller by ring_collect after the
+// stream has been synchronised.
+struct RingPending {
+    const double *res_h;
+    int C;
+    double *ll_host;  // nullable
+    hmm_info *info;   // nullable
+};
+void ring_collect(std::vector<RingPending> &pend);
+void ring_new_epoch();      // called once per C-ABI entry: programs used by the current call are never evicted
+void ring_drop_programs();  // frees every cached decode program (hmm_release_workspace)
+// models[C] must share topology (N, K).  Leaves x in x_dev; ll (nullable, HOST pointer) via path scoring.
+// model_id != 0 identifies (models, blob_dev) for the program cache: a repeated decode of the same buffers with the
+// same model re-launches one CUDA graph.  Without `defer` the call synchronises the stream once and delivers ll /
+// info; with it, the caller synchronises and calls ring_collect (many channels per call).
 void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, const std::vector<HostModel> &models,
-                      const FaithfulLayout &L, const char *blob_dev, int16_t *x_dev, int64_t x_stride, double *ll_dev,
-                      cudaStream_t st, hmm_info *info);
+                      const FaithfulLayout &L, const char *blob_dev, uint64_t model_id, int16_t *x_dev,
+                      int64_t x_stride, double *ll_host, cudaStream_t st, hmm_info *info,
+                      std::vector<RingPending> *defer);
 
 // Staged decode (used directly by the time-shard API in api.cu).
 struct VitParams;
@@ -56,6 +73,10 @@ class VitPlan {
     void trace(cudaStream_t st);
     void verify_trace(cudaStream_t st);  // boundary check + repair
     void path_ll(cudaStream_t st, double *ll_dev, int64_t t_lo, int64_t t_hi, int64_t t_off, int64_t T_glob, bool with_p0);
+    void run_all(cudaStream_t st, bool want_ll, Timer *ttop);  // the whole decode: six launches
+    void set_result_sink(double *res_dev_alias);  // [C x 4] mapped pinned memory the kernels leave ll / repair counts in
+    void retarget(const double *y_dev, int16_t *x_dev);
+    double *ll_dev() { return ll_dev_; }
     void read_counters(cudaStream_t st, int *fwd_rep, int *bwd_rep);
     void reset_counters(cudaStream_t st);
     int nchunks() const;
@@ -78,7 +99,7 @@ class VitPlan {
     HostModel M0;
     FaithfulLayout FL;
     const char *blob_dev = nullptr;
-    double *part = nullptr;
+    double *part = nullptr, *ll_dev_ = nullptr;
     int C = 1;
     char *arena_base = nullptr;
     size_t arena_cap = 0, arena_used = 0;

@@ -78,6 +78,11 @@ int hmm_set_ring_params(int64_t chunk_len, int64_t warmup);
  * for the next call; a pageable-host decode of T samples leaves 10 T bytes of pinned staging behind). */
 int hmm_release_workspace(void);
 
+/* Repeated decodes of the same device buffers with the same model re-launch one cached CUDA graph (no per-kernel
+ * timing possible).  hmm_set_profiling(1) makes the calling process launch eagerly with CUDA-event timers instead, so
+ * that hmm_info.top_kernel_ms is filled (benchmarks / roofline reports); 0 restores the default. */
+int hmm_set_profiling(int on);
+
 /* ---- Viterbi ------------------------------------------------------------- */
 /*
  * viterbi(y, lA::StateMatrix, mu, sigma) -> (x, ll)       src/viterbi.jl:44-98
