@@ -737,7 +737,20 @@ struct hmm_vshard {
     int device = 0;
     int last_fwd_rep = 0, last_bwd_rep = 0;
     std::vector<void *> owned;
+    // peer-memory exchange (hmm_vshard_p2p_*)
+    int rank = -1, world = 0;
+    char *xblock = nullptr;                  // this rank's exchange block (flags + summaries, double-buffered)
+    char **peers_dev = nullptr;              // device array [world]: every rank's exchange block
+    std::vector<void *> ipc_opened;          // peers' blocks opened through CUDA IPC (closed on destroy)
+    unsigned long long *epoch_dev = nullptr; // decode counter (parity selects the buffer)
+    double *out_h = nullptr, *out_d = nullptr;  // mapped pinned: [total ll, inconsistent boundaries]
+    cudaGraphExec_t p2p_exec = nullptr;
+    int16_t *p2p_x = nullptr;
+    int p2p_runs = 0;
     ~hmm_vshard() {
+        if (p2p_exec) cudaGraphExecDestroy(p2p_exec);
+        for (void *q : ipc_opened) cudaIpcCloseMemHandle(q);
+        if (out_h) cudaFreeHost(out_h);
         for (void *q : owned) cudaFree(q);
     }
 };
@@ -1015,6 +1028,137 @@ int hmm_vshard_judge_dev(hmm_vshard *h, const double *gathered_dev, int32_t n_ra
         shard_dev(h);
         if (!gathered_dev || !out_dev || n_ranks < 1) fail(HMM_EINVAL, "bad judge arguments");
         vshard_judge_run(gathered_dev, n_ranks, h->plan.bvec(), out_dev, main_stream());
+    });
+}
+
+// ---- peer-memory protocol: summaries travel by direct stores into every peer's exchange block ---------------
+int hmm_vshard_p2p_init(hmm_vshard *h, int32_t rank, int32_t world, void *ipc_handle_out, void **block_ptr_out) {
+    return guarded([&] {
+        shard_dev(h);
+        if (rank < 0 || world < 1 || rank >= world || world > 64) fail(HMM_EINVAL, "bad rank / world");
+        if (h->xblock) fail(HMM_EINVAL, "p2p already initialised for this shard");
+        cudaStream_t st = main_stream();
+        const size_t bytes = vshard_exchange_block_bytes(world, h->plan.bvec());
+        h->xblock = (char *)shard_alloc(h, bytes);
+        h->peers_dev = (char **)shard_alloc(h, sizeof(char *) * (size_t)world);
+        h->epoch_dev = (unsigned long long *)shard_alloc(h, sizeof(unsigned long long));
+        HMM_CUDA(cudaMemsetAsync(h->xblock, 0, bytes, st));
+        HMM_CUDA(cudaMemsetAsync(h->epoch_dev, 0, sizeof(unsigned long long), st));
+        HMM_CUDA(cudaHostAlloc((void **)&h->out_h, 2 * sizeof(double), cudaHostAllocMapped));
+        HMM_CUDA(cudaHostGetDevicePointer((void **)&h->out_d, h->out_h, 0));
+        h->out_h[0] = h->out_h[1] = 0.0;
+        HMM_CUDA(cudaStreamSynchronize(st));
+        h->rank = rank;
+        h->world = world;
+        if (ipc_handle_out) {
+            cudaIpcMemHandle_t hd;
+            HMM_CUDA(cudaIpcGetMemHandle(&hd, h->xblock));
+            static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+            memcpy(ipc_handle_out, &hd, sizeof hd);
+        }
+        if (block_ptr_out) *block_ptr_out = h->xblock;
+    });
+}
+
+int hmm_vshard_p2p_attach(hmm_vshard *h, const void *ipc_handles, void *const *block_ptrs) {
+    return guarded([&] {
+        shard_dev(h);
+        if (!h->xblock) fail(HMM_EINVAL, "hmm_vshard_p2p_init first");
+        if (!ipc_handles && !block_ptrs) fail(HMM_EINVAL, "need IPC handles (other processes) or block pointers (this process)");
+        std::vector<char *> peers((size_t)h->world, nullptr);
+        for (int r = 0; r < h->world; r++) {
+            if (r == h->rank) {
+                peers[r] = h->xblock;
+            } else if (block_ptrs) {
+                peers[r] = (char *)block_ptrs[r];
+                // same process, possibly another device: make its memory reachable from this one
+                cudaPointerAttributes a;
+                HMM_CUDA(cudaPointerGetAttributes(&a, peers[r]));
+                if (a.device != h->device) {
+                    int can = 0;
+                    HMM_CUDA(cudaDeviceCanAccessPeer(&can, h->device, a.device));
+                    if (!can) fail(HMM_EUNSUPPORTED, "device %d cannot access device %d's memory", h->device, a.device);
+                    cudaError_t e = cudaDeviceEnablePeerAccess(a.device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) HMM_CUDA(e);
+                    cudaGetLastError();
+                }
+            } else {
+                cudaIpcMemHandle_t hd;
+                memcpy(&hd, (const char *)ipc_handles + (size_t)r * sizeof hd, sizeof hd);
+                void *q = nullptr;
+                HMM_CUDA(cudaIpcOpenMemHandle(&q, hd, cudaIpcMemLazyEnablePeerAccess));
+                h->ipc_opened.push_back(q);
+                peers[r] = (char *)q;
+            }
+        }
+        cudaStream_t st = main_stream();
+        HMM_CUDA(cudaMemcpyAsync(h->peers_dev, peers.data(), sizeof(char *) * peers.size(), cudaMemcpyHostToDevice, st));
+        HMM_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+static void p2p_local_sequence(hmm_vshard *h, int16_t *x_main_dev, cudaStream_t st) {
+    const int64_t lo = h->main_begin - h->local_begin, hi = h->main_end - h->local_begin;
+    h->plan.forward(st, nullptr);
+    h->plan.verify_fwd(st);
+    h->plan.trace(st);
+    h->plan.verify_trace(st);
+    h->plan.path_ll(st, h->ll_dev, lo, hi, h->local_begin, h->T_global, h->first);
+    vshard_exchange_run(h->last ? nullptr : h->plan.eb_ptr(h->c_main1 - 1), h->first ? nullptr : h->plan.sb_ptr(h->c_main0),
+                        h->first ? nullptr : h->plan.own_start_ptr(h->c_main0),
+                        h->last ? nullptr : h->plan.own_start_ptr(h->c_main1), h->ll_dev, 8 * (long long)h->local_begin,
+                        h->plan.bvec(), h->peers_dev, h->rank, h->world, h->epoch_dev, st);
+    if (x_main_dev)
+        HMM_CUDA(cudaMemcpyAsync(x_main_dev, h->x_loc + lo, sizeof(int16_t) * (size_t)(hi - lo), cudaMemcpyDeviceToDevice, st));
+}
+
+int hmm_vshard_p2p_launch(hmm_vshard *h, int16_t *x_main_dev) {
+    return guarded([&] {
+        shard_dev(h);
+        if (!h->peers_dev || h->rank < 0) fail(HMM_EINVAL, "hmm_vshard_p2p_init / attach first");
+        cudaStream_t st = main_stream();
+        const bool no_graph = getenv("HMMCUDA_NO_GRAPH") && atoi(getenv("HMMCUDA_NO_GRAPH"));
+        h->p2p_runs++;
+        if (!no_graph && h->p2p_runs >= 2) {
+            if (h->p2p_exec && h->p2p_x != x_main_dev) {
+                cudaGraphExecDestroy(h->p2p_exec);
+                h->p2p_exec = nullptr;
+            }
+            if (!h->p2p_exec) {
+                cudaGraph_t graph = nullptr;
+                HMM_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                try {
+                    p2p_local_sequence(h, x_main_dev, st);
+                } catch (...) {
+                    cudaStreamEndCapture(st, &graph);
+                    if (graph) cudaGraphDestroy(graph);
+                    throw;
+                }
+                HMM_CUDA(cudaStreamEndCapture(st, &graph));
+                cudaError_t e = cudaGraphInstantiate(&h->p2p_exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (e != cudaSuccess) {
+                    h->p2p_exec = nullptr;
+                    fail(HMM_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+                }
+                h->p2p_x = x_main_dev;
+            }
+            HMM_CUDA(cudaGraphLaunch(h->p2p_exec, st));
+        } else
+            p2p_local_sequence(h, x_main_dev, st);
+    });
+}
+
+int hmm_vshard_p2p_finish(hmm_vshard *h, double *ll_total_out, int32_t *bad_out) {
+    return guarded([&] {
+        shard_dev(h);
+        if (!h->peers_dev) fail(HMM_EINVAL, "hmm_vshard_p2p_init / attach first");
+        cudaStream_t st = main_stream();
+        vshard_judge_p2p_run(h->xblock, h->world, h->plan.bvec(), h->epoch_dev, h->out_d, st);
+        HMM_CUDA(cudaStreamSynchronize(st));
+        if (h->out_h[1] < 0) fail(HMM_ECUDA, "time-sharded decode: a peer's boundary summary never arrived (2 s)");
+        if (ll_total_out) *ll_total_out = h->out_h[0];
+        if (bad_out) *bad_out = (int32_t)h->out_h[1];
     });
 }
 

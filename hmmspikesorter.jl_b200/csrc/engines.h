@@ -101,10 +101,19 @@ class VitPlan {
     const char *blob_dev = nullptr;
     double *part = nullptr, *ll_dev_ = nullptr;
     int C = 1;
+    bool per_channel = false;  // long recordings: every channel is launched on its own (see run_all)
+    int launch_C() const;
     char *arena_base = nullptr;
     size_t arena_cap = 0, arena_used = 0;
 };
 void vshard_judge_run(const double *gathered_dev, int n_ranks, int bvec, double *out_dev, cudaStream_t st);
+// peer-memory exchange of the shard summaries (see ring_viterbi.cu)
+size_t vshard_exchange_block_bytes(int world, int bvec);
+void vshard_exchange_run(const double *eb_last, const double *sb_first, const long long *own_first,
+                         const long long *own_ghost, const double *ll, long long shift, int bvec, char *const *peers_dev,
+                         int rank, int world, const unsigned long long *epoch_dev, cudaStream_t st);
+void vshard_judge_p2p_run(char *own_block, int world, int bvec, unsigned long long *epoch_dev, double *out_mapped,
+                          cudaStream_t st);
 void ring_path_ll_run(const double *y_dev, int64_t T, const FaithfulLayout &FL, const char *blob_dev, const HostModel &M0,
                       const int16_t *x_dev, double *ll_dev, double *part, cudaStream_t st);
 // Default chunk length / warm-up for a recording of T_total samples decoded on n_gpus GPUs.

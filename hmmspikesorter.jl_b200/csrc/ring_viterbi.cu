@@ -138,6 +138,7 @@ struct VitParams {
     int dbg_flag_every;    // > 0: the boundary checks also flag every k-th chunk (tests force the repair paths with it)
     unsigned *sync_cnt;    // [C x 4] arrival counters of the fused check+repair kernels ("last CTA continues"), self-resetting
     double *res_host;      // [C x 4] device alias of mapped pinned host memory: ll, chunks repaired (forward, traceback); nullable
+    int ch0;               // channel offset of this launch (long recordings: one channel per launch out of a C-channel plan)
 };
 
 enum StartKind { START_PROLOGUE = 0, START_SPEC = 1, START_EXACT = 2 };
@@ -180,7 +181,7 @@ struct CtaModel {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) ring_vit_prologue(VitParams p, int q_in_smem) {
     extern __shared__ __align__(16) double psm[];
-    const int ch = blockIdx.x;
+    const int ch = blockIdx.x + p.ch0;
     const int ns = p.ns, N = p.RL.N, L = p.RL.L, cols = L + 1, ND = N + 1;
     const char *mb = p.fblob + (size_t)ch * p.fblob_stride;
     const double *sc = (const double *)(mb + p.FL.scal);
@@ -361,9 +362,27 @@ struct SlotSmem {  // one chunk slot of the warp-specialised kernel, in doubles
     static constexpr int DOUBLES = BAR + 4;
 };
 
+// Number of super-windows the forward pass of chunk c covers (0 if there is no such chunk).
+__device__ __forceinline__ int chunk_superwindows(const VitParams &p, int c, int SW) {
+    if (c >= p.nchunks) return 0;
+    const int64_t s = (int64_t)c * p.Lc;
+    int64_t e = s + p.Lc;
+    if (c == p.nchunks - 1 || e > p.T) e = p.T;
+    int64_t base0 = (c == 0 && p.first_prologue) ? 0 : s - p.W;
+    if (base0 < 0) base0 = 0;
+    return (int)((e - base0 + SW - 1) / SW);
+}
+
+// The two FIR producers that share an SM sub-partition meet at a named barrier once per super-window.
+__device__ __forceinline__ void pair_sync(int bar_id) {
+    asm volatile("bar.sync %0, 64;\n" ::"r"(bar_id) : "memory");
+}
+
 template <int N, int R, int LPC, int ROLE>
 __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coef, int ch, int c, int kind,
-                                  const double *mdl /*smem model*/, double *ws /*per-warp or per-slot smem*/) {
+                                  const double *mdl /*smem model*/, double *ws /*per-warp or per-slot smem*/,
+                                  int pair_bar = 0 /*named barrier shared with the partner producer, 0 = none*/,
+                                  int pair_nsw = 0 /*super-windows of the longer chunk of the pair*/) {
     using G = FirGeom<R>;
     constexpr int NP = (N + 1) & ~1;
     const int lane = threadIdx.x & 31;
@@ -385,6 +404,10 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
     const double *cL = mdl + RL.cL;
     const double *y = p.y + (size_t)ch * p.y_stride;
     const int64_t T = p.T;
+    if (ROLE == ROLE_FIR && c >= p.nchunks) {  // no chunk of its own: keep the partner's barrier company
+        for (int k = 0; k < pair_nsw; k++) pair_sync(pair_bar);
+        return;
+    }
     const int64_t s = (int64_t)c * p.Lc;                 // main range [s, e)
     int64_t e = s + p.Lc;
     const bool last = (c == p.nchunks - 1);
@@ -450,6 +473,10 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
 #ifdef HMM_PHASE_TIMING
             const long long q1 = clock64();
 #endif
+            // Both producers of an SM sub-partition start their FIR together: the warp scheduler otherwise lets one
+            // of them run ahead at nearly full rate while the other crawls (measured: 4.5 k vs 8.5 k cycles per
+            // super-window), and with one chunk per slot the kernel lasts as long as its slowest slot.
+            if (pair_bar) pair_sync(pair_bar);
             mbar_wait(bar_empty + buf, ((k >> 1) & 1) ^ 1);  // the consumer is done with this F tile
 #ifdef HMM_PHASE_TIMING
             const long long q2 = clock64();
@@ -471,6 +498,8 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
             printf("producer %d: %d super-windows, staging %lld, wait-for-empty %lld, FIR %lld cyc/sw\n", c, k,
                    pt_stage / (k ? k : 1), pt_wait / (k ? k : 1), pt_fir / (k ? k : 1));
 #endif
+        if (pair_bar)
+            for (; k < pair_nsw; k++) pair_sync(pair_bar);  // the partner's chunk is longer
         return;
     }
     // decision words / mask words of this chunk's first super-window: indexed with 32-bit relative steps below
@@ -759,26 +788,34 @@ __device__ void load_model_smem(const VitParams &p, int ch, double *mdl) {
     __syncthreads();
 }
 
-// Warp-specialised forward kernel: 8 warps = 4 chunk slots x {FIR producer, recursion consumer}.
-template <int N, int R, int LPC>
-__global__ void __launch_bounds__(256, 2)
+// Warp-specialised forward kernel: SLOTS chunk slots per CTA, each a {FIR producer, recursion consumer} warp pair.
+// SLOTS = 8: one CTA of 16 warps per SM -- the producers of slots s and s + 4 run on the same SM sub-partition and
+// advance in step (pair_sync); SLOTS = 4: two CTAs of 8 warps per SM (models whose slots are too large for 8).
+template <int N, int R, int LPC, int SLOTS>
+__global__ void __launch_bounds__(SLOTS * 64, SLOTS == 8 ? 1 : 2)
     ring_vit_forward_ws(const __grid_constant__ VitParams p, const __grid_constant__ FirCoef<N, LPC> coef) {
     extern __shared__ __align__(16) double smem_d[];
-    const int ch = blockIdx.y;
+    using G = FirGeom<R>;
+    const int ch = blockIdx.y + p.ch0;
     double *mdl = smem_d;
-    const int warp = warp_index_uniform(), slot = warp & 3;
+    const int warp = warp_index_uniform(), slot = warp & (SLOTS - 1);
     double *ws = smem_d + ((p.RL.hot + 1) & ~1) + (size_t)slot * SlotSmem<N, R>::DOUBLES;
-    if ((threadIdx.x & 31) == 0 && warp < 4) {
+    if ((threadIdx.x & 31) == 0 && warp < SLOTS) {
         uint64_t *bars = reinterpret_cast<uint64_t *>(ws + SlotSmem<N, R>::BAR);
         for (int k = 0; k < 4; k++) mbar_init(bars + k, 1);
     }
     load_model_smem<N, R>(p, ch, mdl);  // ends with __syncthreads(): barriers initialised, model staged
-    const int c = blockIdx.x * 4 + slot;
-    if (c >= p.nchunks) return;
+    const int c = blockIdx.x * SLOTS + slot;
     const int kind = (c == 0 && p.first_prologue) ? START_PROLOGUE : START_SPEC;
-    if (warp < 4)
-        vit_process_chunk<N, R, LPC, ROLE_FIR>(p, coef, ch, c, kind, mdl, ws);
-    else
+    if (warp < SLOTS) {
+        int pair_bar = 0, pair_nsw = 0;
+        if (SLOTS == 8) {
+            pair_bar = 1 + (slot & 3);
+            const int a = chunk_superwindows(p, c, G::SW), b = chunk_superwindows(p, blockIdx.x * SLOTS + (slot ^ 4), G::SW);
+            pair_nsw = a > b ? a : b;
+        }
+        vit_process_chunk<N, R, LPC, ROLE_FIR>(p, coef, ch, c, kind, mdl, ws, pair_bar, pair_nsw);
+    } else if (c < p.nchunks)
         vit_process_chunk<N, R, LPC, ROLE_DP>(p, coef, ch, c, kind, mdl, ws);
 }
 
@@ -833,6 +870,113 @@ __global__ void vshard_judge_kernel(const double *g, int n, int bvec, double *ou
     }
 }
 
+// ---- peer-memory exchange (time-sharded decode, one process or one rank per GPU) --------------------------
+// Every rank owns an "exchange block": [2][world] arrival flags (u64) followed by [2][world][slen] summaries,
+// double-buffered by decode parity.  After its local decode a rank stores its summary straight into EVERY
+// peer's block over NVLink (peer-mapped or CUDA-IPC pointers) and then raises its flag there with a system-
+// scope release; the judge kernel of each rank spins on the `world` flags of its own block, checks every shard
+// boundary and leaves [total ll, inconsistent boundaries] in mapped pinned host memory.  No NCCL call, no
+// host round trip between the decode and the verdict.  A rank cannot be two decodes ahead of a peer (its
+// judge needs that peer's summary of the current decode), so two buffers suffice.
+__device__ __forceinline__ size_t xchg_data_off(int world) { return ((size_t)2 * world * sizeof(unsigned long long) + 255) & ~size_t(255); }
+
+__global__ void __launch_bounds__(256)
+    vshard_exchange_kernel(const double *eb_last, const double *sb_first, const long long *own_first,
+                           const long long *own_ghost, const double *ll, long long shift, int bvec,
+                           char *const *peers /*[world] exchange blocks*/, int rank, int world,
+                           const unsigned long long *epoch) {
+    const int slen = 2 * bvec + 4;
+    const unsigned long long e = *epoch;
+    const int par = (int)(e & 1);
+    auto glob = [&](const long long *q) {
+        if (!q) return -2.0;
+        const long long v = *q;
+        return (double)(v >= 0 ? v + shift : v);  // < 2^53: exact
+    };
+    for (int q = 0; q < world; q++) {
+        double *dst = reinterpret_cast<double *>(peers[q] + xchg_data_off(world)) + ((size_t)par * world + rank) * slen;
+        for (int k = threadIdx.x; k < bvec; k += blockDim.x) {
+            dst[k] = eb_last ? eb_last[k] : 0.0;
+            dst[bvec + k] = sb_first ? sb_first[k] : 0.0;
+        }
+        if (threadIdx.x == 0) {
+            dst[2 * bvec + 0] = glob(own_first);
+            dst[2 * bvec + 1] = glob(own_ghost);
+            dst[2 * bvec + 2] = ll[0];
+            dst[2 * bvec + 3] = 0.0;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) {
+        unsigned long long *flag = reinterpret_cast<unsigned long long *>(peers[threadIdx.x]) + (size_t)par * world + rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(flag), "l"(e + 1) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    vshard_judge_p2p_kernel(char *own_block, int world, int bvec, unsigned long long *epoch, double *out /*mapped host*/,
+                            long long timeout_ns) {
+    __shared__ int bad[8], s_timeout;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned long long e = *epoch;
+    const int par = (int)(e & 1);
+    const int slen = 2 * bvec + 4;
+    if (threadIdx.x == 0) s_timeout = 0;
+    if (lane == 0) bad[w] = 0;
+    __syncthreads();
+    if (threadIdx.x < world) {
+        const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(own_block) + (size_t)par * world + threadIdx.x;
+        unsigned long long t0, t1, v;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(flag) : "memory");
+            if (v == e + 1) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if ((long long)(t1 - t0) > timeout_ns) {  // a peer never arrived (crashed rank, missing launch): report
+                s_timeout = 1;
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    const double *g = reinterpret_cast<const double *>(own_block + xchg_data_off(world)) + (size_t)par * world * slen;
+    if (!s_timeout)
+        for (int r = w; r < world - 1; r += (blockDim.x >> 5)) {
+            const double *left = g + (size_t)r * slen, *right = g + (size_t)(r + 1) * slen;
+            const bool okf = boundary_matches(right + bvec, left, bvec, lane);
+            const bool okt = left[2 * bvec + 1] == right[2 * bvec + 0];
+            if (lane == 0 && !(okf && okt)) bad[w]++;
+        }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ll = 0.0;
+        int nb = 0;
+        for (int r = 0; r < world; r++) ll += g[(size_t)r * slen + 2 * bvec + 2];
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) nb += bad[k];
+        out[0] = ll;
+        out[1] = s_timeout ? -1.0 : (double)nb;
+        *epoch = e + 1;
+    }
+}
+
+void vshard_exchange_run(const double *eb_last, const double *sb_first, const long long *own_first,
+                         const long long *own_ghost, const double *ll, long long shift, int bvec, char *const *peers_dev,
+                         int rank, int world, const unsigned long long *epoch_dev, cudaStream_t st) {
+    vshard_exchange_kernel<<<1, 256, 0, st>>>(eb_last, sb_first, own_first, own_ghost, ll, shift, bvec, peers_dev, rank,
+                                              world, epoch_dev);
+    HMM_CUDA(cudaGetLastError());
+}
+void vshard_judge_p2p_run(char *own_block, int world, int bvec, unsigned long long *epoch_dev, double *out_mapped,
+                          cudaStream_t st) {
+    vshard_judge_p2p_kernel<<<1, 256, 0, st>>>(own_block, world, bvec, epoch_dev, out_mapped, 2000000000LL);
+    HMM_CUDA(cudaGetLastError());
+}
+size_t vshard_exchange_block_bytes(int world, int bvec) {
+    return (((size_t)2 * world * sizeof(unsigned long long) + 255) & ~size_t(255)) + sizeof(double) * 2 * (size_t)world * (2 * bvec + 4);
+}
+
 void vshard_judge_run(const double *gathered_dev, int n_ranks, int bvec, double *out_dev, cudaStream_t st) {
     vshard_judge_kernel<<<1, 256, 0, st>>>(gathered_dev, n_ranks, bvec, out_dev);
     HMM_CUDA(cudaGetLastError());
@@ -861,7 +1005,7 @@ template <int N, int R>
 __global__ void __launch_bounds__(256) ring_vit_verify_fwd(VitParams p) {
     extern __shared__ __align__(16) double smem_d[];
     __shared__ int s_flag;
-    const int ch = blockIdx.y;
+    const int ch = blockIdx.y + p.ch0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int *flag = p.fwd_flag + (size_t)ch * p.nchunks;
     {
@@ -1114,7 +1258,7 @@ __device__ __forceinline__ long long state_from_xend(int j, int64_t T, int L) {
 template <int N>
 __global__ void __launch_bounds__(128) ring_vit_trace(VitParams p) {
     extern __shared__ __align__(16) uint32_t trsm[];
-    const int ch = blockIdx.y;
+    const int ch = blockIdx.y + p.ch0;
     const int warp = warp_index_uniform();
     uint32_t *tws = trsm + (size_t)warp * TR_WARP_U32;
     int16_t *t2s_all = reinterpret_cast<int16_t *>(trsm + (size_t)(blockDim.x >> 5) * TR_WARP_U32);
@@ -1146,7 +1290,7 @@ template <int N>
 __global__ void __launch_bounds__(128) ring_vit_verify_trace(VitParams p) {
     extern __shared__ __align__(16) uint32_t trsm[];
     __shared__ int s_flag;
-    const int ch = blockIdx.y;
+    const int ch = blockIdx.y + p.ch0;
     const size_t o = (size_t)ch * p.nchunks_t;
     {
         const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1209,11 +1353,11 @@ __global__ void __launch_bounds__(256)
                  FaithfulLayout L, int ns, int nt, const int16_t *__restrict__ x, int64_t x_stride,
                  double *__restrict__ partial /*[C x gridDim.x]*/, int64_t t_lo, int64_t t_hi, int64_t t_off,
                  int64_t T_glob, unsigned *sync_cnt /*[C x 4], slot 2*/, double *__restrict__ ll_out, int with_p0,
-                 double *res_host) {
+                 double *res_host, int ch0) {
     // steps t in [t_lo, t_hi) of this (local) buffer; global time = t + t_off, weights use T_glob
     extern __shared__ __align__(16) char llsm[];
     __shared__ int s_flag;
-    const int ch = blockIdx.y;
+    const int ch = blockIdx.y + ch0;
     const char *mb = blob + (size_t)ch * blob_stride;
     const double *sc = (const double *)(mb + L.scal);
     const double c_emit = sc[2], inv2s2 = 1.0 / sc[3];
@@ -1331,19 +1475,25 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------
+// Chunk slots per CTA: 8 (one 16-warp CTA per SM, paired producers) whenever 8 slots fit the 227 KB of shared memory.
+template <int N, int R>
+constexpr int fwd_slots() {
+    return (sizeof(double) * ((size_t)8 * SlotSmem<N, R>::DOUBLES + 1024) <= 220 * 1024) ? 8 : 4;
+}
 template <int N, int R, int LPC>
 static size_t fwd_smem_bytes(const RingLayout &RL) {
-    return sizeof(double) * (((RL.hot + 1) & ~1) + (size_t)4 * SlotSmem<N, R>::DOUBLES);
+    return sizeof(double) * (((RL.hot + 1) & ~1) + (size_t)fwd_slots<N, R>() * SlotSmem<N, R>::DOUBLES);
 }
 
 // Resident warps per SM of the forward kernel (sets the one-wave chunk count).
 template <int N, int R, int LPC>
 static int fwd_warps_per_sm(const RingLayout &RL) {
     const size_t sm_fwd = fwd_smem_bytes<N, R, LPC>(RL);
-    HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws<N, R, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+    constexpr int SLOTS = fwd_slots<N, R>();
+    HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws<N, R, LPC, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
     int nb = 0;
-    HMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ring_vit_forward_ws<N, R, LPC>, 256, sm_fwd));
-    return (nb > 0 ? nb : 1) * 4;  // chunk slots (producer/consumer warp pairs) per SM
+    HMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ring_vit_forward_ws<N, R, LPC, SLOTS>, SLOTS * 64, sm_fwd));
+    return (nb > 0 ? nb : 1) * SLOTS;  // chunk slots (producer/consumer warp pairs) per SM
 }
 
 static size_t prologue_smem(const VitParams &p, int *q_in_smem) {
@@ -1361,7 +1511,7 @@ static size_t trace_smem(const VitParams &p, int warps) {
 template <int N, int R, int LPC>
 static void stage_prepare(const VitParams &p) {
     const size_t sm_fwd = fwd_smem_bytes<N, R, LPC>(p.RL);
-    HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws<N, R, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+    HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws<N, R, LPC, fwd_slots<N, R>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
     int qs = 0;
     const size_t sm_pro = prologue_smem(p, &qs);
     if (sm_pro > 227 * 1024) fail(HMM_EUNSUPPORTED, "prologue does not fit shared memory");
@@ -1375,7 +1525,7 @@ static void stage_prepare(const VitParams &p) {
 template <int N, int R, int LPC>
 static void stage_forward(VitParams &p, const double *hmodel /*host ring model of channel 0*/, int C, cudaStream_t st,
                           Timer *ttop) {
-    constexpr int WPB = 4;
+    constexpr int WPB = fwd_slots<N, R>();
     const size_t sm_fwd = fwd_smem_bytes<N, R, LPC>(p.RL);
     FirCoef<N, LPC> coef{};
     if (LPC > 0)
@@ -1391,7 +1541,7 @@ static void stage_forward(VitParams &p, const double *hmodel /*host ring model o
         ring_vit_prologue<<<C, nth, sm_pro, st>>>(p, qs);
     }
     if (ttop) ttop->start();
-    ring_vit_forward_ws<N, R, LPC><<<gridc, 256, sm_fwd, st>>>(p, coef);
+    ring_vit_forward_ws<N, R, LPC, WPB><<<gridc, WPB * 64, sm_fwd, st>>>(p, coef);
     if (ttop) ttop->stop();
     HMM_CUDA(cudaGetLastError());
 }
@@ -1445,7 +1595,7 @@ static VitVariant pick_variant(int N, int L, bool const_ok) {
         case 2: return make_variant<2, 8, 0>();
         case 3:
             return pick_lp<3, 8>(L, const_ok);
-        case 4: return pick_lp<4, 8>(L, const_ok);
+        case 4: return pick_lp<4, 4>(L, const_ok);  // R = 4: eight chunk slots fit one SM's shared memory (R = 8: four)
         case 5: return pick_lp<5, 4>(L, const_ok);
         case 6: return make_variant<6, 4, 0>();
         case 7: return make_variant<7, 4, 0>();
@@ -1488,7 +1638,7 @@ void *VitPlan::alloc(int slot, size_t bytes) {
 
 int ring_default_chunking(const HostModel &M0, int64_t T_total, int C, int n_gpus, int64_t *Lc_out, int64_t *W_out) {
     const int N = M0.N, L = M0.K - 1;
-    const int R = (N <= 4) ? 8 : 4, SW = 32 * R;
+    const int R = (N <= 3) ? 8 : 4, SW = 32 * R;
     RingLayout RL = ring_layout(N, L);
     const bool no_const = getenv("HMMCUDA_NO_CONST_FIR") && atoi(getenv("HMMCUDA_NO_CONST_FIR")) != 0;
     const VitVariant variant = pick_variant(N, RL.L, C == 1 && !no_const);
@@ -1500,11 +1650,18 @@ int ring_default_chunking(const HostModel &M0, int64_t T_total, int C, int n_gpu
     if (const char *e = getenv("HMMCUDA_DEBUG_WARMUP")) W = (std::max<int64_t>(0, atoll(e)) / SW) * SW;
     int64_t Lc = ring_config().chunk_len;
     if (Lc <= 0) {
-        int dev = 0, sms = 148;
+        // (queried once per model shape: this runs on every decode call)
+        static thread_local int c_dev = -1, c_sms = 0, c_N = 0, c_L = 0, c_const = -1, c_wps = 0;
+        int dev = 0;
         HMM_CUDA(cudaGetDevice(&dev));
-        HMM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int is_const = (C == 1 && !no_const) ? 1 : 0;
+        if (dev != c_dev || N != c_N || L != c_L || is_const != c_const) {
+            HMM_CUDA(cudaDeviceGetAttribute(&c_sms, cudaDevAttrMultiProcessorCount, dev));
+            c_wps = variant.warps_per_sm(RL);
+            c_dev = dev; c_N = N; c_L = L; c_const = is_const;
+        }
         // one chunk per resident warp: a single, full wave over every GPU
-        const int64_t target_warps = (int64_t)sms * variant.warps_per_sm(RL) * (n_gpus > 0 ? n_gpus : 1);
+        const int64_t target_warps = (int64_t)c_sms * c_wps * (n_gpus > 0 ? n_gpus : 1);
         int64_t per_channel = (target_warps + C - 1) / C;
         Lc = (T_total + per_channel - 1) / per_channel;
         if (Lc < 4 * W) Lc = 4 * W;
@@ -1527,7 +1684,8 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     const int N = M0.N, L = M0.K - 1, ns = M0.nstates;
     RingLayout RL = ring_layout(N, L);
     const bool no_const = getenv("HMMCUDA_NO_CONST_FIR") && atoi(getenv("HMMCUDA_NO_CONST_FIR")) != 0;
-    impl->variant = pick_variant(N, RL.L, C == 1 && !no_const);
+    per_channel = C > 1 && T >= 262144 && !no_const;
+    impl->variant = pick_variant(N, RL.L, (C == 1 || per_channel) && !no_const);
     int nchunks = (int)((T + Lc - 1) / Lc);
     // the last chunk must be long enough to hold the final look-back of L steps
     if (nchunks > 1 && T - (int64_t)(nchunks - 1) * Lc < RING_Q) nchunks--;
@@ -1618,6 +1776,7 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     p.dbg_flag_every = getenv("HMMCUDA_DEBUG_FLAG_EVERY") ? atoi(getenv("HMMCUDA_DEBUG_FLAG_EVERY")) : 0;
     p.sync_cnt = (unsigned *)(base + o_sync);
     p.res_host = nullptr;
+    p.ch0 = 0;
     part = (double *)(base + o_part);
     ll_dev_ = (double *)(base + o_ll);
     impl->variant.prepare(p);
@@ -1627,11 +1786,12 @@ void VitPlan::forward(cudaStream_t st, Timer *ttop) {
     // A plan can be run repeatedly without clearing anything: the decision words and non-zero masks are written
     // for every step of every chunk's main range, the last chunk rewrites every Pfin slot the final state reads,
     // the repair counters are overwritten by every verification and the arrival counters re-arm themselves.
-    impl->variant.forward(*p_, hmdl.data(), C, st, ttop);
+    impl->variant.forward(*p_, hmdl.data() + (size_t)p_->ch0 * p_->RL.total, launch_C(), st, ttop);
 }
-void VitPlan::verify_fwd(cudaStream_t st) { impl->variant.verify_fwd(*p_, C, st); }
-void VitPlan::trace(cudaStream_t st) { impl->variant.trace(*p_, C, st); }
-void VitPlan::verify_trace(cudaStream_t st) { impl->variant.verify_trace(*p_, C, st); }
+void VitPlan::verify_fwd(cudaStream_t st) { impl->variant.verify_fwd(*p_, launch_C(), st); }
+void VitPlan::trace(cudaStream_t st) { impl->variant.trace(*p_, launch_C(), st); }
+void VitPlan::verify_trace(cudaStream_t st) { impl->variant.verify_trace(*p_, launch_C(), st); }
+int VitPlan::launch_C() const { return per_channel ? 1 : C; }
 
 static size_t ll_smem(const HostModel &M0) {
     return sizeof(double) * (2 * (size_t)M0.nstates + M0.ntrans) + sizeof(int) * (2 * (size_t)M0.nstates + 1 + M0.ntrans) + 16;
@@ -1641,10 +1801,10 @@ void VitPlan::path_ll(cudaStream_t st, double *ll_dev, int64_t t_lo, int64_t t_h
                       bool with_p0) {
     VitParams &p = *p_;
     const int nparts = 592;
-    ring_path_ll<<<dim3(nparts, C), 256, ll_smem(M0), st>>>(p.y, p.T, p.y_stride, blob_dev, FL.bytes, FL, M0.nstates,
+    ring_path_ll<<<dim3(nparts, launch_C()), 256, ll_smem(M0), st>>>(p.y, p.T, p.y_stride, blob_dev, FL.bytes, FL, M0.nstates,
                                                             (int)M0.ntrans, p.x, p.x_stride, part, t_lo, t_hi, t_off,
                                                             T_glob, p.sync_cnt, ll_dev ? ll_dev : ll_dev_,
-                                                            with_p0 ? 1 : 0, p.res_host);
+                                                            with_p0 ? 1 : 0, p.res_host, p.ch0);
     HMM_CUDA(cudaGetLastError());
 }
 
@@ -1657,7 +1817,7 @@ void ring_path_ll_run(const double *y_dev, int64_t T, const FaithfulLayout &FL, 
     HMM_CUDA(cudaMemsetAsync(cnt, 0, 4 * sizeof(unsigned), st));
     ring_path_ll<<<dim3(nparts, 1), 256, ll_smem(M0), st>>>(y_dev, T, T, blob_dev, FL.bytes, FL, M0.nstates,
                                                             (int)M0.ntrans, x_dev, T, scratch, 0, T, 0, T, cnt, ll_dev, 1,
-                                                            nullptr);
+                                                            nullptr, 0);
     HMM_CUDA(cudaGetLastError());
 }
 
@@ -1700,13 +1860,19 @@ double *VitPlan::eb_ptr(int chunk) { return p_->EB + (size_t)chunk * p_->bvec; }
 double *VitPlan::sb_ptr(int chunk) { return p_->SB + (size_t)chunk * p_->bvec; }
 long long *VitPlan::own_start_ptr(int chunk) { return p_->own_start + (size_t)chunk * p_->tfac; }
 
-// The whole decode of a plan: six launches, nothing else.
+// The whole decode of a plan: six launches (per channel, when the channels are long enough to fill the GPU on
+// their own: the FIR then takes its coefficients from the constant bank), nothing else.
 void VitPlan::run_all(cudaStream_t st, bool want_ll, Timer *ttop) {
-    forward(st, ttop);
-    verify_fwd(st);
-    trace(st);
-    verify_trace(st);
-    if (want_ll) path_ll(st, nullptr, 0, p_->T, 0, p_->T, true);
+    const int nrun = per_channel ? C : 1;
+    for (int k = 0; k < nrun; k++) {
+        p_->ch0 = per_channel ? k : 0;
+        forward(st, k == 0 ? ttop : nullptr);
+        verify_fwd(st);
+        trace(st);
+        verify_trace(st);
+        if (want_ll) path_ll(st, nullptr, 0, p_->T, 0, p_->T, true);
+    }
+    p_->ch0 = 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -1774,27 +1940,14 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
                       const FaithfulLayout &FL, const char *blob_dev, uint64_t model_id, int16_t *x_dev,
                       int64_t x_stride, double *ll_host, cudaStream_t st, hmm_info *info,
                       std::vector<RingPending> *defer) {
-    // Long recordings: one channel per launch (each already fills the GPU), which lets the
-    // FIR take its coefficients from the constant bank.
+    // Long recordings: one channel per LAUNCH (each already fills the GPU, and the FIR then takes its coefficients
+    // from the constant bank) out of one C-channel plan -- and one CUDA graph for all of them.
     const bool no_const = getenv("HMMCUDA_NO_CONST_FIR") && atoi(getenv("HMMCUDA_NO_CONST_FIR")) != 0;
+    const bool per_channel = C > 1 && T >= 262144 && !no_const;
     std::vector<RingPending> local;
     std::vector<RingPending> *pend = defer ? defer : &local;
-    if (C > 1 && T >= 262144 && !no_const) {
-        for (int ch = 0; ch < C; ch++) {
-            std::vector<HostModel> one(1, models[ch]);
-            // (model_id identifies the whole batch; channel ch of it is told apart by its y / x pointers)
-            ring_viterbi_run(y_dev + (size_t)ch * y_stride, T, y_stride, 1, one, FL, blob_dev + (size_t)ch * FL.bytes,
-                             model_id, x_dev + (size_t)ch * x_stride, x_stride, ll_host ? ll_host + ch : nullptr, st,
-                             info, pend);
-        }
-        if (!defer) {
-            HMM_CUDA(cudaStreamSynchronize(st));
-            ring_collect(local);
-        }
-        return;
-    }
     int64_t Lc = 0, W = 0;
-    ring_default_chunking(models[0], T, C, 1, &Lc, &W);
+    ring_default_chunking(models[0], T, per_channel ? 1 : C, 1, &Lc, &W);
     ProgKey key{};
     HMM_CUDA(cudaGetDevice(&key.dev));
     key.y = y_dev; key.x = x_dev; key.T = T; key.y_stride = y_stride; key.x_stride = x_stride; key.Lc = Lc; key.W = W;
@@ -1865,7 +2018,7 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
         prog->plan.run_all(st, want_ll, ttop);
     }
     if (info) {
-        info->kernel_launches += want_ll ? 6 : 5;
+        info->kernel_launches += (int64_t)(want_ll ? 6 : 5) * (per_channel ? C : 1);
         info->n_chunks = prog->plan.nchunks();
     }
     pend->push_back(RingPending{prog->res_h, C, ll_host, info});

@@ -181,6 +181,37 @@ class Shard:
         self._dev()
         check(lib().hmm_vshard_judge_dev(self._h, C.c_void_p(gathered_ptr), i32(n_ranks), C.c_void_p(out_ptr)))
 
+    # -- peer-memory protocol (hmm_vshard_p2p_*) ---------------------------------------------------------------
+    def p2p_init(self, rank: int, world: int):
+        """Allocates this shard's exchange block; returns (ipc_handle: 64 bytes, block_ptr: int)."""
+        self._dev()
+        hd = (C.c_ubyte * 64)()
+        ptr = C.c_void_p()
+        check(lib().hmm_vshard_p2p_init(self._h, i32(rank), i32(world), hd, C.byref(ptr)))
+        return bytes(hd), int(ptr.value)
+
+    def p2p_attach(self, ipc_handles=None, block_ptrs=None):
+        """ipc_handles: list of `world` 64-byte handles (shards in other processes); block_ptrs: list of `world`
+        device pointers (shards driven from this process)."""
+        self._dev()
+        if block_ptrs is not None:
+            arr = (C.c_void_p * len(block_ptrs))(*[C.c_void_p(int(q)) for q in block_ptrs])
+            check(lib().hmm_vshard_p2p_attach(self._h, None, arr))
+        else:
+            buf = b"".join(ipc_handles)
+            check(lib().hmm_vshard_p2p_attach(self._h, C.c_char_p(buf), None))
+
+    def p2p_launch(self, x_ptr):
+        self._dev()
+        check(lib().hmm_vshard_p2p_launch(self._h, C.c_void_p(x_ptr) if x_ptr else None))
+
+    def p2p_finish(self):
+        """(total ll, inconsistent shard boundaries) -- the decode's single synchronisation."""
+        self._dev()
+        ll, bad = f64(0), i32(0)
+        check(lib().hmm_vshard_p2p_finish(self._h, C.byref(ll), C.byref(bad)))
+        return ll.value, int(bad.value)
+
     def close(self):
         if self._h:
             self._dev()
@@ -253,7 +284,7 @@ class DistDecoder:
     stream cannot carry the library's work, so one is created when needed)."""
 
     def __init__(self, y_local_dev_ptr: int, span, T: int, chunk_len: int, warmup: int, lA, mu, sigma,
-                 x_main_dev_ptr: int, device, shard=None):
+                 x_main_dev_ptr: int, device, shard=None, protocol: str = "auto"):
         import torch
         import torch.distributed as dist
 
@@ -276,6 +307,19 @@ class DistDecoder:
         self.cnt = torch.zeros(1, dtype=i8, device=device)
         self._own_stream = None
         self.stats = {"decodes": 0, "fwd_rounds": 0, "trace_rounds": 0, "fallbacks": 0}
+        # Peer-memory protocol (the default on GPUs): the exchange blocks are opened once, through CUDA IPC -- the
+        # only collective it ever needs is this one-off all-gather of 64-byte handles.  "allgather": one NCCL
+        # all-gather of the summaries per decode (also what the CPU stand-in of the tests drives).
+        on_gpu = getattr(device, "type", "cuda") == "cuda"
+        self.p2p = protocol == "p2p" or (protocol == "auto" and on_gpu and hasattr(self.sh, "p2p_init"))
+        if self.p2p:
+            hd, _ = self.sh.p2p_init(self.rank, self.world)
+            if self.world > 1:
+                hs = [None] * self.world
+                dist.all_gather_object(hs, hd)
+            else:
+                hs = [hd]
+            self.sh.p2p_attach(ipc_handles=hs)
 
     # -- stream plumbing -------------------------------------------------------------------------------------
     def _enter_stream(self):
@@ -368,9 +412,13 @@ class DistDecoder:
         """One decode of the whole recording; returns the total ll (identical on every rank)."""
         tok = self._enter_stream()
         try:
-            self.local_decode()
-            self.gather_and_judge()
-            ll, bad = self.res.tolist()  # the decode's only host synchronisation
+            if self.p2p:
+                self.sh.p2p_launch(self.x_ptr)      # local decode + summary stored into every peer's block (one graph)
+                ll, bad = self.sh.p2p_finish()      # judge spins on the peers' flags; the decode's only synchronisation
+            else:
+                self.local_decode()
+                self.gather_and_judge()
+                ll, bad = self.res.tolist()  # the decode's only host synchronisation
             self.stats["decodes"] += 1
             self.stats["fwd_rounds"] += 1
             self.stats["trace_rounds"] += 1

@@ -177,6 +177,22 @@ int hmm_vshard_finish_ex(hmm_vshard *h, int16_t *x_main_out, int32_t x_is_device
 int hmm_vshard_summary_len(const hmm_vshard *h);
 int hmm_vshard_summary_dev(hmm_vshard *h, int16_t *x_main_dev, double *summary_dev);
 int hmm_vshard_judge_dev(hmm_vshard *h, const double *gathered_dev, int32_t n_ranks, double *out_dev);
+/* Peer-memory protocol: the same summaries, but every rank STORES its summary straight into every peer's exchange block
+ * over NVLink (CUDA-IPC pointers between processes, peer access inside one process) and raises a flag there; the judge
+ * kernel spins on the flags of its own block.  No collective call and no host round trip between decode and verdict;
+ * the local decode + exchange is one CUDA graph from the second call on.
+ *   p2p_init   : allocates this rank's exchange block; ipc_handle_out (64 bytes, nullable) for other processes,
+ *                block_ptr_out (nullable) for shards driven from the same process;
+ *   [caller: all-gather the handles (or pointers) once, rank order]
+ *   p2p_attach : opens the peers' blocks (ipc_handles: world x 64 bytes) or takes their pointers (block_ptrs[world]);
+ *   p2p_launch : local decode, x of the main span into x_main_dev (nullable), summary to all peers -- asynchronous;
+ *   p2p_finish : judge + the decode's single synchronisation: total ll and the number of inconsistent shard
+ *                boundaries (non-zero: fall back to the exchange / verify rounds above).  Every rank must call
+ *                launch and finish the same number of times. */
+int hmm_vshard_p2p_init(hmm_vshard *h, int32_t rank, int32_t world, void *ipc_handle_out, void **block_ptr_out);
+int hmm_vshard_p2p_attach(hmm_vshard *h, const void *ipc_handles, void *const *block_ptrs);
+int hmm_vshard_p2p_launch(hmm_vshard *h, int16_t *x_main_dev);
+int hmm_vshard_p2p_finish(hmm_vshard *h, double *ll_total_out, int32_t *bad_out);
 int hmm_vshard_repairs(hmm_vshard *h, int32_t *fwd_repaired, int32_t *trace_repaired); /* of the last fwd_verify / trace_verify */
 int hmm_vshard_destroy(hmm_vshard *h);
 

@@ -177,3 +177,40 @@ def test_shard_plan_short_tail_is_merged(hm, O, case_factory):
     x_ref, ll_ref = O.viterbi(S, lA, mu, sig)
     x, ll = hm.viterbi_time_sharded(S, lA, mu, sig, 5, chunk_len=4096, warmup=512)
     assert np.array_equal(x, x_ref) and abs(ll - ll_ref) <= 1e-9 * abs(ll_ref)
+
+
+@pytest.mark.parametrize("n", [1, 3, 5])
+def test_peer_memory_protocol_single_process(hm, O, case_factory, n):
+    """hmm_vshard_p2p_*: every shard stores its summary straight into every other shard's exchange block and raises
+    a flag; each shard's judge waits for all flags and checks every boundary.  Here the shards are driven from one
+    process on one device (block pointers instead of CUDA-IPC handles); three decodes -- the second and third
+    re-launch the captured CUDA graph and use the other half of the double-buffered exchange block."""
+    import torch
+
+    ts = hm.timeshard
+    T = 300_000
+    S, lA, mu, sig = case_factory(3, 60, T, 69)
+    x_ref, ll_ref = O.viterbi(S, lA, mu, sig)
+    dev = torch.device("cuda", 0)
+    spans = ts.shard_plan(T, n, 4096)
+    shards, ys, xs, ptrs = [], [], [], []
+    for r, span in enumerate(spans):
+        y_loc = torch.from_numpy(np.ascontiguousarray(S[span[0]:span[1]])).to(dev)
+        sh = ts.Shard(y_loc.data_ptr(), False, span, T, 4096, 512, lA, mu, sig)
+        _, ptr = sh.p2p_init(r, n)
+        shards.append(sh); ys.append(y_loc); ptrs.append(ptr)
+        xs.append(torch.zeros(span[3] - span[2], dtype=torch.int16, device=dev))
+    for sh in shards:
+        sh.p2p_attach(block_ptrs=ptrs)
+    for it in range(3):
+        for x in xs:
+            x.zero_()
+        for sh, x in zip(shards, xs):
+            sh.p2p_launch(x.data_ptr())
+        verdicts = [sh.p2p_finish() for sh in shards]
+        for ll, bad in verdicts:
+            assert bad == 0 and abs(ll - ll_ref) <= 1e-9 * abs(ll_ref), (it, ll, bad)
+        assert len({v[0] for v in verdicts}) == 1  # every shard computes the same total, bit for bit
+        assert np.array_equal(np.concatenate([x.cpu().numpy() for x in xs]), x_ref)
+    for sh in shards:
+        sh.close()
