@@ -134,7 +134,9 @@ __device__ __forceinline__ void fir_stage(const double *__restrict__ y, int64_t 
 }
 __device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
-template <int N, int R>
+// I0, I1: the neurons [I0, I1) this call computes (the FIR of one super-window can be split between the producer
+// and the consumer warp of a slot; both read the same y tile and write disjoint planes of the F tile).
+template <int N, int R, int I0 = 0, int I1 = N>
 __device__ __forceinline__ void fir_compute(const double *A, const double *Bc, int LP, const double *ytile,
                                             double *fbuf, int lane) {
     using G = FirGeom<R>;
@@ -144,7 +146,7 @@ __device__ __forceinline__ void fir_compute(const double *A, const double *Bc, i
     __builtin_assume(__isShared(A));
     double acc[N][R];
 #pragma unroll
-    for (int i = 0; i < N; i++)
+    for (int i = I0; i < I1; i++)
 #pragma unroll
         for (int j = 0; j < R; j++) acc[i][j] = Bc[i];
     double w[R];
@@ -172,7 +174,7 @@ __device__ __forceinline__ void fir_compute(const double *A, const double *Bc, i
             for (int j = 0; j < R; j++) {
                 const double yv = w[(u + j) % R];
 #pragma unroll
-                for (int i = 0; i < N; i++) acc[i][j] = fma(a0[i], yv, acc[i][j]);
+                for (int i = I0; i < I1; i++) acc[i][j] = fma(a0[i], yv, acc[i][j]);
             }
             w[u] = ynew;
             load_coef(r0 + u + 2 < LP ? r0 + u + 2 : LP - 1, a0);
@@ -181,14 +183,14 @@ __device__ __forceinline__ void fir_compute(const double *A, const double *Bc, i
             for (int j = 0; j < R; j++) {
                 const double yv = w[(u + 1 + j) % R];
 #pragma unroll
-                for (int i = 0; i < N; i++) acc[i][j] = fma(a1[i], yv, acc[i][j]);
+                for (int i = I0; i < I1; i++) acc[i][j] = fma(a1[i], yv, acc[i][j]);
             }
             w[u + 1] = ynew;
         }
     }
     __syncwarp();  // every lane is done with the y tile before F overwrites it
 #pragma unroll
-    for (int i = 0; i < N; i++)
+    for (int i = I0; i < I1; i++)
 #pragma unroll
         for (int j = 0; j < R; j++) fbuf[i * G::FTILE + j * G::FS + lane] = acc[i][j];
     __syncwarp();
@@ -205,7 +207,7 @@ __device__ __forceinline__ void fir_superwindow(const double *__restrict__ y, in
 }
 
 
-template <int N, int R, int LPC>
+template <int N, int R, int LPC, int I0 = 0, int I1 = N>
 __device__ __forceinline__ void fir_compute_c(const FirCoef<N, LPC> &coef, const double *Bc, const double *ytile,
                                               double *fbuf, int lane) {
     using G = FirGeom<R>;
@@ -213,7 +215,7 @@ __device__ __forceinline__ void fir_compute_c(const FirCoef<N, LPC> &coef, const
     __builtin_assume(__isShared(fbuf));
     double acc[N][R];
 #pragma unroll
-    for (int i = 0; i < N; i++)
+    for (int i = I0; i < I1; i++)
 #pragma unroll
         for (int j = 0; j < R; j++) acc[i][j] = Bc[i];
     double w[R];
@@ -242,7 +244,7 @@ __device__ __forceinline__ void fir_compute_c(const FirCoef<N, LPC> &coef, const
                 for (int j = 0; j < R; j++) {
                     const double yv = w[(u + j) % R];
 #pragma unroll
-                    for (int i = 0; i < N; i++) acc[i][j] = fma(coef.a[r * N + i], yv, acc[i][j]);
+                    for (int i = I0; i < I1; i++) acc[i][j] = fma(coef.a[r * N + i], yv, acc[i][j]);
                 }
                 w[u] = ynew;
             }
@@ -250,7 +252,7 @@ __device__ __forceinline__ void fir_compute_c(const FirCoef<N, LPC> &coef, const
     }
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < N; i++)
+    for (int i = I0; i < I1; i++)
 #pragma unroll
         for (int j = 0; j < R; j++) fbuf[i * G::FTILE + j * G::FS + lane] = acc[i][j];
     __syncwarp();

@@ -358,8 +358,8 @@ struct SlotSmem {  // one chunk slot of the warp-specialised kernel, in doubles
     static constexpr int YT = 0;                                   // 2 y tiles
     static constexpr int FT = 2 * G::YTILE;                        // 2 F tiles
     static constexpr int RING = FT + 2 * N * G::FTILE;             // ring + prologue scratch
-    static constexpr int BAR = RING + N * RING_Q + 104;            // full[2], empty[2] mbarriers
-    static constexpr int DOUBLES = BAR + 4;
+    static constexpr int BAR = RING + N * RING_Q + 104;            // full[2], empty[2], yready[2], yfree[2] mbarriers
+    static constexpr int DOUBLES = BAR + 8;
 };
 
 // Number of super-windows the forward pass of chunk c covers (0 if there is no such chunk).
@@ -378,7 +378,11 @@ __device__ __forceinline__ void pair_sync(int bar_id) {
     asm volatile("bar.sync %0, 64;\n" ::"r"(bar_id) : "memory");
 }
 
-template <int N, int R, int LPC, int ROLE>
+// NC: neurons whose FIR the CONSUMER warp computes itself (warp-specialised roles only).  A single warp cannot keep
+// the FP64 pipe busy (back-to-back DFMAs of one warp issue at half the pipe rate), and a consumer spends a third of its
+// time waiting for its producer: with the FIR of a super-window split N - NC : NC, four warps per SM sub-partition feed
+// the pipe instead of two, and producer and consumer finish a super-window at about the same time.
+template <int N, int R, int LPC, int ROLE, int NC = 0>
 __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coef, int ch, int c, int kind,
                                   const double *mdl /*smem model*/, double *ws /*per-warp or per-slot smem*/,
                                   int pair_bar = 0 /*named barrier shared with the partner producer, 0 = none*/,
@@ -396,8 +400,11 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
     double *ring = ws + (ROLE == ROLE_BOTH ? WarpSmem<N, R>::TILE : SlotSmem<N, R>::RING);
     double *zs = ring + N * RING_Q;  // [L+1] <= 97 doubles
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(ws + SlotSmem<N, R>::BAR), *bar_empty = bar_full + 2;
+    uint64_t *bar_yready = bar_full + 4, *bar_yfree = bar_full + 6;
     (void)bar_full;
     (void)bar_empty;
+    (void)bar_yready;
+    (void)bar_yfree;
     const double *A = mdl + RL.A;
     const double *Bc = mdl + RL.Bc, *eG = mdl + RL.eG, *eH = mdl + RL.eH, *eT = mdl + RL.eT;
     const double eTmax = mdl[RL.scal + 5], eHmin = mdl[RL.scal + 6];
@@ -464,12 +471,17 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
 #ifdef HMM_PHASE_TIMING
             const long long q0 = clock64();
 #endif
-            if (more) fir_stage<R>(y, T, b + G::SW, need, yt[buf ^ 1], lane);
+            if (more) {
+                // the consumer reads the y tiles too (its share of the FIR): tile buf^1 last held super-window k-1
+                if (NC > 0 && k >= 1) mbar_wait(bar_yfree + (buf ^ 1), ((k - 1) >> 1) & 1);
+                fir_stage<R>(y, T, b + G::SW, need, yt[buf ^ 1], lane);
+            }
             if (more)
                 cp_async_wait_but_one();
             else
                 cp_async_wait_all();
             __syncwarp();
+            if (NC > 0 && lane == 0) mbar_arrive(bar_yready + buf);  // y tile k has landed
 #ifdef HMM_PHASE_TIMING
             const long long q1 = clock64();
 #endif
@@ -482,9 +494,9 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
             const long long q2 = clock64();
 #endif
             if constexpr (LPC > 0)
-                fir_compute_c<N, R, LPC>(coef, Bc, yt[buf], ft[buf], lane);
+                fir_compute_c<N, R, LPC, 0, N - NC>(coef, Bc, yt[buf], ft[buf], lane);
             else
-                fir_compute<N, R>(A, Bc, LP, yt[buf], ft[buf], lane);
+                fir_compute<N, R, 0, N - NC>(A, Bc, LP, yt[buf], ft[buf], lane);
             if (lane == 0) mbar_arrive(bar_full + buf);   // fir_compute ends with __syncwarp()
 #ifdef HMM_PHASE_TIMING
             const long long q3 = clock64();
@@ -539,10 +551,20 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
         const long long tm0 = clock64();
 #endif
         if (ROLE == ROLE_DP) {
-            // ---- consumer: wait for the producer's F tile of this super-window ----
             const int buf = swk & 1;
-            mbar_wait(bar_full + buf, (swk >> 1) & 1);
             fbuf = ws + SlotSmem<N, R>::FT + buf * N * G::FTILE;
+            if constexpr (NC > 0) {
+                // ---- consumer's share of the FIR: the last NC neurons, from the y tile the producer staged ----
+                const double *ytk = ws + SlotSmem<N, R>::YT + buf * G::YTILE;
+                mbar_wait(bar_yready + buf, (swk >> 1) & 1);
+                if constexpr (LPC > 0)
+                    fir_compute_c<N, R, LPC, N - NC, N>(coef, Bc, ytk, fbuf, lane);
+                else
+                    fir_compute<N, R, N - NC, N>(A, Bc, LP, ytk, fbuf, lane);
+                if (lane == 0) mbar_arrive(bar_yfree + buf);
+            }
+            // ---- consumer: wait for the producer's F planes of this super-window ----
+            mbar_wait(bar_full + buf, (swk >> 1) & 1);
         } else {
             // ---- stage y and run the FIR: F_i(b + t) for the whole super-window ----
             if constexpr (LPC > 0)
@@ -593,9 +615,18 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
         }
         // ---- max-plus recursion over the super-window, 32 steps per window ----
         const int b_rel = (int)(b - base0);
+        // Per-super-window invariants, hoisted by hand: the quiet-window path below is the consumer's inner loop
+        // (80 % of the windows) and the compiler otherwise rebuilds every 64-bit address from the kernel
+        // parameters in each window (110 instructions per quiet window, most of them address arithmetic).
+        const bool regular = Lq >= 32 && b_rel >= tf_rel && b_rel + G::SW <= e_rel;  // 8 full windows of recursion steps
+        const double *fp0 = fbuf + (lane & (R - 1)) * G::FS + (lane >> G::LOGR);       // F of (window 0, this lane's step)
+        double *rp0 = ring + lane;                                                      // ring slot of that step
+        uint32_t *dq = decb + b_rel + lane;
+        uint32_t *nq = nzb + (b_rel >> 5);
+        double *pfin = p.Pfin + (size_t)ch * N * RING_Q + lane;
         for (int wdw = 0; wdw < R; wdw++) {
             const int t0_rel = b_rel + 32 * wdw;
-            if (t0_rel + 32 <= tf_rel) {  // before the first recursion step: pre-loaded entries only
+            if (!regular && t0_rel + 32 <= tf_rel) {  // before the first recursion step: pre-loaded entries only
                 lq4 = lq3; lq3 = lq2; lq2 = lq1;
                 lq1 = (kind == START_SPEC) ? 0u : 0xffffffffu;
                 if (t0_rel >= s_rel) {  // (prologue columns: the traceback takes them from T2pro)
@@ -604,19 +635,20 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
                 }
                 continue;
             }
-            if (t0_rel >= e_rel) break;
-            const int tl = 32 * wdw + lane;
+            if (!regular && t0_rel >= e_rel) break;
             const int t_rel = t0_rel + lane;
-            // ring slots: base0 is a multiple of RING_Q, so absolute and relative indices agree mod RING_Q
-            const int slot_w = t_rel & (RING_Q - 1);
+            // ring slots: base0 and the super-window are multiples of RING_Q, so the slot of step (window, lane) is
+            // (32 window mod RING_Q) + lane
+            const int slot0 = (32 * wdw) & (RING_Q - 1);
+            const int slot_w = slot0 + lane;
             double Fv[N];
 #pragma unroll
-            for (int i = 0; i < N; i++) Fv[i] = fbuf[i * G::FTILE + (tl & (R - 1)) * G::FS + (tl >> G::LOGR)];
+            for (int i = 0; i < N; i++) Fv[i] = fp0[i * G::FTILE + (32 / R) * wdw];
             // Quiet-window fast path: if none of the pending chain scores that arrive in this
             // window was live when it was created, no tail can win any decision here: G stays,
             // every head is entered from noise and all backpointers are 0 -- the tails are not
             // even read.
-            if (L >= 32 && t0_rel >= tf_rel && t0_rel + 32 <= e_rel) {
+            if (regular || (L >= 32 && t0_rel >= tf_rel && t0_rel + 32 <= e_rel)) {
                 const uint32_t lo = qq == 1 ? lq1 : qq == 2 ? lq2 : qq == 3 ? lq3 : lq4;
                 const uint32_t hi = qq == 1 ? 0u : qq == 2 ? lq1 : qq == 3 ? lq2 : lq3;
                 if (__funnelshift_r(lo, hi, lsh) == 0u) {
@@ -633,18 +665,18 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
 #pragma unroll
                     for (int i = 0; i < N; i++) {
                         const double q = ghq[i] + Fv[i];
-                        ring[i * RING_Q + slot_w] = q;
+                        rp0[i * RING_Q + slot0] = q;
                         live = live || (q > thq[i]);
                     }
                     if (last) {
 #pragma unroll
-                        for (int i = 0; i < N; i++) p.Pfin[((size_t)ch * N + i) * RING_Q + slot_w] = ghq[i];
+                        for (int i = 0; i < N; i++) pfin[i * RING_Q + slot0] = ghq[i];
                     }
                     lq4 = lq3; lq3 = lq2; lq2 = lq1;
                     lq1 = __ballot_sync(0xffffffffu, live);
                     if (t0_rel >= s_rel) {  // all-noise decisions: one coalesced 128-byte store
-                        decb[t0_rel + lane] = 0u;
-                        if (lane == 0) nzb[t0_rel >> 5] = 0u;
+                        dq[32 * wdw] = 0u;
+                        if (lane == 0) nq[wdw] = 0u;
                     }
                     __syncwarp();
                     continue;
@@ -791,6 +823,15 @@ __device__ void load_model_smem(const VitParams &p, int ch, double *mdl) {
 // Warp-specialised forward kernel: SLOTS chunk slots per CTA, each a {FIR producer, recursion consumer} warp pair.
 // SLOTS = 8: one CTA of 16 warps per SM -- the producers of slots s and s + 4 run on the same SM sub-partition and
 // advance in step (pair_sync); SLOTS = 4: two CTAs of 8 warps per SM (models whose slots are too large for 8).
+template <int N>
+struct ConsumerFirShare {  // neurons whose FIR the consumer warp computes (see vit_process_chunk)
+#ifdef HMM_CONSUMER_FIR
+    static constexpr int value = HMM_CONSUMER_FIR < N ? HMM_CONSUMER_FIR : N - 1;
+#else
+    static constexpr int value = 0;  // measured at N = 3, 4, 5: the consumer is co-critical, any share slows the kernel down
+#endif
+};
+
 template <int N, int R, int LPC, int SLOTS>
 __global__ void __launch_bounds__(SLOTS * 64, SLOTS == 8 ? 1 : 2)
     ring_vit_forward_ws(const __grid_constant__ VitParams p, const __grid_constant__ FirCoef<N, LPC> coef) {
@@ -802,7 +843,7 @@ __global__ void __launch_bounds__(SLOTS * 64, SLOTS == 8 ? 1 : 2)
     double *ws = smem_d + ((p.RL.hot + 1) & ~1) + (size_t)slot * SlotSmem<N, R>::DOUBLES;
     if ((threadIdx.x & 31) == 0 && warp < SLOTS) {
         uint64_t *bars = reinterpret_cast<uint64_t *>(ws + SlotSmem<N, R>::BAR);
-        for (int k = 0; k < 4; k++) mbar_init(bars + k, 1);
+        for (int k = 0; k < 8; k++) mbar_init(bars + k, 1);
     }
     load_model_smem<N, R>(p, ch, mdl);  // ends with __syncthreads(): barriers initialised, model staged
     const int c = blockIdx.x * SLOTS + slot;
@@ -814,9 +855,9 @@ __global__ void __launch_bounds__(SLOTS * 64, SLOTS == 8 ? 1 : 2)
             const int a = chunk_superwindows(p, c, G::SW), b = chunk_superwindows(p, blockIdx.x * SLOTS + (slot ^ 4), G::SW);
             pair_nsw = a > b ? a : b;
         }
-        vit_process_chunk<N, R, LPC, ROLE_FIR>(p, coef, ch, c, kind, mdl, ws, pair_bar, pair_nsw);
+        vit_process_chunk<N, R, LPC, ROLE_FIR, ConsumerFirShare<N>::value>(p, coef, ch, c, kind, mdl, ws, pair_bar, pair_nsw);
     } else if (c < p.nchunks)
-        vit_process_chunk<N, R, LPC, ROLE_DP>(p, coef, ch, c, kind, mdl, ws);
+        vit_process_chunk<N, R, LPC, ROLE_DP, ConsumerFirShare<N>::value>(p, coef, ch, c, kind, mdl, ws);
 }
 
 // Boundary check: speculative start vector of chunk c vs true end vector of c-1
