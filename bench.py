@@ -85,6 +85,11 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def wait_first(self, timeout):
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -157,12 +162,15 @@ def run_ours(args):
                                             C.c_void_p(x_dev.data_ptr()), C.byref(ll), i32(hm.MODES["ring"]),
                                             C.byref(info)))
 
-    for _ in range(args.warmup):
-        step_dev()
+    # nvidia-smi takes a second or two to start (NVML initialisation, which briefly stalls work on the GPUs it
+    # enumerates): it is started first and has delivered its first sample before anything is timed
     sampler = ClockSampler(local)
-    barrier()
     if rank == 0:
         sampler.start()
+        sampler.wait_first(5.0)
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
     top_ms, kern_ms, launches = [], [], 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -213,7 +221,6 @@ def run_ours(args):
     barrier()
     dt_e = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
     e2e_val = world * T / (dt_e / args.steps) / 1e6
-    clocks = sampler.stop() if rank == 0 else None
     same = bool(np.array_equal(x_first, x_pin)) and ll.value == ll2.value
     # the same call with ordinary (pageable) numpy arrays, as a Julia Array would be: the driver stages the copies
     e2e_pageable = None
@@ -254,6 +261,7 @@ def run_ours(args):
         L.hmm_release_workspace()
         c5 = block_c5(env, args)
         c4 = block_c4(env, args)
+    clocks = sampler.stop() if rank == 0 else None  # sampled across every timed region above
     cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, parity = cpu_baseline_viterbi(S, lA, mu, sigma, x_gpu=x_first, ll_gpu=ll.value, seconds=args.cpu_seconds)

@@ -2004,7 +2004,7 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
     if (!prog) {
         fresh.reset(new RingProgram);
         fresh->key = key;
-        fresh->plan.own_memory = true;
+        fresh->plan.own_memory = cacheable;  // a one-off plan lives in the thread's grow-only workspace (no cudaMalloc)
         HMM_CUDA(cudaHostAlloc((void **)&fresh->res_h, sizeof(double) * 4 * (size_t)C, cudaHostAllocMapped));
         memset(fresh->res_h, 0, sizeof(double) * 4 * (size_t)C);
         double *res_d = nullptr;
