@@ -649,7 +649,7 @@ int viterbi_host(const double *y, int64_t T, int C, const int16_t *states, int s
                 if (info) {
                     info->engine = HMM_MODE_RING;
                     info->device_ms = tall.ms();
-                    info->kernel_launches = (int64_t)C * (ll_out ? 6 : 5);
+                    info->kernel_launches = (int64_t)C * 5;
                 }
                 return;
             }
@@ -830,6 +830,7 @@ int hmm_vshard_create(const double *y_local, int32_t y_is_host, int64_t local_be
         h->plan.own_memory = true;
         h->plan.build(h->y_dev, Tl, Tl, 1, h->models, h->FL, h->blob_dev, h->x_loc, Tl, chunk_len, warmup, first, last,
                       st);
+        h->plan.set_ll_range(main_begin - local_begin, main_end - local_begin, local_begin, T_global, first);
         h->c_main0 = (int)((main_begin - local_begin) / chunk_len);
         h->c_main1 = last ? h->plan.nchunks() : (int)((main_end - local_begin) / chunk_len);
         if (h->c_main1 > h->plan.nchunks()) h->c_main1 = h->plan.nchunks();

@@ -73,6 +73,9 @@ class VitPlan {
     void trace(cudaStream_t st);
     void verify_trace(cudaStream_t st);  // boundary check + repair
     void path_ll(cudaStream_t st, double *ll_dev, int64_t t_lo, int64_t t_hi, int64_t t_off, int64_t T_glob, bool with_p0);
+    // local sample range [lo, hi) the path score covers (chunk aligned), global time offset and length, whether the
+    // t = 0 term belongs to it; verify_trace leaves the score in ll_dev()
+    void set_ll_range(int64_t lo, int64_t hi, int64_t t_off, int64_t T_glob, bool with_p0, bool want = true);
     void run_all(cudaStream_t st, bool want_ll, Timer *ttop);  // the whole decode: six launches
     void set_result_sink(double *res_dev_alias);  // [C x 4] mapped pinned memory the kernels leave ll / repair counts in
     void retarget(const double *y_dev, int16_t *x_dev);

@@ -134,11 +134,30 @@ __device__ __forceinline__ void fir_stage(const double *__restrict__ y, int64_t 
 }
 __device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 
+// Path-score piece 1 (ring_viterbi.cu ll_assemble): the FIR's initial register window holds exactly the super-window's
+// own samples, R per lane (element e = R lane + j): accumulate sum (w0 - e) (y_e - m0)^2 over the first nvalid of them.
+// The dozen extra FP64 operations per lane sit in the issue gaps of the DFMA stream that follows.
+template <int R>
+__device__ __forceinline__ void ll_noise_from_window(const double (&w)[R], double *nacc, double m0, double w0, int lane,
+                                                     int nvalid) {
+    double acc = *nacc;
+    const int e0 = R * lane;
+    double wg = w0 - (double)e0;
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        const double dd = w[j] - m0;
+        if (e0 + j < nvalid) acc = fma(wg, dd * dd, acc);
+        wg -= 1.0;
+    }
+    *nacc = acc;
+}
+
 // I0, I1: the neurons [I0, I1) this call computes (the FIR of one super-window can be split between the producer
 // and the consumer warp of a slot; both read the same y tile and write disjoint planes of the F tile).
 template <int N, int R, int I0 = 0, int I1 = N>
 __device__ __forceinline__ void fir_compute(const double *A, const double *Bc, int LP, const double *ytile,
-                                            double *fbuf, int lane) {
+                                            double *fbuf, int lane, double *nacc = nullptr, double m0 = 0.0,
+                                            double w0 = 0.0, int nvalid = 0) {
     using G = FirGeom<R>;
     constexpr int NP = (N + 1) & ~1;
     __builtin_assume(__isShared(ytile));
@@ -152,6 +171,7 @@ __device__ __forceinline__ void fir_compute(const double *A, const double *Bc, i
     double w[R];
 #pragma unroll
     for (int j = 0; j < R; j++) w[j] = ytile[j * G::YS + lane];  // elements R*lane + j
+    if (nacc) ll_noise_from_window<R>(w, nacc, m0, w0, lane, nvalid);
     auto load_coef = [&](int r, double *dst) {
         const double2 *src = reinterpret_cast<const double2 *>(A + r * NP);
 #pragma unroll
@@ -209,7 +229,8 @@ __device__ __forceinline__ void fir_superwindow(const double *__restrict__ y, in
 
 template <int N, int R, int LPC, int I0 = 0, int I1 = N>
 __device__ __forceinline__ void fir_compute_c(const FirCoef<N, LPC> &coef, const double *Bc, const double *ytile,
-                                              double *fbuf, int lane) {
+                                              double *fbuf, int lane, double *nacc = nullptr, double m0 = 0.0,
+                                              double w0 = 0.0, int nvalid = 0) {
     using G = FirGeom<R>;
     __builtin_assume(__isShared(ytile));
     __builtin_assume(__isShared(fbuf));
@@ -221,6 +242,7 @@ __device__ __forceinline__ void fir_compute_c(const FirCoef<N, LPC> &coef, const
     double w[R];
 #pragma unroll
     for (int j = 0; j < R; j++) w[j] = ytile[j * G::YS + lane];
+    if (nacc) ll_noise_from_window<R>(w, nacc, m0, w0, lane, nvalid);
     // Fully unrolled over exactly LPC = L taps, so that every coefficient is a compile-time constant-bank offset
     // (the compiler keeps them in uniform registers: LDCU.128 + DFMA R, R, UR, R -- no register-file or
     // shared-memory traffic for them).  Measured at C2 (forward kernel, 18 M samples): full unroll 0.36 ms

@@ -126,7 +126,7 @@ struct VitParams {
     int *fwd_flag;         // [C x nchunks] boundary mismatch flags
     int *counters;         // [C x 4]: 0 fwd repaired, 1 trace repaired
     // trace
-    int16_t *T2pro;        // [C x ns x (L+1)]
+    int16_t *T2pro;        // [C x (L+1) x 8] prologue backpointers of the DECISION states (noise, heads), 1-based source
     int16_t *xend;         // [C] final state (0-based), written by the last chunk's warp
     int16_t *x;            // [T x C]
     int64_t x_stride;
@@ -139,6 +139,14 @@ struct VitParams {
     unsigned *sync_cnt;    // [C x 4] arrival counters of the fused check+repair kernels ("last CTA continues"), self-resetting
     double *res_host;      // [C x 4] device alias of mapped pinned host memory: ll, chunks repaired (forward, traceback); nullable
     int ch0;               // channel offset of this launch (long recordings: one channel per launch out of a C-channel plan)
+    // ll = sum_t T1[x_t, t] assembled from pieces the decode produces anyway (see ll_assemble):
+    double *ll_noise;      // [C x nchunks]   per forward chunk: sum over its main range of (Tg - g) (y_g - m0)^2
+    double *ll_spike;      // [C x nchunks_t] per traceback chunk: sum over its steps of (Tg - g) * (normalised increment)
+    double *ll_out;        // [C]
+    int64_t ll_lo, ll_hi;  // local sample range the sum runs over (chunk aligned; a shard's main span)
+    int64_t t_off, T_glob; // global time of local step t is t + t_off; the weights are T_glob - (t + t_off)
+    int ll_with_p0;        // add (T_glob - 1) * T1[x_1, 1] (the first shard / the whole recording)
+    int want_ll;
 };
 
 enum StartKind { START_PROLOGUE = 0, START_SPEC = 1, START_EXACT = 2 };
@@ -190,7 +198,7 @@ __global__ void __launch_bounds__(1024) ring_vit_prologue(VitParams p, int q_in_
     const int *gp = (const int *)(mb + p.FL.in_ptr), *gs = (const int *)(mb + p.FL.in_src);
     const double *y = p.y + (size_t)ch * p.y_stride;
     double *t1 = p.T1pro + (size_t)ch * ns * cols;
-    int16_t *t2 = p.T2pro + (size_t)ch * ns * cols;
+    int16_t *t2 = p.T2pro + (size_t)ch * cols * 8;
     double *wc = psm;                       // [ns]   weight of the single in-edge of a chain-interior state
     double *tailv = wc + ns;                // [L][N] tail_i at column t
     double *bT = tailv + (size_t)L * N;     // [cols][ND] best tail candidate of a decision state at column t
@@ -225,11 +233,7 @@ __global__ void __launch_bounds__(1024) ring_vit_prologue(VitParams p, int q_in_
         }
     }
     for (int j = tid; j < ns; j += nth) wc[j] = glp[gp[j]];
-    // static backpointers: chain-interior state j (0-based) comes from j - 1, stored 1-based; column 0 is all ones (:53)
-    for (int idx = tid; idx < cols * ns; idx += nth) {
-        const int t = idx / ns, j = idx - t * ns;
-        t2[idx] = (int16_t)(t == 0 ? 1 : j);
-    }
+    // (backpointers: a chain-interior state j comes from j - 1, nothing to store; the decision states' are written in B2)
     __syncthreads();
     // ---- A: the chains already running at column 0 ----
     for (int k = tid; k < N * L; k += nth) {
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(1024) ring_vit_prologue(VitParams p, int q_in_
                 const bool tail = bt > cn;
                 v = __dadd_rn(tail ? bt : cn, q[(size_t)t * ns + sd]);
                 t1[(size_t)t * ns + sd] = v;
-                t2[(size_t)t * ns + sd] = (int16_t)((tail ? aT[t * ND + d] : 0) + 1);
+                t2[t * 8 + d] = (int16_t)((tail ? aT[t * ND + d] : 0) + 1);
             }
             noise = __shfl_sync(0xffffffffu, v, 0);
         }
@@ -361,6 +365,24 @@ struct SlotSmem {  // one chunk slot of the warp-specialised kernel, in doubles
     static constexpr int BAR = RING + N * RING_Q + 104;            // full[2], empty[2], yready[2], yfree[2] mbarriers
     static constexpr int DOUBLES = BAR + 8;
 };
+
+#ifndef HMM_LL_NOISE_MODE
+#define HMM_LL_NOISE_MODE 1  // 1: path-score piece 1 by a pass over the staged y tile (measured 1 % faster than 0: from the FIR register window)
+#endif
+// sum over the first min(n, SW) samples of a staged (transposed) y tile of w(e) (y_e - m0)^2, w(e) = w0 - e
+template <int R>
+__device__ __forceinline__ double ll_noise_tile(const double *ytile, double acc, double m0, double w0, int lane, int n) {
+    using G = FirGeom<R>;
+    const double *src = ytile + (lane & (R - 1)) * G::YS + (lane >> G::LOGR);
+    double w = w0 - (double)lane;
+#pragma unroll
+    for (int m = 0; m < R; m++) {  // element e = lane + 32 m
+        const double dd = src[(32 / R) * m] - m0;
+        if (lane + 32 * m < n) acc = fma(w, dd * dd, acc);
+        w -= 32.0;
+    }
+    return acc;
+}
 
 // Number of super-windows the forward pass of chunk c covers (0 if there is no such chunk).
 __device__ __forceinline__ int chunk_superwindows(const VitParams &p, int c, int SW) {
@@ -462,6 +484,11 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
         double *ft[2] = {ws + SlotSmem<N, R>::FT, ws + SlotSmem<N, R>::FT + N * G::FTILE};
         fir_stage<R>(y, T, base0, need, yt[0], lane);
         int k = 0;
+        // path-score piece 1 (see ll_assemble): sum over the chunk's main range of (Tg - g) (y_g - m0)^2, from the y
+        // tiles this warp stages anyway -- the recording is not read a second time for ll
+        double nacc = 0.0;
+        const double m0n = mdl[RL.scal + 3];
+        const double wg0 = (double)(p.T_glob - p.t_off - s);  // weight of local step s
 #ifdef HMM_PHASE_TIMING
         long long pt_stage = 0, pt_wait = 0, pt_fir = 0;
 #endif
@@ -482,6 +509,7 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
                 cp_async_wait_all();
             __syncwarp();
             if (NC > 0 && lane == 0) mbar_arrive(bar_yready + buf);  // y tile k has landed
+
 #ifdef HMM_PHASE_TIMING
             const long long q1 = clock64();
 #endif
@@ -493,10 +521,22 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
 #ifdef HMM_PHASE_TIMING
             const long long q2 = clock64();
 #endif
+            // (own samples of a main-range super-window also feed the path score, from the FIR's register window)
+#if HMM_LL_NOISE_MODE == 1
+            if (b >= s) nacc = ll_noise_tile<R>(yt[buf], nacc, m0n, wg0 - (double)(b - s), lane, (int)(e - b > G::SW ? G::SW : e - b));
+            double *llp = nullptr;
+#elif HMM_LL_NOISE_MODE == 2
+            double *llp = nullptr;  // (timing experiments only: ll is wrong)
+#else
+            double *llp = b >= s ? &nacc : nullptr;
+#endif
+            const double w0 = wg0 - (double)(b - s);
+            const int64_t left = e - b;
+            const int nval = left > G::SW ? G::SW : (int)left;
             if constexpr (LPC > 0)
-                fir_compute_c<N, R, LPC, 0, N - NC>(coef, Bc, yt[buf], ft[buf], lane);
+                fir_compute_c<N, R, LPC, 0, N - NC>(coef, Bc, yt[buf], ft[buf], lane, llp, m0n, w0, nval);
             else
-                fir_compute<N, R, 0, N - NC>(A, Bc, LP, yt[buf], ft[buf], lane);
+                fir_compute<N, R, 0, N - NC>(A, Bc, LP, yt[buf], ft[buf], lane, llp, m0n, w0, nval);
             if (lane == 0) mbar_arrive(bar_full + buf);   // fir_compute ends with __syncwarp()
 #ifdef HMM_PHASE_TIMING
             const long long q3 = clock64();
@@ -510,6 +550,11 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
             printf("producer %d: %d super-windows, staging %lld, wait-for-empty %lld, FIR %lld cyc/sw\n", c, k,
                    pt_stage / (k ? k : 1), pt_wait / (k ? k : 1), pt_fir / (k ? k : 1));
 #endif
+        {
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) nacc += __shfl_xor_sync(0xffffffffu, nacc, d);
+            if (lane == 0) p.ll_noise[(size_t)ch * p.nchunks + c] = nacc;
+        }
         if (pair_bar)
             for (; k < pair_nsw; k++) pair_sync(pair_bar);  // the partner's chunk is longer
         return;
@@ -1106,7 +1151,7 @@ constexpr int TR_WARP_U32 = TR_TILE_W /*mw*/ + TR_TILE_W /*pre*/ + 2 * TR_CAP /*
 
 template <int N>
 __device__ void trace_chunk(const VitParams &p, int ch, int c, int64_t tau_hi, long long st, bool record_look,
-                            int16_t *t2s /*smem, chunk 0 only*/, uint32_t *tws /*per-warp, TR_WARP_U32 words*/) {
+                            uint32_t *tws /*per-warp, TR_WARP_U32 words*/) {
     const int lane = threadIdx.x & 31;
     const int L = p.RL.L;
     const int64_t T = p.T;
@@ -1134,6 +1179,27 @@ __device__ void trace_chunk(const VitParams &p, int ch, int c, int64_t tau_hi, l
     int cur = (int)(tau_hi - s);
     int tile_wlo = 0, tile_whi = -1;  // invalid
     const int wlo = lo_r >> 5;
+    // path-score piece 2 (see ll_assemble): sum over this chunk's own steps of (Tg - g) * inc', inc' being the
+    // increment of the path score relative to the all-noise path -- non-zero only inside spikes (A y + BW per
+    // step), where a chain is entered (eH or eT) and where noise is re-entered from a tail (eG).  The y values
+    // of a spike are loaded when it is painted and consumed one spike later, so the walk never waits for them.
+    const RingLayout &RLt = p.RL;
+    const double *mdl_g = p.model + (size_t)ch * RLt.total;
+    const double *gA = mdl_g + RLt.A, *gBW = mdl_g + RLt.BW, *geG = mdl_g + RLt.eG, *geH = mdl_g + RLt.eH,
+                 *geT = mdl_g + RLt.eT;
+    const int NPt = RLt.NP;
+    const double *ys = p.y + (size_t)ch * p.y_stride + s;
+    const double wgs = (double)(p.T_glob - p.t_off - s);  // weight of the chunk's first step
+    double sacc = 0.0;
+    double pd_y0 = 0.0, pd_a0 = 0.0, pd_c0 = 0.0, pd_w0 = 0.0, pd_y1 = 0.0, pd_a1 = 0.0, pd_c1 = 0.0, pd_w1 = 0.0;
+    auto flush_pending = [&]() {
+        sacc = fma(pd_w0, fma(pd_a0, pd_y0, pd_c0), sacc);
+        sacc = fma(pd_w1, fma(pd_a1, pd_y1, pd_c1), sacc);
+        pd_w0 = pd_w1 = 0.0;
+    };
+    auto add_point = [&](int t, double v) {  // (one lane) a transition weight at own step t
+        if (lane == 0 && t >= xlo_r && t < xhi_r) sacc = fma(wgs - (double)t, v, sacc);
+    };
     // ---- noise everywhere first (16-byte stores); the spikes are painted over it ----
     if (xhi_r > xlo_r) {
         const uintptr_t addr = reinterpret_cast<uintptr_t>(xs + xlo_r);
@@ -1157,8 +1223,37 @@ __device__ void trace_chunk(const VitParams &p, int ch, int c, int64_t tau_hi, l
     auto emit_spike = [&](int a, int b, long long state, int t0_r) {
         see(a, b, state);
         const int wa = a < xlo_r ? xlo_r : a, wb = b < xhi_r - 1 ? b : xhi_r - 1;
-        const int base = 2 + (int)(state & 7) * L - t0_r;
-        for (int t = wa + lane; t <= wb; t += 32) xs[t] = (int16_t)(base + t);
+        const int ni = (int)(state & 7);
+        const int base = 2 + ni * L - t0_r;
+        if (p.want_ll) flush_pending();
+        int t = wa + lane;
+        if (t <= wb) {
+            xs[t] = (int16_t)(base + t);
+            if (p.want_ll) {
+                const int r = t - t0_r;  // phase index 0 .. L-1
+                pd_y0 = __ldg(ys + t);
+                pd_a0 = __ldg(gA + r * NPt + ni);
+                pd_c0 = __ldg(gBW + r * NPt + ni);
+                pd_w0 = wgs - (double)t;
+            }
+            t += 32;
+            if (t <= wb) {
+                xs[t] = (int16_t)(base + t);
+                if (p.want_ll) {
+                    const int r = t - t0_r;
+                    pd_y1 = __ldg(ys + t);
+                    pd_a1 = __ldg(gA + r * NPt + ni);
+                    pd_c1 = __ldg(gBW + r * NPt + ni);
+                    pd_w1 = wgs - (double)t;
+                }
+                for (t += 32; t <= wb; t += 32) {  // (chains longer than 64 steps: K > 65)
+                    xs[t] = (int16_t)(base + t);
+                    const int r = t - t0_r;
+                    if (p.want_ll)
+                        sacc = fma(wgs - (double)t, fma(__ldg(gA + r * NPt + ni), __ldg(ys + t), __ldg(gBW + r * NPt + ni)), sacc);
+                }
+            }
+        }
     };
     while (cur >= lo_r) {
         if (st < 0) {
@@ -1249,6 +1344,7 @@ __device__ void trace_chunk(const VitParams &p, int ch, int c, int64_t tau_hi, l
             const int j = (int)(d1 & 15u);  // 1..N: noise at tp was entered from tail_j at tp-1
             const int t0 = tp - L;          // that chain was entered at t0 and occupies [t0, tp-1]
             const long long sp = enc_spike(s + t0, j - 1);
+            if (p.want_ll) add_point(tp, __ldg(geG + (j - 1)));
             emit_spike(t0 < lo_r ? lo_r : t0, tp - 1, sp, t0);
             if (t0 < lo_r) {
                 st = sp;
@@ -1256,6 +1352,7 @@ __device__ void trace_chunk(const VitParams &p, int ch, int c, int64_t tau_hi, l
                 break;
             }
             const int k = (int)((d2 >> (4 * j)) & 15u);
+            if (p.want_ll) add_point(t0, k == 0 ? __ldg(geH + (j - 1)) : __ldg(geT + (k - 1) * NPt + (j - 1)));
             cur = t0 - 1;
             st = (k == 0) ? -1 : enc_spike(s + t0 - L, k - 1);
         } else {
@@ -1268,25 +1365,104 @@ __device__ void trace_chunk(const VitParams &p, int ch, int c, int64_t tau_hi, l
                 break;
             }
             const int k = (int)((dec_s[t0] >> (4 * (i + 1))) & 15u);
+            if (p.want_ll) add_point(t0, k == 0 ? __ldg(geH + i) : __ldg(geT + (k - 1) * NPt + i));
             cur = t0 - 1;
             st = (k == 0) ? -1 : enc_spike(s + t0 - L, k - 1);
         }
     }
+    if (p.want_ll) flush_pending();
     if (c == 0 && p.first_prologue) {
         // steps L .. 0 from the faithful prologue's backpointers (reference arithmetic)
+        // (inside a chain the predecessor of state j is j - 1; the decision states' backpointers come from the
+        // prologue kernel's compact table, staged into this warp's -- by now idle -- tile workspace)
         int curj = (st < 0) ? 0 : (1 + (int)(st & 7) * L + (int)(L - (st >> 3)));
+        int16_t *t2d = reinterpret_cast<int16_t *>(tws);
+        const int16_t *g2 = p.T2pro + (size_t)ch * (L + 1) * 8;
+        __syncwarp();
+        for (int k = lane; k < (L + 1) * 8; k += 32) t2d[k] = g2[k];
+        __syncwarp();
+        int16_t *xpro = t2d + (L + 1) * 8;  // states of columns 0..L (0-based), for the parallel ll terms below
         if (lane == 0) {
             for (int t = L; t >= 1; t--) {
                 x[t] = (int16_t)(curj + 1);
-                curj = t2s[(size_t)t * p.ns + curj] - 1;
+                xpro[t] = (int16_t)curj;
+                const int ph = curj == 0 ? 0 : (curj - 1) % L;  // 0: noise or a chain head
+                const int d = curj == 0 ? 0 : 1 + (curj - 1) / L;
+                curj = ph == 0 ? t2d[t * 8 + d] - 1 : curj - 1;
             }
             x[0] = (int16_t)(curj + 1);
+            xpro[0] = (int16_t)curj;
         }
+        __syncwarp();
+        if (p.want_ll)
+            for (int t = 1 + lane; t <= L; t += 32) {  // columns 1..L: one lane per column
+                const int cj = xpro[t], pj = xpro[t - 1];
+                double inc = 0.0;
+                if (cj == 0) {
+                    if (pj != 0) inc = __ldg(geG + (pj - 1) / L);
+                } else {
+                    const int ni = (cj - 1) / L, ph = (cj - 1) % L;
+                    inc = fma(__ldg(gA + ph * NPt + ni), __ldg(ys + t), __ldg(gBW + ph * NPt + ni));
+                    if (ph == 0) inc += pj == 0 ? __ldg(geH + ni) : __ldg(geT + ((pj - 1) / L) * NPt + ni);
+                }
+                sacc = fma(wgs - (double)t, inc, sacc);
+            }
         own = 0;  // nothing precedes chunk 0
+    }
+    if (p.want_ll) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, d);
+        if (lane == 0) p.ll_spike[(size_t)ch * p.nchunks_t + c] = sacc;
     }
     if (lane == 0) {
         p.own_start[(size_t)ch * p.nchunks_t + c] = own;
         if (record_look) p.look_end[(size_t)ch * p.nchunks_t + c] = look;
+    }
+}
+
+// ll = sum_{t >= 1} T1[x_t, t] = (Tg - 1) T1[x_0, 0] + sum_{g >= 1} (Tg - g) inc_g, and with the increment split into the
+// all-noise part and the rest, inc_g = (w_nn + c_emit - (y_g - m0)^2 / (2 sigma^2)) + inc'_g:
+//   ll = (Tg - 1) p0 + (w_nn + c_emit) sum (Tg - g) - (1 / 2 sigma^2) sum (Tg - g) (y_g - m0)^2 + sum (Tg - g) inc'_g
+// The second sum is piece 1 (forward producers, per forward chunk), the third piece 2 (traceback, per traceback
+// chunk); both are added here in chunk order by one warp, so the result does not depend on scheduling.
+__device__ void ll_assemble(const VitParams &p, int ch, int lane) {
+    const int64_t lo = p.ll_lo, hi = p.ll_hi;
+    const int cf0 = (int)(lo / p.Lc), cf1 = hi >= p.T ? p.nchunks : (int)(hi / p.Lc);
+    const int ct0 = (int)(lo / p.Lc_t), ct1 = hi >= p.T ? p.nchunks_t : (int)(hi / p.Lc_t);
+    double a = 0.0, b = 0.0;
+    for (int c = cf0 + lane; c < cf1; c += 32) a += __ldcg(p.ll_noise + (size_t)ch * p.nchunks + c);
+    for (int c = ct0 + lane; c < ct1; c += 32) b += __ldcg(p.ll_spike + (size_t)ch * p.nchunks_t + c);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, d);
+        b += __shfl_xor_sync(0xffffffffu, b, d);
+    }
+    if (lane == 0) {
+        const double *sc = p.model + (size_t)ch * p.RL.total + p.RL.scal;  // 0 w_nn, 1 c_emit, 2 two_s2, 3 m0
+        const double *y = p.y + (size_t)ch * p.y_stride;
+        int64_t g0 = lo + p.t_off, g1 = hi + p.t_off - 1;  // global steps [g0, g1]
+        if (g0 == 0) {  // step 0 carries no increment: take its (y - m0)^2 term out of piece 1 again
+            const double dd = y[0] - sc[3];
+            a -= (double)p.T_glob * (dd * dd);
+            g0 = 1;
+        }
+        const double n = (double)(g1 - g0 + 1);
+        const double sumw = n * (double)p.T_glob - 0.5 * n * (double)(g0 + g1);  // sum_{g0..g1} (Tg - g)
+        double ll = (sc[0] + sc[1]) * sumw - a / sc[2] + b;
+        if (p.ll_with_p0) {
+            const int x0 = p.x[(size_t)ch * p.x_stride] - 1;
+            if (x0 != 0) {  // T1[j, 1] = emission for j != noise (:55-62), 0 for the noise state (:63)
+                const RingLayout &RL = p.RL;
+                const int ni = (x0 - 1) / RL.L, ph = (x0 - 1) % RL.L;
+                const double *mdl = p.model + (size_t)ch * RL.total;
+                const double dd0 = y[0] - sc[3];
+                const double qn = sc[1] - (dd0 * dd0) / sc[2];
+                // emission of state x0 = noise emission + (a y + b) with the plain b (no transition weight)
+                ll += (double)(p.T_glob - 1) * (qn + fma(mdl[RL.A + ph * RL.NP + ni], y[0], mdl[RL.B0 + ph * RL.NP + ni]));
+            }
+        }
+        p.ll_out[ch] = ll;
+        if (p.res_host) p.res_host[ch * 4 + 0] = ll;
     }
 }
 
@@ -1302,14 +1478,8 @@ __global__ void __launch_bounds__(128) ring_vit_trace(VitParams p) {
     const int ch = blockIdx.y + p.ch0;
     const int warp = warp_index_uniform();
     uint32_t *tws = trsm + (size_t)warp * TR_WARP_U32;
-    int16_t *t2s_all = reinterpret_cast<int16_t *>(trsm + (size_t)(blockDim.x >> 5) * TR_WARP_U32);
     const int c = blockIdx.x * (blockDim.x >> 5) + warp;
     const int L = p.RL.L;
-    if (blockIdx.x == 0 && p.first_prologue) {  // chunk 0 lives in CTA 0: stage the prologue backpointers
-        const int16_t *g = p.T2pro + (size_t)ch * p.ns * (L + 1);
-        for (int k = threadIdx.x; k < p.ns * (L + 1); k += blockDim.x) t2s_all[k] = g[k];
-    }
-    __syncthreads();
     if (c >= p.nchunks_t) return;
     const int64_t T = p.T;
     const int64_t s = (int64_t)c * p.Lc_t;
@@ -1322,7 +1492,7 @@ __global__ void __launch_bounds__(128) ring_vit_trace(VitParams p) {
         tau_hi = T - 1;
         if (p.last_true_end) st = state_from_xend(p.xend[ch], T, L);  // else: ghost chunk, speculative noise
     }
-    trace_chunk<N>(p, ch, c, tau_hi, st, !last, t2s_all, tws);
+    trace_chunk<N>(p, ch, c, tau_hi, st, !last, tws);
 }
 
 // Traceback verification in ONE launch: the state a chunk assumed at its end (after a look-ahead of W steps) must
@@ -1350,13 +1520,6 @@ __global__ void __launch_bounds__(128) ring_vit_verify_trace(VitParams p) {
     int repaired = 0;
     if (any) {
         uint32_t *tws = trsm;
-        int16_t *t2s_all = reinterpret_cast<int16_t *>(trsm + TR_WARP_U32);
-        const int L = p.RL.L;
-        if (p.first_prologue) {
-            const int16_t *g = p.T2pro + (size_t)ch * p.ns * (L + 1);
-            for (int k = lane; k < p.ns * (L + 1); k += 32) t2s_all[k] = g[k];
-        }
-        __syncwarp();
         bool next_changed = false;
         for (int c = p.nchunks_t - 2; c >= 0; c--) {
             bool need = __ldcg(p.tr_flag + o + c) != 0;
@@ -1365,7 +1528,7 @@ __global__ void __launch_bounds__(128) ring_vit_verify_trace(VitParams p) {
                 // true state at time e_c is the (final) start state of chunk c+1
                 int64_t e = (int64_t)(c + 1) * p.Lc_t;
                 long long before = __ldcg(p.own_start + o + c);
-                trace_chunk<N>(p, ch, c, e, __ldcg(p.own_start + o + c + 1), false, t2s_all, tws);
+                trace_chunk<N>(p, ch, c, e, __ldcg(p.own_start + o + c + 1), false, tws);
                 __threadfence();
                 __syncwarp();
                 next_changed = (__ldcg(p.own_start + o + c) != before);
@@ -1377,6 +1540,11 @@ __global__ void __launch_bounds__(128) ring_vit_verify_trace(VitParams p) {
     if (lane == 0) {
         p.counters[ch * 4 + 1] = repaired;
         if (p.res_host) p.res_host[ch * 4 + 2] = (double)repaired;
+    }
+    if (p.want_ll) {
+        __threadfence();
+        __syncwarp();
+        ll_assemble(p, ch, lane);
     }
 }
 
@@ -1544,9 +1712,7 @@ static size_t prologue_smem(const VitParams &p, int *q_in_smem) {
     *q_in_smem = withq <= 200 * 1024 ? 1 : 0;  // else the emissions live in the (otherwise unused) T1pro scratch
     return *q_in_smem ? withq : small;
 }
-static size_t trace_smem(const VitParams &p, int warps) {
-    return sizeof(int16_t) * (size_t)p.ns * (p.RL.L + 1) + 16 + sizeof(uint32_t) * (size_t)warps * TR_WARP_U32;
-}
+static size_t trace_smem(const VitParams &p, int warps) { return sizeof(uint32_t) * (size_t)warps * TR_WARP_U32; }
 
 // Kernel attributes are set once per plan (not per launch: the launches may be captured into a CUDA graph).
 template <int N, int R, int LPC>
@@ -1746,7 +1912,7 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     const int64_t Lc_t = Lc / tfac;
     const int nchunks_t = (int)((T + Lc_t - 1) / Lc_t);
     const int64_t pcols = L + 1;
-    double *T1pro = (double *)alloc(Workspace::PROLOG, (sizeof(double) + sizeof(int16_t)) * (size_t)C * ns * pcols + 64);
+    double *T1pro = (double *)alloc(Workspace::PROLOG, sizeof(double) * (size_t)C * ns * pcols + sizeof(int16_t) * (size_t)C * pcols * 8 + 64);
     int16_t *T2pro = (int16_t *)(T1pro + (size_t)C * ns * pcols);
     hmdl.assign((size_t)C * RL.total, 0.0);
     for (int c = 0; c < C; c++) ring_pack(models[c], RL, hmdl.data() + (size_t)c * RL.total);
@@ -1771,6 +1937,8 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     size_t o_part = carve(sizeof(double) * (size_t)C * 1024);
     size_t o_sync = carve(sizeof(unsigned) * (size_t)C * 4);
     size_t o_ll = carve(sizeof(double) * (size_t)C);
+    size_t o_lln = carve(sizeof(double) * (size_t)C * nchunks);
+    size_t o_lls = carve(sizeof(double) * (size_t)C * nchunks_t);
     char *base = (char *)alloc(Workspace::CHUNKS, off);
     // pageable source: the copy is staged before cudaMemcpyAsync returns, and hmdl outlives it anyway
     HMM_CUDA(cudaMemcpyAsync(base + o_model, hmdl.data(), sizeof(double) * hmdl.size(), cudaMemcpyHostToDevice, st));
@@ -1820,6 +1988,15 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     p.ch0 = 0;
     part = (double *)(base + o_part);
     ll_dev_ = (double *)(base + o_ll);
+    p.ll_noise = (double *)(base + o_lln);
+    p.ll_spike = (double *)(base + o_lls);
+    p.ll_out = ll_dev_;
+    p.ll_lo = 0;
+    p.ll_hi = T;
+    p.t_off = 0;
+    p.T_glob = T;
+    p.ll_with_p0 = first_prologue ? 1 : 0;
+    p.want_ll = 1;
     impl->variant.prepare(p);
 }
 
@@ -1838,15 +2015,20 @@ static size_t ll_smem(const HostModel &M0) {
     return sizeof(double) * (2 * (size_t)M0.nstates + M0.ntrans) + sizeof(int) * (2 * (size_t)M0.nstates + 1 + M0.ntrans) + 16;
 }
 
+// The path score is assembled by verify_trace from the pieces the forward pass and the traceback leave behind
+// (ll_assemble); this only hands it over.  The range must be the one configured with set_ll_range.
 void VitPlan::path_ll(cudaStream_t st, double *ll_dev, int64_t t_lo, int64_t t_hi, int64_t t_off, int64_t T_glob,
                       bool with_p0) {
     VitParams &p = *p_;
-    const int nparts = 592;
-    ring_path_ll<<<dim3(nparts, launch_C()), 256, ll_smem(M0), st>>>(p.y, p.T, p.y_stride, blob_dev, FL.bytes, FL, M0.nstates,
-                                                            (int)M0.ntrans, p.x, p.x_stride, part, t_lo, t_hi, t_off,
-                                                            T_glob, p.sync_cnt, ll_dev ? ll_dev : ll_dev_,
-                                                            with_p0 ? 1 : 0, p.res_host, p.ch0);
-    HMM_CUDA(cudaGetLastError());
+    if (t_lo != p.ll_lo || t_hi != p.ll_hi || t_off != p.t_off || T_glob != p.T_glob || (with_p0 ? 1 : 0) != p.ll_with_p0 ||
+        !p.want_ll)
+        fail(HMM_EINVAL, "path_ll: range differs from the plan's configured ll range");
+    if (ll_dev && ll_dev != ll_dev_)
+        HMM_CUDA(cudaMemcpyAsync(ll_dev, ll_dev_, sizeof(double) * (size_t)C, cudaMemcpyDeviceToDevice, st));
+}
+void VitPlan::set_ll_range(int64_t lo, int64_t hi, int64_t t_off, int64_t T_glob, bool with_p0, bool want) {
+    VitParams &p = *p_;
+    p.ll_lo = lo; p.ll_hi = hi; p.t_off = t_off; p.T_glob = T_glob; p.ll_with_p0 = with_p0 ? 1 : 0; p.want_ll = want ? 1 : 0;
 }
 
 // Stand-alone path score of a decoded x (host-pointer pipeline: one pass over the whole recording at the end).
@@ -1901,17 +2083,17 @@ double *VitPlan::eb_ptr(int chunk) { return p_->EB + (size_t)chunk * p_->bvec; }
 double *VitPlan::sb_ptr(int chunk) { return p_->SB + (size_t)chunk * p_->bvec; }
 long long *VitPlan::own_start_ptr(int chunk) { return p_->own_start + (size_t)chunk * p_->tfac; }
 
-// The whole decode of a plan: six launches (per channel, when the channels are long enough to fill the GPU on
+// The whole decode of a plan: five launches (per channel, when the channels are long enough to fill the GPU on
 // their own: the FIR then takes its coefficients from the constant bank), nothing else.
 void VitPlan::run_all(cudaStream_t st, bool want_ll, Timer *ttop) {
+    p_->want_ll = want_ll ? 1 : 0;
     const int nrun = per_channel ? C : 1;
     for (int k = 0; k < nrun; k++) {
         p_->ch0 = per_channel ? k : 0;
         forward(st, k == 0 ? ttop : nullptr);
         verify_fwd(st);
         trace(st);
-        verify_trace(st);
-        if (want_ll) path_ll(st, nullptr, 0, p_->T, 0, p_->T, true);
+        verify_trace(st);  // (assembles ll as well)
     }
     p_->ch0 = 0;
 }
@@ -2059,7 +2241,7 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
         prog->plan.run_all(st, want_ll, ttop);
     }
     if (info) {
-        info->kernel_launches += (int64_t)(want_ll ? 6 : 5) * (per_channel ? C : 1);
+        info->kernel_launches += (int64_t)5 * (per_channel ? C : 1);
         info->n_chunks = prog->plan.nchunks();
     }
     pend->push_back(RingPending{prog->res_h, C, ll_host, info});
