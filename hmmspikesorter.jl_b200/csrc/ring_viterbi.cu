@@ -140,7 +140,7 @@ struct VitParams {
     double *res_host;      // [C x 4] device alias of mapped pinned host memory: ll, chunks repaired (forward, traceback); nullable
     int ch0;               // channel offset of this launch (long recordings: one channel per launch out of a C-channel plan)
     // ll = sum_t T1[x_t, t] assembled from pieces the decode produces anyway (see ll_assemble):
-    double *ll_noise;      // [C x nchunks]   per forward chunk: sum over its main range of (Tg - g) (y_g - m0)^2
+    double *ll_noise;      // [C x nchunks x 2] per forward chunk (and FIR producer warp of its slot): sum over its main range of (Tg - g) (y_g - m0)^2
     double *ll_spike;      // [C x nchunks_t] per traceback chunk: sum over its steps of (Tg - g) * (normalised increment)
     double *ll_out;        // [C]
     int64_t ll_lo, ll_hi;  // local sample range the sum runs over (chunk aligned; a shard's main span)
@@ -356,16 +356,22 @@ __device__ void final_state(const VitParams &p, int ch) {  // called by all 256 
 // mbarriers, so the FP64-pipe-bound FIR and the latency-bound recursion overlap.
 enum { ROLE_BOTH = 0, ROLE_FIR = 1, ROLE_DP = 2 };
 
-template <int N, int R>
-struct SlotSmem {  // one chunk slot of the warp-specialised kernel, in doubles
+template <int N, int R, int FW = 1>
+struct SlotSmem {  // one chunk slot of the warp-specialised kernel, in doubles (FW = FIR producer warps of the slot)
     using G = FirGeom<R>;
-    static constexpr int YT = 0;                                   // 2 y tiles
-    static constexpr int FT = 2 * G::YTILE;                        // 2 F tiles
+    static constexpr int YT = 0;                                   // 2 y tiles per producer
+    static constexpr int FT = 2 * FW * G::YTILE;                   // 2 F tiles
     static constexpr int RING = FT + 2 * N * G::FTILE;             // ring + prologue scratch
     static constexpr int BAR = RING + N * RING_Q + 104;            // full[2], empty[2], yready[2], yfree[2] mbarriers
     static constexpr int DOUBLES = BAR + 8;
 };
 
+// -DHMM_WS2 selects the dual-producer forward kernel (ring_vit_forward_ws2: four FIR warps and two recursions per SM
+// sub-partition, registers re-divided with setmaxnreg).  Measured on B200 it is SLOWER than the paired single-producer
+// kernel (N=3: 330 vs 302 us, N=4: 371 vs 326, N=5: 645 vs 513 at 18 M samples), so it is off by default.
+#ifndef HMM_WS2
+#define HMM_NO_WS2
+#endif
 #ifndef HMM_LL_NOISE_MODE
 #define HMM_LL_NOISE_MODE 1  // 1: path-score piece 1 by a pass over the staged y tile (measured 1 % faster than 0: from the FIR register window)
 #endif
@@ -404,11 +410,15 @@ __device__ __forceinline__ void pair_sync(int bar_id) {
 // the FP64 pipe busy (back-to-back DFMAs of one warp issue at half the pipe rate), and a consumer spends a third of its
 // time waiting for its producer: with the FIR of a super-window split N - NC : NC, four warps per SM sub-partition feed
 // the pipe instead of two, and producer and consumer finish a super-window at about the same time.
-template <int N, int R, int LPC, int ROLE, int NC = 0>
+// FW: FIR producer warps per slot.  FW = 2: producer `half` (0 / 1) computes the even / odd super-windows into F tile
+// `half`, from its own pair of y tiles -- four FIR warps per SM sub-partition keep the FP64 pipe busy where two leave
+// it idle a quarter of the time (back-to-back DFMAs of one warp issue at half the pipe rate).
+template <int N, int R, int LPC, int ROLE, int NC = 0, int FW = 1>
 __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coef, int ch, int c, int kind,
                                   const double *mdl /*smem model*/, double *ws /*per-warp or per-slot smem*/,
                                   int pair_bar = 0 /*named barrier shared with the partner producer, 0 = none*/,
-                                  int pair_nsw = 0 /*super-windows of the longer chunk of the pair*/) {
+                                  int pair_nsw = 0 /*iterations of the longer chunk of the pair*/, int half = 0) {
+    using SS = SlotSmem<N, R, FW>;
     using G = FirGeom<R>;
     constexpr int NP = (N + 1) & ~1;
     const int lane = threadIdx.x & 31;
@@ -419,9 +429,9 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
     __builtin_assume(__isShared(mdl));
     double *ytile = ws;
     double *fbuf = ws;  // ROLE_BOTH: aliases ytile (see WarpSmem); specialised roles: set per super-window
-    double *ring = ws + (ROLE == ROLE_BOTH ? WarpSmem<N, R>::TILE : SlotSmem<N, R>::RING);
+    double *ring = ws + (ROLE == ROLE_BOTH ? WarpSmem<N, R>::TILE : SS::RING);
     double *zs = ring + N * RING_Q;  // [L+1] <= 97 doubles
-    uint64_t *bar_full = reinterpret_cast<uint64_t *>(ws + SlotSmem<N, R>::BAR), *bar_empty = bar_full + 2;
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(ws + SS::BAR), *bar_empty = bar_full + 2;
     uint64_t *bar_yready = bar_full + 4, *bar_yfree = bar_full + 6;
     (void)bar_full;
     (void)bar_empty;
@@ -480,10 +490,11 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
     if (ROLE == ROLE_FIR) {
         // ---- producer: stage tile k+1 while the FIR of tile k runs; hand F tiles to the consumer ----
         const int need = G::SW + (LPC > 0 ? LPC : LP);
-        double *yt[2] = {ws + SlotSmem<N, R>::YT, ws + SlotSmem<N, R>::YT + G::YTILE};
-        double *ft[2] = {ws + SlotSmem<N, R>::FT, ws + SlotSmem<N, R>::FT + N * G::FTILE};
-        fir_stage<R>(y, T, base0, need, yt[0], lane);
-        int k = 0;
+        double *yt[2] = {ws + SS::YT + (2 * half) * G::YTILE, ws + SS::YT + (2 * half + 1) * G::YTILE};
+        double *ft[2] = {ws + SS::FT, ws + SS::FT + N * G::FTILE};
+        const int64_t bstep = (int64_t)FW * G::SW, bfirst = base0 + (int64_t)half * G::SW;
+        if (bfirst < e) fir_stage<R>(y, T, bfirst, need, yt[0], lane);
+        int k = 0;  // this producer's iteration; it computes super-window FW * k + half
         // path-score piece 1 (see ll_assemble): sum over the chunk's main range of (Tg - g) (y_g - m0)^2, from the y
         // tiles this warp stages anyway -- the recording is not read a second time for ll
         double nacc = 0.0;
@@ -492,16 +503,18 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
 #ifdef HMM_PHASE_TIMING
         long long pt_stage = 0, pt_wait = 0, pt_fir = 0;
 #endif
-        for (int64_t b = base0; b < e; b += G::SW, k++) {
-            const int buf = k & 1;
-            const bool more = b + G::SW < e;
+        for (int64_t b = bfirst; b < e; b += bstep, k++) {
+            const int ybuf = k & 1;                              // own y tile pair
+            const int buf = FW == 1 ? (k & 1) : half;            // F tile and its barriers
+            const unsigned fpar = FW == 1 ? ((k >> 1) & 1) : (k & 1);
+            const bool more = b + bstep < e;
 #ifdef HMM_PHASE_TIMING
             const long long q0 = clock64();
 #endif
             if (more) {
                 // the consumer reads the y tiles too (its share of the FIR): tile buf^1 last held super-window k-1
                 if (NC > 0 && k >= 1) mbar_wait(bar_yfree + (buf ^ 1), ((k - 1) >> 1) & 1);
-                fir_stage<R>(y, T, b + G::SW, need, yt[buf ^ 1], lane);
+                fir_stage<R>(y, T, b + bstep, need, yt[ybuf ^ 1], lane);
             }
             if (more)
                 cp_async_wait_but_one();
@@ -517,13 +530,13 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
             // of them run ahead at nearly full rate while the other crawls (measured: 4.5 k vs 8.5 k cycles per
             // super-window), and with one chunk per slot the kernel lasts as long as its slowest slot.
             if (pair_bar) pair_sync(pair_bar);
-            mbar_wait(bar_empty + buf, ((k >> 1) & 1) ^ 1);  // the consumer is done with this F tile
+            mbar_wait(bar_empty + buf, fpar ^ 1);  // the consumer is done with this F tile
 #ifdef HMM_PHASE_TIMING
             const long long q2 = clock64();
 #endif
             // (own samples of a main-range super-window also feed the path score, from the FIR's register window)
 #if HMM_LL_NOISE_MODE == 1
-            if (b >= s) nacc = ll_noise_tile<R>(yt[buf], nacc, m0n, wg0 - (double)(b - s), lane, (int)(e - b > G::SW ? G::SW : e - b));
+            if (b >= s) nacc = ll_noise_tile<R>(yt[ybuf], nacc, m0n, wg0 - (double)(b - s), lane, (int)(e - b > G::SW ? G::SW : e - b));
             double *llp = nullptr;
 #elif HMM_LL_NOISE_MODE == 2
             double *llp = nullptr;  // (timing experiments only: ll is wrong)
@@ -534,9 +547,9 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
             const int64_t left = e - b;
             const int nval = left > G::SW ? G::SW : (int)left;
             if constexpr (LPC > 0)
-                fir_compute_c<N, R, LPC, 0, N - NC>(coef, Bc, yt[buf], ft[buf], lane, llp, m0n, w0, nval);
+                fir_compute_c<N, R, LPC, 0, N - NC>(coef, Bc, yt[ybuf], ft[buf], lane, llp, m0n, w0, nval);
             else
-                fir_compute<N, R, 0, N - NC>(A, Bc, LP, yt[buf], ft[buf], lane, llp, m0n, w0, nval);
+                fir_compute<N, R, 0, N - NC>(A, Bc, LP, yt[ybuf], ft[buf], lane, llp, m0n, w0, nval);
             if (lane == 0) mbar_arrive(bar_full + buf);   // fir_compute ends with __syncwarp()
 #ifdef HMM_PHASE_TIMING
             const long long q3 = clock64();
@@ -553,7 +566,7 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
         {
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) nacc += __shfl_xor_sync(0xffffffffu, nacc, d);
-            if (lane == 0) p.ll_noise[(size_t)ch * p.nchunks + c] = nacc;
+            if (lane == 0) p.ll_noise[((size_t)ch * p.nchunks + c) * 2 + half] = nacc;
         }
         if (pair_bar)
             for (; k < pair_nsw; k++) pair_sync(pair_bar);  // the partner's chunk is longer
@@ -597,10 +610,10 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
 #endif
         if (ROLE == ROLE_DP) {
             const int buf = swk & 1;
-            fbuf = ws + SlotSmem<N, R>::FT + buf * N * G::FTILE;
+            fbuf = ws + SS::FT + buf * N * G::FTILE;
             if constexpr (NC > 0) {
                 // ---- consumer's share of the FIR: the last NC neurons, from the y tile the producer staged ----
-                const double *ytk = ws + SlotSmem<N, R>::YT + buf * G::YTILE;
+                const double *ytk = ws + SS::YT + buf * G::YTILE;
                 mbar_wait(bar_yready + buf, (swk >> 1) & 1);
                 if constexpr (LPC > 0)
                     fir_compute_c<N, R, LPC, N - NC, N>(coef, Bc, ytk, fbuf, lane);
@@ -903,6 +916,52 @@ __global__ void __launch_bounds__(SLOTS * 64, SLOTS == 8 ? 1 : 2)
         vit_process_chunk<N, R, LPC, ROLE_FIR, ConsumerFirShare<N>::value>(p, coef, ch, c, kind, mdl, ws, pair_bar, pair_nsw);
     } else if (c < p.nchunks)
         vit_process_chunk<N, R, LPC, ROLE_DP, ConsumerFirShare<N>::value>(p, coef, ch, c, kind, mdl, ws);
+}
+
+// Dual-producer variant (N <= 5, R = 4): ONE CTA of 24 warps per SM -- 8 chunk slots x {2 FIR producers, 1 recursion
+// consumer}.  Warps 0..15 are producers (slot = w & 7, half = w >> 3), warps 16..23 consumers; the slots s and s + 4 live
+// on the same SM sub-partition, so each sub-partition runs four FIR warps and two recursions.  Registers are
+// re-divided between the roles after launch (setmaxnreg, per warpgroup): the FIR needs ~60, the recursion ~125,
+// and 24 x 32 x 80 is all a CTA can be launched with.
+// setmaxnreg draws from the CTA's own pool: what the 16 producer warps give back ((80 - P) x 512) must cover what the
+// 8 consumer warps ask for ((C - 80) x 256), i.e. C <= 240 - 2 P -- otherwise the consumers wait forever.
+template <int N>
+struct Ws2Regs {
+    static constexpr int producer = N <= 4 ? 56 : 64;  // FIR: 4 N accumulators x 2 + window + addressing
+    static constexpr int consumer = N <= 4 ? 128 : 112;
+    static_assert(consumer <= 240 - 2 * producer, "consumers would starve");
+};
+template <int N, int LPC>
+__global__ void __launch_bounds__(768, 1)
+    ring_vit_forward_ws2(const __grid_constant__ VitParams p, const __grid_constant__ FirCoef<N, LPC> coef) {
+    extern __shared__ __align__(16) double smem_d[];
+    constexpr int R = 4, SLOTS = 8;
+    using G = FirGeom<R>;
+    using SS = SlotSmem<N, R, 2>;
+    const int ch = blockIdx.y + p.ch0;
+    double *mdl = smem_d;
+    const int warp = warp_index_uniform();
+    const bool producer = warp < 2 * SLOTS;
+    const int slot = producer ? (warp & (SLOTS - 1)) : warp - 2 * SLOTS;
+    double *ws = smem_d + ((p.RL.hot + 1) & ~1) + (size_t)slot * SS::DOUBLES;
+    if ((threadIdx.x & 31) == 0 && warp < SLOTS) {
+        uint64_t *bars = reinterpret_cast<uint64_t *>(ws + SS::BAR);
+        for (int k = 0; k < 8; k++) mbar_init(bars + k, 1);
+    }
+    load_model_smem<N, R>(p, ch, mdl);  // ends with __syncthreads(): barriers initialised, model staged
+    const int c = blockIdx.x * SLOTS + slot;
+    const int kind = (c == 0 && p.first_prologue) ? START_PROLOGUE : START_SPEC;
+    if (producer) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(Ws2Regs<N>::producer));
+        const int half = warp >> 3;
+        const int a = chunk_superwindows(p, c, G::SW), b = chunk_superwindows(p, blockIdx.x * SLOTS + (slot ^ 4), G::SW);
+        const int ia = a > half ? (a - half + 1) / 2 : 0, ib = b > half ? (b - half + 1) / 2 : 0;
+        vit_process_chunk<N, R, LPC, ROLE_FIR, 0, 2>(p, coef, ch, c, kind, mdl, ws, 1 + (slot & 3) + 4 * half,
+                                                     ia > ib ? ia : ib, half);
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(Ws2Regs<N>::consumer));
+        if (c < p.nchunks) vit_process_chunk<N, R, LPC, ROLE_DP, 0, 2>(p, coef, ch, c, kind, mdl, ws);
+    }
 }
 
 // Boundary check: speculative start vector of chunk c vs true end vector of c-1
@@ -1430,7 +1489,7 @@ __device__ void ll_assemble(const VitParams &p, int ch, int lane) {
     const int cf0 = (int)(lo / p.Lc), cf1 = hi >= p.T ? p.nchunks : (int)(hi / p.Lc);
     const int ct0 = (int)(lo / p.Lc_t), ct1 = hi >= p.T ? p.nchunks_t : (int)(hi / p.Lc_t);
     double a = 0.0, b = 0.0;
-    for (int c = cf0 + lane; c < cf1; c += 32) a += __ldcg(p.ll_noise + (size_t)ch * p.nchunks + c);
+    for (int c = 2 * cf0 + lane; c < 2 * cf1; c += 32) a += __ldcg(p.ll_noise + (size_t)ch * p.nchunks * 2 + c);
     for (int c = ct0 + lane; c < ct1; c += 32) b += __ldcg(p.ll_spike + (size_t)ch * p.nchunks_t + c);
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
@@ -1689,8 +1748,18 @@ template <int N, int R>
 constexpr int fwd_slots() {
     return (sizeof(double) * ((size_t)8 * SlotSmem<N, R>::DOUBLES + 1024) <= 220 * 1024) ? 8 : 4;
 }
+// The dual-producer kernel (ring_vit_forward_ws2) serves the R = 4 geometries whose eight slots fit shared memory.
+template <int N, int R>
+constexpr bool use_ws2() {
+#ifdef HMM_NO_WS2
+    return false;
+#else
+    return R == 4 && sizeof(double) * ((size_t)8 * SlotSmem<N, 4, 2>::DOUBLES + 1024) <= 222 * 1024;
+#endif
+}
 template <int N, int R, int LPC>
 static size_t fwd_smem_bytes(const RingLayout &RL) {
+    if (use_ws2<N, R>()) return sizeof(double) * (((RL.hot + 1) & ~1) + (size_t)8 * SlotSmem<N, 4, 2>::DOUBLES);
     return sizeof(double) * (((RL.hot + 1) & ~1) + (size_t)fwd_slots<N, R>() * SlotSmem<N, R>::DOUBLES);
 }
 
@@ -1698,11 +1767,16 @@ static size_t fwd_smem_bytes(const RingLayout &RL) {
 template <int N, int R, int LPC>
 static int fwd_warps_per_sm(const RingLayout &RL) {
     const size_t sm_fwd = fwd_smem_bytes<N, R, LPC>(RL);
-    constexpr int SLOTS = fwd_slots<N, R>();
-    HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws<N, R, LPC, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
-    int nb = 0;
-    HMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ring_vit_forward_ws<N, R, LPC, SLOTS>, SLOTS * 64, sm_fwd));
-    return (nb > 0 ? nb : 1) * SLOTS;  // chunk slots (producer/consumer warp pairs) per SM
+    if constexpr (use_ws2<N, R>()) {
+        HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws2<N, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+        return 8;  // one CTA of 8 slots per SM
+    } else {
+        constexpr int SLOTS = fwd_slots<N, R>();
+        HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws<N, R, LPC, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+        int nb = 0;
+        HMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ring_vit_forward_ws<N, R, LPC, SLOTS>, SLOTS * 64, sm_fwd));
+        return (nb > 0 ? nb : 1) * SLOTS;  // chunk slots (producer/consumer warp pairs) per SM
+    }
 }
 
 static size_t prologue_smem(const VitParams &p, int *q_in_smem) {
@@ -1718,7 +1792,10 @@ static size_t trace_smem(const VitParams &p, int warps) { return sizeof(uint32_t
 template <int N, int R, int LPC>
 static void stage_prepare(const VitParams &p) {
     const size_t sm_fwd = fwd_smem_bytes<N, R, LPC>(p.RL);
-    HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws<N, R, LPC, fwd_slots<N, R>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+    if constexpr (use_ws2<N, R>())
+        HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws2<N, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+    else
+        HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws<N, R, LPC, fwd_slots<N, R>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
     int qs = 0;
     const size_t sm_pro = prologue_smem(p, &qs);
     if (sm_pro > 227 * 1024) fail(HMM_EUNSUPPORTED, "prologue does not fit shared memory");
@@ -1732,7 +1809,7 @@ static void stage_prepare(const VitParams &p) {
 template <int N, int R, int LPC>
 static void stage_forward(VitParams &p, const double *hmodel /*host ring model of channel 0*/, int C, cudaStream_t st,
                           Timer *ttop) {
-    constexpr int WPB = fwd_slots<N, R>();
+    constexpr int WPB = use_ws2<N, R>() ? 8 : fwd_slots<N, R>();
     const size_t sm_fwd = fwd_smem_bytes<N, R, LPC>(p.RL);
     FirCoef<N, LPC> coef{};
     if (LPC > 0)
@@ -1748,7 +1825,10 @@ static void stage_forward(VitParams &p, const double *hmodel /*host ring model o
         ring_vit_prologue<<<C, nth, sm_pro, st>>>(p, qs);
     }
     if (ttop) ttop->start();
-    ring_vit_forward_ws<N, R, LPC, WPB><<<gridc, WPB * 64, sm_fwd, st>>>(p, coef);
+    if constexpr (use_ws2<N, R>())
+        ring_vit_forward_ws2<N, LPC><<<gridc, 768, sm_fwd, st>>>(p, coef);
+    else
+        ring_vit_forward_ws<N, R, LPC, WPB><<<gridc, WPB * 64, sm_fwd, st>>>(p, coef);
     if (ttop) ttop->stop();
     HMM_CUDA(cudaGetLastError());
 }
@@ -1798,10 +1878,15 @@ static VitVariant pick_lp(int L, bool const_ok) {
 }
 static VitVariant pick_variant(int N, int L, bool const_ok) {
     switch (N) {
+#ifdef HMM_NO_WS2
         case 1: return make_variant<1, 8, 0>();
         case 2: return make_variant<2, 8, 0>();
-        case 3:
-            return pick_lp<3, 8>(L, const_ok);
+        case 3: return pick_lp<3, 8>(L, const_ok);
+#else
+        case 1: return make_variant<1, 4, 0>();
+        case 2: return make_variant<2, 4, 0>();
+        case 3: return pick_lp<3, 4>(L, const_ok);
+#endif
         case 4: return pick_lp<4, 4>(L, const_ok);  // R = 4: eight chunk slots fit one SM's shared memory (R = 8: four)
         case 5: return pick_lp<5, 4>(L, const_ok);
         case 6: return make_variant<6, 4, 0>();
@@ -1845,7 +1930,11 @@ void *VitPlan::alloc(int slot, size_t bytes) {
 
 int ring_default_chunking(const HostModel &M0, int64_t T_total, int C, int n_gpus, int64_t *Lc_out, int64_t *W_out) {
     const int N = M0.N, L = M0.K - 1;
+#ifdef HMM_NO_WS2
     const int R = (N <= 3) ? 8 : 4, SW = 32 * R;
+#else
+    const int R = 4, SW = 32 * R;
+#endif
     RingLayout RL = ring_layout(N, L);
     const bool no_const = getenv("HMMCUDA_NO_CONST_FIR") && atoi(getenv("HMMCUDA_NO_CONST_FIR")) != 0;
     const VitVariant variant = pick_variant(N, RL.L, C == 1 && !no_const);
@@ -1937,13 +2026,14 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     size_t o_part = carve(sizeof(double) * (size_t)C * 1024);
     size_t o_sync = carve(sizeof(unsigned) * (size_t)C * 4);
     size_t o_ll = carve(sizeof(double) * (size_t)C);
-    size_t o_lln = carve(sizeof(double) * (size_t)C * nchunks);
+    size_t o_lln = carve(sizeof(double) * (size_t)C * nchunks * 2);  // one partial per FIR producer warp of a slot
     size_t o_lls = carve(sizeof(double) * (size_t)C * nchunks_t);
     char *base = (char *)alloc(Workspace::CHUNKS, off);
     // pageable source: the copy is staged before cudaMemcpyAsync returns, and hmdl outlives it anyway
     HMM_CUDA(cudaMemcpyAsync(base + o_model, hmdl.data(), sizeof(double) * hmdl.size(), cudaMemcpyHostToDevice, st));
     HMM_CUDA(cudaMemsetAsync(base + o_sync, 0, sizeof(unsigned) * (size_t)C * 4, st));  // self-resetting afterwards
     HMM_CUDA(cudaMemsetAsync(base + o_cnt, 0, sizeof(int) * (size_t)C * 4, st));
+    HMM_CUDA(cudaMemsetAsync(base + o_lln, 0, sizeof(double) * (size_t)C * nchunks * 2, st));
 
     p = VitParams{};
     p.y = y_dev;
