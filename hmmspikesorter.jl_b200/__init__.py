@@ -32,7 +32,7 @@ from .timeshard import viterbi_time_sharded
 __all__ = [
     "StateMatrix", "viterbi", "viterbi_batch", "forward", "backward", "update", "train_model", "em_step",
     "reconstruct_signal", "unroll_mlseq", "TrainContext", "create_signal", "create_spike_template", "make_rng",
-    "HmmError", "HmmArgumentError", "device_count", "set_ring_params", "viterbi_time_sharded",
+    "HmmError", "HmmArgumentError", "device_count", "set_ring_params", "set_devices", "viterbi_time_sharded",
 ]
 
 i64, i32, f64 = C.c_int64, C.c_int32, C.c_double
@@ -44,6 +44,14 @@ def _p(a):
 
 def device_count() -> int:
     return int(lib().hmm_device_count())
+
+
+def set_devices(devices=None) -> None:
+    """Devices the host-pointer decodes spread their work over inside the library (hmm_set_devices): the channels
+    of viterbi_batch in blocks, one long recording of viterbi as time shards.  None / one device: single-device."""
+    d = [] if devices is None else [int(v) for v in devices]
+    arr = (C.c_int * max(1, len(d)))(*d)
+    check(lib().hmm_set_devices(arr, C.c_int(len(d))))
 
 
 def set_ring_params(chunk_len: int = 0, warmup: int = 0) -> None:

@@ -10,6 +10,10 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <future>
 
 #include "engines.h"
 
@@ -27,9 +31,14 @@ static int set_err(int code, const std::string &m) {
 
 static void begin_call();  // advances the cache epochs (entries used by the running call are never evicted)
 
+// Worker threads of the multi-device dispatcher call the public entry points on behalf of a caller that already
+// holds the entry lock: they do not take it again.
+static thread_local bool t_worker = false;
+
 template <class F>
 static int guarded(F &&f) {
-    std::lock_guard<std::mutex> lk(g_entry);
+    std::unique_lock<std::mutex> lk(g_entry, std::defer_lock);
+    if (!t_worker) lk.lock();
     try {
         g_err.clear();
         begin_call();
@@ -136,6 +145,137 @@ int hmm_host_free(void *ptr) {
 }  // extern "C"
 
 // ---------------------------------------------------------------------------
+// Multi-device dispatch inside the library (hmm_set_devices): one persistent worker thread per selected GPU, each
+// with its own thread-local streams, workspace and caches.  A host-pointer call made by the application is split
+// by the calling thread (which holds the entry lock) and the pieces run on the workers through the same public
+// entry points.
+// ---------------------------------------------------------------------------
+namespace {
+
+class DeviceWorker {
+  public:
+    explicit DeviceWorker(int dev) : dev_(dev), th_([this] { loop(); }) {}
+    ~DeviceWorker() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        if (th_.joinable()) th_.join();
+    }
+    int device() const { return dev_; }
+    // runs f on the worker thread (device selected); the future carries (status, message)
+    std::future<std::pair<int, std::string>> run(std::function<int()> f) {
+        auto task = std::make_shared<std::packaged_task<std::pair<int, std::string>()>>([f] {
+            const int rc = f();
+            return std::make_pair(rc, rc ? std::string(hmm_last_error()) : std::string());
+        });
+        auto fut = task->get_future();
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            q_.push_back([task] { (*task)(); });
+        }
+        cv_.notify_one();
+        return fut;
+    }
+
+  private:
+    void loop() {
+        t_worker = true;
+        cudaSetDevice(dev_);
+        for (;;) {
+            std::function<void()> job;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                job = std::move(q_.front());
+                q_.pop_front();
+            }
+            job();
+        }
+    }
+    int dev_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+    bool stop_ = false;
+    std::thread th_;
+};
+
+std::vector<std::unique_ptr<DeviceWorker>> g_workers;  // under the entry lock
+bool g_devices_from_env = false;
+
+void set_devices_locked(const int *devs, int n) {
+    g_workers.clear();
+    if (!devs || n <= 1) return;  // zero or one device: the ordinary single-device path on the current device
+    int have = 0;
+    HMM_CUDA(cudaGetDeviceCount(&have));
+    for (int k = 0; k < n; k++) {
+        if (devs[k] < 0 || devs[k] >= have) fail(HMM_EINVAL, "device %d does not exist (%d visible)", devs[k], have);
+        // (HMMCUDA_DEBUG_ALLOW_DUP_DEVICES=1: tests drive the dispatcher with several workers on one GPU)
+        const bool dup_ok = getenv("HMMCUDA_DEBUG_ALLOW_DUP_DEVICES") && atoi(getenv("HMMCUDA_DEBUG_ALLOW_DUP_DEVICES"));
+        for (int j = 0; j < k && !dup_ok; j++)
+            if (devs[j] == devs[k]) fail(HMM_EINVAL, "device %d listed twice", devs[k]);
+    }
+    for (int k = 0; k < n; k++) g_workers.emplace_back(new DeviceWorker(devs[k]));
+}
+
+// HMMCUDA_DEVICES=0,1,2,3 selects the devices without a call (read once, at the first decode)
+void devices_from_env_once() {
+    if (g_devices_from_env) return;
+    g_devices_from_env = true;
+    const char *e = getenv("HMMCUDA_DEVICES");
+    if (!e || !*e || !g_workers.empty()) return;
+    std::vector<int> d;
+    for (const char *q = e; *q;) {
+        char *end = nullptr;
+        long v = strtol(q, &end, 10);
+        if (end == q) break;
+        d.push_back((int)v);
+        q = *end == ',' ? end + 1 : end;
+    }
+    set_devices_locked(d.data(), (int)d.size());
+}
+
+// waits for every piece; the first failure becomes the call's failure
+void join_all(std::vector<std::future<std::pair<int, std::string>>> &futs) {
+    int rc = HMM_OK;
+    std::string msg;
+    for (auto &f : futs) {
+        auto r = f.get();
+        if (r.first != HMM_OK && rc == HMM_OK) {
+            rc = r.first;
+            msg = r.second;
+        }
+    }
+    futs.clear();
+    if (rc != HMM_OK) throw Error{rc, msg};
+}
+
+}  // namespace
+
+extern "C" {
+
+int hmm_set_devices(const int *devices, int n) {
+    return guarded([&] {
+        require_device();
+        if (n < 0) fail(HMM_EINVAL, "negative device count");
+        g_devices_from_env = true;  // an explicit call wins over HMMCUDA_DEVICES
+        set_devices_locked(devices, n);
+    });
+}
+
+int hmm_get_devices(int *devices_out, int cap) {
+    std::lock_guard<std::mutex> lk(g_entry);
+    const int n = (int)g_workers.size();
+    for (int k = 0; k < n && k < cap; k++) devices_out[k] = g_workers[k]->device();
+    return n;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
 // Viterbi
 // ---------------------------------------------------------------------------
 namespace {
@@ -158,8 +298,8 @@ struct BatchModels {
 // Validating a StateMatrix, building its CSR forms, packing and uploading them costs tens of microseconds per
 // channel; callers decode many recordings (or one recording many times) with the same model.  Entries are keyed by
 // the bytes of the arrays that crossed the ABI (hash first, then compared byte for byte).
-std::vector<std::unique_ptr<BatchModels>> g_models;
-uint64_t g_model_seq = 0, g_call_epoch = 0;
+thread_local std::vector<std::unique_ptr<BatchModels>> g_models;  // per host thread, like the workspace
+thread_local uint64_t g_model_seq = 0, g_call_epoch = 0;
 constexpr size_t MAX_MODELS = 48;
 
 inline uint64_t mix64(uint64_t h, const void *data, size_t n) {
@@ -569,6 +709,143 @@ void viterbi_host_pipelined(const double *y, int64_t T, BatchModels &B, int16_t 
     cleanup();
 }
 
+// ---- multi-device: a batch of channels, contiguous blocks of channels per device --------------------------------
+void viterbi_batch_multidev(const double *y, int64_t T, int C, const int16_t *states, int states_shared, int N, int K,
+                            int nstates, const hmm_trans *tr, int64_t ntrans, const double *mu, const double *sigma,
+                            int16_t *x_out, double *ll_out, int mode, hmm_info *info) {
+    const int nd = (int)std::min<size_t>(g_workers.size(), (size_t)C);
+    std::vector<hmm_info> infos((size_t)nd);
+    std::vector<std::future<std::pair<int, std::string>>> futs;
+    for (int k = 0; k < nd; k++) {
+        const int c0 = (int)((int64_t)C * k / nd), c1 = (int)((int64_t)C * (k + 1) / nd);
+        if (c1 <= c0) continue;
+        hmm_info *ik = &infos[(size_t)k];
+        futs.push_back(g_workers[(size_t)k]->run([=] {
+            return hmm_viterbi_batch_f64(y + (size_t)c0 * T, T, c1 - c0, states_shared ? states : states + (size_t)c0 * N * nstates,
+                                         states_shared, N, K, nstates, tr + (size_t)c0 * ntrans, ntrans,
+                                         mu + (size_t)c0 * K * N, sigma + c0, x_out + (size_t)c0 * T,
+                                         ll_out ? ll_out + c0 : nullptr, mode, ik);
+        }));
+    }
+    join_all(futs);
+    if (info) {
+        memset(info, 0, sizeof *info);
+        for (auto &q : infos) {
+            info->engine = q.engine;
+            info->n_chunks += q.n_chunks;
+            info->fwd_repaired += q.fwd_repaired;
+            info->bwd_repaired += q.bwd_repaired;
+            info->kernel_launches += q.kernel_launches;
+            info->device_ms = std::max(info->device_ms, q.device_ms);
+        }
+    }
+}
+
+// ---- multi-device: ONE long recording as time shards, one per device, peer-memory boundary exchange -----------
+struct ShardSpan {
+    int64_t lb, le, mb, me;
+};
+std::vector<ShardSpan> plan_shards(int64_t T, int n, int64_t Lc, int64_t W) {
+    int64_t nchunks = (T + Lc - 1) / Lc;
+    const int64_t tail = T - (nchunks - 1) * Lc;
+    if (nchunks > 1 && tail < std::min<int64_t>(W + 128, Lc)) nchunks--;  // a short tail joins the chunk before it
+    if (n > nchunks / 2) n = (int)std::max<int64_t>(1, nchunks / 2);      // at least two chunks per shard
+    std::vector<ShardSpan> out((size_t)n);
+    const int64_t q = nchunks / n, r = nchunks % n;
+    int64_t c0 = 0;
+    for (int k = 0; k < n; k++) {
+        const int64_t c1 = c0 + q + (k < r ? 1 : 0);
+        out[(size_t)k].mb = c0 * Lc;
+        out[(size_t)k].me = k == n - 1 ? T : c1 * Lc;
+        out[(size_t)k].lb = std::max<int64_t>(0, out[(size_t)k].mb - Lc);
+        out[(size_t)k].le = std::min<int64_t>(T, out[(size_t)k].me + Lc);
+        c0 = c1;
+    }
+    return out;
+}
+
+bool viterbi_timeshard_multidev(const double *y, int64_t T, const int16_t *states, int N, int K, int nstates,
+                                const hmm_trans *tr, int64_t ntrans, const double *mu, double sigma, int16_t *x_out,
+                                double *ll_out, hmm_info *info) {
+    int64_t Lc = 0, W = 0;
+    {
+        HostModel M;
+        M.N = N;
+        M.K = K;
+        M.nstates = nstates;
+        M.is_ring = true;
+        ring_default_chunking(M, T, 1, (int)g_workers.size(), &Lc, &W);
+        W = 256;  // short chunks per GPU: a short speculative warm-up (every boundary is verified anyway)
+    }
+    const std::vector<ShardSpan> spans = plan_shards(T, (int)g_workers.size(), Lc, W);
+    const int n = (int)spans.size();
+    if (n < 2) return false;
+    std::vector<hmm_vshard *> sh((size_t)n, nullptr);
+    std::vector<void *> blocks((size_t)n, nullptr);
+    std::vector<double> ll((size_t)n, 0.0);
+    std::vector<int32_t> bad((size_t)n, 0);
+    std::vector<std::future<std::pair<int, std::string>>> futs;
+    auto destroy_all = [&] {
+        std::vector<std::future<std::pair<int, std::string>>> f2;
+        for (int k = 0; k < n; k++)
+            if (sh[(size_t)k]) {
+                hmm_vshard *h = sh[(size_t)k];
+                f2.push_back(g_workers[(size_t)k]->run([h] { return hmm_vshard_destroy(h); }));
+            }
+        for (auto &f : f2) f.get();
+    };
+    try {
+        for (int k = 0; k < n; k++) {
+            const ShardSpan sp = spans[(size_t)k];
+            hmm_vshard **hk = &sh[(size_t)k];
+            void **bk = &blocks[(size_t)k];
+            futs.push_back(g_workers[(size_t)k]->run([=] {
+                int rc = hmm_vshard_create(y + sp.lb, 1, sp.lb, sp.le, sp.mb, sp.me, T, Lc, W, states, N, K, nstates, tr,
+                                           ntrans, mu, sigma, hk);
+                if (rc) return rc;
+                return hmm_vshard_p2p_init(*hk, k, n, nullptr, bk);
+            }));
+        }
+        join_all(futs);
+        for (int k = 0; k < n; k++) {
+            hmm_vshard *h = sh[(size_t)k];
+            void *const *bp = blocks.data();
+            futs.push_back(g_workers[(size_t)k]->run([=] {
+                int rc = hmm_vshard_p2p_attach(h, nullptr, bp);
+                if (rc) return rc;
+                return hmm_vshard_p2p_launch(h, nullptr);
+            }));
+        }
+        join_all(futs);  // every shard has launched its decode and its summary stores: the judges cannot wait in vain
+        for (int k = 0; k < n; k++) {
+            hmm_vshard *h = sh[(size_t)k];
+            const ShardSpan sp = spans[(size_t)k];
+            double *lk = &ll[(size_t)k];
+            int32_t *bk = &bad[(size_t)k];
+            futs.push_back(g_workers[(size_t)k]->run([=] {
+                int rc = hmm_vshard_p2p_finish(h, lk, bk);
+                if (rc) return rc;
+                return hmm_vshard_finish(h, x_out + sp.mb, 0, nullptr);  // x of the main span -> the caller's array
+            }));
+        }
+        join_all(futs);
+    } catch (...) {
+        destroy_all();
+        throw;
+    }
+    destroy_all();
+    for (int k = 0; k < n; k++)
+        if (bad[(size_t)k] != 0) return false;  // a ghost chunk guessed wrong (not seen on real data): exact single-GPU decode
+    if (ll_out) *ll_out = ll[0];
+    if (info) {
+        memset(info, 0, sizeof *info);
+        info->engine = HMM_MODE_RING;
+        info->n_chunks = (int32_t)((T + Lc - 1) / Lc);
+        info->kernel_launches = 8 * (int64_t)n;
+    }
+    return true;
+}
+
 int viterbi_host(const double *y, int64_t T, int C, const int16_t *states, int states_shared, int N, int K,
                  int nstates, const hmm_trans *tr, int64_t ntrans, const double *mu, const double *sigma,
                  int16_t *x_out, double *ll_out, int16_t *T2_out, double *T1_out, int mode, hmm_info *info) {
@@ -578,6 +855,24 @@ int viterbi_host(const double *y, int64_t T, int C, const int16_t *states, int s
         if (T < 1 || C < 1) fail(HMM_EINVAL, "T and C must be positive");
         if ((T1_out || T2_out) && C != 1) fail(HMM_EINVAL, "trellis output is single-channel");
         require_device();
+        // ---- several devices selected (hmm_set_devices / HMMCUDA_DEVICES): split the call over them ----
+        if (!t_worker) {
+            devices_from_env_once();
+            if (g_workers.size() > 1 && !T1_out && !T2_out && mode != HMM_MODE_FAITHFUL) {
+                if (C > 1) {
+                    viterbi_batch_multidev(y, T, C, states, states_shared, N, K, nstates, tr, ntrans, mu, sigma, x_out,
+                                           ll_out, mode, info);
+                    return;
+                }
+                if (T >= ((int64_t)1 << 23)) {
+                    HostModel M;
+                    analyse_model(states, N, K, nstates, tr, ntrans, mu, sigma[0], M);
+                    if (M.is_ring && ring_supported(M, T) &&
+                        viterbi_timeshard_multidev(y, T, states, N, K, nstates, tr, ntrans, mu, sigma[0], x_out, ll_out, info))
+                        return;
+                }
+            }
+        }
         cudaStream_t st = main_stream();
         Workspace &ws = workspace();
         Timer tall(st);

@@ -2223,8 +2223,9 @@ struct RingProgram {
     }
 };
 
-std::vector<std::unique_ptr<RingProgram>> g_programs;  // all entry points hold the library's entry lock
-uint64_t g_epoch = 0;
+// per host thread, like the workspace (the multi-device dispatcher runs one worker thread per GPU)
+thread_local std::vector<std::unique_ptr<RingProgram>> g_programs;
+thread_local uint64_t g_epoch = 0;
 constexpr size_t MAX_PROGRAMS = 40;
 
 }  // namespace

@@ -1,24 +1,54 @@
-# HMMCuda.jl -- the `ccall` shim that makes libhmmcuda.so a drop-in for the
-# hot-path methods of HMMSpikeSorter.jl.  `include` it AFTER the package's own
-# files (src/HMMSpikeSorter.jl:14-20): the methods below have the same
-# signatures as the reference's and therefore REPLACE them, so every caller
-# (src/fit.jl:7,23,45,50,55; README.md:33-35; test/runtests.jl) keeps working
-# unmodified.
+# HMMCuda.jl -- the `ccall` shim that makes libhmmcuda.so a drop-in for the hot-path methods of
+# HMMSpikeSorter.jl.  It is a SUBMODULE: `include("HMMCuda.jl")` goes into src/HMMSpikeSorter.jl right after
+# `include("types.jl")` (it needs `StateMatrix`), and each hot-path method of the package gets a one-line guard as
+# its first statement (INTEGRATION.md lists the six lines), e.g.
 #
-# NOTE: Julia is not installed in the environment this library is built and
-# tested in, so this file has not been executed there.  It is kept mechanical
-# on purpose: every call passes exactly the arrays the Python ctypes mirror
-# (hmmspikesorter.jl_b200/__init__.py) passes to the same symbols, and that
-# mirror is what the test-suite exercises.
+#     function viterbi(y::AbstractArray{Float64,1}, lA::StateMatrix, μ::Array{Float64,2}, σ::Float64)
+#         HMMCuda.enabled() && return HMMCuda.viterbi(y, lA, μ, σ)
+#         ...                                   # the reference's body, untouched
+#
+# Nothing is overwritten: Julia >= 1.10 refuses method overwriting during precompilation, so the earlier form of
+# this file (same-signature methods included at the end of the module) could not be precompiled.  Every caller
+# (src/fit.jl:7,23,45,50,55; README.md:33-35; test/runtests.jl) keeps working unmodified, and
+# `HMMSPIKESORTER_BACKEND=julia` (or a missing library / device) leaves the reference's own code in charge.
+#
+# NOTE: Julia is not installed in the environment this library is built and tested in, so this file has not been
+# executed there.  It is kept mechanical on purpose: every call passes exactly the arrays the Python ctypes mirror
+# (hmmspikesorter.jl_b200/__init__.py) passes to the same symbols, and that mirror is what the test-suite exercises.
 #
 # Memory layout facts relied upon (src/types.jl:1-9):
 #   lA.states       :: Matrix{Int16}  [N x nstates], column-major, 1-based ring phases
 #   lA.transitions  :: Vector{Tuple{Int64,Int64,Float64}}  isbits => contiguous 24-byte records
 #   μ               :: Matrix{Float64} [K x N], column-major
+module HMMCuda
+
+import ..StateMatrix
 
 const libhmmcuda = get(ENV, "LIBHMMCUDA", "libhmmcuda.so")
 
 const HMM_EINVAL = 1
+
+# ---- backend switch ------------------------------------------------------------------------------------------
+# "cuda": always (errors if the library or a device is missing); "julia": never; "auto" (default): when
+# libhmmcuda.so loads and reports at least one device.  Decided once, at first use.
+const _enabled = Ref{Union{Nothing,Bool}}(nothing)
+function enabled()
+    e = _enabled[]
+    e === nothing || return e
+    want = lowercase(get(ENV, "HMMSPIKESORTER_BACKEND", "auto"))
+    ok = false
+    if want != "julia"
+        try
+            ok = ccall((:hmm_device_count, libhmmcuda), Cint, ()) > 0
+        catch err
+            want == "cuda" && rethrow(err)
+        end
+        want == "cuda" && !ok && error("HMMSPIKESORTER_BACKEND=cuda but libhmmcuda reports no CUDA device")
+    end
+    _enabled[] = ok
+    ok
+end
+enable!(on::Bool=true) = (_enabled[] = on)
 
 struct HmmInfo
     engine::Int32; n_chunks::Int32; fwd_repaired::Int32; bwd_repaired::Int32
@@ -167,3 +197,32 @@ function pinned_vector(::Type{T}, n::Integer) where T
     unsafe_wrap(Array, convert(Ptr{T}, p[]), n; own=false)
 end
 free_pinned(v::Array) = (ccall((:hmm_host_free, libhmmcuda), Cint, (Ptr{Cvoid},), pointer(v)); nothing)
+
+# ---- fit(HMMSpikingModel, templates, X, chunksize)        replaces the chunk loop of src/fit.jl:11-42
+# The reference decodes 100k-sample chunks independently and stitches them at noise samples (approximate, and its
+# `gc()` call no longer exists in Julia >= 1.0).  The GPU decode is exact and time-parallel inside one call, so the
+# chunked method simply decodes the whole vector; `chunksize` is accepted and ignored.  Guard line for src/fit.jl:12:
+#     HMMCuda.enabled() && return HMMSpikingModel(templates, HMMCuda.viterbi_whole(templates, X)..., X)
+viterbi_whole(templates, X::AbstractVector{Float64}) = viterbi(X, templates.state_matrix, templates.μ, templates.σ)
+
+# ---- unroll_mlseq(mlseq, state_matrix)                    replaces src/extraction.jl:4-13
+function unroll_mlseq(mlseq::AbstractVector{Int16}, lA::StateMatrix)
+    x = mlseq isa Vector{Int16} ? mlseq : collect(mlseq)
+    out = Matrix{Int16}(undef, lA.N, length(x))
+    GC.@preserve x lA out begin
+        _check(ccall((:hmm_unroll_mlseq_i16, libhmmcuda), Cint,
+            (Ptr{Int16}, Int64, Ptr{Int16}, Int32, Int32, Ptr{Int16}),
+            x, length(x), lA.states, lA.N, lA.nstates, out))
+    end
+    out
+end
+
+# ---- devices ---------------------------------------------------------------------------------------------------
+# set_devices([0,1,2,3]): subsequent viterbi / batch calls spread their work over these GPUs inside the library
+# (channels of a batch round-robin; one long recording as time shards with peer-memory boundary exchange).
+function set_devices(devs::AbstractVector{<:Integer})
+    d = convert(Vector{Cint}, devs)
+    GC.@preserve d _check(ccall((:hmm_set_devices, libhmmcuda), Cint, (Ptr{Cint}, Cint), d, length(d)))
+end
+
+end # module HMMCuda

@@ -64,6 +64,14 @@ const char *hmm_last_error(void);   /* thread-local, never NULL */
 int hmm_device_count(void);         /* number of CUDA devices, 0 if none */
 int hmm_set_device(int device);     /* device used by subsequent calls from this thread */
 int hmm_get_device(void);
+/* Devices the host-pointer decode entry points spread their work over, INSIDE the library (one worker thread and
+ * stream set per device): the channels of hmm_viterbi_batch_f64 in contiguous blocks, one long recording of
+ * hmm_viterbi_f64 (>= 8 M samples, ring model) as time shards with peer-memory boundary exchange -- so a Julia caller
+ * of viterbi / the batch call uses the whole box (the reference sorts one channel per process, src/hmmsort.jl:79-83).
+ * n <= 1 or NULL restores the single-device behaviour (the device of hmm_set_device).  The environment variable
+ * HMMCUDA_DEVICES=0,1,2,... does the same without a call.  Results are identical to the single-device decode. */
+int hmm_set_devices(const int *devices, int n);
+int hmm_get_devices(int *devices_out, int cap); /* returns the number of selected devices (0: single-device mode) */
 /* Run the calling thread's subsequent work on `cuda_stream` (a cudaStream_t owned by the caller, e.g.
  * torch.cuda.current_stream().cuda_stream) so that it is stream-ordered with the caller's own kernels
  * and NCCL collectives; NULL restores the library's private stream (so the legacy default stream, whose
