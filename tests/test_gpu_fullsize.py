@@ -254,3 +254,44 @@ def test_config1_readme_example(hm, O):
     assert np.array_equal(x, xo) and abs(ll - llo) <= 1e-9 * abs(llo)
     Y = hm.reconstruct_signal(x, lA_fit, mu_fit, s_fit)
     assert np.allclose(Y, O.reconstruct_signal(xo, smo, muo), atol=1e-6)
+
+
+def test_config1_end_to_end_with_merge_and_prune(hm, O):
+    """BASELINE config 1 replayed through the reference's WHOLE training driver (src/baumwelch.jl:324-354): 10 E/M
+    steps, condense_templates -> remove_sparse -> remove_small, 5 more E/M steps, then viterbi + reconstruct_signal.
+    The host-side merge / prune code is the literal restatement in tests/train_harness.py (quirks included); the
+    E/M steps come once from the CPU oracle and once from libhmmcuda.  Same discrete decisions, fits within 1e-6,
+    identical decoded path."""
+    import train_harness as th
+
+    K, N, T = 60, 3, 20_000
+    temps2 = np.stack([hm.create_spike_template(K, 3.0, 0.8, 0.2), hm.create_spike_template(K, 4.0, 0.3, 0.2)], 1)
+    S = hm.create_signal(T, 0.3, np.array([0.003, 0.001]), temps2, hm.make_rng(1234))
+    rng = np.random.default_rng(7)
+    sig0 = float(np.std(S))
+    mu0 = np.asfortranarray(np.stack([hm.create_spike_template(K, 3 * sig0 * rng.random(), 0.5 + 0.1 * rng.normal(),
+                                                               1.5 * rng.random()) for _ in range(N)], 1))
+    mu0[0, :] = 0.0
+    sm0 = hm.StateMatrix(N, K, np.log(np.full(N, 2.0 ** (-3 * K / 2))), False)  # p0 of src/baumwelch.jl:311
+
+    def em_gpu(X, sm, mu, sigma):
+        return hm.em_step(X, sm, np.asfortranarray(mu), sigma)
+
+    def em_cpu(X, sm, mu, sigma):
+        return O.em_step(X, sm, np.asfortranarray(mu), sigma)
+
+    sm_g, mu_g, s_g, log_g = th.train_model(em_gpu, hm.StateMatrix, S, sm0, mu0, sig0, 10)
+    sm_c, mu_c, s_c, log_c = th.train_model(em_cpu, hm.StateMatrix, S, sm0, mu0, sig0, 10)
+    # the discrete decisions of the merge / prune phase
+    assert log_g["after_condense"][0] == log_c["after_condense"][0]
+    assert log_g["after_sparse"] == log_c["after_sparse"] and log_g["after_small"] == log_c["after_small"]
+    assert np.abs(log_g["after_phase1"][1] - log_c["after_phase1"][1]).max() < FIT_ATOL
+    assert sm_g is not None and sm_g.N == sm_c.N and mu_g.shape == mu_c.shape
+    assert np.abs(mu_g - mu_c).max() < FIT_ATOL and abs(s_g - s_c) < FIT_ATOL
+    assert np.abs(sm_g.transitions["lp"] - sm_c.transitions["lp"]).max() < FIT_ATOL
+    x, ll = hm.viterbi(S, sm_g, mu_g, s_g)
+    xo, llo = O.viterbi(S, sm_c, mu_c, s_c)
+    assert np.array_equal(x, xo) and abs(ll - llo) <= LL_RTOL * abs(llo)
+    Y = hm.reconstruct_signal(x, sm_g, mu_g, s_g)
+    assert np.allclose(Y, O.reconstruct_signal(xo, sm_c, mu_c), atol=1e-6)
+    assert 0.2 < 1 - np.std(Y - S) / np.std(S) < 0.7  # sanity only: from this seeded init the literal driver keeps one template
