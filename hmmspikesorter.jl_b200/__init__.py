@@ -32,7 +32,7 @@ from .timeshard import viterbi_time_sharded
 __all__ = [
     "StateMatrix", "viterbi", "viterbi_batch", "forward", "backward", "update", "train_model", "em_step",
     "reconstruct_signal", "unroll_mlseq", "TrainContext", "create_signal", "create_spike_template", "make_rng",
-    "HmmError", "HmmArgumentError", "device_count", "set_ring_params", "set_devices", "viterbi_time_sharded",
+    "HmmError", "HmmArgumentError", "device_count", "set_ring_params", "set_devices", "set_precision", "viterbi_f32", "viterbi_time_sharded",
 ]
 
 i64, i32, f64 = C.c_int64, C.c_int32, C.c_double
@@ -52,6 +52,26 @@ def set_devices(devices=None) -> None:
     d = [] if devices is None else [int(v) for v in devices]
     arr = (C.c_int * max(1, len(d)))(*d)
     check(lib().hmm_set_devices(arr, C.c_int(len(d))))
+
+
+def set_precision(precision: str = "f64") -> None:
+    """"f64" (default) or "f32": FP32 mode of the ring decode (hmm_set_precision): the FIR in FP32, everything
+    else FP64; ll within 1e-4 relative, x not promised bit-exact."""
+    check(lib().hmm_set_precision(i32({"f64": 0, "f32": 1}[precision])))
+
+
+def viterbi_f32(y, lA, mu, sigma, *, mode: str = "auto", return_info: bool = False):
+    """FP32 mode with a Float32 recording (hmm_viterbi_ex_f32): returns (x, ll) like viterbi."""
+    y = np.ascontiguousarray(np.asarray(y), dtype=np.float32)
+    if y.ndim != 1:
+        raise HmmArgumentError(_lib.HMM_EINVAL, "y must be a vector")
+    st, tr, mu = _model_args(lA, mu)
+    x = np.empty(y.size, dtype=np.int16)
+    ll = f64(0)
+    info = HmmInfo()
+    check(lib().hmm_viterbi_ex_f32(_p(y), i64(y.size), _p(st), i32(lA.N), i32(lA.K), i32(lA.nstates), _p(tr),
+                                   i64(tr.size), _p(mu), f64(sigma), _p(x), C.byref(ll), i32(MODES[mode]), C.byref(info)))
+    return (x, ll.value, info.asdict()) if return_info else (x, ll.value)
 
 
 def set_ring_params(chunk_len: int = 0, warmup: int = 0) -> None:

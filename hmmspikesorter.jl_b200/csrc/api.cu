@@ -73,6 +73,14 @@ static void d2h(void *dst, const void *src, size_t bytes, cudaStream_t st) {
 }
 
 static void drop_caches();
+static bool g_precision_from_env = false;
+// HMMCUDA_PRECISION=f32 selects FP32 mode without a call (read once, at the first decode)
+static void precision_from_env_once() {
+    if (g_precision_from_env) return;
+    g_precision_from_env = true;
+    const char *e = getenv("HMMCUDA_PRECISION");
+    if (e && (!strcmp(e, "f32") || !strcmp(e, "F32") || !strcmp(e, "float32"))) ring_config().precision = HMM_PREC_F32;
+}
 
 extern "C" {
 
@@ -128,6 +136,15 @@ int hmm_release_workspace(void) {
 int hmm_set_profiling(int on) {
     return guarded([&] { ring_config().profile = on ? 1 : 0; });
 }
+
+int hmm_set_precision(int32_t precision) {
+    return guarded([&] {
+        if (precision != HMM_PREC_F64 && precision != HMM_PREC_F32) fail(HMM_EINVAL, "precision must be HMM_PREC_F64 or HMM_PREC_F32");
+        g_precision_from_env = true;  // an explicit call wins over HMMCUDA_PRECISION
+        ring_config().precision = precision;
+    });
+}
+int hmm_get_precision(void) { return ring_config().precision; }
 
 int hmm_host_alloc(void **ptr_out, uint64_t bytes) {
     return guarded([&] {
@@ -855,6 +872,7 @@ int viterbi_host(const double *y, int64_t T, int C, const int16_t *states, int s
         if (T < 1 || C < 1) fail(HMM_EINVAL, "T and C must be positive");
         if ((T1_out || T2_out) && C != 1) fail(HMM_EINVAL, "trellis output is single-channel");
         require_device();
+        precision_from_env_once();
         // ---- several devices selected (hmm_set_devices / HMMCUDA_DEVICES): split the call over them ----
         if (!t_worker) {
             devices_from_env_once();
@@ -1003,6 +1021,7 @@ int hmm_viterbi_dev_f64(const double *y_dev, int64_t T, int32_t C, const int16_t
         if (!y_dev || !x_dev || !sigma) fail(HMM_EINVAL, "null y_dev / x_dev / sigma");
         if (T < 1 || C < 1) fail(HMM_EINVAL, "T and C must be positive");
         require_device();
+        precision_from_env_once();
         cudaStream_t st = main_stream();
         BatchModels &B = get_models(C, states, states_shared, N, K, nstates, tr, ntrans, mu, sigma, st);
         Timer tk(st);
@@ -1011,6 +1030,91 @@ int hmm_viterbi_dev_f64(const double *y_dev, int64_t T, int32_t C, const int16_t
         tk.stop();
         HMM_CUDA(cudaStreamSynchronize(st));
         if (info) info->device_ms = info->kernel_ms = tk.ms();
+    });
+}
+
+// ---------------------------------------------------------------------------
+// FP32 mode: Float32 recordings (half the PCIe / HBM bytes per sample) and the FIR of the ring decode in FP32.
+// The recording is widened to FP64 on the device (exact), so every downstream kernel is the FP64 one; what
+// differs from hmm_viterbi_f64 on the same values is the rounding of the FIR (~1e-4 absolute on scores of O(100)):
+// T1 / ll agree to <= 1e-4 relative, x can differ where a decision margin is below that (rate reported by tests).
+// ---------------------------------------------------------------------------
+__global__ void widen_f32_kernel(const float *__restrict__ src, double *__restrict__ dst, int64_t n) {
+    const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 + 4 <= n && ((reinterpret_cast<uintptr_t>(src + i4) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst + i4) & 15) == 0)) {
+        const float4 v = *reinterpret_cast<const float4 *>(src + i4);
+        *reinterpret_cast<double2 *>(dst + i4) = make_double2((double)v.x, (double)v.y);
+        *reinterpret_cast<double2 *>(dst + i4 + 2) = make_double2((double)v.z, (double)v.w);
+    } else
+        for (int64_t i = i4; i < n && i < i4 + 4; i++) dst[i] = (double)src[i];
+}
+
+struct PrecisionScope {  // FP32 mode for the duration of one call
+    int saved;
+    PrecisionScope() : saved(ring_config().precision) { ring_config().precision = HMM_PREC_F32; }
+    ~PrecisionScope() { ring_config().precision = saved; }
+};
+
+static void viterbi_f32_body(const float *y, bool y_on_device, int64_t T, int C, const int16_t *states, int states_shared,
+                             int N, int K, int nstates, const hmm_trans *tr, int64_t ntrans, const double *mu,
+                             const double *sigma, int16_t *x_out, bool x_on_device, double *ll_out, int mode,
+                             hmm_info *info) {
+    if (info) memset(info, 0, sizeof *info);
+    if (!y || !x_out || !sigma) fail(HMM_EINVAL, "null y / x_out / sigma");
+    if (T < 1 || C < 1) fail(HMM_EINVAL, "T and C must be positive");
+    require_device();
+    PrecisionScope fp32;
+    cudaStream_t st = main_stream();
+    Workspace &ws = workspace();
+    Timer tall(st);
+    tall.start();
+    BatchModels &B = get_models(C, states, states_shared, N, K, nstates, tr, ntrans, mu, sigma, st);
+    const size_t n = (size_t)T * C;
+    const float *src = y;
+    if (!y_on_device) {
+        float *yf = (float *)ws.get(Workspace::FWDF, sizeof(float) * n);
+        h2d(yf, y, sizeof(float) * n, st);
+        src = yf;
+    }
+    double *y_dev = (double *)ws.get(Workspace::Y, sizeof(double) * n);
+    widen_f32_kernel<<<(unsigned)((n / 4 + 256) / 256), 256, 0, st>>>(src, y_dev, (int64_t)n);
+    HMM_CUDA(cudaGetLastError());
+    int16_t *x_dev = x_on_device ? x_out : (int16_t *)ws.get(Workspace::X, sizeof(int16_t) * n);
+    viterbi_core(y_dev, T, C, B, x_dev, ll_out, nullptr, nullptr, mode, st, info);
+    if (!x_on_device) d2h(x_out, x_dev, sizeof(int16_t) * n, st);
+    tall.stop();
+    HMM_CUDA(cudaStreamSynchronize(st));
+    if (info) {
+        info->device_ms = tall.ms();
+        info->kernel_launches += 1;
+    }
+}
+
+int hmm_viterbi_ex_f32(const float *y, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                       const hmm_trans *tr, int64_t ntrans, const double *mu, double sigma, int16_t *x_out,
+                       double *ll_out, int32_t mode, hmm_info *info) {
+    return guarded([&] {
+        viterbi_f32_body(y, false, T, 1, states, 1, N, K, nstates, tr, ntrans, mu, &sigma, x_out, false, ll_out, mode, info);
+    });
+}
+int hmm_viterbi_f32(const float *y, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                    const hmm_trans *tr, int64_t ntrans, const double *mu, double sigma, int16_t *x_out, double *ll_out) {
+    return hmm_viterbi_ex_f32(y, T, states, N, K, nstates, tr, ntrans, mu, sigma, x_out, ll_out, HMM_MODE_AUTO, nullptr);
+}
+int hmm_viterbi_batch_f32(const float *y, int64_t T, int32_t C, const int16_t *states, int32_t states_shared, int32_t N,
+                          int32_t K, int32_t nstates, const hmm_trans *tr, int64_t ntrans, const double *mu,
+                          const double *sigma, int16_t *x_out, double *ll_out, int32_t mode, hmm_info *info) {
+    return guarded([&] {
+        viterbi_f32_body(y, false, T, C, states, states_shared, N, K, nstates, tr, ntrans, mu, sigma, x_out, false, ll_out,
+                         mode, info);
+    });
+}
+int hmm_viterbi_dev_f32(const float *y_dev, int64_t T, int32_t C, const int16_t *states, int32_t states_shared, int32_t N,
+                        int32_t K, int32_t nstates, const hmm_trans *tr, int64_t ntrans, const double *mu,
+                        const double *sigma, int16_t *x_dev, double *ll_out, int32_t mode, hmm_info *info) {
+    return guarded([&] {
+        viterbi_f32_body(y_dev, true, T, C, states, states_shared, N, K, nstates, tr, ntrans, mu, sigma, x_dev, true, ll_out,
+                         mode, info);
     });
 }
 

@@ -32,6 +32,7 @@ struct RingConfig {
     int64_t chunk_len = 0;  // 0 = auto
     int64_t warmup = 0;     // 0 = default
     int profile = 0;        // hmm_set_profiling: eager launches with per-kernel event timers instead of a CUDA graph
+    int precision = 0;      // 0: FP64 throughout; 1: FP32 mode (the FIR of the ring decode in FP32; hmm_set_precision)
 };
 RingConfig &ring_config();
 bool ring_supported(const HostModel &M, int64_t T);

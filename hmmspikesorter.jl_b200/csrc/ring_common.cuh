@@ -100,9 +100,10 @@ struct FirGeom {
 // register operands is limited by register-file read bandwidth to one per 3
 // cycles per SM sub-partition; with a constant operand it issues at the FP64
 // pipe rate (one per 2 cycles) and the coefficient LDS traffic disappears.
-template <int N, int LPC>
+template <int N, int LPC, typename S = double>
 struct FirCoef {
-    double a[(LPC > 0 ? LPC : 1) * N];  // a[r*N + i]
+    using scalar = S;           // double, or float in FP32 mode (hmm_set_precision / hmm_viterbi_f32)
+    S a[(LPC > 0 ? LPC : 1) * N];  // a[r*N + i]
 };
 
 // Issue the asynchronous staging of y[b, b + need) into a transposed tile (zero beyond T) and
@@ -154,7 +155,11 @@ __device__ __forceinline__ void ll_noise_from_window(const double (&w)[R], doubl
 
 // I0, I1: the neurons [I0, I1) this call computes (the FIR of one super-window can be split between the producer
 // and the consumer warp of a slot; both read the same y tile and write disjoint planes of the F tile).
-template <int N, int R, int I0 = 0, int I1 = N>
+// FP32 mode (typename S = float): the samples and the coefficients are rounded to float when they are loaded and the
+// multiply-accumulates run in FP32 (twice the FP64 rate); everything downstream of F -- the recursion, the
+// normalisation, the boundary vectors, ll -- stays FP64.  The rounding is a pure function of (y, model, t0), the
+// same in every chunk and in the repair kernel, so speculation / verification work unchanged.
+template <int N, int R, int I0 = 0, int I1 = N, typename S = double>
 __device__ __forceinline__ void fir_compute(const double *A, const double *Bc, int LP, const double *ytile,
                                             double *fbuf, int lane, double *nacc = nullptr, double m0 = 0.0,
                                             double w0 = 0.0, int nvalid = 0) {
@@ -163,25 +168,30 @@ __device__ __forceinline__ void fir_compute(const double *A, const double *Bc, i
     __builtin_assume(__isShared(ytile));
     __builtin_assume(__isShared(fbuf));
     __builtin_assume(__isShared(A));
-    double acc[N][R];
+    S acc[N][R];
 #pragma unroll
     for (int i = I0; i < I1; i++)
 #pragma unroll
-        for (int j = 0; j < R; j++) acc[i][j] = Bc[i];
-    double w[R];
+        for (int j = 0; j < R; j++) acc[i][j] = (S)Bc[i];
+    S w[R];
+    {
+        double wd[R];
 #pragma unroll
-    for (int j = 0; j < R; j++) w[j] = ytile[j * G::YS + lane];  // elements R*lane + j
-    if (nacc) ll_noise_from_window<R>(w, nacc, m0, w0, lane, nvalid);
-    auto load_coef = [&](int r, double *dst) {
+        for (int j = 0; j < R; j++) wd[j] = ytile[j * G::YS + lane];  // elements R*lane + j
+        if (nacc) ll_noise_from_window<R>(wd, nacc, m0, w0, lane, nvalid);
+#pragma unroll
+        for (int j = 0; j < R; j++) w[j] = (S)wd[j];
+    }
+    auto load_coef = [&](int r, S *dst) {
         const double2 *src = reinterpret_cast<const double2 *>(A + r * NP);
 #pragma unroll
         for (int i2 = 0; i2 < NP / 2; i2++) {
             double2 v = src[i2];
-            if (2 * i2 < N) dst[2 * i2] = v.x;
-            if (2 * i2 + 1 < N) dst[2 * i2 + 1] = v.y;
+            if (2 * i2 < N) dst[2 * i2] = (S)v.x;
+            if (2 * i2 + 1 < N) dst[2 * i2 + 1] = (S)v.y;
         }
     };
-    double a0[N], a1[N];
+    S a0[N], a1[N];
     load_coef(0, a0);
     for (int r0 = 0; r0 < LP; r0 += R) {
         const int col = lane + 1 + (r0 >> G::LOGR);
@@ -189,19 +199,19 @@ __device__ __forceinline__ void fir_compute(const double *A, const double *Bc, i
         for (int u = 0; u < R; u += 2) {
             // coefficients are fetched one tap ahead into the other register set
             load_coef(r0 + u + 1, a1);
-            double ynew = ytile[u * G::YS + col];  // element R*lane + (r0+u) + R
+            S ynew = (S)ytile[u * G::YS + col];  // element R*lane + (r0+u) + R
 #pragma unroll
             for (int j = 0; j < R; j++) {
-                const double yv = w[(u + j) % R];
+                const S yv = w[(u + j) % R];
 #pragma unroll
                 for (int i = I0; i < I1; i++) acc[i][j] = fma(a0[i], yv, acc[i][j]);
             }
             w[u] = ynew;
             load_coef(r0 + u + 2 < LP ? r0 + u + 2 : LP - 1, a0);
-            ynew = ytile[(u + 1) * G::YS + col];
+            ynew = (S)ytile[(u + 1) * G::YS + col];
 #pragma unroll
             for (int j = 0; j < R; j++) {
-                const double yv = w[(u + 1 + j) % R];
+                const S yv = w[(u + 1 + j) % R];
 #pragma unroll
                 for (int i = I0; i < I1; i++) acc[i][j] = fma(a1[i], yv, acc[i][j]);
             }
@@ -212,37 +222,42 @@ __device__ __forceinline__ void fir_compute(const double *A, const double *Bc, i
 #pragma unroll
     for (int i = I0; i < I1; i++)
 #pragma unroll
-        for (int j = 0; j < R; j++) fbuf[i * G::FTILE + j * G::FS + lane] = acc[i][j];
+        for (int j = 0; j < R; j++) fbuf[i * G::FTILE + j * G::FS + lane] = (double)acc[i][j];
     __syncwarp();
 }
 
-template <int N, int R>
+template <int N, int R, typename S = double>
 __device__ __forceinline__ void fir_superwindow(const double *__restrict__ y, int64_t T, int64_t b,
                                                 const double *A, const double *Bc, int LP, double *ytile,
                                                 double *fbuf, int lane) {
     fir_stage<R>(y, T, b, FirGeom<R>::SW + LP, ytile, lane);
     cp_async_wait_all();
     __syncwarp();
-    fir_compute<N, R>(A, Bc, LP, ytile, fbuf, lane);
+    fir_compute<N, R, 0, N, S>(A, Bc, LP, ytile, fbuf, lane);
 }
 
 
-template <int N, int R, int LPC, int I0 = 0, int I1 = N>
-__device__ __forceinline__ void fir_compute_c(const FirCoef<N, LPC> &coef, const double *Bc, const double *ytile,
+template <int N, int R, int LPC, int I0 = 0, int I1 = N, typename S = double>
+__device__ __forceinline__ void fir_compute_c(const FirCoef<N, LPC, S> &coef, const double *Bc, const double *ytile,
                                               double *fbuf, int lane, double *nacc = nullptr, double m0 = 0.0,
                                               double w0 = 0.0, int nvalid = 0) {
     using G = FirGeom<R>;
     __builtin_assume(__isShared(ytile));
     __builtin_assume(__isShared(fbuf));
-    double acc[N][R];
+    S acc[N][R];
 #pragma unroll
     for (int i = I0; i < I1; i++)
 #pragma unroll
-        for (int j = 0; j < R; j++) acc[i][j] = Bc[i];
-    double w[R];
+        for (int j = 0; j < R; j++) acc[i][j] = (S)Bc[i];
+    S w[R];
+    {
+        double wd[R];
 #pragma unroll
-    for (int j = 0; j < R; j++) w[j] = ytile[j * G::YS + lane];
-    if (nacc) ll_noise_from_window<R>(w, nacc, m0, w0, lane, nvalid);
+        for (int j = 0; j < R; j++) wd[j] = ytile[j * G::YS + lane];
+        if (nacc) ll_noise_from_window<R>(wd, nacc, m0, w0, lane, nvalid);
+#pragma unroll
+        for (int j = 0; j < R; j++) w[j] = (S)wd[j];
+    }
     // Fully unrolled over exactly LPC = L taps, so that every coefficient is a compile-time constant-bank offset
     // (the compiler keeps them in uniform registers: LDCU.128 + DFMA R, R, UR, R -- no register-file or
     // shared-memory traffic for them).  Measured at C2 (forward kernel, 18 M samples): full unroll 0.36 ms
@@ -261,10 +276,10 @@ __device__ __forceinline__ void fir_compute_c(const FirCoef<N, LPC> &coef, const
         for (int u = 0; u < R; u++) {
             const int r = r0 + u;
             if (r < LPC) {
-                const double ynew = ytile[u * G::YS + lane + 1 + (r0 >> G::LOGR)];
+                const S ynew = (S)ytile[u * G::YS + lane + 1 + (r0 >> G::LOGR)];
 #pragma unroll
                 for (int j = 0; j < R; j++) {
-                    const double yv = w[(u + j) % R];
+                    const S yv = w[(u + j) % R];
 #pragma unroll
                     for (int i = I0; i < I1; i++) acc[i][j] = fma(coef.a[r * N + i], yv, acc[i][j]);
                 }
@@ -276,18 +291,18 @@ __device__ __forceinline__ void fir_compute_c(const FirCoef<N, LPC> &coef, const
 #pragma unroll
     for (int i = I0; i < I1; i++)
 #pragma unroll
-        for (int j = 0; j < R; j++) fbuf[i * G::FTILE + j * G::FS + lane] = acc[i][j];
+        for (int j = 0; j < R; j++) fbuf[i * G::FTILE + j * G::FS + lane] = (double)acc[i][j];
     __syncwarp();
 }
 
-template <int N, int R, int LPC>
+template <int N, int R, int LPC, typename S = double>
 __device__ __forceinline__ void fir_superwindow_c(const double *__restrict__ y, int64_t T, int64_t b,
-                                                  const FirCoef<N, LPC> &coef, const double *Bc, double *ytile,
+                                                  const FirCoef<N, LPC, S> &coef, const double *Bc, double *ytile,
                                                   double *fbuf, int lane) {
     fir_stage<R>(y, T, b, FirGeom<R>::SW + LPC, ytile, lane);
     cp_async_wait_all();
     __syncwarp();
-    fir_compute_c<N, R, LPC>(coef, Bc, ytile, fbuf, lane);
+    fir_compute_c<N, R, LPC, 0, N, S>(coef, Bc, ytile, fbuf, lane);
 }
 
 // ---- mbarrier helpers (producer / consumer hand-off between warps of one CTA) ----

@@ -413,8 +413,8 @@ __device__ __forceinline__ void pair_sync(int bar_id) {
 // FW: FIR producer warps per slot.  FW = 2: producer `half` (0 / 1) computes the even / odd super-windows into F tile
 // `half`, from its own pair of y tiles -- four FIR warps per SM sub-partition keep the FP64 pipe busy where two leave
 // it idle a quarter of the time (back-to-back DFMAs of one warp issue at half the pipe rate).
-template <int N, int R, int LPC, int ROLE, int NC = 0, int FW = 1>
-__device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coef, int ch, int c, int kind,
+template <int N, int R, int LPC, int ROLE, int NC = 0, int FW = 1, typename S = double>
+__device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC, S> &coef, int ch, int c, int kind,
                                   const double *mdl /*smem model*/, double *ws /*per-warp or per-slot smem*/,
                                   int pair_bar = 0 /*named barrier shared with the partner producer, 0 = none*/,
                                   int pair_nsw = 0 /*iterations of the longer chunk of the pair*/, int half = 0) {
@@ -547,9 +547,9 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
             const int64_t left = e - b;
             const int nval = left > G::SW ? G::SW : (int)left;
             if constexpr (LPC > 0)
-                fir_compute_c<N, R, LPC, 0, N - NC>(coef, Bc, yt[ybuf], ft[buf], lane, llp, m0n, w0, nval);
+                fir_compute_c<N, R, LPC, 0, N - NC, S>(coef, Bc, yt[ybuf], ft[buf], lane, llp, m0n, w0, nval);
             else
-                fir_compute<N, R, 0, N - NC>(A, Bc, LP, yt[ybuf], ft[buf], lane, llp, m0n, w0, nval);
+                fir_compute<N, R, 0, N - NC, S>(A, Bc, LP, yt[ybuf], ft[buf], lane, llp, m0n, w0, nval);
             if (lane == 0) mbar_arrive(bar_full + buf);   // fir_compute ends with __syncwarp()
 #ifdef HMM_PHASE_TIMING
             const long long q3 = clock64();
@@ -616,9 +616,9 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
                 const double *ytk = ws + SS::YT + buf * G::YTILE;
                 mbar_wait(bar_yready + buf, (swk >> 1) & 1);
                 if constexpr (LPC > 0)
-                    fir_compute_c<N, R, LPC, N - NC, N>(coef, Bc, ytk, fbuf, lane);
+                    fir_compute_c<N, R, LPC, N - NC, N, S>(coef, Bc, ytk, fbuf, lane);
                 else
-                    fir_compute<N, R, N - NC, N>(A, Bc, LP, ytk, fbuf, lane);
+                    fir_compute<N, R, N - NC, N, S>(A, Bc, LP, ytk, fbuf, lane);
                 if (lane == 0) mbar_arrive(bar_yfree + buf);
             }
             // ---- consumer: wait for the producer's F planes of this super-window ----
@@ -626,9 +626,9 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
         } else {
             // ---- stage y and run the FIR: F_i(b + t) for the whole super-window ----
             if constexpr (LPC > 0)
-                fir_superwindow_c<N, R, LPC>(y, T, b, coef, Bc, ytile, fbuf, lane);
+                fir_superwindow_c<N, R, LPC, S>(y, T, b, coef, Bc, ytile, fbuf, lane);
             else
-                fir_superwindow<N, R>(y, T, b, A, Bc, LP, ytile, fbuf, lane);
+                fir_superwindow<N, R, S>(y, T, b, A, Bc, LP, ytile, fbuf, lane);
         }
 #ifdef HMM_PHASE_TIMING
         const long long tm1 = clock64();
@@ -716,16 +716,17 @@ __device__ void vit_process_chunk(const VitParams &p, const FirCoef<N, LPC> &coe
 #pragma unroll
                         for (int i = 0; i < N; i++) {
                             ghq[i] = Gprev + eHr[i];
-                            thq[i] = (Gprev - cLr[i]) - marg;  // live <=> q + cL + marg > G (margins >> rounding)
+                            // live <=> q + cL + marg > G with q = ghq + F, i.e. F > (G - cL - marg) - ghq: tested on F
+                            // itself, so that the vote does not wait for the addition below (FP64 latency is long
+                            // and this chain is the consumer's critical path); the margins dwarf the rounding
+                            thq[i] = ((Gprev - cLr[i]) - marg) - ghq[i];
                         }
                     }
                     bool live = false;
 #pragma unroll
-                    for (int i = 0; i < N; i++) {
-                        const double q = ghq[i] + Fv[i];
-                        rp0[i * RING_Q + slot0] = q;
-                        live = live || (q > thq[i]);
-                    }
+                    for (int i = 0; i < N; i++) live = live | (Fv[i] > thq[i]);
+#pragma unroll
+                    for (int i = 0; i < N; i++) rp0[i * RING_Q + slot0] = ghq[i] + Fv[i];
                     if (last) {
 #pragma unroll
                         for (int i = 0; i < N; i++) pfin[i * RING_Q + slot0] = ghq[i];
@@ -890,9 +891,9 @@ struct ConsumerFirShare {  // neurons whose FIR the consumer warp computes (see 
 #endif
 };
 
-template <int N, int R, int LPC, int SLOTS>
+template <int N, int R, int LPC, int SLOTS, typename S>
 __global__ void __launch_bounds__(SLOTS * 64, SLOTS == 8 ? 1 : 2)
-    ring_vit_forward_ws(const __grid_constant__ VitParams p, const __grid_constant__ FirCoef<N, LPC> coef) {
+    ring_vit_forward_ws(const __grid_constant__ VitParams p, const __grid_constant__ FirCoef<N, LPC, S> coef) {
     extern __shared__ __align__(16) double smem_d[];
     using G = FirGeom<R>;
     const int ch = blockIdx.y + p.ch0;
@@ -913,9 +914,9 @@ __global__ void __launch_bounds__(SLOTS * 64, SLOTS == 8 ? 1 : 2)
             const int a = chunk_superwindows(p, c, G::SW), b = chunk_superwindows(p, blockIdx.x * SLOTS + (slot ^ 4), G::SW);
             pair_nsw = a > b ? a : b;
         }
-        vit_process_chunk<N, R, LPC, ROLE_FIR, ConsumerFirShare<N>::value>(p, coef, ch, c, kind, mdl, ws, pair_bar, pair_nsw);
+        vit_process_chunk<N, R, LPC, ROLE_FIR, ConsumerFirShare<N>::value, 1, S>(p, coef, ch, c, kind, mdl, ws, pair_bar, pair_nsw);
     } else if (c < p.nchunks)
-        vit_process_chunk<N, R, LPC, ROLE_DP, ConsumerFirShare<N>::value>(p, coef, ch, c, kind, mdl, ws);
+        vit_process_chunk<N, R, LPC, ROLE_DP, ConsumerFirShare<N>::value, 1, S>(p, coef, ch, c, kind, mdl, ws);
 }
 
 // Dual-producer variant (N <= 5, R = 4): ONE CTA of 24 warps per SM -- 8 chunk slots x {2 FIR producers, 1 recursion
@@ -931,9 +932,9 @@ struct Ws2Regs {
     static constexpr int consumer = N <= 4 ? 128 : 112;
     static_assert(consumer <= 240 - 2 * producer, "consumers would starve");
 };
-template <int N, int LPC>
+template <int N, int LPC, typename S>
 __global__ void __launch_bounds__(768, 1)
-    ring_vit_forward_ws2(const __grid_constant__ VitParams p, const __grid_constant__ FirCoef<N, LPC> coef) {
+    ring_vit_forward_ws2(const __grid_constant__ VitParams p, const __grid_constant__ FirCoef<N, LPC, S> coef) {
     extern __shared__ __align__(16) double smem_d[];
     constexpr int R = 4, SLOTS = 8;
     using G = FirGeom<R>;
@@ -956,11 +957,11 @@ __global__ void __launch_bounds__(768, 1)
         const int half = warp >> 3;
         const int a = chunk_superwindows(p, c, G::SW), b = chunk_superwindows(p, blockIdx.x * SLOTS + (slot ^ 4), G::SW);
         const int ia = a > half ? (a - half + 1) / 2 : 0, ib = b > half ? (b - half + 1) / 2 : 0;
-        vit_process_chunk<N, R, LPC, ROLE_FIR, 0, 2>(p, coef, ch, c, kind, mdl, ws, 1 + (slot & 3) + 4 * half,
+        vit_process_chunk<N, R, LPC, ROLE_FIR, 0, 2, S>(p, coef, ch, c, kind, mdl, ws, 1 + (slot & 3) + 4 * half,
                                                      ia > ib ? ia : ib, half);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(Ws2Regs<N>::consumer));
-        if (c < p.nchunks) vit_process_chunk<N, R, LPC, ROLE_DP, 0, 2>(p, coef, ch, c, kind, mdl, ws);
+        if (c < p.nchunks) vit_process_chunk<N, R, LPC, ROLE_DP, 0, 2, S>(p, coef, ch, c, kind, mdl, ws);
     }
 }
 
@@ -1146,7 +1147,7 @@ __device__ __forceinline__ bool last_cta_of_row(unsigned *cnt, int *s_flag) {
 // chunk c against the true end vector of chunk c-1; (2) the last CTA to finish re-runs the flagged chunks from the
 // true vectors, sequentially (a re-run changes EB[c], so chunk c+1 is re-checked against it), and (3) computes
 // the final state x[T] = argmax_j T1[j,T] when the sequence really ends in this plan.
-template <int N, int R>
+template <int N, int R, typename S>
 __global__ void __launch_bounds__(256) ring_vit_verify_fwd(VitParams p) {
     extern __shared__ __align__(16) double smem_d[];
     __shared__ int s_flag;
@@ -1182,7 +1183,7 @@ __global__ void __launch_bounds__(256) ring_vit_verify_fwd(VitParams p) {
                     need = !boundary_matches(sb, eb, p.bvec, lane);
                 }
                 if (need) {
-                    vit_process_chunk<N, R, 0, ROLE_BOTH>(p, FirCoef<N, 0>{}, ch, c, START_EXACT, mdl, ws);
+                    vit_process_chunk<N, R, 0, ROLE_BOTH, 0, 1, S>(p, FirCoef<N, 0, S>{}, ch, c, START_EXACT, mdl, ws);
                     __threadfence();
                     repaired++;
                 }
@@ -1764,17 +1765,17 @@ static size_t fwd_smem_bytes(const RingLayout &RL) {
 }
 
 // Resident warps per SM of the forward kernel (sets the one-wave chunk count).
-template <int N, int R, int LPC>
+template <int N, int R, int LPC, typename S>
 static int fwd_warps_per_sm(const RingLayout &RL) {
     const size_t sm_fwd = fwd_smem_bytes<N, R, LPC>(RL);
     if constexpr (use_ws2<N, R>()) {
-        HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws2<N, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+        HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws2<N, LPC, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
         return 8;  // one CTA of 8 slots per SM
     } else {
         constexpr int SLOTS = fwd_slots<N, R>();
-        HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws<N, R, LPC, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+        HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws<N, R, LPC, SLOTS, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
         int nb = 0;
-        HMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ring_vit_forward_ws<N, R, LPC, SLOTS>, SLOTS * 64, sm_fwd));
+        HMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ring_vit_forward_ws<N, R, LPC, SLOTS, S>, SLOTS * 64, sm_fwd));
         return (nb > 0 ? nb : 1) * SLOTS;  // chunk slots (producer/consumer warp pairs) per SM
     }
 }
@@ -1789,32 +1790,32 @@ static size_t prologue_smem(const VitParams &p, int *q_in_smem) {
 static size_t trace_smem(const VitParams &p, int warps) { return sizeof(uint32_t) * (size_t)warps * TR_WARP_U32; }
 
 // Kernel attributes are set once per plan (not per launch: the launches may be captured into a CUDA graph).
-template <int N, int R, int LPC>
+template <int N, int R, int LPC, typename S>
 static void stage_prepare(const VitParams &p) {
     const size_t sm_fwd = fwd_smem_bytes<N, R, LPC>(p.RL);
     if constexpr (use_ws2<N, R>())
-        HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws2<N, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+        HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws2<N, LPC, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
     else
-        HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws<N, R, LPC, fwd_slots<N, R>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+        HMM_CUDA(cudaFuncSetAttribute(ring_vit_forward_ws<N, R, LPC, fwd_slots<N, R>(), S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
     int qs = 0;
     const size_t sm_pro = prologue_smem(p, &qs);
     if (sm_pro > 227 * 1024) fail(HMM_EUNSUPPORTED, "prologue does not fit shared memory");
     HMM_CUDA(cudaFuncSetAttribute(ring_vit_prologue, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_pro));
     const size_t sm_rep = sizeof(double) * (((p.RL.hot + 1) & ~1) + WarpSmem<N, R>::DOUBLES);
-    HMM_CUDA(cudaFuncSetAttribute(ring_vit_verify_fwd<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rep));
+    HMM_CUDA(cudaFuncSetAttribute(ring_vit_verify_fwd<N, R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rep));
     HMM_CUDA(cudaFuncSetAttribute(ring_vit_trace<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem(p, 4)));
     HMM_CUDA(cudaFuncSetAttribute(ring_vit_verify_trace<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem(p, 1)));
 }
 
-template <int N, int R, int LPC>
+template <int N, int R, int LPC, typename S>
 static void stage_forward(VitParams &p, const double *hmodel /*host ring model of channel 0*/, int C, cudaStream_t st,
                           Timer *ttop) {
     constexpr int WPB = use_ws2<N, R>() ? 8 : fwd_slots<N, R>();
     const size_t sm_fwd = fwd_smem_bytes<N, R, LPC>(p.RL);
-    FirCoef<N, LPC> coef{};
+    FirCoef<N, LPC, S> coef{};
     if (LPC > 0)
         for (int r = 0; r < LPC; r++)
-            for (int i = 0; i < N; i++) coef.a[r * N + i] = hmodel[p.RL.A + r * p.RL.NP + i];
+            for (int i = 0; i < N; i++) coef.a[r * N + i] = (S)hmodel[p.RL.A + r * p.RL.NP + i];
     dim3 gridc((p.nchunks + WPB - 1) / WPB, C);
     if (p.first_prologue) {
         int qs = 0;
@@ -1826,21 +1827,21 @@ static void stage_forward(VitParams &p, const double *hmodel /*host ring model o
     }
     if (ttop) ttop->start();
     if constexpr (use_ws2<N, R>())
-        ring_vit_forward_ws2<N, LPC><<<gridc, 768, sm_fwd, st>>>(p, coef);
+        ring_vit_forward_ws2<N, LPC, S><<<gridc, 768, sm_fwd, st>>>(p, coef);
     else
-        ring_vit_forward_ws<N, R, LPC, WPB><<<gridc, WPB * 64, sm_fwd, st>>>(p, coef);
+        ring_vit_forward_ws<N, R, LPC, WPB, S><<<gridc, WPB * 64, sm_fwd, st>>>(p, coef);
     if (ttop) ttop->stop();
     HMM_CUDA(cudaGetLastError());
 }
 
-template <int N, int R, int LPC>
+template <int N, int R, int LPC, typename S>
 static void stage_verify_fwd(VitParams &p, int C, cudaStream_t st) {
     const size_t sm_rep = sizeof(double) * (((p.RL.hot + 1) & ~1) + WarpSmem<N, R>::DOUBLES);
-    ring_vit_verify_fwd<N, R><<<dim3((p.nchunks + 7) / 8, C), 256, sm_rep, st>>>(p);
+    ring_vit_verify_fwd<N, R, S><<<dim3((p.nchunks + 7) / 8, C), 256, sm_rep, st>>>(p);
     HMM_CUDA(cudaGetLastError());
 }
 
-template <int N, int R, int LPC>
+template <int N, int R, int LPC, typename S>
 static void stage_trace(VitParams &p, int C, cudaStream_t st) {
     constexpr int WPB = 4;
     dim3 gridc((p.nchunks_t + WPB - 1) / WPB, C);
@@ -1848,7 +1849,7 @@ static void stage_trace(VitParams &p, int C, cudaStream_t st) {
     HMM_CUDA(cudaGetLastError());
 }
 
-template <int N, int R, int LPC>
+template <int N, int R, int LPC, typename S>
 static void stage_verify_trace(VitParams &p, int C, cudaStream_t st) {
     ring_vit_verify_trace<N><<<dim3((p.nchunks_t + 127) / 128, C), 128, trace_smem(p, 1), st>>>(p);
     HMM_CUDA(cudaGetLastError());
@@ -1865,10 +1866,15 @@ struct VitVariant {
     void (*trace)(VitParams &, int, cudaStream_t);
     void (*verify_trace)(VitParams &, int, cudaStream_t);
 };
+template <int N, int R, int LPC, typename S>
+static VitVariant make_variant_s() {
+    return VitVariant{&fwd_warps_per_sm<N, R, LPC, S>, &stage_prepare<N, R, LPC, S>, &stage_forward<N, R, LPC, S>,
+                      &stage_verify_fwd<N, R, LPC, S>, &stage_trace<N, R, LPC, S>, &stage_verify_trace<N, R, LPC, S>};
+}
+static thread_local bool t_pick_f32 = false;  // set by pick_variant for the helpers below
 template <int N, int R, int LPC>
 static VitVariant make_variant() {
-    return VitVariant{&fwd_warps_per_sm<N, R, LPC>, &stage_prepare<N, R, LPC>, &stage_forward<N, R, LPC>, &stage_verify_fwd<N, R, LPC>,
-                      &stage_trace<N, R, LPC>, &stage_verify_trace<N, R, LPC>};
+    return t_pick_f32 ? make_variant_s<N, R, LPC, float>() : make_variant_s<N, R, LPC, double>();
 }
 template <int N, int R>
 static VitVariant pick_lp(int L, bool const_ok) {
@@ -1876,7 +1882,8 @@ static VitVariant pick_lp(int L, bool const_ok) {
     if (const_ok && L == 47) return make_variant<N, R, 47>();  // K = 48 templates
     return make_variant<N, R, 0>();
 }
-static VitVariant pick_variant(int N, int L, bool const_ok) {
+static VitVariant pick_variant(int N, int L, bool const_ok, bool f32 = false) {
+    t_pick_f32 = f32;
     switch (N) {
 #ifdef HMM_NO_WS2
         case 1: return make_variant<1, 8, 0>();
@@ -1937,7 +1944,7 @@ int ring_default_chunking(const HostModel &M0, int64_t T_total, int C, int n_gpu
 #endif
     RingLayout RL = ring_layout(N, L);
     const bool no_const = getenv("HMMCUDA_NO_CONST_FIR") && atoi(getenv("HMMCUDA_NO_CONST_FIR")) != 0;
-    const VitVariant variant = pick_variant(N, RL.L, C == 1 && !no_const);
+    const VitVariant variant = pick_variant(N, RL.L, C == 1 && !no_const, ring_config().precision == 1);
     int64_t W = ring_config().warmup > 0 ? ring_config().warmup : 512;
     W = ((W + SW - 1) / SW) * SW;
     if (W < ((L + 32 + SW - 1) / SW) * SW) W = ((L + 32 + SW - 1) / SW) * SW;
@@ -1981,7 +1988,7 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     RingLayout RL = ring_layout(N, L);
     const bool no_const = getenv("HMMCUDA_NO_CONST_FIR") && atoi(getenv("HMMCUDA_NO_CONST_FIR")) != 0;
     per_channel = C > 1 && T >= 262144 && !no_const;
-    impl->variant = pick_variant(N, RL.L, (C == 1 || per_channel) && !no_const);
+    impl->variant = pick_variant(N, RL.L, (C == 1 || per_channel) && !no_const, ring_config().precision == 1);
     int nchunks = (int)((T + Lc - 1) / Lc);
     // the last chunk must be long enough to hold the final look-back of L steps
     if (nchunks > 1 && T - (int64_t)(nchunks - 1) * Lc < RING_Q) nchunks--;
@@ -2202,11 +2209,12 @@ struct ProgKey {
     const double *y;
     int16_t *x;
     int64_t T, y_stride, x_stride, Lc, W;
-    int C, want_ll, dbg;
+    int C, want_ll, dbg, prec;
     uint64_t model_id;
     bool operator==(const ProgKey &o) const {
         return dev == o.dev && y == o.y && x == o.x && T == o.T && y_stride == o.y_stride && x_stride == o.x_stride &&
-               Lc == o.Lc && W == o.W && C == o.C && want_ll == o.want_ll && dbg == o.dbg && model_id == o.model_id;
+               Lc == o.Lc && W == o.W && C == o.C && want_ll == o.want_ll && dbg == o.dbg && prec == o.prec &&
+               model_id == o.model_id;
     }
 };
 
@@ -2267,6 +2275,7 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
     key.y = y_dev; key.x = x_dev; key.T = T; key.y_stride = y_stride; key.x_stride = x_stride; key.Lc = Lc; key.W = W;
     key.C = C; key.want_ll = ll_host ? 1 : 0; key.model_id = model_id;
     key.dbg = getenv("HMMCUDA_DEBUG_FLAG_EVERY") ? atoi(getenv("HMMCUDA_DEBUG_FLAG_EVERY")) : 0;
+    key.prec = ring_config().precision;
     const bool profiling = ring_config().profile != 0;
     const bool cacheable = model_id != 0 && !(getenv("HMMCUDA_NO_GRAPH") && atoi(getenv("HMMCUDA_NO_GRAPH")));
     RingProgram *prog = nullptr;

@@ -131,6 +131,35 @@ int hmm_viterbi_dev_f64(const double *y_dev, int64_t T, int32_t C, const int16_t
                         const double *mu, const double *sigma, int16_t *x_dev, double *ll_out, int32_t mode,
                         hmm_info *info);
 
+/* ---- FP32 mode (BASELINE north_star: "T1 and log-likelihoods within ... 1e-4 in FP32 mode") ------------------
+ * The reference is Float64 only (src/viterbi.jl:44), so this mode is defined by the build: the recording may be
+ * Float32 (half the PCIe / HBM bytes per sample; widened exactly on the device) and the matched-filter FIR of the
+ * ring decode -- 99 % of its arithmetic -- runs in FP32 with Float32-rounded templates, at twice the FP64 rate.
+ * The recursion, the per-chunk normalisation, the boundary verification and ll stay FP64, which is the periodic
+ * FP64 renormalisation unnormalised FP32 scores would need.  T1 / ll agree with the FP64 decode of the
+ * same values to <= 1e-4 relative; x is NOT promised bit-exact: it can differ where a decision margin is below the
+ * FIR's FP32 rounding (~1e-4 on scores of O(100)).  hmm_set_precision(HMM_PREC_F32) (or HMMCUDA_PRECISION=f32)
+ * makes the *_f64 decode entry points compute that way too; the *_f32 entry points always do.  Models other than
+ * non-overlap ring models (faithful engine) and the Baum-Welch entry points compute in FP64 in either mode. */
+#define HMM_PREC_F64 0
+#define HMM_PREC_F32 1
+int hmm_set_precision(int32_t precision);
+int hmm_get_precision(void);
+int hmm_viterbi_f32(const float *y, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                    const hmm_trans *tr, int64_t ntrans, const double *mu, double sigma, int16_t *x_out,
+                    double *ll_out);
+int hmm_viterbi_ex_f32(const float *y, int64_t T, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
+                       const hmm_trans *tr, int64_t ntrans, const double *mu, double sigma, int16_t *x_out,
+                       double *ll_out, int32_t mode, hmm_info *info);
+int hmm_viterbi_batch_f32(const float *y, int64_t T, int32_t C, const int16_t *states, int32_t states_shared,
+                          int32_t N, int32_t K, int32_t nstates, const hmm_trans *tr, int64_t ntrans,
+                          const double *mu, const double *sigma, int16_t *x_out, double *ll_out, int32_t mode,
+                          hmm_info *info);
+int hmm_viterbi_dev_f32(const float *y_dev, int64_t T, int32_t C, const int16_t *states, int32_t states_shared,
+                        int32_t N, int32_t K, int32_t nstates, const hmm_trans *tr, int64_t ntrans,
+                        const double *mu, const double *sigma, int16_t *x_dev, double *ll_out, int32_t mode,
+                        hmm_info *info);
+
 /* ---- time-sharded decode of ONE long recording across GPUs (BASELINE config 5) ------------- */
 /*
  * Every rank owns a contiguous span [main_begin, main_end) of the recording (multiples of
