@@ -1781,6 +1781,95 @@ int hmm_train_destroy(hmm_train_ctx *ctx) {
 }
 
 // ---------------------------------------------------------------------------
+// time-sharded Baum-Welch (one recording over several GPUs)
+// ---------------------------------------------------------------------------
+struct hmm_emshard {
+    double *X_dev = nullptr;
+    bool owned = false;
+    int64_t local_begin = 0, local_end = 0, main_begin = 0, main_end = 0, T_global = 0, Lc = 0, W = 0;
+    int device = 0;
+};
+
+int hmm_emshard_create(const double *X_local, int32_t x_is_host, int64_t local_begin, int64_t local_end,
+                       int64_t main_begin, int64_t main_end, int64_t T_global, int64_t chunk_len, int64_t warmup,
+                       hmm_emshard **out) {
+    return guarded([&] {
+        if (!X_local || !out) fail(HMM_EINVAL, "null argument");
+        if (!(0 <= local_begin && local_begin <= main_begin && main_begin < main_end && main_end <= local_end &&
+              local_end <= T_global))
+            fail(HMM_EINVAL, "inconsistent shard spans");
+        if (chunk_len < 256 || chunk_len % 256 || warmup < 0 || warmup > chunk_len) fail(HMM_EINVAL, "bad chunk_len / warmup");
+        const bool first = main_begin == 0, last = main_end == T_global;
+        if ((main_begin - local_begin) % chunk_len || (!last && (main_end - local_begin) % chunk_len))
+            fail(HMM_EINVAL, "shard spans must be multiples of chunk_len from local_begin");
+        if (first != (local_begin == 0)) fail(HMM_EINVAL, "only the first shard may start at sample 0");
+        if (!first && main_begin - local_begin < chunk_len) fail(HMM_EINVAL, "left ghost must be at least one chunk");
+        if (!last && local_end - main_end < chunk_len) fail(HMM_EINVAL, "right ghost must be at least one chunk");
+        require_device();
+        std::unique_ptr<hmm_emshard> h(new hmm_emshard);
+        HMM_CUDA(cudaGetDevice(&h->device));
+        const int64_t Tl = local_end - local_begin;
+        if (x_is_host) {
+            cudaStream_t st = main_stream();
+            cudaError_t e = cudaMalloc((void **)&h->X_dev, sizeof(double) * (size_t)Tl);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                fail(HMM_ENOMEM, "device allocation failed: %s", cudaGetErrorString(e));
+            }
+            h->owned = true;
+            h2d(h->X_dev, X_local, sizeof(double) * (size_t)Tl, st);
+            HMM_CUDA(cudaStreamSynchronize(st));
+        } else
+            h->X_dev = const_cast<double *>(X_local);
+        h->local_begin = local_begin; h->local_end = local_end; h->main_begin = main_begin; h->main_end = main_end;
+        h->T_global = T_global; h->Lc = chunk_len; h->W = warmup;
+        *out = h.release();
+    });
+}
+
+int hmm_emshard_stats_len(int32_t N, int32_t nstates) { return ring_em_xvec_len(N, nstates); }
+int hmm_emshard_boundary_len(int32_t N, int32_t K) { return ring_em_bnd_len(N, K); }
+
+int hmm_emshard_estep(hmm_emshard *h, const int16_t *states, int32_t N, int32_t K, int32_t nstates, const hmm_trans *tr,
+                      int64_t ntrans, const double *mu, double sigma, double *stats_dev, double *boundary_dev) {
+    return guarded([&] {
+        if (!h || !stats_dev || !boundary_dev) fail(HMM_EINVAL, "null argument");
+        HMM_CUDA(cudaSetDevice(h->device));
+        HostModel M;
+        analyse_model(states, N, K, nstates, tr, ntrans, mu, sigma, M);
+        const int64_t Tl = h->local_end - h->local_begin;
+        if (!M.is_ring || !ring_supported(M, Tl)) fail(HMM_EUNSUPPORTED, "time-sharded E/M needs a non-overlap ring model");
+        EmShardOpts o{h->Lc, h->W, h->main_begin - h->local_begin, h->main_end - h->local_begin, h->main_begin == 0,
+                      h->main_end == h->T_global, stats_dev, boundary_dev};
+        ring_em_shard_estep(h->X_dev, Tl, M, o, main_stream(), nullptr);
+    });
+}
+
+int hmm_emshard_mstep(hmm_emshard *h, const int16_t *states, int32_t N, int32_t K, int32_t nstates, const hmm_trans *tr,
+                      int64_t ntrans, const double *stats_sum_dev, double lS_global, double *mu_inout, double *sigma_inout,
+                      double *lp_out, double *pp_out, double *loglik_out) {
+    return guarded([&] {
+        if (!h || !stats_sum_dev || !mu_inout || !sigma_inout) fail(HMM_EINVAL, "null argument");
+        HMM_CUDA(cudaSetDevice(h->device));
+        HostModel M;
+        analyse_model(states, N, K, nstates, tr, ntrans, mu_inout, *sigma_inout, M);
+        EmResult r;
+        ring_em_shard_mstep(stats_sum_dev, M, h->T_global, lS_global, r, main_stream());
+        export_em(r, M, mu_inout, sigma_inout, lp_out, pp_out, loglik_out);
+    });
+}
+
+int hmm_emshard_destroy(hmm_emshard *h) {
+    return guarded([&] {
+        if (!h) return;
+        cudaSetDevice(h->device);
+        cudaDeviceSynchronize();
+        if (h->owned && h->X_dev) cudaFree(h->X_dev);
+        delete h;
+    });
+}
+
+// ---------------------------------------------------------------------------
 // reconstruct / unroll
 // ---------------------------------------------------------------------------
 static void check_model_small(const int16_t *states, int N, int K, int nstates, const double *mu) {

@@ -131,6 +131,20 @@ struct EmResult {
     double sigma = 0, loglik = 0;
 };
 void ring_em_run(const double *X_dev, int64_t T, const HostModel &M, EmResult &out, cudaStream_t st, hmm_info *info);
+// Time-sharded E/M step: the E-step of one shard (local samples incl. one ghost chunk per side; statistics over the
+// local steps [st_lo, st_hi) only) leaves its statistics vector (ring_em_xvec_len doubles) and its four boundary
+// vectors + local lS (ring_em_bnd_len doubles) in device buffers, asynchronously; the M-step consumes the summed vector.
+struct EmShardOpts {
+    int64_t Lc, W, st_lo, st_hi;
+    bool first, last;
+    double *xvec_dev, *bnd_dev;
+};
+int ring_em_xvec_len(int N, int nstates);
+int ring_em_bnd_len(int N, int K);
+void ring_em_shard_estep(const double *X_dev, int64_t T_local, const HostModel &M, const EmShardOpts &sh, cudaStream_t st,
+                         hmm_info *info);
+void ring_em_shard_mstep(const double *xsum_dev, const HostModel &M, int64_t T_glob, double lS_glob, EmResult &out,
+                         cudaStream_t st);
 // dense alpha and/or beta [nstates x T] (device pointers, nullable) from the semi-Markov engine
 void ring_fb_dense_run(const double *X_dev, int64_t T, const HostModel &M, double *alpha_dev, double *beta_dev,
                        cudaStream_t st);

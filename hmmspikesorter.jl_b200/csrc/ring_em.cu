@@ -48,6 +48,9 @@ struct EmParams {
     int nblk, pstride;
     double *out;                      // finalize output
     int dbg;                          // debug switch (HMMCUDA_EM_DBG): 1 = log-domain live windows
+    // time-sharded E-step (hmm_emshard_*): the statistics are accumulated over the local steps [st_lo, st_hi) only
+    // (this shard's main span; the ghost chunks on either side only make the posteriors there exact)
+    int64_t st_lo, st_hi;
 };
 
 enum { EM_INIT = 0, EM_SPEC = 1, EM_EXACT = 2 };
@@ -887,8 +890,8 @@ __global__ void __launch_bounds__(128) em_stats(EmParams p) {
     for (int64_t w = gw; w < nwin; w += nw) {
         if (w + nw < nwin) issue(w + nw, nxt);
         const int64_t t = w * 32 + lane;
-        const bool ok = t < T;
-        const int64_t tc = ok ? t : T - 1;
+        const bool ok = t < T && t >= p.st_lo && t < p.st_hi;
+        const int64_t tc = t < T ? t : T - 1;
         const bool e_in = tc + L - 1 <= T - 1, x_in = tc + L <= T - 1, has_next = tc <= T - 2;
 #pragma unroll
         for (int q = 0; q < 4; q++)
@@ -1078,6 +1081,99 @@ __global__ void __launch_bounds__(1024) em_finalize(EmParams p) {
 }
 
 // ---------------------------------------------------------------------------
+// Time-sharded E/M step (contiguous spans of the recording on different GPUs).  Every shard runs the whole
+// E-step on its span PLUS one ghost chunk on either side as a stand-alone problem: sum-product messages forget their
+// start exponentially, so inside the main span the local posteriors are the global ones -- which is VERIFIED, not
+// assumed: the forward / backward boundary vectors two neighbours hold for the same instant must agree up to a constant
+// (em_shard_boundaries; compared by the caller after one all-gather).  The sufficient statistics are accumulated over the
+// main span only (em_stats with [st_lo, st_hi)), extended by the end-of-recording corrections on the first / last shard
+// and by gamma[:,1] on the first (em_shard_pack), summed over the shards by ONE all-reduce, and finalised identically on
+// every rank (em_shard_finalize).
+//   xvec layout: tot[pstride] | S0adj[N][S1_LAGS] | S1adj[N][S1_LAGS] | pp[ns] | 2 spare
+// ---------------------------------------------------------------------------
+__host__ __device__ inline int em_xvec_len(int N, int ns) { return (4 + 2 * N + N * S1_LAGS) + 2 * N * S1_LAGS + ns + 2; }
+
+template <int N>
+__global__ void __launch_bounds__(1024) em_shard_pack(EmParams p, int first, int last, double *xvec) {
+    extern __shared__ __align__(16) double sm[];
+    const RingLayout &RL = p.RL;
+    const int L = RL.L;
+    const int64_t T = p.T;
+    const int nx = em_xvec_len(N, p.ns);
+    for (int k = threadIdx.x; k < nx; k += blockDim.x) xvec[k] = k < p.pstride ? p.tot[k] : 0.0;
+    const double lS = p.lS[0], lam0 = p.lambda[0], kapl = p.kappa[p.nchunks - 1];
+    double *piv = sm, *pie = sm + (size_t)N * S1_LAGS;
+    for (int idx = threadIdx.x; idx < N * L; idx += blockDim.x) {
+        const int i = idx / L, r = idx % L;
+        double v = 0.0, w2 = 0.0;
+        if (first && r >= 1) v = exp(p.LQneg[i * L + r] + p.LE[(size_t)i * T + (L - 1 - r)] + lam0 - lS);  // running at t = 0
+        if (last && r <= L - 2) w2 = exp(p.LQ[(size_t)i * T + (T - 1 - r)] + kapl - lS);                    // run past the end
+        piv[i * S1_LAGS + r] = v;
+        pie[i * S1_LAGS + r] = w2;
+    }
+    __syncthreads();
+    double *S0adj = xvec + p.pstride, *S1adj = S0adj + (size_t)N * S1_LAGS, *pp = S1adj + (size_t)N * S1_LAGS;
+    for (int idx = threadIdx.x; idx < N * L; idx += blockDim.x) {
+        const int i = idx / L, sph = idx % L;
+        double a0 = 0.0, a1 = 0.0;
+        for (int k = 0; k < sph; k++) a0 -= pie[i * S1_LAGS + k];
+        for (int r0 = 1; r0 <= sph; r0++) {
+            const double pi = piv[i * S1_LAGS + r0];
+            a0 += pi;
+            if (first) a1 = fma(pi, p.y[sph - r0], a1);
+        }
+        S0adj[i * S1_LAGS + sph] = a0;
+        S1adj[i * S1_LAGS + sph] = a1;
+        if (first) pp[1 + i * L + sph] = p.LQneg[i * L + sph] + p.LE[(size_t)i * T + (L - 1 - sph)] + lam0 - lS;
+    }
+    if (threadIdx.x == 0 && first) pp[0] = p.LG[0] + p.LH[0] + lam0 - lS;
+}
+
+// The four boundary vectors of a shard in its own (chunk-0 consistent) normalisation: forward at main_begin and at
+// main_end, backward at main_begin and at main_end; a vector that does not exist (no ghost on that side) is zero.
+__global__ void em_shard_boundaries(EmParams p, int c_mb, int c_me, double *out /*[4][bvec]*/) {
+    const int n = p.bvec;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        out[k] = c_mb >= 1 ? p.EBf[(size_t)(c_mb - 1) * n + k] + p.kappa[c_mb - 1] : 0.0;
+        out[n + k] = (c_me >= 1 && c_me < p.nchunks) ? p.EBf[(size_t)(c_me - 1) * n + k] + p.kappa[c_me - 1] : 0.0;
+        out[2 * n + k] = c_mb >= 1 ? p.EBb[(size_t)c_mb * n + k] + p.lambda[c_mb] : 0.0;
+        out[3 * n + k] = c_me < p.nchunks ? p.EBb[(size_t)c_me * n + k] + p.lambda[c_me] : 0.0;
+    }
+    if (threadIdx.x == 0) out[4 * n] = p.lS[0];
+}
+
+// out layout as em_finalize: [0] sigma [1] loglik [2..2+N) lp  then mu [K*N] then pp [ns]
+template <int N>
+__global__ void __launch_bounds__(1024)
+    em_shard_finalize(const double *xsum, int L, int ns, int pstride, double T_glob, double lS_glob, double w_nn,
+                      double c_emit, double two_s2, double m0, double *out) {
+    extern __shared__ __align__(16) double sm[];
+    const int K = L + 1;
+    const double *tot = xsum, *S1t = xsum + 4 + 2 * N, *S0adj = xsum + pstride, *S1adj = S0adj + (size_t)N * S1_LAGS,
+                 *ppx = S1adj + (size_t)N * S1_LAGS;
+    double *qterm = sm;
+    double *mu = out + 2 + N, *pp = mu + (size_t)K * N;
+    for (int idx = threadIdx.x; idx < N * L; idx += blockDim.x) {
+        const int i = idx / L, sph = idx % L;
+        const double s0 = tot[4 + N + i] + S0adj[i * S1_LAGS + sph];
+        const double s1 = S1t[i * S1_LAGS + sph] + S1adj[i * S1_LAGS + sph];
+        mu[(sph + 1) + (size_t)K * i] = s1 / s0;  // src/baumwelch.jl:283-287
+        qterm[idx] = s1 * s1 / s0;
+    }
+    for (int k = threadIdx.x; k < ns; k += blockDim.x) pp[k] = ppx[k];  // gamma[:,1], src/baumwelch.jl:263
+    if (threadIdx.x < N) mu[(size_t)K * threadIdx.x] = 0.0;             // row 1 stays 0 (src/baumwelch.jl:268)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double q = 0.0;
+        for (int k = 0; k < N * L; k++) q += qterm[k];
+        out[0] = sqrt((tot[2] - q) / T_glob);  // src/baumwelch.jl:288-307
+        const double ssq = tot[2] - 2.0 * m0 * tot[1] + T_glob * m0 * m0;
+        out[1] = T_glob * c_emit - ssq / two_s2 + (T_glob - 1.0) * w_nn + lS_glob;
+        for (int i = 0; i < N; i++) out[2 + i] = log(tot[4 + i]) - log(tot[0]);  // xb[2:end], :254-265
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Dense alpha / beta on request (forward / backward of src/baumwelch.jl:25-51, 73-98 as
 // stand-alone calls): materialised from the semi-Markov quantities.
 //   alpha[noise, t]  = Z_t + lg_t                     Z_t = sum_{tau<=t} q_tau(noise) + t * w_nn
@@ -1231,7 +1327,7 @@ static thread_local EmStageTimes g_em_times;
 
 template <int N, int R>
 static void em_launch(EmParams &p, const double *hmdl, cudaStream_t st, hmm_info *info, Timer &ttop, int mode,
-                      double *alpha_out, double *beta_out, double *Zs, double *bsum) {
+                      double *alpha_out, double *beta_out, double *Zs, double *bsum, const EmShardOpts *sh) {
     EmStageTimes &tm = g_em_times;
     tm.on = getenv("HMMCUDA_EM_TIMING") != nullptr;
     tm.n = 0;
@@ -1270,7 +1366,14 @@ static void em_launch(EmParams &p, const double *hmdl, cudaStream_t st, hmm_info
     em_fixup<N, R><<<2, 1024, sm_rep, st>>>(p, dirs);
     tm.mark("fixup", st);
     if (info) info->kernel_launches += (mode != 1 ? 5 : 4);
-    if (mode == 0) {
+    if (mode == 0 && sh) {  // time shard: statistics of the main span, packed for the all-reduce; boundary vectors
+        em_stats<N><<<p.nblk, 32 * WPB, sm_stats, st>>>(p);
+        em_reduce<<<(p.pstride + 31) / 32, 1024, 0, st>>>(p);
+        const size_t sm_pack = sizeof(double) * 2 * (size_t)N * S1_LAGS;
+        em_shard_pack<N><<<1, 1024, sm_pack, st>>>(p, sh->first ? 1 : 0, sh->last ? 1 : 0, sh->xvec_dev);
+        em_shard_boundaries<<<1, 256, 0, st>>>(p, (int)(sh->st_lo / p.Lc), sh->last ? p.nchunks : (int)(sh->st_hi / p.Lc), sh->bnd_dev);
+        if (info) info->kernel_launches += 4;
+    } else if (mode == 0) {
         em_stats<N><<<p.nblk, 32 * WPB, sm_stats, st>>>(p);
         tm.mark("stats", st);
         HMM_CUDA(cudaFuncSetAttribute(em_finalize<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fin));
@@ -1292,17 +1395,19 @@ static void em_launch(EmParams &p, const double *hmdl, cudaStream_t st, hmm_info
 }
 
 static void ring_em_core(const double *X_dev, int64_t T, const HostModel &M, EmResult *outp, cudaStream_t st,
-                        hmm_info *info, int mode, double *alpha_out, double *beta_out) {
+                        hmm_info *info, int mode, double *alpha_out, double *beta_out, const EmShardOpts *sh = nullptr) {
     Workspace &ws = workspace();
     const int N = M.N, L = M.K - 1, K = M.K, ns = M.nstates;
     const int R = (N <= 4) ? 8 : 4, SW = 32 * R;
     RingLayout RL = ring_layout(N, L);
     // The E-step is latency-bound per warp (log-sum-exp chains), so short chunks and a short
     // warm-up pay: every boundary is verified (and repaired if needed) anyway.
-    int64_t W = ring_config().warmup > 0 ? ring_config().warmup : 256;
+    int64_t W = sh ? sh->W : (ring_config().warmup > 0 ? ring_config().warmup : 256);
     W = ((W + SW - 1) / SW) * SW;
     if (W < ((L + 32 + SW - 1) / SW) * SW) W = ((L + 32 + SW - 1) / SW) * SW;
-    int64_t Lc = ring_config().chunk_len;
+    int64_t Lc = sh ? sh->Lc : ring_config().chunk_len;
+    if (sh && (Lc % SW || Lc < W || sh->st_lo % Lc || (!sh->last && sh->st_hi % Lc)))
+        fail(HMM_EINVAL, "time shard: chunk_len must be a multiple of %d and the main span chunk aligned", SW);
     if (Lc <= 0) {
         int dev = 0, sms = 148;
         HMM_CUDA(cudaGetDevice(&dev));
@@ -1392,6 +1497,8 @@ static void ring_em_core(const double *X_dev, int64_t T, const HostModel &M, EmR
     double *out_host = (double *)ws.pinned(1, sizeof(double) * nout, &out_dev);
     p.out = (double *)out_dev;
     p.dbg = getenv("HMMCUDA_EM_DBG") ? atoi(getenv("HMMCUDA_EM_DBG")) : 0;
+    p.st_lo = sh ? sh->st_lo : 0;
+    p.st_hi = sh ? sh->st_hi : T;
     (void)o_out;
 
     double *Zs = nullptr, *bsum = nullptr;
@@ -1402,17 +1509,21 @@ static void ring_em_core(const double *X_dev, int64_t T, const HostModel &M, EmR
     }
     Timer ttop(st);
     switch (N) {
-        case 1: em_launch<1, 8>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
-        case 2: em_launch<2, 8>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
-        case 3: em_launch<3, 8>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
-        case 4: em_launch<4, 8>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
-        case 5: em_launch<5, 4>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
-        case 6: em_launch<6, 4>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
-        case 7: em_launch<7, 4>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum); break;
+        case 1: em_launch<1, 8>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum, sh); break;
+        case 2: em_launch<2, 8>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum, sh); break;
+        case 3: em_launch<3, 8>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum, sh); break;
+        case 4: em_launch<4, 8>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum, sh); break;
+        case 5: em_launch<5, 4>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum, sh); break;
+        case 6: em_launch<6, 4>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum, sh); break;
+        case 7: em_launch<7, 4>(p, hmdl, st, info, ttop, mode, alpha_out, beta_out, Zs, bsum, sh); break;
         default: fail(HMM_EUNSUPPORTED, "ring E/M engine supports 1..%d neurons", RING_MAX_N);
     }
     if (mode != 0) {
         HMM_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+    if (sh) {  // asynchronous: the caller synchronises after its collectives
+        if (info) info->n_chunks = nchunks;
         return;
     }
     EmResult &out = *outp;
@@ -1435,6 +1546,46 @@ static void ring_em_core(const double *X_dev, int64_t T, const HostModel &M, EmR
 
 void ring_em_run(const double *X_dev, int64_t T, const HostModel &M, EmResult &out, cudaStream_t st, hmm_info *info) {
     ring_em_core(X_dev, T, M, &out, st, info, 0, nullptr, nullptr);
+}
+
+// ---- time-sharded E/M step (see the kernels above) ----
+int ring_em_xvec_len(int N, int nstates) { return em_xvec_len(N, nstates); }
+int ring_em_bnd_len(int N, int K) { return 4 * (1 + N * (K - 1)) + 1; }
+
+void ring_em_shard_estep(const double *X_dev, int64_t T_local, const HostModel &M, const EmShardOpts &sh, cudaStream_t st,
+                         hmm_info *info) {
+    ring_em_core(X_dev, T_local, M, nullptr, st, info, 0, nullptr, nullptr, &sh);
+}
+
+void ring_em_shard_mstep(const double *xsum_dev, const HostModel &M, int64_t T_glob, double lS_glob, EmResult &out,
+                         cudaStream_t st) {
+    const int N = M.N, L = M.K - 1, K = M.K, ns = M.nstates;
+    const int pstride = 4 + 2 * N + N * S1_LAGS;
+    const int nout = 2 + N + K * N + ns + 2;
+    Workspace &ws = workspace();
+    void *out_dev = nullptr;
+    double *out_host = (double *)ws.pinned(1, sizeof(double) * nout, &out_dev);
+    const double LOG2PI = 0.9189385332046727;
+    const double w_nn = M.ring.w_nn, c_emit = (-LOG2PI) - M.lsig, two_s2 = 2 * (M.sigma * M.sigma), m0 = M.m[0];
+    const size_t smf = sizeof(double) * (size_t)N * S1_LAGS;
+#define HMM_EMSH(NN)                                                                                                \
+    case NN:                                                                                                        \
+        em_shard_finalize<NN><<<1, 1024, smf, st>>>(xsum_dev, L, ns, pstride, (double)T_glob, lS_glob, w_nn, c_emit, \
+                                                    two_s2, m0, (double *)out_dev);                                 \
+        break;
+    switch (N) {
+        HMM_EMSH(1) HMM_EMSH(2) HMM_EMSH(3) HMM_EMSH(4) HMM_EMSH(5) HMM_EMSH(6) HMM_EMSH(7)
+        default: fail(HMM_EUNSUPPORTED, "ring E/M engine supports 1..%d neurons", RING_MAX_N);
+    }
+#undef HMM_EMSH
+    HMM_CUDA(cudaGetLastError());
+    HMM_CUDA(cudaStreamSynchronize(st));
+    const double *h = out_host;
+    out.sigma = h[0];
+    out.loglik = h[1];
+    out.lp.assign(h + 2, h + 2 + N);
+    out.mu.assign(h + 2 + N, h + 2 + N + (size_t)K * N);
+    out.pp.assign(h + 2 + N + (size_t)K * N, h + 2 + N + (size_t)K * N + ns);
 }
 
 void ring_fb_dense_run(const double *X_dev, int64_t T, const HostModel &M, double *alpha_dev, double *beta_dev,

@@ -440,3 +440,131 @@ def viterbi_time_sharded_dist(y_local_dev_ptr: int, span, T: int, chunk_len: int
         return d.decode(), dict(d.stats)
     finally:
         d.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Time-sharded Baum-Welch (hmm_emshard_*): one recording over several GPUs, one all-reduce of the sufficient
+# statistics and one all-gather of the boundary vectors per E/M iteration.
+# ---------------------------------------------------------------------------------------------------------------
+class EmShard:
+    """One hmm_emshard handle: this shard's samples [span[0], span[1]) (ghost chunks included) stay in HBM."""
+
+    def __init__(self, X_local, x_is_host, span, T, chunk_len, warmup=256, device=None):
+        L = lib()
+        if device is not None:
+            check(L.hmm_set_device(i32(device)))
+        self.device, self.span, self.T = device, span, T
+        self._h = C.c_void_p()
+        xp = _p(X_local) if x_is_host else C.c_void_p(int(X_local))
+        check(L.hmm_emshard_create(xp, i32(1 if x_is_host else 0), i64(span[0]), i64(span[1]), i64(span[2]), i64(span[3]),
+                                   i64(T), i64(chunk_len), i64(warmup), C.byref(self._h)))
+
+    def _model(self, lA, mu):
+        st = np.asfortranarray(lA.states, dtype=np.int16)
+        tr = np.ascontiguousarray(lA.transitions, dtype=TRANS_DTYPE)
+        return st, tr, np.asfortranarray(mu, dtype=np.float64)
+
+    def estep(self, lA, mu, sigma, stats_ptr, bnd_ptr):
+        if self.device is not None:
+            check(lib().hmm_set_device(i32(self.device)))
+        st, tr, mu = self._model(lA, mu)
+        check(lib().hmm_emshard_estep(self._h, _p(st), i32(lA.N), i32(lA.K), i32(lA.nstates), _p(tr), i64(tr.size), _p(mu),
+                                      f64(sigma), C.c_void_p(stats_ptr), C.c_void_p(bnd_ptr)))
+
+    def mstep(self, lA, mu, sigma, stats_sum_ptr, lS_global):
+        if self.device is not None:
+            check(lib().hmm_set_device(i32(self.device)))
+        st, tr, mu = self._model(lA, mu)
+        mu = mu.copy(order="F")
+        nxi = int((lA.transitions["src"] == 1).sum())
+        lp = np.empty(max(nxi - 1, 1), dtype=np.float64)
+        pp = np.empty(lA.nstates, dtype=np.float64)
+        s, ll = f64(sigma), f64(0)
+        check(lib().hmm_emshard_mstep(self._h, _p(st), i32(lA.N), i32(lA.K), i32(lA.nstates), _p(tr), i64(tr.size),
+                                      C.c_void_p(stats_sum_ptr), f64(lS_global), _p(mu), C.byref(s), _p(lp), _p(pp),
+                                      C.byref(ll)))
+        return lp[:nxi - 1].copy(), pp, mu, s.value, ll.value
+
+    def close(self):
+        if self._h:
+            lib().hmm_emshard_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _vectors_agree(a, b, rtol=1e-12, atol=1e-9):
+    """Two boundary vectors describe the same distribution iff they differ by a constant; entries more than 745 below
+    the maximum cannot influence a double.  Returns (ok, constant a - b)."""
+    fa, fb = np.isfinite(a), np.isfinite(b)
+    ra, rb = a - a[fa].max(), b - b[fb].max()
+    live = (ra > -745.0) | (rb > -745.0)
+    if not np.array_equal(fa[live], fb[live]):
+        return False, 0.0
+    m = live & fa & fb
+    d = a[m] - b[m]
+    c = d[0] if d.size else 0.0
+    return bool(np.all(np.abs(d - c) <= atol + rtol * np.abs(b[m]))), float(a[0] - b[0])
+
+
+class EmSharded:
+    """Baum-Welch E/M iterations of ONE recording cut into time shards.  `shards`: the EmShard objects this process
+    drives -- all of them (single process, e.g. several shards on one GPU: tests) or one per torch.distributed rank
+    (NCCL).  em_step(lA, mu, sigma) -> (lp, pp, mu, sigma, loglik), the same on every rank, like the single-GPU
+    em_step; raises if a shard boundary does not verify (the ghost chunk was too short for the messages to forget
+    their start: use a longer chunk_len)."""
+
+    def __init__(self, shards, N, K, nstates, device, distributed=False):
+        import torch
+
+        self.torch = torch
+        self.shards = list(shards)
+        self.dist = None
+        if distributed:
+            import torch.distributed as dist
+
+            self.dist = dist
+        L = lib()
+        self.nstat = int(L.hmm_emshard_stats_len(i32(N), i32(nstates)))
+        self.nbnd = int(L.hmm_emshard_boundary_len(i32(N), i32(K)))
+        self.bvec = 1 + N * (K - 1)
+        f8 = torch.float64
+        self.stats = [torch.zeros(self.nstat, dtype=f8, device=device) for _ in self.shards]
+        self.bnd = [torch.zeros(self.nbnd, dtype=f8, device=device) for _ in self.shards]
+        self.device = device
+        self.last_check = None
+
+    def em_step(self, lA, mu, sigma):
+        torch, dist = self.torch, self.dist
+        for sh, st, bd in zip(self.shards, self.stats, self.bnd):
+            sh.estep(lA, mu, sigma, st.data_ptr(), bd.data_ptr())
+        torch.cuda.synchronize(self.device)  # (the library's stream is not torch's unless hmm_set_stream says so)
+        if dist is not None:
+            total = self.stats[0].clone()
+            dist.all_reduce(total)
+            gath = torch.empty(dist.get_world_size() * self.nbnd, dtype=torch.float64, device=self.device)
+            dist.all_gather_into_tensor(gath, self.bnd[0])
+            B = gath.cpu().numpy().reshape(-1, self.nbnd)
+        else:
+            total = torch.stack(self.stats).sum(dim=0)
+            B = torch.stack(self.bnd).cpu().numpy()
+        n, bv = B.shape[0], self.bvec
+        lS = float(B[n - 1][4 * bv])
+        worst = True
+        for r in range(n - 1):
+            okf, df = _vectors_agree(B[r][bv:2 * bv], B[r + 1][0:bv])            # forward: r at its end, r+1 at its begin
+            okb, _ = _vectors_agree(B[r][3 * bv:4 * bv], B[r + 1][2 * bv:3 * bv])  # backward, same instant
+            worst = worst and okf and okb
+            lS += df
+        self.last_check = worst
+        if not worst:
+            raise RuntimeError("time-sharded E/M: a shard boundary did not verify (ghost chunk too short)")
+        return self.shards[0].mstep(lA, mu, sigma, total.data_ptr(), lS)
+
+    def close(self):
+        for sh in self.shards:
+            sh.close()

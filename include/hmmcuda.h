@@ -283,6 +283,33 @@ int hmm_train_em_step(hmm_train_ctx *ctx, const int16_t *states, int32_t N, int3
                       double *pp_out, double *loglik_out, hmm_info *info);
 int hmm_train_destroy(hmm_train_ctx *ctx);
 
+/* ---- time-sharded Baum-Welch: one recording over several GPUs ------------------------------------
+ * Every rank owns a contiguous span [main_begin, main_end) of X (chunk aligned) and holds [local_begin, local_end) with at
+ * least one ghost chunk on either side.  One E/M iteration of src/baumwelch.jl:362-370 over all ranks:
+ *   estep  (every rank, asynchronous on the library's stream): forward, backward and the sufficient statistics of the
+ *          rank's main span -> stats_dev (hmm_emshard_stats_len doubles: sum gamma, sum gamma y, sum y^2, the xi sums,
+ *          S1[i][s] = sum pi_i(t0) y[t0+s], end-of-recording corrections on the first / last rank, gamma[:,1] on the
+ *          first) and boundary_dev (hmm_emshard_boundary_len doubles: the forward and backward boundary vectors at
+ *          main_begin and at main_end in the rank's own normalisation, then its local log-likelihood term);
+ *   [caller: ALL-REDUCE (sum) of stats over the ranks; ALL-GATHER of boundary.  Neighbours' vectors for the same instant
+ *    must agree up to a constant (1e-11 relative): that verifies that one ghost chunk made the main-span posteriors
+ *    exact; the constants chain the ranks' normalisations: lS_global = lS_last + sum_r (fwd_r-1@end - fwd_r@begin)]
+ *   mstep  (every rank, identical result): new mu (in place, src/baumwelch.jl:268), sigma, lp = xb[2:end], pp = gamma[:,1],
+ *          log-likelihood.
+ * hmmspikesorter.jl_b200/timeshard.py (EmSharded) drives this over torch.distributed (NCCL) or over shards on one GPU. */
+typedef struct hmm_emshard hmm_emshard;
+int hmm_emshard_create(const double *X_local, int32_t x_is_host, int64_t local_begin, int64_t local_end,
+                       int64_t main_begin, int64_t main_end, int64_t T_global, int64_t chunk_len, int64_t warmup,
+                       hmm_emshard **out);
+int hmm_emshard_stats_len(int32_t N, int32_t nstates);
+int hmm_emshard_boundary_len(int32_t N, int32_t K);
+int hmm_emshard_estep(hmm_emshard *h, const int16_t *states, int32_t N, int32_t K, int32_t nstates, const hmm_trans *tr,
+                      int64_t ntrans, const double *mu, double sigma, double *stats_dev, double *boundary_dev);
+int hmm_emshard_mstep(hmm_emshard *h, const int16_t *states, int32_t N, int32_t K, int32_t nstates, const hmm_trans *tr,
+                      int64_t ntrans, const double *stats_sum_dev, double lS_global, double *mu_inout, double *sigma_inout,
+                      double *lp_out, double *pp_out, double *loglik_out);
+int hmm_emshard_destroy(hmm_emshard *h);
+
 /* ---- reconstruction ------------------------------------------------------ */
 /* reconstruct_signal(x, lA, mu, sigma) -> Y [T]             src/reconstruction.jl:1-9 */
 int hmm_reconstruct_f64(const int16_t *x, int64_t T, const int16_t *states, int32_t N, int32_t nstates,
