@@ -72,6 +72,8 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
+        if os.environ.get("BENCH_NO_SAMPLER"):  # (diagnostic: does polling nvidia-smi perturb the timed region?)
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
@@ -168,6 +170,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
         sampler.wait_first(5.0)
+    barrier()  # all ranks start their warm-up together: no rank idles (and drops its clocks) waiting at the next barrier
     for _ in range(args.warmup):
         step_dev()
     barrier()
@@ -210,6 +213,7 @@ def run_ours(args):
                                            i64(tr.size), p(mu), C.c_double(sigma), xh, C.byref(ll2), None, None,
                                            i32(hm.MODES["ring"]), C.byref(info)))
 
+    barrier()
     for _ in range(max(3, args.warmup // 2)):
         step_e2e()
     barrier()
@@ -256,9 +260,10 @@ def run_ours(args):
             bw = {"unavailable": str(e)}
     # ---- CPU baseline: oracle port on a bounded sample (rank 0, N=1 only) ---------
     # ---- the two scaling configurations of north_star, in the same line (and the same driver run) ---------------
-    c4 = c5 = None
+    c3 = c4 = c5 = None
     if not args.no_scaling_blocks and args.samples == T_C2:
         L.hmm_release_workspace()
+        c3 = block_c3(env, args)
         c5 = block_c5(env, args)
         c4 = block_c4(env, args)
     clocks = sampler.stop() if rank == 0 else None  # sampled across every timed region above
@@ -304,6 +309,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "parity": parity,
             "baum_welch": bw,
+            "config3_sharded": c3,
             "config5": c5,
             "config4": c4,
             "clocks": clocks,
@@ -397,6 +403,7 @@ def block_c5(env, args, T=108_000_000):
     x_main = torch.empty(span[3] - span[2], dtype=torch.int16, device=dev)
     dec = ts.DistDecoder(y_loc.data_ptr(), span, T, chunk_len, warm, lA, mu, sigma, x_main.data_ptr(), dev)
     steps, warmup = args.steps, max(3, args.warmup)
+    env.barrier()
     for _ in range(warmup):
         dec.decode()
     env.barrier()
@@ -424,6 +431,40 @@ def block_c5(env, args, T=108_000_000):
                                    "shard summaries per decode",
                        "fallbacks": stats["fallbacks"], "ll": ll, "x_checksum": chk,
                        "l2": "inputs larger than L2 (>= 108 MB of y per GPU)"}}
+
+
+def block_c3(env, args, T=T_C3, iters=20):
+    """BASELINE config 3 over the GPUs: ONE 1-minute recording (1.8 M samples, N=3, K=60), 20 Baum-Welch iterations,
+    time-sharded (hmm_emshard_*): per iteration one all-reduce of the sufficient statistics and one all-gather of the
+    boundary vectors (NCCL), the M-step identical on every rank.  Strong scaling of a 0.4 ms step: reported as measured."""
+    hm, torch, world, rank, dev = env.hm, env.torch, env.world, env.rank, env.dev
+    ts = hm.timeshard
+    S, lA_true, mu_true, _ = make_c2(hm, seed=3, T=T)
+    N, K = 3, 60
+    chunk_len, warm = ts.em_default_chunking(T, world, N, K)
+    span = ts.shard_plan(T, world, chunk_len, warm)[rank]
+    x_loc = torch.from_numpy(np.ascontiguousarray(S[span[0]:span[1]])).to(dev)
+    sh = ts.EmShard(x_loc.data_ptr(), False, span, T, chunk_len)
+    lA = hm.StateMatrix(N, K, np.log(np.full(N, 0.01)), False)
+    em = ts.EmSharded([sh], N, K, lA.nstates, dev, distributed=world > 1)
+    mu = np.asfortranarray(0.7 * mu_true)
+    sigma = float(np.std(S))
+    env.barrier()
+    for _ in range(3):
+        em.em_step(lA, mu, sigma)
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        lp, pp, mu, sigma, ll = em.em_step(lA, mu, sigma)
+        lA = hm.StateMatrix.from_states(lA.states, pp, K, lp, False)
+    env.torch.cuda.synchronize()
+    dt = env.max_over_ranks(time.perf_counter() - t0)
+    em.close()
+    return {"metric": "Baum-Welch iters/s, one recording time-sharded over the GPUs", "value": round(iters / dt, 2),
+            "unit": "iters/s", "ms_per_iter": round(dt / iters * 1e3, 3), "scaling": "strong", "iterations": iters, "T": T,
+            "config": {"workload": "BASELINE config 3 time-sharded: 30 kHz x 1 min, N=3 x K=60, 20 Baum-Welch iterations",
+                       "chunk_len": chunk_len, "collectives_per_iteration": "1 all-reduce (statistics) + 1 all-gather "
+                       "(boundary vectors)" if world > 1 else "none (one shard)", "final_sigma": sigma, "final_loglik": ll}}
 
 
 def make_c4_channel(hm, c, T):
@@ -487,6 +528,7 @@ def block_c4(env, args, T=T_C2, C_total=128):
                                             C.c_void_p(x_dev.data_ptr()), p(ll), i32(hm.MODES["ring"]), C.byref(info)))
 
     steps, warmup = max(2, min(args.steps, 10)), 3
+    env.barrier()
     for _ in range(warmup):
         step_dev()
     env.barrier()
@@ -713,7 +755,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-bw", action="store_true")
     ap.add_argument("--no-scaling-blocks", action="store_true", help="skip the config-4 / config-5 blocks of the line")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"],
                     help="c2 (default, the driver's contract line): one 18M-sample channel per GPU; "
                          "c4: 128 channels (N=4, K=48) sharded by channel; "
                          "c5: one 108M-sample recording time-sharded over the GPUs")
@@ -722,10 +764,15 @@ def main():
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload in ("c4", "c5"):
+    elif args.workload in ("c3", "c4", "c5"):
         env = Env()
         T = args.samples
-        blk = block_c5(env, args, T=T if T != T_C2 else 108_000_000) if args.workload == "c5" else block_c4(env, args, T=T)
+        if args.workload == "c3":
+            blk = block_c3(env, args, T=T if T != T_C2 else T_C3)
+        elif args.workload == "c5":
+            blk = block_c5(env, args, T=T if T != T_C2 else 108_000_000)
+        else:
+            blk = block_c4(env, args, T=T)
         if env.rank == 0:
             blk.update({"n_gpus": env.world, "higher_is_better": True, "vs_baseline": None, "dtype": "f64",
                         "data": "synthetic"})

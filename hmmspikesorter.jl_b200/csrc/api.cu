@@ -1827,6 +1827,14 @@ int hmm_emshard_create(const double *X_local, int32_t x_is_host, int64_t local_b
     });
 }
 
+int hmm_emshard_chunking(int64_t T_global, int32_t n_ranks, int32_t N, int32_t K, int64_t *chunk_len_out,
+                         int64_t *warmup_out) {
+    return guarded([&] {
+        if (!chunk_len_out || !warmup_out || T_global < 1 || n_ranks < 1 || N < 1 || N > 7 || K < 3) fail(HMM_EINVAL, "bad arguments");
+        require_device();
+        ring_em_default_chunking(N, K, (T_global + n_ranks - 1) / n_ranks, chunk_len_out, warmup_out);
+    });
+}
 int hmm_emshard_stats_len(int32_t N, int32_t nstates) { return ring_em_xvec_len(N, nstates); }
 int hmm_emshard_boundary_len(int32_t N, int32_t K) { return ring_em_bnd_len(N, K); }
 

@@ -139,6 +139,7 @@ struct EmShardOpts {
     bool first, last;
     double *xvec_dev, *bnd_dev;
 };
+void ring_em_default_chunking(int N, int K, int64_t T_local, int64_t *Lc_out, int64_t *W_out);
 int ring_em_xvec_len(int N, int nstates);
 int ring_em_bnd_len(int N, int K);
 void ring_em_shard_estep(const double *X_dev, int64_t T_local, const HostModel &M, const EmShardOpts &sh, cudaStream_t st,

@@ -1549,6 +1549,34 @@ void ring_em_run(const double *X_dev, int64_t T, const HostModel &M, EmResult &o
 }
 
 // ---- time-sharded E/M step (see the kernels above) ----
+// Chunk length / warm-up the E-step would choose for T_local samples on one GPU (one chunk per resident warp).
+void ring_em_default_chunking(int N, int K, int64_t T_local, int64_t *Lc_out, int64_t *W_out) {
+    const int L = K - 1;
+    const int R = (N <= 4) ? 8 : 4, SW = 32 * R;
+    RingLayout RL = ring_layout(N, L);
+    int64_t W = 256;
+    W = ((W + SW - 1) / SW) * SW;
+    if (W < ((L + 32 + SW - 1) / SW) * SW) W = ((L + 32 + SW - 1) / SW) * SW;
+    int dev = 0, sms = 148;
+    HMM_CUDA(cudaGetDevice(&dev));
+    HMM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int wps = 16;
+    switch (N) {
+        case 1: wps = em_warps_per_sm<1, 8>(RL); break;
+        case 2: wps = em_warps_per_sm<2, 8>(RL); break;
+        case 3: wps = em_warps_per_sm<3, 8>(RL); break;
+        case 4: wps = em_warps_per_sm<4, 8>(RL); break;
+        case 5: wps = em_warps_per_sm<5, 4>(RL); break;
+        case 6: wps = em_warps_per_sm<6, 4>(RL); break;
+        case 7: wps = em_warps_per_sm<7, 4>(RL); break;
+        default: break;
+    }
+    int64_t Lc = (T_local + (int64_t)sms * wps - 1) / ((int64_t)sms * wps);
+    if (Lc < 3 * W) Lc = 3 * W;
+    Lc = ((Lc + 255) / 256) * 256;
+    *Lc_out = Lc;
+    *W_out = W;
+}
 int ring_em_xvec_len(int N, int nstates) { return em_xvec_len(N, nstates); }
 int ring_em_bnd_len(int N, int K) { return 4 * (1 + N * (K - 1)) + 1; }
 

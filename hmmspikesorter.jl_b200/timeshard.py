@@ -497,6 +497,12 @@ class EmShard:
             pass
 
 
+def em_default_chunking(T: int, n_ranks: int, N: int, K: int) -> Tuple[int, int]:
+    lc, w = i64(0), i64(0)
+    check(lib().hmm_emshard_chunking(i64(T), i32(n_ranks), i32(N), i32(K), C.byref(lc), C.byref(w)))
+    return int(lc.value), int(w.value)
+
+
 def _vectors_agree(a, b, rtol=1e-12, atol=1e-9):
     """Two boundary vectors describe the same distribution iff they differ by a constant; entries more than 745 below
     the maximum cannot influence a double.  Returns (ok, constant a - b)."""

@@ -301,6 +301,9 @@ typedef struct hmm_emshard hmm_emshard;
 int hmm_emshard_create(const double *X_local, int32_t x_is_host, int64_t local_begin, int64_t local_end,
                        int64_t main_begin, int64_t main_end, int64_t T_global, int64_t chunk_len, int64_t warmup,
                        hmm_emshard **out);
+/* chunk length / warm-up the E-step of a rank's share would choose on its own (one chunk per resident warp) */
+int hmm_emshard_chunking(int64_t T_global, int32_t n_ranks, int32_t N, int32_t K, int64_t *chunk_len_out,
+                         int64_t *warmup_out);
 int hmm_emshard_stats_len(int32_t N, int32_t nstates);
 int hmm_emshard_boundary_len(int32_t N, int32_t K);
 int hmm_emshard_estep(hmm_emshard *h, const int16_t *states, int32_t N, int32_t K, int32_t nstates, const hmm_trans *tr,
