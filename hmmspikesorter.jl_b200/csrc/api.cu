@@ -137,6 +137,14 @@ int hmm_set_profiling(int on) {
     return guarded([&] { ring_config().profile = on ? 1 : 0; });
 }
 
+int hmm_measure_peaks(double *fp64_gdfma_per_s, double *copy_gb_per_s) {
+    return guarded([&] {
+        if (!fp64_gdfma_per_s || !copy_gb_per_s) fail(HMM_EINVAL, "null argument");
+        require_device();
+        measure_peaks(fp64_gdfma_per_s, copy_gb_per_s, main_stream());
+    });
+}
+
 int hmm_set_precision(int32_t precision) {
     return guarded([&] {
         if (precision != HMM_PREC_F64 && precision != HMM_PREC_F32) fail(HMM_EINVAL, "precision must be HMM_PREC_F64 or HMM_PREC_F32");
@@ -1557,6 +1565,7 @@ int hmm_vshard_p2p_finish(hmm_vshard *h, double *ll_total_out, int32_t *bad_out)
         vshard_judge_p2p_run(h->xblock, h->world, h->plan.bvec(), h->epoch_dev, h->out_d, st);
         HMM_CUDA(cudaStreamSynchronize(st));
         if (h->out_h[1] < 0) fail(HMM_ECUDA, "time-sharded decode: a peer's boundary summary never arrived (2 s)");
+        h->plan.check_guards(st);
         if (ll_total_out) *ll_total_out = h->out_h[0];
         if (bad_out) *bad_out = (int32_t)h->out_h[1];
     });

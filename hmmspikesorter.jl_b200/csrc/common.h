@@ -2,6 +2,7 @@
 // by every translation unit of libhmmcuda.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 
 #include <cstdarg>
@@ -102,6 +103,13 @@ void analyse_model(const int16_t *states, int N, int K, int nstates, const hmm_t
                    const double *mu, double sigma, HostModel &out);
 
 void state_means(const int16_t *states, int N, int K, int nstates, const double *mu, std::vector<double> &m);
+
+// NVTX range around a stage (visible in Nsight Systems / Compute timelines; a no-op without a profiler attached:
+// NVTX v3 is header-only and binds lazily).
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct Timer {  // CUDA-event stopwatch on a stream
     cudaEvent_t a = nullptr, b = nullptr;

@@ -81,6 +81,7 @@ class VitPlan {
     void set_result_sink(double *res_dev_alias);  // [C x 4] mapped pinned memory the kernels leave ll / repair counts in
     void retarget(const double *y_dev, int16_t *x_dev);
     double *ll_dev() { return ll_dev_; }
+    void check_guards(cudaStream_t st);  // HMMCUDA_DEBUG_GUARD: fails if any kernel wrote outside a plan buffer
     void read_counters(cudaStream_t st, int *fwd_rep, int *bwd_rep);
     void reset_counters(cudaStream_t st);
     int nchunks() const;
@@ -99,6 +100,7 @@ class VitPlan {
     Impl *impl;
     VitParams *p_;  // owned; defined in ring_viterbi.cu
     std::vector<void *> owned;
+    std::vector<char *> guards;  // HMMCUDA_DEBUG_GUARD: guard zones around every owned buffer
     std::vector<double> hmdl;
     HostModel M0;
     FaithfulLayout FL;
@@ -154,6 +156,9 @@ void ring_fb_dense_run(const double *X_dev, int64_t T, const HostModel &M, doubl
 // update() on dense alpha/beta (device pointers), src/baumwelch.jl:205-309
 void dense_update_run(const double *alpha_dev, const double *beta_dev, const double *x_dev, int64_t T,
                       const HostModel &M, const int16_t *states_host, EmResult &out, cudaStream_t st);
+
+// roofline denominators measured live (reconstruct.cu)
+void measure_peaks(double *gdfma_per_s, double *copy_gb_per_s, cudaStream_t st);
 
 // ---- reconstruct (reconstruct.cu) ------------------------------------------
 void reconstruct_run(const int16_t *x_dev, int64_t T, const std::vector<double> &m, double *Y_dev, cudaStream_t st);

@@ -4,6 +4,8 @@
 // Y[i] = sum_j mu[states[j, x[i]], j] is folded on the host once per call into
 // a state-mean table with the reference's own accumulation order, so the
 // kernel is one table lookup per sample.
+#include <algorithm>
+
 #include "engines.h"
 
 namespace hmm {
@@ -123,4 +125,66 @@ void unroll_run(const int16_t *x_dev, int64_t T, const int16_t *states_host, int
     check_flag(flag, st, "unroll_mlseq");
 }
 
+}  // namespace hmm
+
+
+// ---------------------------------------------------------------------------
+// Roofline denominators measured on the device the caller is using (bench.py reports them live instead of quoting
+// constants): the FP64 fused-multiply-add issue rate (DFMA with one constant-bank operand, the form the FIR uses)
+// and the device-memory copy bandwidth.
+// ---------------------------------------------------------------------------
+namespace hmm {
+__constant__ double peak_cc[16];
+
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, double b, int iters) {
+    double x[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = 1.0 + i + threadIdx.x * 1e-3;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] = fma(peak_cc[i], b, x[i]);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += x[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) copy_peak_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+void measure_peaks(double *gdfma_per_s, double *copy_gb_per_s, cudaStream_t st) {
+    int dev = 0, sms = 148;
+    HMM_CUDA(cudaGetDevice(&dev));
+    HMM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8, iters = 4096;
+    const size_t nvec = (size_t)32 << 20;  // 512 MB read + 512 MB written per copy: far beyond L2
+    double *buf = nullptr;
+    HMM_CUDA(cudaMalloc((void **)&buf, 2 * nvec * sizeof(double2)));
+    double h[16];
+    for (int i = 0; i < 16; i++) h[i] = 1.0 + 1e-9 * i;
+    HMM_CUDA(cudaMemcpyToSymbolAsync(peak_cc, h, sizeof h, 0, cudaMemcpyHostToDevice, st));
+    HMM_CUDA(cudaMemsetAsync(buf, 0, 2 * nvec * sizeof(double2), st));
+    Timer t(st);
+    fp64_peak_kernel<<<blocks, 256, 0, st>>>(buf, 0.999, 64);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        t.start();
+        fp64_peak_kernel<<<blocks, 256, 0, st>>>(buf, 0.999, iters);
+        t.stop();
+        best = std::min(best, t.ms());
+    }
+    *gdfma_per_s = (double)blocks * 256 * iters * 16 / (best * 1e-3) / 1e9;
+    best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        t.start();
+        copy_peak_kernel<<<sms * 16, 256, 0, st>>>((const double2 *)buf, (double2 *)buf + nvec, nvec);
+        t.stop();
+        best = std::min(best, t.ms());
+    }
+    *copy_gb_per_s = 2.0 * nvec * sizeof(double2) / (best * 1e-3) / 1e9;
+    HMM_CUDA(cudaGetLastError());
+    cudaFree(buf);
+}
 }  // namespace hmm

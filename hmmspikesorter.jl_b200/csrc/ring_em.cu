@@ -1328,6 +1328,7 @@ static thread_local EmStageTimes g_em_times;
 template <int N, int R>
 static void em_launch(EmParams &p, const double *hmdl, cudaStream_t st, hmm_info *info, Timer &ttop, int mode,
                       double *alpha_out, double *beta_out, double *Zs, double *bsum, const EmShardOpts *sh) {
+    NvtxRange nvtx_step(sh ? "hmm.em.shard_estep" : mode == 0 ? "hmm.em.step" : "hmm.em.dense_forward_backward");
     EmStageTimes &tm = g_em_times;
     tm.on = getenv("HMMCUDA_EM_TIMING") != nullptr;
     tm.n = 0;

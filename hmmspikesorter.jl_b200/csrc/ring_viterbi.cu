@@ -1925,14 +1925,39 @@ void *VitPlan::alloc(int slot, size_t bytes) {
         return arena_base + o;
     }
     if (!own_memory) return workspace().get((Workspace::Slot)slot, bytes);
+    // HMMCUDA_DEBUG_GUARD=1 (compute-sanitizer is not available on every pool): every buffer of the plan sits between
+    // two 4 KB guard zones filled with a pattern; check_guards() verifies them after a run, so an out-of-bounds write of
+    // any kernel of the decode is caught by the tests that run with the switch on.
+    const bool guard = getenv("HMMCUDA_DEBUG_GUARD") && atoi(getenv("HMMCUDA_DEBUG_GUARD"));
+    const size_t G = guard ? 4096 : 0;
+    const size_t body = ((bytes ? bytes : 16) + 255) & ~size_t(255);
     void *q = nullptr;
-    cudaError_t e = cudaMalloc(&q, bytes ? bytes : 16);
+    cudaError_t e = cudaMalloc(&q, body + 2 * G);
     if (e != cudaSuccess) {
         cudaGetLastError();
         fail(HMM_ENOMEM, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
     }
     owned.push_back(q);
-    return q;
+    if (guard) {
+        HMM_CUDA(cudaMemset(q, 0xA5, G));
+        HMM_CUDA(cudaMemset((char *)q + G + body, 0xA5, G));
+        guards.push_back((char *)q);
+        guards.push_back((char *)q + G + body);
+    }
+    return (char *)q + G;
+}
+
+void VitPlan::check_guards(cudaStream_t st) {
+    if (guards.empty()) return;
+    HMM_CUDA(cudaStreamSynchronize(st));
+    std::vector<unsigned char> h(4096);
+    for (size_t k = 0; k < guards.size(); k++) {
+        HMM_CUDA(cudaMemcpy(h.data(), guards[k], h.size(), cudaMemcpyDeviceToHost));
+        for (size_t b = 0; b < h.size(); b++)
+            if (h[b] != 0xA5)
+                fail(HMM_ECUDA, "guard zone %zu (%s buffer %zu) overwritten at byte %zu: a kernel wrote out of bounds", k,
+                     (k & 1) ? "after" : "before", k / 2, b);
+    }
 }
 
 int ring_default_chunking(const HostModel &M0, int64_t T_total, int C, int n_gpus, int64_t *Lc_out, int64_t *W_out) {
@@ -1952,6 +1977,8 @@ int ring_default_chunking(const HostModel &M0, int64_t T_total, int C, int n_gpu
     // are wrong wherever a spike straddles a boundary, and only verification + repair make the decode exact
     if (const char *e = getenv("HMMCUDA_DEBUG_WARMUP")) W = (std::max<int64_t>(0, atoll(e)) / SW) * SW;
     int64_t Lc = ring_config().chunk_len;
+    if (Lc <= 0)
+        if (const char *e = getenv("HMMCUDA_CHUNK")) Lc = std::max<int64_t>(0, atoll(e));  // chunk length without a call
     if (Lc <= 0) {
         // (queried once per model shape: this runs on every decode call)
         static thread_local int c_dev = -1, c_sms = 0, c_N = 0, c_L = 0, c_const = -1, c_wps = 0;
@@ -2187,10 +2214,22 @@ void VitPlan::run_all(cudaStream_t st, bool want_ll, Timer *ttop) {
     const int nrun = per_channel ? C : 1;
     for (int k = 0; k < nrun; k++) {
         p_->ch0 = per_channel ? k : 0;
-        forward(st, k == 0 ? ttop : nullptr);
-        verify_fwd(st);
-        trace(st);
-        verify_trace(st);  // (assembles ll as well)
+        {
+            NvtxRange r("hmm.viterbi.forward");
+            forward(st, k == 0 ? ttop : nullptr);
+        }
+        {
+            NvtxRange r("hmm.viterbi.verify_forward");
+            verify_fwd(st);
+        }
+        {
+            NvtxRange r("hmm.viterbi.traceback");
+            trace(st);
+        }
+        {
+            NvtxRange r("hmm.viterbi.verify_traceback+ll");
+            verify_trace(st);  // (assembles ll as well)
+        }
     }
     p_->ch0 = 0;
 }
@@ -2345,6 +2384,7 @@ void ring_viterbi_run(const double *y_dev, int64_t T, int64_t y_stride, int C, c
         info->n_chunks = prog->plan.nchunks();
     }
     pend->push_back(RingPending{prog->res_h, C, ll_host, info});
+    prog->plan.check_guards(st);  // (HMMCUDA_DEBUG_GUARD only; synchronises)
     if (!defer || fresh || ttop) {
         // an uncached program dies with this call, and a profiled run reads its event timer: synchronise here
         HMM_CUDA(cudaStreamSynchronize(st));

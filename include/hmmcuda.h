@@ -131,6 +131,11 @@ int hmm_viterbi_dev_f64(const double *y_dev, int64_t T, int32_t C, const int16_t
                         const double *mu, const double *sigma, int16_t *x_dev, double *ll_out, int32_t mode,
                         hmm_info *info);
 
+/* Roofline denominators measured on the current device: the FP64 FMA issue rate in GDFMA/s (DFMA with a constant-bank
+ * operand, the form the matched-filter FIR uses) and the device-memory copy bandwidth in GB/s (read + written bytes of a
+ * 512 MB copy).  Takes ~30 ms; benchmarks report their fractions against these instead of quoting constants. */
+int hmm_measure_peaks(double *fp64_gdfma_per_s, double *copy_gb_per_s);
+
 /* ---- FP32 mode (BASELINE north_star: "T1 and log-likelihoods within ... 1e-4 in FP32 mode") ------------------
  * The reference is Float64 only (src/viterbi.jl:44), so this mode is defined by the build: the recording may be
  * Float32 (half the PCIe / HBM bytes per sample; widened exactly on the device) and the matched-filter FIR of the

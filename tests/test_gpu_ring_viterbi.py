@@ -142,3 +142,21 @@ def test_ring_equals_faithful_1m(hm, case_factory):
     xf, llf = hm.viterbi(S, lA, mu, sig, mode="faithful")
     assert np.array_equal(xr, xf)
     assert abs(llr - llf) <= LL_RTOL * abs(llf)
+
+
+@pytest.mark.parametrize("N,K,T,seed,chunk", [(3, 60, 70_001, 501, 0), (4, 48, 50_123, 502, 2048), (5, 60, 33_333, 503, 1024),
+                                              (7, 97, 40_000, 504, 0), (1, 4, 9_999, 505, 512), (2, 33, 262_144 + 17, 506, 0)])
+def test_no_kernel_writes_outside_its_buffers(hm, O, case_factory, monkeypatch, N, K, T, seed, chunk):
+    """compute-sanitizer is not available on this GPU pool, so the decode checks itself: with HMMCUDA_DEBUG_GUARD=1
+    every buffer of the decode plan lies between two guard zones that are verified after the run (the call fails if a
+    kernel wrote out of bounds), on ragged lengths, the smallest and the largest models, forced repairs included."""
+    S, lA, mu, sig = case_factory(N, K, T, seed)
+    monkeypatch.setenv("HMMCUDA_DEBUG_GUARD", "1")
+    monkeypatch.setenv("HMMCUDA_DEBUG_FLAG_EVERY", "4")
+    try:
+        hm.set_ring_params(chunk, 0)
+        for _ in range(2):  # the second call re-uses the cached program (CUDA graph)
+            _check(hm, O, S, lA, mu, sig)
+    finally:
+        hm.set_ring_params(0, 0)
+        hm.lib().hmm_release_workspace()
