@@ -32,7 +32,7 @@ from .timeshard import viterbi_time_sharded
 __all__ = [
     "StateMatrix", "viterbi", "viterbi_batch", "forward", "backward", "update", "train_model", "em_step",
     "reconstruct_signal", "unroll_mlseq", "TrainContext", "create_signal", "create_spike_template", "make_rng",
-    "HmmError", "HmmArgumentError", "device_count", "set_ring_params", "set_devices", "set_precision", "viterbi_f32", "viterbi_time_sharded",
+    "HmmError", "HmmArgumentError", "device_count", "set_ring_params", "set_devices", "set_precision", "viterbi_f32", "viterbi_rawfile", "save_sort_result", "viterbi_time_sharded",
 ]
 
 i64, i32, f64 = C.c_int64, C.c_int32, C.c_double
@@ -72,6 +72,47 @@ def viterbi_f32(y, lA, mu, sigma, *, mode: str = "auto", return_info: bool = Fal
     check(lib().hmm_viterbi_ex_f32(_p(y), i64(y.size), _p(st), i32(lA.N), i32(lA.K), i32(lA.nstates), _p(tr),
                                    i64(tr.size), _p(mu), f64(sigma), _p(x), C.byref(ll), i32(MODES[mode]), C.byref(info)))
     return (x, ll.value, info.asdict()) if return_info else (x, ll.value)
+
+
+RAW_DTYPES = {np.dtype(np.float64): 0, np.dtype(np.float32): 1, np.dtype(np.int16): 2}
+
+
+def viterbi_rawfile(path, dtype, n_file_channels: int, T: int, channels, models, *, interleaved: bool = True,
+                    scale: float = 1.0, byte_offset: int = 0, mode: str = "auto", return_info: bool = False):
+    """I/O front-end (hmm_viterbi_rawfile; src/hmmsort.jl:66-90 reads the data file, converts it to Float64 and
+    decodes): decode `channels` (0-based indices) of a raw recording file -- int16 / float32 / float64 samples,
+    interleaved [T x n_file_channels] or channel-major, starting at `byte_offset` -- straight from the file through
+    pinned staging; models = [(lA, mu, sigma)] per requested channel.  Returns (x [T x C] Int16, ll [C])."""
+    ch = np.ascontiguousarray(channels, dtype=np.int32)
+    if len(models) != ch.size:
+        raise HmmArgumentError(_lib.HMM_EINVAL, "one model per requested channel")
+    lA0 = models[0][0]
+    sts, trs, mus, sig = [], [], [], []
+    for lA, mu, s in models:
+        st, tr, mu = _model_args(lA, mu)
+        sts.append(st.ravel(order="F")); trs.append(tr); mus.append(mu.ravel(order="F")); sig.append(float(s))
+    st = np.ascontiguousarray(np.concatenate(sts)); tr = np.ascontiguousarray(np.concatenate(trs))
+    mu = np.ascontiguousarray(np.concatenate(mus)); sig = np.asarray(sig, dtype=np.float64)
+    x = np.empty((T, ch.size), dtype=np.int16, order="F")
+    ll = np.empty(ch.size, dtype=np.float64)
+    info = HmmInfo()
+    check(lib().hmm_viterbi_rawfile(str(path).encode(), i64(byte_offset), i32(RAW_DTYPES[np.dtype(dtype)]),
+                                    i32(n_file_channels), i32(1 if interleaved else 0), f64(scale), i64(T), i32(ch.size),
+                                    _p(ch), _p(st), i32(0), i32(lA0.N), i32(lA0.K), i32(lA0.nstates), _p(tr),
+                                    i64(lA0.transitions.size), _p(mu), _p(sig), _p(x), _p(ll), i32(MODES[mode]),
+                                    C.byref(info)))
+    return (x, ll, info.asdict()) if return_info else (x, ll)
+
+
+def save_sort_result(outputfile, x, lA, mu, sigma, ll):
+    """The .mat file sort_data writes for one channel (src/hmmsort.jl:92-101): the unrolled most likely sequence
+    (Int16 [N x T], src/extraction.jl:4-13), ll, the templates, the noise -> active log-probabilities and sigma."""
+    from scipy.io import savemat
+
+    lp, _ = lA.get_lp()
+    out = {"mlseq": unroll_mlseq(x, lA), "ll": float(ll), "waveforms": np.asarray(mu), "lp": lp, "sigma": float(sigma)}
+    savemat(str(outputfile), out)
+    return out
 
 
 def set_ring_params(chunk_len: int = 0, warmup: int = 0) -> None:

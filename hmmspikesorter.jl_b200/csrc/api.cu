@@ -10,6 +10,9 @@
 #include <memory>
 #include <mutex>
 #include <thread>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <condition_variable>
 #include <deque>
 #include <functional>
@@ -1786,6 +1789,177 @@ int hmm_train_destroy(hmm_train_ctx *ctx) {
         if (!ctx) return;
         if (ctx->owned && ctx->X_dev) cudaFree(ctx->X_dev);
         delete ctx;
+    });
+}
+
+// ---------------------------------------------------------------------------
+// I/O front-end: raw recording file -> pinned staging -> HBM -> decode (src/hmmsort.jl:36-104 reads an HDF5 file,
+// converts the samples to Float64 and decodes one channel per run; a contiguous HDF5 dataset is a raw block at a byte
+// offset, which is what this entry point takes).  The file is read block by block by a reader thread into two pinned
+// buffers, each block crosses PCIe while the next one is being read, and one kernel picks the requested channels out
+// of the (interleaved or channel-major) block and widens int16 / float32 / float64 samples to the Float64 [T x C]
+// layout the decoders take.  Then all channels are decoded from HBM and only x travels back.
+// ---------------------------------------------------------------------------
+}  // extern "C"
+
+template <typename RAW>
+__global__ void __launch_bounds__(256)
+    raw_pick_kernel(const RAW *__restrict__ blk, int64_t t0, int64_t nt, int nfile, int interleaved, int64_t T_file,
+                    const int *__restrict__ chans, int C, double scale, double *__restrict__ y /*[T x C]*/, int64_t T) {
+    // one thread per (sample of the block, requested channel); consecutive threads walk consecutive samples
+    const int64_t n = nt * C;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(k / nt);
+        const int64_t t = k - (int64_t)c * nt;
+        const int fc = chans[c];
+        // interleaved: the block holds samples [t0, t0 + nt) of every file channel; channel-major: the block is a
+        // slab [nfile x nt] gathered by the reader (row fc, column t)
+        const RAW v = interleaved ? blk[t * nfile + fc] : blk[(int64_t)fc * nt + t];
+        y[(size_t)c * T + t0 + t] = (double)v * scale;
+    }
+}
+
+static void rawfile_decode_body(const char *path, int64_t byte_offset, int dtype, int nfile, int interleaved, double scale,
+                                int64_t T, int C, const int32_t *channels, const int16_t *states, int states_shared, int N,
+                                int K, int nstates, const hmm_trans *tr, int64_t ntrans, const double *mu,
+                                const double *sigma, int16_t *x_out, double *ll_out, int mode, hmm_info *info) {
+    if (info) memset(info, 0, sizeof *info);
+    if (!path || !channels || !x_out || !sigma) fail(HMM_EINVAL, "null argument");
+    if (T < 1 || C < 1 || nfile < 1) fail(HMM_EINVAL, "T, C and the file's channel count must be positive");
+    const size_t esz = dtype == HMM_RAW_I16 ? 2 : dtype == HMM_RAW_F32 ? 4 : dtype == HMM_RAW_F64 ? 8 : 0;
+    if (!esz) fail(HMM_EINVAL, "sample_dtype must be HMM_RAW_I16, HMM_RAW_F32 or HMM_RAW_F64");
+    for (int c = 0; c < C; c++)
+        if (channels[c] < 0 || channels[c] >= nfile) fail(HMM_EINVAL, "channel index %d outside the file's %d channels", channels[c], nfile);
+    require_device();
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) fail(HMM_EINVAL, "cannot open %s", path);
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || (int64_t)sb.st_size < byte_offset + (int64_t)esz * nfile * T) {
+        close(fd);
+        fail(HMM_EINVAL, "%s is shorter than offset + %lld samples x %d channels", path, (long long)T, nfile);
+    }
+    cudaStream_t st = main_stream(), sh = copy_stream();
+    Workspace &ws = workspace();
+    double *y_dev = (double *)ws.get(Workspace::Y, sizeof(double) * (size_t)T * C);
+    int16_t *x_dev = (int16_t *)ws.get(Workspace::X, sizeof(int16_t) * (size_t)T * C);
+    int *ch_dev = (int *)ws.get(Workspace::MISC, sizeof(int) * (size_t)C);
+    HMM_CUDA(cudaMemcpyAsync(ch_dev, channels, sizeof(int) * (size_t)C, cudaMemcpyHostToDevice, st));
+    // block = nt samples of every file channel, ~32 MB
+    int64_t nt = std::max<int64_t>(4096, ((int64_t)32 << 20) / (int64_t)(esz * nfile));
+    nt = std::min<int64_t>(nt, T);
+    const size_t bbytes = (size_t)nt * nfile * esz;
+    char *pin = (char *)ws.pinned(4, 2 * bbytes);
+    char *blk_dev = (char *)ws.get(Workspace::FWDF, 2 * bbytes);
+    cudaEvent_t ev_free[2], ev_copied[2];
+    for (int k = 0; k < 2; k++) {
+        HMM_CUDA(cudaEventCreateWithFlags(&ev_free[k], cudaEventDisableTiming));
+        HMM_CUDA(cudaEventCreateWithFlags(&ev_copied[k], cudaEventDisableTiming));
+    }
+    const int64_t nblk = (T + nt - 1) / nt;
+    // reader thread: block b into pinned buffer b & 1 as soon as that buffer's previous upload has left it
+    std::mutex m;
+    std::condition_variable cv;
+    int64_t filled = 0, released = 2;  // blocks read so far / blocks whose pinned buffer may be refilled (b < released)
+    bool io_error = false;
+    std::thread reader([&] {
+        for (int64_t b = 0; b < nblk; b++) {
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return b < released; });
+            }
+            const int64_t t0 = b * nt, n = std::min<int64_t>(nt, T - t0);
+            char *dst = pin + (size_t)(b & 1) * bbytes;
+            bool ok = true;
+            if (interleaved) {
+                const size_t want = (size_t)n * nfile * esz;
+                ok = pread(fd, dst, want, byte_offset + (int64_t)t0 * nfile * (int64_t)esz) == (ssize_t)want;
+            } else {  // channel-major file: gather the requested time range of every channel into a [nfile x n] slab
+                for (int fc = 0; fc < nfile && ok; fc++)
+                    ok = pread(fd, dst + (size_t)fc * n * esz, (size_t)n * esz,
+                               byte_offset + ((int64_t)fc * T + t0) * (int64_t)esz) == (ssize_t)((size_t)n * esz);
+            }
+            std::lock_guard<std::mutex> lk(m);
+            if (!ok) io_error = true;
+            filled = b + 1;
+            cv.notify_all();
+            if (!ok) return;
+        }
+    });
+    auto finish_reader = [&] {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            released = nblk + 2;
+        }
+        cv.notify_all();
+        if (reader.joinable()) reader.join();
+        close(fd);
+        for (int k = 0; k < 2; k++) {
+            cudaEventDestroy(ev_free[k]);
+            cudaEventDestroy(ev_copied[k]);
+        }
+    };
+    try {
+        Timer tall(st);
+        tall.start();
+        for (int64_t b = 0; b < nblk; b++) {
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return filled > b || io_error; });
+                if (io_error) fail(HMM_EINVAL, "read error on %s", path);
+            }
+            const int k = (int)(b & 1);
+            const int64_t t0 = b * nt, n = std::min<int64_t>(nt, T - t0);
+            if (b >= 2) HMM_CUDA(cudaStreamWaitEvent(sh, ev_free[k], 0));  // the pick kernel of block b-2 is done with blk_dev[k]
+            HMM_CUDA(cudaMemcpyAsync(blk_dev + (size_t)k * bbytes, pin + (size_t)k * bbytes, (size_t)n * nfile * esz,
+                                     cudaMemcpyHostToDevice, sh));
+            HMM_CUDA(cudaEventRecord(ev_copied[k], sh));
+            HMM_CUDA(cudaStreamWaitEvent(st, ev_copied[k], 0));
+            const unsigned grid = (unsigned)std::min<int64_t>(148 * 16, (n * C + 255) / 256);
+            const void *bd = blk_dev + (size_t)k * bbytes;
+            if (dtype == HMM_RAW_I16)
+                raw_pick_kernel<int16_t><<<grid, 256, 0, st>>>((const int16_t *)bd, t0, n, nfile, interleaved, T, ch_dev, C, scale, y_dev, T);
+            else if (dtype == HMM_RAW_F32)
+                raw_pick_kernel<float><<<grid, 256, 0, st>>>((const float *)bd, t0, n, nfile, interleaved, T, ch_dev, C, scale, y_dev, T);
+            else
+                raw_pick_kernel<double><<<grid, 256, 0, st>>>((const double *)bd, t0, n, nfile, interleaved, T, ch_dev, C, scale, y_dev, T);
+            HMM_CUDA(cudaGetLastError());
+            HMM_CUDA(cudaEventRecord(ev_free[k], st));
+            // the pinned buffer may be refilled once its upload has completed
+            HMM_CUDA(cudaEventSynchronize(ev_copied[k]));
+            {
+                std::lock_guard<std::mutex> lk(m);
+                released = b + 3;
+            }
+            cv.notify_all();
+        }
+        BatchModels &B = get_models(C, states, states_shared, N, K, nstates, tr, ntrans, mu, sigma, st);
+        viterbi_core(y_dev, T, C, B, x_dev, ll_out, nullptr, nullptr, mode, st, info);
+        d2h(x_out, x_dev, sizeof(int16_t) * (size_t)T * C, st);
+        tall.stop();
+        HMM_CUDA(cudaStreamSynchronize(st));
+        if (info) {
+            info->device_ms = tall.ms();
+            info->kernel_launches += nblk;
+        }
+    } catch (...) {
+        cudaStreamSynchronize(st);
+        cudaStreamSynchronize(sh);
+        finish_reader();
+        throw;
+    }
+    finish_reader();
+}
+
+extern "C" {
+
+int hmm_viterbi_rawfile(const char *path, int64_t byte_offset, int32_t sample_dtype, int32_t n_file_channels,
+                        int32_t interleaved, double scale, int64_t T, int32_t C, const int32_t *channels,
+                        const int16_t *states, int32_t states_shared, int32_t N, int32_t K, int32_t nstates,
+                        const hmm_trans *tr, int64_t ntrans, const double *mu, const double *sigma, int16_t *x_out,
+                        double *ll_out, int32_t mode, hmm_info *info) {
+    return guarded([&] {
+        rawfile_decode_body(path, byte_offset, sample_dtype, n_file_channels, interleaved, scale, T, C, channels, states,
+                            states_shared, N, K, nstates, tr, ntrans, mu, sigma, x_out, ll_out, mode, info);
     });
 }
 

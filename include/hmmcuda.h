@@ -288,6 +288,23 @@ int hmm_train_em_step(hmm_train_ctx *ctx, const int16_t *states, int32_t N, int3
                       double *pp_out, double *loglik_out, hmm_info *info);
 int hmm_train_destroy(hmm_train_ctx *ctx);
 
+/* ---- I/O front-end (src/hmmsort.jl:36-104: data file -> Float64 -> decode -> unrolled sequence) ------------------
+ * Decodes C channels of a raw recording FILE without the samples ever passing through a caller array: the file is read
+ * block by block into pinned staging by a reader thread, every block crosses PCIe while the next is read, one kernel
+ * picks the requested channels out of it and widens the samples (value = raw * scale) into the Float64 [T x C] layout,
+ * and all channels are decoded from HBM.  The file holds n_file_channels channels of T samples from byte_offset on, either
+ * interleaved ([T x n_file_channels], sample-major, the usual acquisition layout) or channel-major; a contiguous
+ * (uncompressed) HDF5 dataset -- what the reference memory-maps, src/hmmsort.jl:72-76 -- is such a block at its data
+ * offset.  channels[C]: 0-based indices into the file's channels; the model arrays as in hmm_viterbi_batch_f64. */
+#define HMM_RAW_F64 0
+#define HMM_RAW_F32 1
+#define HMM_RAW_I16 2
+int hmm_viterbi_rawfile(const char *path, int64_t byte_offset, int32_t sample_dtype, int32_t n_file_channels,
+                        int32_t interleaved, double scale, int64_t T, int32_t C, const int32_t *channels,
+                        const int16_t *states, int32_t states_shared, int32_t N, int32_t K, int32_t nstates,
+                        const hmm_trans *tr, int64_t ntrans, const double *mu, const double *sigma, int16_t *x_out,
+                        double *ll_out, int32_t mode, hmm_info *info);
+
 /* ---- time-sharded Baum-Welch: one recording over several GPUs ------------------------------------
  * Every rank owns a contiguous span [main_begin, main_end) of X (chunk aligned) and holds [local_begin, local_end) with at
  * least one ghost chunk on either side.  One E/M iteration of src/baumwelch.jl:362-370 over all ranks:
