@@ -446,7 +446,9 @@ void viterbi_core(const double *y_dev, int64_t T, int C, BatchModels &B, int16_t
         if (!ring_supported(M0, T)) fail(HMM_EUNSUPPORTED, "HMM_MODE_RING: sequence too short or K/N outside the ring engine's range");
         engine = HMM_MODE_RING;
     } else
-        engine = (all_ring && ring_supported(M0, T) && T >= 32768) ? HMM_MODE_RING : HMM_MODE_FAITHFUL;
+        // every ring model the time-parallel engine supports goes to it (T >= 2048): even a 20 000-sample decode
+        // (config 1) is two orders of magnitude faster there than in the sequential per-state engine, and as exact
+        engine = (all_ring && ring_supported(M0, T)) ? HMM_MODE_RING : HMM_MODE_FAITHFUL;
     if (info) info->engine = engine;
     if (engine == HMM_MODE_FAITHFUL) {
         double *ll_dev = nullptr;

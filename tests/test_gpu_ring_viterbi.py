@@ -108,7 +108,7 @@ def test_ring_viterbi_auto_and_batch(hm, O, case_factory):
     Y = np.asfortranarray(np.stack([c[0] for c in cases], axis=1))
     models = [(c[1], np.asfortranarray(c[2] * (1 + 0.05 * i)), 0.3 + 0.01 * i) for i, c in enumerate(cases)]
     x, ll, info = hm.viterbi_batch(Y, models, mode="auto", return_info=True)
-    assert info["engine"] == 2  # T >= 32768 and ring-structured -> ring engine
+    assert info["engine"] == 2  # ring-structured and T >= 2048 -> ring engine
     for c in range(6):
         xo, llo = O.viterbi(Y[:, c], models[c][0], models[c][1], models[c][2])
         assert np.array_equal(x[:, c], xo)
