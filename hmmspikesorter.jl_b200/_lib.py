@@ -56,7 +56,7 @@ EXPORTS = [
     "hmm_vshard_repairs", "hmm_set_stream", "hmm_vshard_finish_ex", "hmm_vshard_summary_len", "hmm_vshard_summary_dev",
     "hmm_vshard_judge_dev", "hmm_release_workspace", "hmm_set_profiling", "hmm_vshard_p2p_init", "hmm_vshard_p2p_attach", "hmm_vshard_p2p_launch",
     "hmm_vshard_p2p_finish", "hmm_set_devices", "hmm_get_devices", "hmm_set_precision", "hmm_get_precision", "hmm_viterbi_f32",
-    "hmm_viterbi_ex_f32", "hmm_viterbi_batch_f32", "hmm_viterbi_dev_f32", "hmm_measure_peaks", "hmm_viterbi_rawfile", "hmm_emshard_create", "hmm_emshard_chunking", "hmm_emshard_stats_len",
+    "hmm_viterbi_ex_f32", "hmm_viterbi_batch_f32", "hmm_viterbi_dev_f32", "hmm_measure_peaks", "hmm_vshard_set_y", "hmm_viterbi_rawfile", "hmm_emshard_create", "hmm_emshard_chunking", "hmm_emshard_stats_len",
     "hmm_emshard_boundary_len", "hmm_emshard_estep", "hmm_emshard_mstep", "hmm_emshard_destroy",
 ]
 

@@ -234,7 +234,10 @@ class DeviceWorker {
 std::vector<std::unique_ptr<DeviceWorker>> g_workers;  // under the entry lock
 bool g_devices_from_env = false;
 
+void drop_shardset();
+
 void set_devices_locked(const int *devs, int n) {
+    drop_shardset();
     g_workers.clear();
     if (!devs || n <= 1) return;  // zero or one device: the ordinary single-device path on the current device
     int have = 0;
@@ -794,62 +797,106 @@ std::vector<ShardSpan> plan_shards(int64_t T, int n, int64_t Lc, int64_t W) {
     return out;
 }
 
+// The shard handles (one per device: buffers, decode plan, CUDA graph, opened peer blocks) are kept between calls and
+// re-used when the next recording has the same length and model: setting them up costs ~200 ms, a decode ~1 ms.
+struct ShardSet {
+    std::vector<hmm_vshard *> sh;
+    std::vector<ShardSpan> spans;
+    std::vector<int> devs;
+    int64_t T = 0, Lc = 0, W = 0;
+    uint64_t model_hash = 0;
+};
+std::unique_ptr<ShardSet> g_shardset;  // under the entry lock
+
+void drop_shardset() {
+    if (!g_shardset) return;
+    std::vector<std::future<std::pair<int, std::string>>> f2;
+    for (size_t k = 0; k < g_shardset->sh.size() && k < g_workers.size(); k++)
+        if (g_shardset->sh[k]) {
+            hmm_vshard *h = g_shardset->sh[k];
+            f2.push_back(g_workers[k]->run([h] { return hmm_vshard_destroy(h); }));
+        }
+    for (auto &f : f2) f.get();
+    g_shardset.reset();
+}
+
 bool viterbi_timeshard_multidev(const double *y, int64_t T, const int16_t *states, int N, int K, int nstates,
                                 const hmm_trans *tr, int64_t ntrans, const double *mu, double sigma, int16_t *x_out,
                                 double *ll_out, hmm_info *info) {
-    int64_t Lc = 0, W = 0;
-    {
-        HostModel M;
-        M.N = N;
-        M.K = K;
-        M.nstates = nstates;
-        M.is_ring = true;
-        ring_default_chunking(M, T, 1, (int)g_workers.size(), &Lc, &W);
-        W = 256;  // short chunks per GPU: a short speculative warm-up (every boundary is verified anyway)
+    uint64_t mh = 0x51ed27ull;
+    mh = mix64(mh, states, sizeof(int16_t) * (size_t)N * nstates);
+    mh = mix64(mh, tr, sizeof(hmm_trans) * (size_t)ntrans);
+    mh = mix64(mh, mu, sizeof(double) * (size_t)K * N);
+    mh = mix64(mh, &sigma, sizeof sigma);
+    std::vector<int> devs;
+    for (auto &w : g_workers) devs.push_back(w->device());
+    std::vector<std::future<std::pair<int, std::string>>> futs;
+    const bool hit = g_shardset && g_shardset->T == T && g_shardset->model_hash == mh && g_shardset->devs == devs;
+    if (!hit) {
+        drop_shardset();
+        int64_t Lc = 0, W = 0;
+        {
+            HostModel M;
+            M.N = N;
+            M.K = K;
+            M.nstates = nstates;
+            M.is_ring = true;
+            ring_default_chunking(M, T, 1, (int)g_workers.size(), &Lc, &W);
+            W = 256;  // short chunks per GPU: a short speculative warm-up (every boundary is verified anyway)
+        }
+        std::unique_ptr<ShardSet> S(new ShardSet);
+        S->spans = plan_shards(T, (int)g_workers.size(), Lc, W);
+        const int n = (int)S->spans.size();
+        if (n < 2) return false;
+        S->sh.assign((size_t)n, nullptr);
+        S->devs = devs; S->T = T; S->Lc = Lc; S->W = W; S->model_hash = mh;
+        std::vector<void *> blocks((size_t)n, nullptr);
+        g_shardset = std::move(S);
+        ShardSet &G = *g_shardset;
+        try {
+            for (int k = 0; k < n; k++) {
+                const ShardSpan sp = G.spans[(size_t)k];
+                hmm_vshard **hk = &G.sh[(size_t)k];
+                void **bk = &blocks[(size_t)k];
+                futs.push_back(g_workers[(size_t)k]->run([=] {
+                    int rc = hmm_vshard_create(y + sp.lb, 1, sp.lb, sp.le, sp.mb, sp.me, T, Lc, W, states, N, K, nstates, tr,
+                                               ntrans, mu, sigma, hk);
+                    if (rc) return rc;
+                    return hmm_vshard_p2p_init(*hk, k, n, nullptr, bk);
+                }));
+            }
+            join_all(futs);
+            for (int k = 0; k < n; k++) {
+                hmm_vshard *h = G.sh[(size_t)k];
+                void *const *bp = blocks.data();
+                futs.push_back(g_workers[(size_t)k]->run([=] { return hmm_vshard_p2p_attach(h, nullptr, bp); }));
+            }
+            join_all(futs);
+        } catch (...) {
+            drop_shardset();
+            throw;
+        }
     }
-    const std::vector<ShardSpan> spans = plan_shards(T, (int)g_workers.size(), Lc, W);
-    const int n = (int)spans.size();
-    if (n < 2) return false;
-    std::vector<hmm_vshard *> sh((size_t)n, nullptr);
-    std::vector<void *> blocks((size_t)n, nullptr);
+    ShardSet &G = *g_shardset;
+    const int n = (int)G.sh.size();
     std::vector<double> ll((size_t)n, 0.0);
     std::vector<int32_t> bad((size_t)n, 0);
-    std::vector<std::future<std::pair<int, std::string>>> futs;
-    auto destroy_all = [&] {
-        std::vector<std::future<std::pair<int, std::string>>> f2;
-        for (int k = 0; k < n; k++)
-            if (sh[(size_t)k]) {
-                hmm_vshard *h = sh[(size_t)k];
-                f2.push_back(g_workers[(size_t)k]->run([h] { return hmm_vshard_destroy(h); }));
-            }
-        for (auto &f : f2) f.get();
-    };
     try {
         for (int k = 0; k < n; k++) {
-            const ShardSpan sp = spans[(size_t)k];
-            hmm_vshard **hk = &sh[(size_t)k];
-            void **bk = &blocks[(size_t)k];
+            hmm_vshard *h = G.sh[(size_t)k];
+            const ShardSpan sp = G.spans[(size_t)k];
             futs.push_back(g_workers[(size_t)k]->run([=] {
-                int rc = hmm_vshard_create(y + sp.lb, 1, sp.lb, sp.le, sp.mb, sp.me, T, Lc, W, states, N, K, nstates, tr,
-                                           ntrans, mu, sigma, hk);
-                if (rc) return rc;
-                return hmm_vshard_p2p_init(*hk, k, n, nullptr, bk);
-            }));
-        }
-        join_all(futs);
-        for (int k = 0; k < n; k++) {
-            hmm_vshard *h = sh[(size_t)k];
-            void *const *bp = blocks.data();
-            futs.push_back(g_workers[(size_t)k]->run([=] {
-                int rc = hmm_vshard_p2p_attach(h, nullptr, bp);
-                if (rc) return rc;
+                if (hit) {  // (a fresh handle already holds this recording)
+                    int rc = hmm_vshard_set_y(h, y + sp.lb);
+                    if (rc) return rc;
+                }
                 return hmm_vshard_p2p_launch(h, nullptr);
             }));
         }
         join_all(futs);  // every shard has launched its decode and its summary stores: the judges cannot wait in vain
         for (int k = 0; k < n; k++) {
-            hmm_vshard *h = sh[(size_t)k];
-            const ShardSpan sp = spans[(size_t)k];
+            hmm_vshard *h = G.sh[(size_t)k];
+            const ShardSpan sp = G.spans[(size_t)k];
             double *lk = &ll[(size_t)k];
             int32_t *bk = &bad[(size_t)k];
             futs.push_back(g_workers[(size_t)k]->run([=] {
@@ -860,17 +907,16 @@ bool viterbi_timeshard_multidev(const double *y, int64_t T, const int16_t *state
         }
         join_all(futs);
     } catch (...) {
-        destroy_all();
+        drop_shardset();
         throw;
     }
-    destroy_all();
     for (int k = 0; k < n; k++)
         if (bad[(size_t)k] != 0) return false;  // a ghost chunk guessed wrong (not seen on real data): exact single-GPU decode
     if (ll_out) *ll_out = ll[0];
     if (info) {
         memset(info, 0, sizeof *info);
         info->engine = HMM_MODE_RING;
-        info->n_chunks = (int32_t)((T + Lc - 1) / Lc);
+        info->n_chunks = (int32_t)((T + G.Lc - 1) / G.Lc);
         info->kernel_launches = 8 * (int64_t)n;
     }
     return true;
@@ -1226,6 +1272,7 @@ int hmm_vshard_create(const double *y_local, int32_t y_is_host, int64_t local_be
         HMM_CUDA(cudaStreamSynchronize(st));
         if (y_is_host) {
             h->y_dev = (double *)shard_alloc(h.get(), sizeof(double) * (size_t)Tl);
+            h->y_owned = true;
             HMM_CUDA(cudaMemcpyAsync(h->y_dev, y_local, sizeof(double) * (size_t)Tl, cudaMemcpyHostToDevice, st));
         } else
             h->y_dev = const_cast<double *>(y_local);
@@ -1253,6 +1300,16 @@ int hmm_vshard_create(const double *y_local, int32_t y_is_host, int64_t local_be
 }
 
 int hmm_vshard_bvec(const hmm_vshard *h) { return h ? h->plan.bvec() : 0; }
+
+int hmm_vshard_set_y(hmm_vshard *h, const double *y_local_host) {
+    return guarded([&] {
+        if (!h || !y_local_host) fail(HMM_EINVAL, "null argument");
+        if (!h->y_owned) fail(HMM_EINVAL, "the shard was created on a caller-owned device buffer: write the new samples there");
+        HMM_CUDA(cudaSetDevice(h->device));
+        HMM_CUDA(cudaMemcpyAsync(h->y_dev, y_local_host, sizeof(double) * (size_t)(h->local_end - h->local_begin),
+                                 cudaMemcpyHostToDevice, main_stream()));
+    });
+}
 
 static void shard_dev(hmm_vshard *h) {
     if (!h) fail(HMM_EINVAL, "null shard");

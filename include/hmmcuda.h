@@ -193,6 +193,8 @@ int hmm_vshard_create(const double *y_local, int32_t y_is_host, int64_t local_be
                       const int16_t *states, int32_t N, int32_t K, int32_t nstates, const hmm_trans *tr,
                       int64_t ntrans, const double *mu, double sigma, hmm_vshard **out);
 int hmm_vshard_bvec(const hmm_vshard *h);
+/* new samples for a shard that was created from a host pointer (same spans): asynchronous upload into its buffer */
+int hmm_vshard_set_y(hmm_vshard *h, const double *y_local_host);
 int hmm_vshard_forward(hmm_vshard *h);
 int hmm_vshard_fwd_boundary_get(hmm_vshard *h, double *out, int32_t out_is_device);        /* at main_end  -> rank r+1 */
 int hmm_vshard_fwd_boundary_set(hmm_vshard *h, const double *in, int32_t in_is_device);   /* at main_begin <- rank r-1 */
