@@ -11,8 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("LIBHMMCUDA", os.path.join(_HERE, "libhmmcuda.so"))  # same override as the Julia shim
 
 HMM_OK, HMM_EINVAL, HMM_ECUDA, HMM_ENOMEM, HMM_ENODEV, HMM_EUNSUPPORTED = range(6)
-MODE_AUTO, MODE_FAITHFUL, MODE_RING = 0, 1, 2
-MODES = {"auto": MODE_AUTO, "faithful": MODE_FAITHFUL, "ring": MODE_RING}
+MODE_AUTO, MODE_FAITHFUL, MODE_RING, MODE_GENERIC = 0, 1, 2, 3
+MODES = {"auto": MODE_AUTO, "faithful": MODE_FAITHFUL, "ring": MODE_RING, "generic": MODE_GENERIC}
 
 
 class HmmInfo(C.Structure):

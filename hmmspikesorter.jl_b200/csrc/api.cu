@@ -448,11 +448,25 @@ void viterbi_core(const double *y_dev, int64_t T, int C, BatchModels &B, int16_t
         if (!all_ring) fail(HMM_EUNSUPPORTED, "HMM_MODE_RING requested but the model is not a non-overlap ring model");
         if (!ring_supported(M0, T)) fail(HMM_EUNSUPPORTED, "HMM_MODE_RING: sequence too short or K/N outside the ring engine's range");
         engine = HMM_MODE_RING;
+    } else if (mode == HMM_MODE_GENERIC) {
+        if (!generic_parallel_supported(M0, T))
+            fail(HMM_EUNSUPPORTED, "HMM_MODE_GENERIC: sequence shorter than 4096 samples or the model does not fit in shared memory");
+        engine = HMM_MODE_GENERIC;
     } else
         // every ring model the time-parallel engine supports goes to it (T >= 2048): even a 20 000-sample decode
-        // (config 1) is two orders of magnitude faster there than in the sequential per-state engine, and as exact
-        engine = (all_ring && ring_supported(M0, T)) ? HMM_MODE_RING : HMM_MODE_FAITHFUL;
+        // (config 1) is two orders of magnitude faster there than in the sequential per-state engine, and as exact;
+        // any other StateMatrix (overlap models, N > 7) takes the time-parallel per-state engine when it is long enough
+        engine = (all_ring && ring_supported(M0, T)) ? HMM_MODE_RING
+                 : generic_parallel_supported(M0, T) ? HMM_MODE_GENERIC
+                                                      : HMM_MODE_FAITHFUL;
     if (info) info->engine = engine;
+    if (engine == HMM_MODE_GENERIC) {
+        for (int ch = 0; ch < C; ch++)
+            generic_parallel_viterbi_run(y_dev + (size_t)ch * T, T, B.layout, B.blob_dev + (size_t)ch * B.layout.bytes,
+                                         B.models[ch < (int)B.models.size() ? ch : 0], x_dev + (size_t)ch * T,
+                                         ll_host ? ll_host + ch : nullptr, st, info);
+        return;
+    }
     if (engine == HMM_MODE_FAITHFUL) {
         double *ll_dev = nullptr;
         if (ll_host) ll_dev = (double *)workspace().get(Workspace::SCRATCH, sizeof(double) * C);
@@ -935,7 +949,7 @@ int viterbi_host(const double *y, int64_t T, int C, const int16_t *states, int s
         // ---- several devices selected (hmm_set_devices / HMMCUDA_DEVICES): split the call over them ----
         if (!t_worker) {
             devices_from_env_once();
-            if (g_workers.size() > 1 && !T1_out && !T2_out && mode != HMM_MODE_FAITHFUL) {
+            if (g_workers.size() > 1 && !T1_out && !T2_out && mode != HMM_MODE_FAITHFUL && mode != HMM_MODE_GENERIC) {
                 if (C > 1) {
                     viterbi_batch_multidev(y, T, C, states, states_shared, N, K, nstates, tr, ntrans, mu, sigma, x_out,
                                            ll_out, mode, info);
@@ -955,7 +969,7 @@ int viterbi_host(const double *y, int64_t T, int C, const int16_t *states, int s
         Timer tall(st);
         tall.start();
         BatchModels &B = get_models(C, states, states_shared, N, K, nstates, tr, ntrans, mu, sigma, st);
-        if (!T1_out && !T2_out && mode != HMM_MODE_FAITHFUL && ring_supported(B.models[0], T) &&
+        if (!T1_out && !T2_out && mode != HMM_MODE_FAITHFUL && mode != HMM_MODE_GENERIC && ring_supported(B.models[0], T) &&
             pipeline_wanted(B.models[0], T, C)) {
             viterbi_host_pipelined(y, T, B, x_out, ll_out, info);
             tall.stop();
@@ -970,7 +984,7 @@ int viterbi_host(const double *y, int64_t T, int C, const int16_t *states, int s
             bool all_ring = true;
             for (auto &m : B.models) all_ring = all_ring && m.is_ring;
             const bool no_pipe = getenv("HMMCUDA_NO_PIPELINE") && atoi(getenv("HMMCUDA_NO_PIPELINE"));
-            if (C > 1 && !T1_out && !T2_out && mode != HMM_MODE_FAITHFUL && all_ring && ring_supported(B.models[0], T) &&
+            if (C > 1 && !T1_out && !T2_out && mode != HMM_MODE_FAITHFUL && mode != HMM_MODE_GENERIC && all_ring && ring_supported(B.models[0], T) &&
                 T >= 262144 && !no_pipe) {
                 cudaStream_t sh = copy_stream(), sd = out_stream();
                 std::vector<cudaEvent_t> evc(C), evx(C);

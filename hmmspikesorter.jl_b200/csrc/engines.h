@@ -27,6 +27,11 @@ void path_score_run(const double *y_dev, int64_t T, int64_t y_stride, int C, con
 void faithful_fb_run(bool backward, const double *V_dev, int64_t T, const FaithfulLayout &L, const char *blob_dev,
                      const HostModel &M, double *out_dev, cudaStream_t st);
 
+// ---- time-parallel per-state engine for any StateMatrix (generic_parallel.cu) ----
+bool generic_parallel_supported(const HostModel &M, int64_t T);
+void generic_parallel_viterbi_run(const double *y_dev, int64_t T, const FaithfulLayout &L, const char *blob_dev,
+                                  const HostModel &M0, int16_t *x_dev, double *ll_host, cudaStream_t st, hmm_info *info);
+
 // ---- ring engine, Viterbi (ring_viterbi.cu) --------------------------------
 struct RingConfig {
     int64_t chunk_len = 0;  // 0 = auto

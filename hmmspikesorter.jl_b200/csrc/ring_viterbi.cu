@@ -2162,6 +2162,8 @@ void ring_path_ll_run(const double *y_dev, int64_t T, const FaithfulLayout &FL, 
     const int nparts = 592;
     unsigned *cnt = reinterpret_cast<unsigned *>(scratch + nparts);
     HMM_CUDA(cudaMemsetAsync(cnt, 0, 4 * sizeof(unsigned), st));
+    if (ll_smem(M0) > 48 * 1024)  // overlap models (thousands of states) through the generic engine
+        HMM_CUDA(cudaFuncSetAttribute(ring_path_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ll_smem(M0)));
     ring_path_ll<<<dim3(nparts, 1), 256, ll_smem(M0), st>>>(y_dev, T, T, blob_dev, FL.bytes, FL, M0.nstates,
                                                             (int)M0.ntrans, x_dev, T, scratch, 0, T, 0, T, cnt, ll_dev, 1,
                                                             nullptr, 0);

@@ -42,13 +42,14 @@ typedef struct hmm_trans {
 } hmm_trans;
 
 /* Decode engines (hmm_viterbi_ex_f64 `mode`). */
-#define HMM_MODE_AUTO 0     /* ring fast path when the model is a non-overlap ring model and T is long, else faithful */
+#define HMM_MODE_AUTO 0     /* ring engine for non-overlap ring models, generic time-parallel engine for other long decodes, else faithful */
 #define HMM_MODE_FAITHFUL 1 /* sequential kernel in the reference's exact operation order (any StateMatrix) */
 #define HMM_MODE_RING 2     /* time-parallel ring kernels; HMM_EUNSUPPORTED if the model is not ring-structured */
+#define HMM_MODE_GENERIC 3  /* time-parallel per-state kernels for any StateMatrix (overlap models, N > 7); T >= 4096 */
 
 /* Diagnostics of one decode / E-M call (all optional outputs). */
 typedef struct hmm_info {
-    int32_t engine;           /* HMM_MODE_FAITHFUL or HMM_MODE_RING actually used */
+    int32_t engine;           /* HMM_MODE_FAITHFUL, _RING or _GENERIC actually used */
     int32_t n_chunks;         /* time chunks per channel (ring engine) */
     int32_t fwd_repaired;     /* chunks whose speculative forward start failed verification and were re-run */
     int32_t bwd_repaired;     /* same for the backward / traceback pass */

@@ -58,7 +58,7 @@ def test_viterbi_reference_testset_overlap_3600_states(hm, O):
     lA = hm.StateMatrix(2, 60, np.log(pp), True)
     assert lA.nstates == 3600 and lA.transitions.size == 3721
     mu = np.asfortranarray(temps)
-    x, ll = hm.viterbi(S, lA, mu, 0.3)
+    x, ll = hm.viterbi(S, lA, mu, 0.3, mode="faithful")
     xo, llo = O.viterbi(S, lA, mu, 0.3)
     assert np.array_equal(x, xo) and ll == llo
     Y = hm.reconstruct_signal(x, lA, mu, 0.3)
