@@ -270,6 +270,25 @@ class TrainContext:
         out = (lp[:_nxi(lA) - 1].copy(), pp, mu, s.value, ll.value)
         return out + (info.asdict(),) if return_info else out
 
+    def run(self, lA, mu, sigma, nsteps, return_info=False):
+        """`nsteps` E/M iterations in one library call (hmm_train_run): the loop of src/baumwelch.jl:325-335 without a
+        callback.  Returns (lA_new, mu, sigma, loglik[steps_done]); steps_done < nsteps only if lp degenerated."""
+        st, tr, mu = _model_args(lA, mu)
+        mu = mu.copy(order="F")
+        tr = tr.copy()
+        nlp = max(_nxi(lA) - 1, 1)
+        lp = np.empty(nlp, dtype=np.float64)
+        pp = np.empty(lA.nstates, dtype=np.float64)
+        ll = np.zeros(max(int(nsteps), 1), dtype=np.float64)
+        s, done = f64(sigma), i32(0)
+        info = HmmInfo()
+        check(lib().hmm_train_run(self._h, _p(st), i32(lA.N), i32(lA.K), i32(lA.nstates), _p(tr), i64(tr.size), _p(mu),
+                                  C.byref(s), _p(lp), i32(nlp), _p(pp), _p(ll), i32(int(nsteps)), C.byref(done),
+                                  C.byref(info)))
+        lA_new = _rebuild(lA, lp[:_nxi(lA) - 1], pp) if done.value > 0 else lA
+        out = (lA_new, mu, s.value, ll[:done.value].copy())
+        return out + (info.asdict(),) if return_info else out
+
     def close(self):
         if self._h:
             lib().hmm_train_destroy(self._h)
@@ -303,6 +322,14 @@ def train_model(X, lA, mu, sigma, nsteps=None, callback=None, *, verbose: int = 
         lp, pp, mu_new, s, _ = em_step(X, lA, mu, sigma)
         mu[...] = mu_new
         return _rebuild(lA, lp, pp), mu, s
+    if callback is None and verbose <= 0:  # the whole loop inside the library
+        with TrainContext(X) as ctx:
+            left = int(nsteps)
+            while left > 0 and not lA.isempty():
+                lA, mu_new, sigma, ll = ctx.run(lA, mu, sigma, left)  # stops early only if lp degenerated:
+                mu[...] = mu_new                                      # lA is then rebuilt here (new topology)
+                left -= max(ll.size, 1)
+        return lA, mu, sigma
     with TrainContext(X) as ctx:
         for i in range(nsteps):
             if verbose > 0:

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <chrono>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -1854,6 +1855,76 @@ int hmm_train_em_step(hmm_train_ctx *ctx, const int16_t *states, int32_t N, int3
         tall.stop();
         HMM_CUDA(cudaStreamSynchronize(st));
         if (info) info->device_ms = tall.ms();
+    });
+}
+
+// The E/M loop of src/baumwelch.jl:325-335 in one call (no callback between the steps): each step's lp goes
+// straight into the next step's transition weights -- the StateMatrix rebuild of src/baumwelch.jl:265 /
+// src/types.jl:94-127 restricted to what it can change, the WEIGHTS: which transitions are finite depends on the
+// state layout only.  Per transition and neuron the term is lpz (silent -> silent), lp[i] (silent -> first phase)
+// or 0 (advance / return), added in neuron order like `lpt += ...`; lpz = log1p(-exp(sum(lp))) over the whole vector.
+// Stops early, reporting the steps done, when a weight stops being finite (the set of transitions would change:
+// the caller rebuilds its StateMatrix and decides).
+int hmm_train_run(hmm_train_ctx *ctx, const int16_t *states, int32_t N, int32_t K, int32_t nstates, hmm_trans *tr_inout,
+                  int64_t ntrans, double *mu_inout, double *sigma_inout, double *lp_out, int32_t nlp, double *pp_out,
+                  double *loglik_out, int32_t nsteps, int32_t *steps_done, hmm_info *info) {
+    return guarded([&] {
+        if (info) memset(info, 0, sizeof *info);
+        if (steps_done) *steps_done = 0;
+        if (!ctx || !states || !tr_inout || !mu_inout || !sigma_inout || !lp_out || !pp_out) fail(HMM_EINVAL, "null argument");
+        if (nsteps < 0 || nlp < N) fail(HMM_EINVAL, "nsteps must be >= 0 and lp_out must hold at least N entries");
+        require_device();
+        cudaStream_t st = main_stream();
+        // term codes per (transition, neuron): 0 -> lpz, 1 -> lp[i], 2 -> 0.0
+        std::vector<unsigned char> code((size_t)ntrans * N);
+        for (int64_t e = 0; e < ntrans; e++) {
+            const int a = tr_inout[e].src - 1, b = tr_inout[e].dst - 1;
+            if (a < 0 || a >= nstates || b < 0 || b >= nstates) fail(HMM_EINVAL, "transition %lld out of range", (long long)e);
+            for (int i = 0; i < N; i++) {
+                const int s1 = states[(size_t)a * N + i], s2 = states[(size_t)b * N + i];
+                code[(size_t)e * N + i] = (s1 == 1 && s2 == 1) ? 0 : (s1 == 1 && s2 == 2) ? 1 : 2;  // phases are 1-based, 1 = silent
+            }
+        }
+        hmm_info acc{}, one{};
+        double dev_ms = 0, ker_ms = 0;
+        for (int it = 0; it < nsteps; it++) {
+            double ll = 0;
+            Timer tall(st);
+            tall.start();
+            em_step_dev(ctx->X_dev, ctx->T, states, N, K, nstates, tr_inout, ntrans, mu_inout, sigma_inout, lp_out, pp_out,
+                        &ll, HMM_MODE_AUTO, st, &one);
+            tall.stop();
+            HMM_CUDA(cudaStreamSynchronize(st));
+            dev_ms += tall.ms();
+            ker_ms += one.top_kernel_ms;
+            acc.engine = one.engine;
+            acc.n_chunks = one.n_chunks;
+            acc.fwd_repaired += one.fwd_repaired;
+            acc.bwd_repaired += one.bwd_repaired;
+            acc.kernel_launches += one.kernel_launches;
+            memset(&one, 0, sizeof one);
+            if (loglik_out) loglik_out[it] = ll;
+            if (steps_done) *steps_done = it + 1;
+            double sum = 0.0;
+            for (int k = 0; k < nlp; k++) sum = k == 0 ? lp_out[0] : sum + lp_out[k];
+            const double lpz = log1p(-exp(sum));
+            bool finite = std::isfinite(lpz);
+            for (int64_t e = 0; e < ntrans && finite; e++) {
+                double w = 0.0;
+                for (int i = 0; i < N; i++) {
+                    const unsigned char c = code[(size_t)e * N + i];
+                    w += c == 0 ? lpz : c == 1 ? lp_out[i] : 0.0;
+                }
+                finite = std::isfinite(w);
+                tr_inout[e].lp = w;
+            }
+            if (!finite) break;
+        }
+        if (info) {
+            *info = acc;
+            info->device_ms = dev_ms;
+            info->top_kernel_ms = ker_ms;
+        }
     });
 }
 

@@ -289,6 +289,17 @@ int hmm_train_create_dev(const double *X_dev, int64_t T, hmm_train_ctx **ctx_out
 int hmm_train_em_step(hmm_train_ctx *ctx, const int16_t *states, int32_t N, int32_t K, int32_t nstates,
                       const hmm_trans *tr, int64_t ntrans, double *mu_inout, double *sigma_inout, double *lp_out,
                       double *pp_out, double *loglik_out, hmm_info *info);
+/*
+ * The E/M loop of train_model (src/baumwelch.jl:325-335) in one call, for callers that pass no callback: nsteps
+ * iterations, each one's lp feeding the next one's transition weights inside the library (the weight part of the
+ * StateMatrix rebuild, src/baumwelch.jl:265 / src/types.jl:94-127; the set of finite transitions depends on the state
+ * layout only).  tr_inout's weights, mu_inout and sigma_inout are updated in place; lp_out [nlp] (nlp = transitions out
+ * of state 1 minus one), pp_out [nstates] and loglik_out [nsteps, nullable] as in hmm_em_step_f64.  *steps_done <
+ * nsteps when a weight stopped being finite (degenerate lp): the caller rebuilds its StateMatrix and decides.
+ */
+int hmm_train_run(hmm_train_ctx *ctx, const int16_t *states, int32_t N, int32_t K, int32_t nstates, hmm_trans *tr_inout,
+                  int64_t ntrans, double *mu_inout, double *sigma_inout, double *lp_out, int32_t nlp, double *pp_out,
+                  double *loglik_out, int32_t nsteps, int32_t *steps_done, hmm_info *info);
 int hmm_train_destroy(hmm_train_ctx *ctx);
 
 /* ---- I/O front-end (src/hmmsort.jl:36-104: data file -> Float64 -> decode -> unrolled sequence) ------------------

@@ -99,6 +99,41 @@ def test_baum_welch_iterations(hm, O, case_factory):
     assert abs(s_fit - 0.3) < 0.01  # converges to the truth (SURVEY appendix B probe)
 
 
+@pytest.mark.parametrize("overlap", [False, True])
+def test_train_loop_inside_the_library_equals_the_host_loop(hm, O, case_factory, overlap):
+    """hmm_train_run: the E/M loop of src/baumwelch.jl:325-335 in one C call (no callback) -- each step's lp becomes the
+    next step's transition weights inside the library.  It must walk the same sequence of models as the host loop
+    (per-step call + StateMatrix rebuild), for a ring model and for an overlap model (generic E/M path)."""
+    if overlap:
+        N, K, T = 2, 12, 6000
+        temps = np.stack([hm.create_spike_template(K, 3.0, 0.8, 0.2), hm.create_spike_template(K, 4.0, 0.3, 0.2)], 1)
+        S = hm.create_signal(T, 0.3, np.array([0.01, 0.005]), temps, hm.make_rng(5))
+        mu_true = np.asfortranarray(temps)
+        lA = hm.StateMatrix(N, K, np.log(np.array([0.01, 0.01, 0.0001])), True)
+    else:
+        N, K, T = 3, 60, 30000
+        S, _, mu_true, _ = case_factory(N, K, T, 21)
+        lA = hm.StateMatrix(N, K, np.log(np.full(N, 0.01)), False)
+    mu0, s0 = np.asfortranarray(0.7 * mu_true), float(np.std(S))
+    steps = 4
+    with hm.TrainContext(S) as ctx:
+        lA_run, mu_run, s_run, ll_run, info = ctx.run(lA, mu0, s0, steps, return_info=True)
+        lA_h, mu_h, s_h, ll_h = lA, mu0.copy(order="F"), s0, []
+        for _ in range(steps):
+            lp, pp, mu_h, s_h, ll = ctx.em_step(lA_h, mu_h, s_h)
+            lA_h = hm.StateMatrix.from_states(lA_h.states, pp, K, lp, overlap)
+            ll_h.append(ll)
+    assert ll_run.size == steps and info["kernel_launches"] >= 4 * steps
+    assert np.abs(mu_run - mu_h).max() < 1e-12 and abs(s_run - s_h) < 1e-12
+    assert np.allclose(ll_run, ll_h, rtol=1e-13, atol=0)
+    assert np.abs(lA_run.transitions["lp"] - lA_h.transitions["lp"]).max() < 1e-12
+    assert np.array_equal(lA_run.transitions["src"], lA_h.transitions["src"])
+    # and train_model without a callback takes that route
+    mu = mu0.copy(order="F")
+    lA_t, mu_t, s_t = hm.train_model(S, lA, mu, s0, steps)
+    assert mu_t is mu and np.abs(mu - mu_h).max() < 1e-12 and abs(s_t - s_h) < 1e-12
+
+
 def test_one_step_train_model_in_place(hm, O, case_factory):
     S, lA_true, mu_true, sig = case_factory(2, 30, 8000, 22, rate_scale=2.0)
     lA, mu0, s0 = _start(hm, S, mu_true, 2, 30)
