@@ -1143,6 +1143,24 @@ __device__ __forceinline__ bool last_cta_of_row(unsigned *cnt, int *s_flag) {
     return *s_flag != 0;
 }
 
+// Same, and the CTAs also tell the last one whether ANY of them saw a failed check (bit 16 and up of the counter
+// count the CTAs that did), so that it does not have to read the flags back.  gridDim.x < 65536.
+__device__ __forceinline__ bool last_cta_of_row_any(unsigned *cnt, int *s_flag, bool bad, int *any_out) {
+    const int bad_cta = __syncthreads_or(bad ? 1 : 0);
+    __threadfence();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(cnt, 1u + (bad_cta ? 0x10000u : 0u));
+        const int last = (prev & 0xffffu) == gridDim.x - 1;
+        s_flag[0] = last;
+        s_flag[1] = ((prev >> 16) != 0u || bad_cta) ? 1 : 0;
+        if (last) *cnt = 0u;
+    }
+    __syncthreads();
+    if (s_flag[0]) __threadfence();
+    *any_out = s_flag[1];
+    return s_flag[0] != 0;
+}
+
 // Forward verification in ONE launch: (1) every warp checks one chunk boundary -- the speculative start vector of
 // chunk c against the true end vector of chunk c-1; (2) the last CTA to finish re-runs the flagged chunks from the
 // true vectors, sequentially (a re-run changes EB[c], so chunk c+1 is re-checked against it), and (3) computes
@@ -1150,10 +1168,11 @@ __device__ __forceinline__ bool last_cta_of_row(unsigned *cnt, int *s_flag) {
 template <int N, int R, typename S>
 __global__ void __launch_bounds__(256) ring_vit_verify_fwd(VitParams p) {
     extern __shared__ __align__(16) double smem_d[];
-    __shared__ int s_flag;
+    __shared__ int s_flag[2];
     const int ch = blockIdx.y + p.ch0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int *flag = p.fwd_flag + (size_t)ch * p.nchunks;
+    bool bad = false;
     {
         const int c = blockIdx.x * 8 + warp;
         if (c >= 1 && c < p.nchunks) {
@@ -1162,12 +1181,11 @@ __global__ void __launch_bounds__(256) ring_vit_verify_fwd(VitParams p) {
             bool ok = boundary_matches(sb, eb, p.bvec, lane);
             if (p.dbg_flag_every > 0 && c % p.dbg_flag_every == 0) ok = false;  // HMMCUDA_DEBUG_FLAG_EVERY: force the repair path
             if (lane == 0) flag[c] = ok ? 0 : 1;
+            bad = !ok;
         }
     }
-    if (!last_cta_of_row(p.sync_cnt + ch * 4 + 0, &s_flag)) return;
     int any = 0;
-    for (int c = 1 + threadIdx.x; c < p.nchunks; c += blockDim.x) any |= __ldcg(flag + c);
-    any = __syncthreads_or(any);
+    if (!last_cta_of_row_any(p.sync_cnt + ch * 4 + 0, s_flag, bad, &any)) return;
     int repaired = 0;
     if (any) {
         double *mdl = smem_d;
@@ -1485,19 +1503,47 @@ __device__ void trace_chunk(const VitParams &p, int ch, int c, int64_t tau_hi, l
 //   ll = (Tg - 1) p0 + (w_nn + c_emit) sum (Tg - g) - (1 / 2 sigma^2) sum (Tg - g) (y_g - m0)^2 + sum (Tg - g) inc'_g
 // The second sum is piece 1 (forward producers, per forward chunk), the third piece 2 (traceback, per traceback
 // chunk); both are added here in chunk order by one warp, so the result does not depend on scheduling.
-__device__ void ll_assemble(const VitParams &p, int ch, int lane) {
+// Strided sum of v[lo .. hi) by the whole CTA, eight independent loads in flight per thread (the pieces are a few
+// thousand doubles straight from L2: the latency of dependent round trips is all this costs); fixed order.
+__device__ __forceinline__ double cta_strided_sum(const double *v, int lo, int hi) {
+    double acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) acc[q] = 0.0;
+    const int nthr = blockDim.x;
+    for (int c = lo + threadIdx.x; c < hi; c += 8 * nthr) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int k = c + q * nthr;
+            acc[q] += k < hi ? __ldcg(v + k) : 0.0;
+        }
+    }
+    return ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+}
+
+__device__ void ll_assemble(const VitParams &p, int ch) {  // called by every thread of the CTA (<= 1024 threads)
+    __shared__ double s_part[2][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
     const int64_t lo = p.ll_lo, hi = p.ll_hi;
     const int cf0 = (int)(lo / p.Lc), cf1 = hi >= p.T ? p.nchunks : (int)(hi / p.Lc);
     const int ct0 = (int)(lo / p.Lc_t), ct1 = hi >= p.T ? p.nchunks_t : (int)(hi / p.Lc_t);
-    double a = 0.0, b = 0.0;
-    for (int c = 2 * cf0 + lane; c < 2 * cf1; c += 32) a += __ldcg(p.ll_noise + (size_t)ch * p.nchunks * 2 + c);
-    for (int c = ct0 + lane; c < ct1; c += 32) b += __ldcg(p.ll_spike + (size_t)ch * p.nchunks_t + c);
+    double a = cta_strided_sum(p.ll_noise + (size_t)ch * p.nchunks * 2, 2 * cf0, 2 * cf1);
+    double b = cta_strided_sum(p.ll_spike + (size_t)ch * p.nchunks_t, ct0, ct1);
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, d);
         b += __shfl_xor_sync(0xffffffffu, b, d);
     }
     if (lane == 0) {
+        s_part[0][warp] = a;
+        s_part[1][warp] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = b = 0.0;
+        for (int w = 0; w < nwarps; w++) {
+            a += s_part[0][w];
+            b += s_part[1][w];
+        }
         const double *sc = p.model + (size_t)ch * p.RL.total + p.RL.scal;  // 0 w_nn, 1 c_emit, 2 two_s2, 3 m0
         const double *y = p.y + (size_t)ch * p.y_stride;
         int64_t g0 = lo + p.t_off, g1 = hi + p.t_off - 1;  // global steps [g0, g1]
@@ -1560,25 +1606,23 @@ __global__ void __launch_bounds__(128) ring_vit_trace(VitParams p) {
 template <int N>
 __global__ void __launch_bounds__(128) ring_vit_verify_trace(VitParams p) {
     extern __shared__ __align__(16) uint32_t trsm[];
-    __shared__ int s_flag;
+    __shared__ int s_flag[2];
     const int ch = blockIdx.y + p.ch0;
     const size_t o = (size_t)ch * p.nchunks_t;
+    bool bad = false;
     {
         const int c = blockIdx.x * blockDim.x + threadIdx.x;
         if (c < p.nchunks_t - 1) {
-            bool bad = p.look_end[o + c] != p.own_start[o + c + 1];
+            bad = p.look_end[o + c] != p.own_start[o + c + 1];
             if (p.dbg_flag_every > 0 && c % p.dbg_flag_every == 0) bad = true;
             p.tr_flag[o + c] = bad ? 1 : 0;
         }
     }
-    if (!last_cta_of_row(p.sync_cnt + ch * 4 + 1, &s_flag)) return;
     int any = 0;
-    for (int c = threadIdx.x; c < p.nchunks_t - 1; c += blockDim.x) any |= __ldcg(p.tr_flag + o + c);
-    any = __syncthreads_or(any);
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
+    if (!last_cta_of_row_any(p.sync_cnt + ch * 4 + 1, s_flag, bad, &any)) return;
+    const int lane = threadIdx.x & 31;
     int repaired = 0;
-    if (any) {
+    if (any && threadIdx.x < 32) {
         uint32_t *tws = trsm;
         bool next_changed = false;
         for (int c = p.nchunks_t - 2; c >= 0; c--) {
@@ -1597,14 +1641,14 @@ __global__ void __launch_bounds__(128) ring_vit_verify_trace(VitParams p) {
                 next_changed = false;
         }
     }
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         p.counters[ch * 4 + 1] = repaired;
         if (p.res_host) p.res_host[ch * 4 + 2] = (double)repaired;
     }
-    if (p.want_ll) {
+    if (p.want_ll) {  // the whole CTA: a repair may have rewritten a chunk's piece
         __threadfence();
-        __syncwarp();
-        ll_assemble(p, ch, lane);
+        __syncthreads();
+        ll_assemble(p, ch);
     }
 }
 

@@ -115,15 +115,18 @@ def test_ring_viterbi_auto_and_batch(hm, O, case_factory):
         assert abs(ll[c] - llo) <= LL_RTOL * abs(llo)
 
 
-def test_ring_range_limits_fall_back_to_faithful(hm, O, case_factory):
-    """N = 8 is outside the ring engine (7 neurons max): explicit ring mode refuses,
-    auto mode decodes with the faithful engine."""
+def test_ring_range_limits_fall_back(hm, O, case_factory):
+    """N = 8 is outside the ring engine (7 neurons max): explicit ring mode refuses, auto mode decodes with the
+    time-parallel per-state engine (T >= 4096) or, for short sequences, the sequential one."""
     S, lA, mu, sig = case_factory(8, 40, 40000, 14)
     with pytest.raises(hm.HmmError) as ei:
         hm.viterbi(S, lA, mu, sig, mode="ring")
     assert ei.value.code == hm._lib.HMM_EUNSUPPORTED
     x, ll, info = hm.viterbi(S, lA, mu, sig, mode="auto", return_info=True)
     xo, llo = O.viterbi(S, lA, mu, sig)
+    assert info["engine"] == 3 and np.array_equal(x, xo) and abs(ll - llo) <= LL_RTOL * abs(llo)
+    x, ll, info = hm.viterbi(S[:3000], lA, mu, sig, mode="auto", return_info=True)
+    xo, llo = O.viterbi(S[:3000], lA, mu, sig)
     assert info["engine"] == 1 and np.array_equal(x, xo) and ll == llo
 
 
