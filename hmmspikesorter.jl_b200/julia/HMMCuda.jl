@@ -187,6 +187,39 @@ function with_resident(f::Function, X::Array{Float64,1})
     end
 end
 
+# ---- n E/M steps in ONE library call (no callback between them) ------------------------------------------------
+# The second loop of train_model (src/baumwelch.jl:351-353, `for i in 1:div(nsteps,2)`) and any caller-side loop with
+# the default callback: X is uploaded once, every step's lp becomes the next step's transition weights inside the
+# library (hmm_train_run), and the StateMatrix is rebuilt once at the end with the unchanged Julia constructor.
+# Stops early if lp degenerates (a weight stops being finite) and finishes the remaining steps one by one.
+function train_steps(X::Array{Float64,1}, lA::StateMatrix, μ::Array{Float64,2}, σ::Float64, nsteps::Integer)
+    nsteps <= 0 && return lA, μ, σ
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve X _check(ccall((:hmm_train_create, libhmmcuda), Cint, (Ptr{Float64}, Int64, Ref{Ptr{Cvoid}}),
+                                X, length(X), ctx))
+    try
+        left = Int(nsteps)
+        while left > 0 && !isempty(lA)
+            nlp = max(_nxi(lA) - 1, 1)
+            lp = Vector{Float64}(undef, nlp); pp = Vector{Float64}(undef, lA.nstates)
+            s = Ref{Float64}(σ); done = Ref{Int32}(0); tr = copy(lA.transitions)
+            GC.@preserve lA μ lp pp tr begin
+                _check(ccall((:hmm_train_run, libhmmcuda), Cint,
+                    (Ptr{Cvoid}, Ptr{Int16}, Int32, Int32, Int32, Ptr{Cvoid}, Int64, Ptr{Float64}, Ref{Float64},
+                     Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Ref{Int32}, Ptr{Cvoid}),
+                    ctx[], lA.states, lA.N, lA.K, lA.nstates, pointer(tr), length(tr), μ, s, lp, nlp, pp, C_NULL,
+                    left, done, C_NULL))
+            end
+            σ = s[]
+            lA = StateMatrix(lA.states .- one(Int16), pp, lA.K, lp[1:_nxi(lA)-1]; allow_overlaps=lA.resolve_overlaps)
+            left -= max(Int(done[]), 1)
+        end
+    finally
+        ccall((:hmm_train_destroy, libhmmcuda), Cint, (Ptr{Cvoid},), ctx[])
+    end
+    lA, μ, σ
+end
+
 # ---- optional: pinned host arrays ------------------------------------------------------------------------
 # A Julia Array is pageable: long decodes then go through the library's pinned staging threads (≈2.9 Gsamples/s).
 # Recordings that live in a pinned buffer reach the PCIe rate (≈5.6 Gsamples/s).  `pinned_vector(Float64, T)`
