@@ -21,14 +21,26 @@ def launches(src, dst, first=0):
         v = agg.setdefault(row["Kernel Name"], [])
         if first <= 0 or len(v) < first:
             v.append(float(row["Metric Value"].replace(",", "")))
-    tot = sum(sum(v) / len(v) for v in agg.values())
+    groups = collections.OrderedDict([
+        ("decode step (config 2, device-resident): one launch of each per step", lambda k: "ring_vit_" in k),
+        ("Baum-Welch iteration (config 3): one launch of each per iteration", lambda k: "::em_" in k),
+        ("not part of a step (peak probes of hmm_measure_peaks, the pipelined host-pointer decode's helpers)", lambda k: True)])
     with open(dst, "w") as f:
         f.write("# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare SHARES)\n\n")
-        f.write(f"source: `{src}`\n\n| kernel | launches | mean us | share of step |\n|---|---|---|---|\n")
-        for k, v in agg.items():
-            m = sum(v) / len(v)
-            f.write(f"| `{k[:90]}` | {len(v)} | {m / 1e3:.1f} | {100 * m / tot:.1f}% |\n")
-        f.write(f"\nsum of per-kernel means: {tot / 1e3:.1f} us per step\n")
+        f.write(f"source: `{src}`\n")
+        left = collections.OrderedDict(agg)
+        for title, pred in groups.items():
+            mine = collections.OrderedDict((k, v) for k, v in left.items() if pred(k))
+            for k in mine:
+                del left[k]
+            if not mine:
+                continue
+            tot = sum(sum(v) / len(v) for v in mine.values())
+            f.write(f"\n## {title}\n\n| kernel | launches | mean us | share |\n|---|---|---|---|\n")
+            for k, v in mine.items():
+                m = sum(v) / len(v)
+                f.write(f"| `{k[:90]}` | {len(v)} | {m / 1e3:.1f} | {100 * m / tot:.1f}% |\n")
+            f.write(f"\nsum of per-kernel means: {tot / 1e3:.1f} us\n")
 
 
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
