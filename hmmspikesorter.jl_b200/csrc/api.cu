@@ -443,22 +443,21 @@ void viterbi_core(const double *y_dev, int64_t T, int C, BatchModels &B, int16_t
     for (auto &m : B.models) all_ring = all_ring && m.is_ring;
     bool want_trellis = T1_dev || T2_dev;
     int engine;
-    if (mode == HMM_MODE_FAITHFUL || want_trellis)
+    if (mode == HMM_MODE_FAITHFUL || want_trellis)  // (models beyond ~5 000 states: HMM_EUNSUPPORTED there)
         engine = HMM_MODE_FAITHFUL;
     else if (mode == HMM_MODE_RING) {
         if (!all_ring) fail(HMM_EUNSUPPORTED, "HMM_MODE_RING requested but the model is not a non-overlap ring model");
         if (!ring_supported(M0, T)) fail(HMM_EUNSUPPORTED, "HMM_MODE_RING: sequence too short or K/N outside the ring engine's range");
         engine = HMM_MODE_RING;
     } else if (mode == HMM_MODE_GENERIC) {
-        if (!generic_parallel_supported(M0, T))
-            fail(HMM_EUNSUPPORTED, "HMM_MODE_GENERIC: sequence shorter than 4096 samples or the model does not fit in shared memory");
+        if (!generic_parallel_supported(M0, T)) fail(HMM_EUNSUPPORTED, "HMM_MODE_GENERIC: more than 32767 states");
         engine = HMM_MODE_GENERIC;
     } else
         // every ring model the time-parallel engine supports goes to it (T >= 2048): even a 20 000-sample decode
         // (config 1) is two orders of magnitude faster there than in the sequential per-state engine, and as exact;
         // any other StateMatrix (overlap models, N > 7) takes the time-parallel per-state engine when it is long enough
         engine = (all_ring && ring_supported(M0, T)) ? HMM_MODE_RING
-                 : generic_parallel_supported(M0, T) ? HMM_MODE_GENERIC
+                 : generic_parallel_preferred(M0, T) ? HMM_MODE_GENERIC
                                                       : HMM_MODE_FAITHFUL;
     if (info) info->engine = engine;
     if (engine == HMM_MODE_GENERIC) {

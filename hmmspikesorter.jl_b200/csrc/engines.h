@@ -29,6 +29,7 @@ void faithful_fb_run(bool backward, const double *V_dev, int64_t T, const Faithf
 
 // ---- time-parallel per-state engine for any StateMatrix (generic_parallel.cu) ----
 bool generic_parallel_supported(const HostModel &M, int64_t T);
+bool generic_parallel_preferred(const HostModel &M, int64_t T);  // auto mode: long, or too large for the sequential engine
 void generic_parallel_viterbi_run(const double *y_dev, int64_t T, const FaithfulLayout &L, const char *blob_dev,
                                   const HostModel &M0, int16_t *x_dev, double *ll_host, cudaStream_t st, hmm_info *info);
 

@@ -35,30 +35,71 @@ struct GenParams {
     int16_t *x;
     double *res_host;      // mapped pinned: [1] fwd repaired [2] traceback repaired (nullable)
     int dbg_flag_every;
+    // Models of many thousand states (the CLI's overlap models: 10 621 states at N=3, 21 123 at N=4, K=60) do not
+    // fit shared memory: `place` says which arrays live there (bit set) and which are read from the model blob /
+    // a per-CTA global scratch (L2-resident) instead.
+    int place;             // GP_COLS | GP_M | GP_DEC | GP_PTR | GP_LP | GP_IDX
+    double *colg;          // [gridDim.x x 2 x ns] score columns when GP_COLS is clear
 };
+enum { GP_COLS = 1, GP_M = 2, GP_DEC = 4, GP_PTR = 8, GP_LP = 16, GP_IDX = 32, GP_ALL = 63 };
 
-struct GenSmem {
-    double *col0, *col1, *m, *lp, *ytile;
-    int *ptr, *idx, *dec;
+struct GenSmem {  // generic pointers: shared memory or global, per `place`
+    double *col0, *col1, *ytile;
+    const double *m, *lp;
+    const int *ptr, *idx, *dec;
 };
 constexpr int GYT = 256;
 
-__device__ __forceinline__ GenSmem gen_carve(char *base, int ns, int nt) {
+__host__ __device__ inline size_t gen_smem_bytes(int ns, int64_t nt, int place) {
+    size_t d = GYT, i = 0;
+    if (place & GP_COLS) d += 2 * (size_t)ns;
+    if (place & GP_M) d += ns;
+    if (place & GP_LP) d += nt;
+    if (place & GP_DEC) i += ns;
+    if (place & GP_PTR) i += (size_t)ns + 1;
+    if (place & GP_IDX) i += nt;
+    return sizeof(double) * d + sizeof(int) * i + 16;
+}
+
+// Carves the CTA's shared memory and copies the arrays placed there; the others point into the model blob.
+__device__ __forceinline__ GenSmem gen_setup(const GenParams &p, char *base, const char *mb, const FaithfulLayout &L) {
+    const int ns = p.ns, nt = p.nt, place = p.place;
+    const double *gm = (const double *)(mb + L.m), *glp = (const double *)(mb + L.in_lp);
+    const int *gp = (const int *)(mb + L.in_ptr), *gs = (const int *)(mb + L.in_src), *gd = (const int *)(mb + L.dec_slot);
     GenSmem s;
     double *d = (double *)base;
-    s.col0 = d; d += ns;
-    s.col1 = d; d += ns;
-    s.m = d; d += ns;
-    s.lp = d; d += nt;
     s.ytile = d; d += GYT;
-    int *i = (int *)d;
-    s.ptr = i; i += ns + 1;
-    s.idx = i; i += nt;
-    s.dec = i;
+    if (place & GP_COLS) {
+        s.col0 = d; d += ns;
+        s.col1 = d; d += ns;
+    } else {
+        s.col0 = p.colg + (size_t)blockIdx.x * 2 * ns;
+        s.col1 = s.col0 + ns;
+    }
+    double *sm_m = nullptr, *sm_lp = nullptr;
+    if (place & GP_M) { sm_m = d; d += ns; }
+    if (place & GP_LP) { sm_lp = d; d += nt; }
+    int *i = (int *)d, *sm_dec = nullptr, *sm_ptr = nullptr, *sm_idx = nullptr;
+    if (place & GP_DEC) { sm_dec = i; i += ns; }
+    if (place & GP_PTR) { sm_ptr = i; i += ns + 1; }
+    if (place & GP_IDX) { sm_idx = i; i += nt; }
+    for (int k = threadIdx.x; k < ns; k += blockDim.x) {
+        if (sm_m) sm_m[k] = gm[k];
+        if (sm_dec) sm_dec[k] = gd[k];
+    }
+    if (sm_ptr)
+        for (int k = threadIdx.x; k <= ns; k += blockDim.x) sm_ptr[k] = gp[k];
+    for (int k = threadIdx.x; k < nt; k += blockDim.x) {
+        if (sm_lp) sm_lp[k] = glp[k];
+        if (sm_idx) sm_idx[k] = gs[k];
+    }
+    s.m = sm_m ? sm_m : gm;
+    s.lp = sm_lp ? sm_lp : glp;
+    s.dec = sm_dec ? sm_dec : gd;
+    s.ptr = sm_ptr ? sm_ptr : gp;
+    s.idx = sm_idx ? sm_idx : gs;
+    __syncthreads();
     return s;
-}
-size_t gen_smem_bytes(int ns, int64_t nt) {
-    return sizeof(double) * (3 * (size_t)ns + nt + GYT) + sizeof(int) * ((size_t)ns + 1 + nt + ns) + 16;
 }
 
 enum { GEN_SPEC = 0, GEN_EXACT = 1 };
@@ -146,26 +187,10 @@ __device__ void gen_run_chunk(const GenParams &p, const GenSmem &S, double c_emi
     __syncthreads();
 }
 
-__device__ void gen_load_model(const char *mb, const FaithfulLayout &L, const GenSmem &S, int ns, int nt) {
-    const double *gm = (const double *)(mb + L.m), *glp = (const double *)(mb + L.in_lp);
-    const int *gp = (const int *)(mb + L.in_ptr), *gs = (const int *)(mb + L.in_src), *gd = (const int *)(mb + L.dec_slot);
-    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
-        S.m[i] = gm[i];
-        S.dec[i] = gd[i];
-    }
-    for (int i = threadIdx.x; i <= ns; i += blockDim.x) S.ptr[i] = gp[i];
-    for (int i = threadIdx.x; i < nt; i += blockDim.x) {
-        S.lp[i] = glp[i];
-        S.idx[i] = gs[i];
-    }
-    __syncthreads();
-}
-
 __global__ void __launch_bounds__(1024) gen_vit_forward(GenParams p, const char *blob, FaithfulLayout L) {
     extern __shared__ __align__(16) char smem_raw[];
     const double *sc = (const double *)(blob + L.scal);
-    GenSmem S = gen_carve(smem_raw, p.ns, p.nt);
-    gen_load_model(blob, L, S, p.ns, p.nt);
+    GenSmem S = gen_setup(p, smem_raw, blob, L);
     gen_run_chunk(p, S, sc[2], sc[3], blockIdx.x, GEN_SPEC);
 }
 
@@ -212,8 +237,7 @@ __global__ void __launch_bounds__(1024) gen_vit_verify_fwd(GenParams p, const ch
     int repaired = 0;
     if (any) {
         const double *sc = (const double *)(blob + L.scal);
-        GenSmem S = gen_carve(smem_raw, p.ns, p.nt);
-        gen_load_model(blob, L, S, p.ns, p.nt);
+        GenSmem S = gen_setup(p, smem_raw, blob, L);
         bool prev_rerun = false;
         for (int k = 1; k < p.nchunks; k++) {
             bool need = __ldcg(p.flag + k) != 0;
@@ -247,8 +271,23 @@ __device__ void gen_trace_chunk(const GenParams &p, int c, int64_t t_hi, int cur
         if (t_hi == e) look_s = cur;
     }
     __syncthreads();
+    if (tile == 0) {
+        // models with many multi-predecessor states (rows of decbp too long to stage): one thread follows the
+        // backpointers straight from global memory -- inside a chain the predecessor is static, no load
+        if (threadIdx.x == 0) {
+            int cs = cur_s;
+            for (int64_t t = t_hi; t > s; t--) {  // step t -> state at t - 1
+                const int slot = dec[cs];
+                cs = slot >= 0 ? p.decbp[(size_t)t * p.ndec + slot] : sp[cs];
+                if (t - 1 < e) p.x[t - 1] = (int16_t)(cs + 1);
+                if (t - 1 == e) look_s = cs;
+            }
+            cur_s = cs;
+        }
+        __syncthreads();
+    }
     // steps t in (s, t_hi], processed in tiles [a, b]: the backpointer of step t gives the state at t - 1
-    for (int64_t b = t_hi; b > s; b -= tile) {
+    for (int64_t b = t_hi; tile > 0 && b > s; b -= tile) {
         int64_t a = b - tile + 1;
         if (a < s + 1) a = s + 1;
         const int n = (int)(b - a + 1);
@@ -290,7 +329,7 @@ __device__ void gen_trace_tables(const char *blob, const FaithfulLayout &L, int 
 __global__ void gen_vit_trace(GenParams p, const char *blob, FaithfulLayout L, int tile) {
     extern __shared__ __align__(16) char smem_raw[];
     int16_t *bpt = (int16_t *)smem_raw, *xt = bpt + (size_t)tile * p.ndec, *dec = xt + tile, *sp = dec + p.ns;
-    gen_trace_tables(blob, L, p.ns, dec, sp);
+    gen_trace_tables(blob, L, p.ns, dec, sp);  // (dec_slot < ndec <= nstates <= 32767: both tables fit int16)
     const int c = blockIdx.x;
     const int64_t T = p.T;
     const int64_t s = (int64_t)c * p.Lc;
@@ -364,15 +403,33 @@ int gen_threads(int ns) {
 
 }  // namespace
 
+// Which arrays go to shared memory: in order of how often a step touches them, as long as they fit.
+static int gen_placement(int ns, int64_t nt, size_t budget) {
+    int place = 0;
+    const int order[] = {GP_COLS, GP_M, GP_DEC, GP_PTR, GP_LP, GP_IDX};
+    for (int bit : order)
+        if (gen_smem_bytes(ns, nt, place | bit) <= budget) place |= bit;
+    return place;
+}
+
 bool generic_parallel_supported(const HostModel &M, int64_t T) {
-    return T >= 4096 && gen_smem_bytes(M.nstates, M.ntrans) <= 220 * 1024 && M.nstates <= 32767;
+    (void)T;  // any length: a short sequence is simply one chunk
+    return M.nstates <= 32767;
+}
+// models the sequential per-state engine cannot hold in shared memory (> ~5 000 states) go here at any length
+bool generic_parallel_preferred(const HostModel &M, int64_t T) {
+    return M.nstates <= 32767 && (T >= 4096 || faithful_smem_bytes(M.nstates, M.ntrans) > 227 * 1024);
 }
 
 void generic_parallel_viterbi_run(const double *y_dev, int64_t T, const FaithfulLayout &L, const char *blob_dev,
                                   const HostModel &M0, int16_t *x_dev, double *ll_host, cudaStream_t st, hmm_info *info) {
     Workspace &ws = workspace();
     const int ns = M0.nstates, nt = (int)M0.ntrans, ndec = M0.ndec > 0 ? M0.ndec : 1;
-    const size_t sm = gen_smem_bytes(ns, nt);
+    // HMMCUDA_DEBUG_GEN_SMEM_KB: a smaller shared-memory budget (tests exercise every placement on small models)
+    const char *dbg_kb = getenv("HMMCUDA_DEBUG_GEN_SMEM_KB");
+    const size_t budget = dbg_kb && atoi(dbg_kb) > 0 ? std::min<size_t>(220, (size_t)atoi(dbg_kb)) * 1024 : 220 * 1024;
+    const int place = gen_placement(ns, nt, budget);
+    const size_t sm = gen_smem_bytes(ns, nt, place);
     const int nth = gen_threads(ns);
     HMM_CUDA(cudaFuncSetAttribute(gen_vit_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     HMM_CUDA(cudaFuncSetAttribute(gen_vit_verify_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -392,8 +449,11 @@ void generic_parallel_viterbi_run(const double *y_dev, int64_t T, const Faithful
     if (Lc < 64) Lc = 64;
     int nchunks = (int)((T + Lc - 1) / Lc);
     if (nchunks > 1 && T - (int64_t)(nchunks - 1) * Lc < 2) nchunks--;
+    if (nchunks < 1) nchunks = 1;
+    // traceback: rows of decbp staged in tiles when they are short enough, else followed straight from global memory
     int tile = 2048;
-    while (tile > 64 && (size_t)tile * (ndec + 1) * 2 + (size_t)ns * 4 > 64 * 1024) tile /= 2;
+    while (tile >= 64 && (size_t)tile * (ndec + 1) * 2 + (size_t)ns * 4 > 96 * 1024) tile /= 2;
+    if (tile < 64 || (getenv("HMMCUDA_DEBUG_GEN_DIRECT_TRACE") && atoi(getenv("HMMCUDA_DEBUG_GEN_DIRECT_TRACE")))) tile = 0;
     const size_t sm_tr = (size_t)tile * (ndec + 1) * 2 + (size_t)ns * 4 + 16;
     HMM_CUDA(cudaFuncSetAttribute(gen_vit_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_tr));
     HMM_CUDA(cudaFuncSetAttribute(gen_vit_verify_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_tr));
@@ -410,7 +470,10 @@ void generic_parallel_viterbi_run(const double *y_dev, int64_t T, const Faithful
     const size_t o_sb = carve(sizeof(double) * (size_t)nchunks * ns), o_eb = carve(sizeof(double) * (size_t)nchunks * ns);
     const size_t o_flag = carve(sizeof(int) * (size_t)nchunks * 4), o_cnt = carve(sizeof(int) * 8);
     const size_t o_arr = carve(sizeof(unsigned) * 8), o_xl = carve(64), o_part = carve(sizeof(double) * 1024);
+    const size_t o_col = carve((place & GP_COLS) ? 0 : sizeof(double) * 2 * (size_t)ns * nchunks);
     char *base = (char *)ws.get(Workspace::CHUNKS, off);
+    p.place = place;
+    p.colg = (double *)(base + o_col);
     p.SB = (double *)(base + o_sb);
     p.EB = (double *)(base + o_eb);
     p.flag = (int *)(base + o_flag);

@@ -237,6 +237,9 @@ __device__ __forceinline__ void fir_superwindow(const double *__restrict__ y, in
 }
 
 
+#define HMM_PRAGMA_(x) _Pragma(#x)
+#define HMM_UNROLL_N(n) HMM_PRAGMA_(unroll n)
+
 template <int N, int R, int LPC, int I0 = 0, int I1 = N, typename S = double>
 __device__ __forceinline__ void fir_compute_c(const FirCoef<N, LPC, S> &coef, const double *Bc, const double *ytile,
                                               double *fbuf, int lane, double *nacc = nullptr, double m0 = 0.0,
@@ -266,7 +269,10 @@ __device__ __forceinline__ void fir_compute_c(const FirCoef<N, LPC, S> &coef, co
     // uniform (warp_index_uniform) the compiler indexes the coefficients through uniform registers
     // (LDCU.64 c[0x0][UR+imm]) and the kernel takes 0.38 ms; before that it used register-indexed LDC and took
     // 0.45 ms.  Shared-memory coefficients: 0.52 ms.
-#ifdef HMM_FIR_ROLLED
+    // -DHMM_FIR_GROUPS=g: g groups of R taps per loop iteration (a partly rolled loop: g*3.7 KB body).
+#if defined(HMM_FIR_GROUPS)
+    HMM_UNROLL_N(HMM_FIR_GROUPS)
+#elif defined(HMM_FIR_ROLLED)
 #pragma unroll 1
 #else
 #pragma unroll

@@ -1666,7 +1666,7 @@ __global__ void __launch_bounds__(256)
                  FaithfulLayout L, int ns, int nt, const int16_t *__restrict__ x, int64_t x_stride,
                  double *__restrict__ partial /*[C x gridDim.x]*/, int64_t t_lo, int64_t t_hi, int64_t t_off,
                  int64_t T_glob, unsigned *sync_cnt /*[C x 4], slot 2*/, double *__restrict__ ll_out, int with_p0,
-                 double *res_host, int ch0) {
+                 double *res_host, int ch0, int tables_in_global) {
     // steps t in [t_lo, t_hi) of this (local) buffer; global time = t + t_off, weights use T_glob
     extern __shared__ __align__(16) char llsm[];
     __shared__ int s_flag;
@@ -1674,22 +1674,32 @@ __global__ void __launch_bounds__(256)
     const char *mb = blob + (size_t)ch * blob_stride;
     const double *sc = (const double *)(mb + L.scal);
     const double c_emit = sc[2], inv2s2 = 1.0 / sc[3];
-    double *sm_m = (double *)llsm, *sm_lp = sm_m + ns, *sm_lp1 = sm_lp + nt;
-    int *sm_ptr = (int *)(sm_lp1 + ns), *sm_src = sm_ptr + ns + 1, *sm_pred = sm_src + nt;
-    {
+    // models of many thousand states (generic engine): the tables stay in the model blob (L2), no single-predecessor
+    // shortcut table
+    const double *sm_m, *sm_lp, *sm_lp1 = nullptr;
+    const int *sm_ptr, *sm_src, *sm_pred = nullptr;
+    if (tables_in_global) {
+        sm_m = (const double *)(mb + L.m);
+        sm_lp = (const double *)(mb + L.in_lp);
+        sm_ptr = (const int *)(mb + L.in_ptr);
+        sm_src = (const int *)(mb + L.in_src);
+    } else {
+        double *w_m = (double *)llsm, *w_lp = w_m + ns, *w_lp1 = w_lp + nt;
+        int *w_ptr = (int *)(w_lp1 + ns), *w_src = w_ptr + ns + 1, *w_pred = w_src + nt;
+        sm_m = w_m; sm_lp = w_lp; sm_lp1 = w_lp1; sm_ptr = w_ptr; sm_src = w_src; sm_pred = w_pred;
         const double *gm = (const double *)(mb + L.m), *glp = (const double *)(mb + L.in_lp);
         const int *gp = (const int *)(mb + L.in_ptr), *gs = (const int *)(mb + L.in_src);
         for (int i = threadIdx.x; i < ns; i += blockDim.x) {
-            sm_m[i] = gm[i];
+            w_m[i] = gm[i];
             // states with exactly one predecessor (chain interiors: nearly every non-noise step of a path): one look-up
             const int e0 = gp[i], e1 = gp[i + 1];
-            sm_pred[i] = e1 - e0 == 1 ? gs[e0] : -1;
-            sm_lp1[i] = e1 - e0 == 1 ? glp[e0] : 0.0;
+            w_pred[i] = e1 - e0 == 1 ? gs[e0] : -1;
+            w_lp1[i] = e1 - e0 == 1 ? glp[e0] : 0.0;
         }
-        for (int i = threadIdx.x; i <= ns; i += blockDim.x) sm_ptr[i] = gp[i];
+        for (int i = threadIdx.x; i <= ns; i += blockDim.x) w_ptr[i] = gp[i];
         for (int i = threadIdx.x; i < nt; i += blockDim.x) {
-            sm_lp[i] = glp[i];
-            sm_src[i] = gs[i];
+            w_lp[i] = glp[i];
+            w_src[i] = gs[i];
         }
     }
     __syncthreads();
@@ -1741,7 +1751,7 @@ __global__ void __launch_bounds__(256)
             const int d = xs[k] - 1;
             if (t >= 1 && t < T && t >= t_lo && t < t_hi && t + t_off >= 1) {
                 double lp;
-                if (sm_pred[d] == s)
+                if (sm_pred && sm_pred[d] == s)
                     lp = sm_lp1[d];
                 else {
                     lp = __longlong_as_double(0x7ff8000000000000LL);
@@ -2206,11 +2216,12 @@ void ring_path_ll_run(const double *y_dev, int64_t T, const FaithfulLayout &FL, 
     const int nparts = 592;
     unsigned *cnt = reinterpret_cast<unsigned *>(scratch + nparts);
     HMM_CUDA(cudaMemsetAsync(cnt, 0, 4 * sizeof(unsigned), st));
-    if (ll_smem(M0) > 48 * 1024)  // overlap models (thousands of states) through the generic engine
-        HMM_CUDA(cudaFuncSetAttribute(ring_path_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ll_smem(M0)));
-    ring_path_ll<<<dim3(nparts, 1), 256, ll_smem(M0), st>>>(y_dev, T, T, blob_dev, FL.bytes, FL, M0.nstates,
-                                                            (int)M0.ntrans, x_dev, T, scratch, 0, T, 0, T, cnt, ll_dev, 1,
-                                                            nullptr, 0);
+    const bool in_global = ll_smem(M0) > 200 * 1024;  // (the CLI's overlap models: 10 000+ states)
+    const size_t smb = in_global ? 16 : ll_smem(M0);
+    if (smb > 48 * 1024)  // overlap models (thousands of states) through the generic engine
+        HMM_CUDA(cudaFuncSetAttribute(ring_path_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+    ring_path_ll<<<dim3(nparts, 1), 256, smb, st>>>(y_dev, T, T, blob_dev, FL.bytes, FL, M0.nstates, (int)M0.ntrans, x_dev, T,
+                                                    scratch, 0, T, 0, T, cnt, ll_dev, 1, nullptr, 0, in_global ? 1 : 0);
     HMM_CUDA(cudaGetLastError());
 }
 

@@ -91,10 +91,40 @@ def test_batch_of_channels(hm, O):
         assert np.array_equal(x[:, c], xo) and abs(ll[c] - llo) <= LL_RTOL * abs(llo)
 
 
-def test_short_sequences_are_refused_in_generic_mode_and_fall_back_in_auto(hm, O):
+def test_short_sequences_one_chunk_in_generic_mode_and_sequential_engine_in_auto(hm, O):
     S, lA, mu, sig = _overlap_case(hm, 12, 3000, 3)
-    with pytest.raises(hm.HmmError):
-        hm.viterbi(S, lA, mu, sig, mode="generic")
+    for T in (1, 2, 3000):
+        _check(hm, O, S[:T], lA, mu, sig)
     x, ll, info = hm.viterbi(S, lA, mu, sig, return_info=True)
     xo, llo = O.viterbi(S, lA, mu, sig)
     assert info["engine"] == 1 and np.array_equal(x, xo) and ll == llo
+
+
+@pytest.mark.parametrize("kb,direct", [(150, 0), (70, 1), (40, 0), (4, 1)])
+def test_every_shared_memory_placement(hm, O, monkeypatch, kb, direct):
+    """Models of 10 000+ states keep part of their tables / the score columns in global memory.  A reduced budget
+    (HMMCUDA_DEBUG_GEN_SMEM_KB) walks the 3 600-state reference test model through every placement -- columns in shared
+    memory with the tables in L2, everything in L2 -- and HMMCUDA_DEBUG_GEN_DIRECT_TRACE through the traceback that
+    follows backpointers straight from global memory; forced flags keep the repair paths in play."""
+    S, lA, mu, sig = _overlap_case(hm, 60, 30000, 77)
+    monkeypatch.setenv("HMMCUDA_DEBUG_GEN_SMEM_KB", str(kb))
+    monkeypatch.setenv("HMMCUDA_DEBUG_GEN_DIRECT_TRACE", str(direct))
+    monkeypatch.setenv("HMMCUDA_DEBUG_FLAG_EVERY", "4")
+    info = _check(hm, O, S, lA, mu, sig)
+    assert info["fwd_repaired"] > 0 and info["bwd_repaired"] > 0, info
+
+
+def test_cli_sized_overlap_model_three_templates(hm, O):
+    """src/hmmsort.jl:54 builds an overlap model from up to four templates: three K=60 templates are 10 621 states --
+    beyond what either per-state engine could hold in shared memory before.  Auto mode decodes it on the
+    time-parallel engine (score columns in shared memory, tables in L2) at any length."""
+    K, T = 60, 9000
+    temps = np.stack([hm.create_spike_template(K, 3.0, 0.8, 0.2), hm.create_spike_template(K, 4.0, 0.3, 0.2),
+                      hm.create_spike_template(K, 2.0, 0.5, 0.3)], 1)
+    pp = np.array([0.004, 0.002, 0.003])
+    S = hm.create_signal(T, 0.3, pp, temps, hm.make_rng(11))
+    lA = hm.StateMatrix(3, K, np.log(pp), True)
+    assert lA.nstates == 10621
+    mu = np.asfortranarray(temps)
+    _check(hm, O, S, lA, mu, 0.3, mode="auto")
+    _check(hm, O, S[:2500], lA, mu, 0.3, mode="auto")  # short: still this engine (the sequential one cannot hold it)
