@@ -913,7 +913,10 @@ __global__ void __launch_bounds__(128) em_stats(EmParams p) {
                 const double le = e_in ? cur.vLEe[i] + cur.lame : 0.0;
                 const double ap = cur.vLQ[i] + cur.kap + le - lS;
                 pi[i] = ap > -745.5 ? exp(ap) : 0.0;
-                a_s0[i] += pi[i];
+                // S0tot counts the chains that run their whole length inside the recording; the last L-1 entry times
+                // are added per phase by the finalize kernel (sums of positive terms only: subtracting them from a
+                // total instead cancels catastrophically when a neuron's mass sits at the very end of the recording)
+                if (e_in) a_s0[i] += pi[i];
                 pmax = fmax(pmax, pi[i]);
                 if (has_next) {
                     const double lex = x_in ? cur.vLEx[i] + cur.lamx : 0.0;
@@ -1031,8 +1034,8 @@ __global__ void __launch_bounds__(1024) em_finalize(EmParams p) {
     for (int idx = threadIdx.x; idx < N * L; idx += blockDim.x) {
         const int i = idx / L, sph = idx % L;  // 0-based phase: template row sph+1
         double s0 = tot[4 + N + i], s1 = S1[i * S1_LAGS + sph];
-        // chains entered in the last sph samples (t0 >= T - sph) never reach phase sph
-        for (int k = 0; k < sph; k++) s0 -= pie[i * S1_LAGS + k];
+        // of the chains entered in the last L-1 samples (t0 = T-1-k), those with k >= sph reach phase sph
+        for (int k = sph; k <= L - 2; k++) s0 += pie[i * S1_LAGS + k];
         // chains already running at t = 0 reach phases >= r0; at phase sph they sit on y[sph - r0]
         for (int r0 = 1; r0 <= sph; r0++) {
             const double pi = piv[i * S1_LAGS + r0];
@@ -1116,7 +1119,7 @@ __global__ void __launch_bounds__(1024) em_shard_pack(EmParams p, int first, int
     for (int idx = threadIdx.x; idx < N * L; idx += blockDim.x) {
         const int i = idx / L, sph = idx % L;
         double a0 = 0.0, a1 = 0.0;
-        for (int k = 0; k < sph; k++) a0 -= pie[i * S1_LAGS + k];
+        for (int k = sph; k <= L - 2; k++) a0 += pie[i * S1_LAGS + k];  // (zero unless this is the last shard)
         for (int r0 = 1; r0 <= sph; r0++) {
             const double pi = piv[i * S1_LAGS + r0];
             a0 += pi;

@@ -176,3 +176,23 @@ def test_em_silent_neuron_and_high_snr(hm, O, case_factory, monkeypatch):
     _compare(r_log, o, tol=1e-8)
     assert abs(r_lin[4] - r_log[4]) <= 1e-12 * abs(r_log[4])
     assert np.abs(r_lin[2] - r_log[2]).max() < 1e-10
+
+
+def test_neuron_whose_mass_sits_at_the_end_of_the_recording(hm, O):
+    """tests/golden/em_end_mass_case.npz (N=5, K=80, T=22 477; found by tools/fuzz_parity.py, regenerated by
+    tests/golden/make_end_mass_case.py): a nearly silent neuron (0.17 expected spikes) whose posterior mass sits in a
+    spike cut off by the end of the recording.  The per-phase occupancies S0[i][s] of its late phases are sums over
+    very few entry times; they must be accumulated as sums of positive terms (chains that fit + the last L-1 entry
+    times per phase), never as `total - those that do not reach the phase`, which cancels catastrophically here
+    (mu was off by 1.5).  Checked against the stored oracle step and against the oracle run now."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "em_end_mass_case.npz"))
+    N, K = int(g["N"]), int(g["K"])
+    lA = hm.StateMatrix(N, K, g["lp0"], False)
+    r = hm.em_step(g["S"], lA, np.asfortranarray(g["mu0"]).copy(order="F"), float(g["sigma0"]), mode="ring")
+    o = O.em_step(g["S"], lA, np.asfortranarray(g["mu0"]).copy(order="F"), float(g["sigma0"]))
+    assert np.array_equal(o[0], g["lp"]) and np.array_equal(o[2], g["mu"])  # the oracle still says what the fixture says
+    tol = 1e-9 + 1e-11 * np.exp(-o[0])  # statistics of a neuron with n expected spikes carry 1e-12 T / n (see tools/fuzz_parity.py)
+    assert np.all(np.abs(r[0] - o[0]) <= tol), (r[0], o[0])
+    assert np.all(np.abs(r[2] - o[2]).max(axis=0) <= tol), np.abs(r[2] - o[2]).max(axis=0)
+    assert abs(r[3] - o[3]) < 1e-9 and abs(r[4] - o[4]) <= LL_RTOL * abs(o[4])
