@@ -61,6 +61,16 @@ def _sweep(hm, O, rng, t_end, stats, em_only, max_cases):
                 if not ok:
                     stats["failures"].append(dict(case, mode=mode, mismatches=int(np.sum(x != xo)), ll=ll, llo=llo, info=info))
             hm.set_ring_params(0, 0)
+            # the same recording as time shards (hmm_vshard_*: ghost chunks, boundary exchange, verify rounds)
+            if not em_only and "ring" in modes and T >= 30_000:
+                n_sh = int(rng.integers(2, 6))
+                try:
+                    xs, lls = hm.viterbi_time_sharded(S, lA, mu, sig_m, n_sh)
+                    stats["sharded"] = stats.get("sharded", 0) + 1
+                    if not (np.array_equal(xs, xo) and abs(lls - llo) <= 1e-9 * abs(llo)):
+                        stats["failures"].append(dict(case, mode=f"sharded x{n_sh}", mismatches=int(np.sum(xs != xo)), ll=lls, llo=llo))
+                except hm.HmmArgumentError:
+                    stats["sharded_refused"] = stats.get("sharded_refused", 0) + 1  # span too short for the plan
             if not overlap and T <= 60_000 and rng.random() < 0.5:
                 mu0 = np.asfortranarray(mu.copy())
                 mu0[0, :] = 0.0
