@@ -504,14 +504,13 @@ def em_default_chunking(T: int, n_ranks: int, N: int, K: int) -> Tuple[int, int]
 
 
 def _vectors_agree(a, b, rtol=1e-12, atol=1e-9):
-    """Two boundary vectors describe the same distribution iff they differ by a constant; entries more than 745 below
-    the maximum cannot influence a double.  Returns (ok, constant a - b)."""
+    """Two boundary vectors describe the same distribution iff they differ by a constant.  EVERY finite entry counts,
+    however far below the maximum: a pending chain's entry is multiplied by its own emission product later, which at
+    high SNR is e^(+1000s) (see em_boundary_matches in csrc/ring_em.cu).  Returns (ok, constant a - b)."""
     fa, fb = np.isfinite(a), np.isfinite(b)
-    ra, rb = a - a[fa].max(), b - b[fb].max()
-    live = (ra > -745.0) | (rb > -745.0)
-    if not np.array_equal(fa[live], fb[live]):
+    if not np.array_equal(fa, fb):
         return False, 0.0
-    m = live & fa & fb
+    m = fa
     d = a[m] - b[m]
     c = d[0] if d.size else 0.0
     return bool(np.all(np.abs(d - c) <= atol + rtol * np.abs(b[m]))), float(a[0] - b[0])

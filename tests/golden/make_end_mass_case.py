@@ -13,7 +13,11 @@ import __graft_entry__ as ge  # noqa: E402
 hm = ge.load_package()
 O = ge.load_oracle()
 O.build()
-rng = np.random.default_rng(1)
+# optional arguments: seed N K T output.npz (replays another case of the sweep, e.g. for debugging)
+SEED, WANT, OUT = 1, (5, 80, 22477), None
+if len(sys.argv) >= 6:
+    SEED, WANT, OUT = int(sys.argv[1]), (int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])), sys.argv[5]
+rng = np.random.default_rng(SEED)
 while True:
     overlap = rng.random() < 0.25
     if overlap:
@@ -33,13 +37,17 @@ while True:
     rng.choice([0, 0, 128, 256, 512])
     if not overlap and T <= 60_000:
         rng.random()
-    if (N, K, T) == (5, 80, 22477):
+    if (N, K, T) == WANT:
         break
 temps = np.stack([hm.create_spike_template(K, *p) for p in pars], axis=1)
 S = hm.create_signal(T, sigma, rates, temps, hm.make_rng(seed))
 mu0 = np.asfortranarray(temps * scale)
 mu0[0, :] = 0.0
 lA = hm.StateMatrix(N, K, lp, False)
+if OUT:  # debugging replay: inputs only
+    np.savez_compressed(OUT, S=S, mu0=mu0, lp0=lp, sigma0=sig_m, N=N, K=K)
+    print(OUT)
+    sys.exit(0)
 o = O.em_step(S, lA, mu0.copy(order="F"), sig_m)
 out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "em_end_mass_case.npz")
 np.savez_compressed(out, S=S, mu0=mu0, lp0=lp, sigma0=sig_m, N=N, K=K, lp=o[0], pp=o[1], mu=o[2], sigma=o[3], loglik=o[4])

@@ -196,3 +196,20 @@ def test_neuron_whose_mass_sits_at_the_end_of_the_recording(hm, O):
     assert np.all(np.abs(r[0] - o[0]) <= tol), (r[0], o[0])
     assert np.all(np.abs(r[2] - o[2]).max(axis=0) <= tol), np.abs(r[2] - o[2]).max(axis=0)
     assert abs(r[3] - o[3]) < 1e-9 and abs(r[4] - o[4]) <= LL_RTOL * abs(o[4])
+
+
+def test_high_snr_boundary_is_not_accepted_on_its_large_entries_alone(hm, O):
+    """tests/golden/em_high_snr_boundary_case.npz (N=6, K=81, T=45 482, template amplitudes of 12 sigma; found by
+    tools/fuzz_parity.py seed 5): a chunk boundary falls inside a spike whose pending chain entry is more than e^745
+    above the noise score.  The boundary check used to skip entries that far below the maximum and accepted a
+    speculative start whose noise score had not converged -- log-likelihood off by 1.2e-3, sigma NaN.  Every finite
+    entry is compared now: the chunk is repaired and the step is the oracle's."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "em_high_snr_boundary_case.npz"))
+    N, K = int(g["N"]), int(g["K"])
+    lA = hm.StateMatrix(N, K, g["lp0"], False)
+    out = hm.em_step(g["S"], lA, np.asfortranarray(g["mu0"]).copy(order="F"), float(g["sigma0"]), mode="ring", return_info=True)
+    r, info = out[:5], out[5]
+    assert info["fwd_repaired"] + info["bwd_repaired"] > 0, info  # the default chunking does hit the case
+    assert np.abs(r[0] - g["lp"]).max() < 1e-9 and np.abs(r[2] - g["mu"]).max() < 1e-9
+    assert abs(r[3] - float(g["sigma"])) < 1e-9 and abs(r[4] - float(g["loglik"])) <= LL_RTOL * abs(float(g["loglik"]))

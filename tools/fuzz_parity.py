@@ -88,6 +88,31 @@ def _sweep(hm, O, rng, t_end, stats, em_only, max_cases):
                           and abs(r[3] - o[3]) <= 1e-9 and rel < 1e-9)
                 err = max(float(np.nanmax(np.abs(r[2] - o[2]))), abs(r[3] - o[3]), float(np.abs(r[0] - o[0]).max()))
                 stats["em"] += 1
+                if T >= 20_000:  # the same step over time shards (hmm_emshard_*), against the single-GPU step
+                    import torch
+                    ts = hm.timeshard
+                    n_sh, cl = int(rng.integers(2, 5)), int(rng.choice([1024, 2048, 4096]))
+                    dev = torch.device("cuda", 0)
+                    em = None
+                    try:
+                        spans = ts.shard_plan(T, n_sh, cl, 256)
+                        xs = [torch.from_numpy(np.ascontiguousarray(S[sp[0]:sp[1]])).to(dev) for sp in spans]
+                        em = ts.EmSharded([ts.EmShard(xd.data_ptr(), False, sp, T, cl) for xd, sp in zip(xs, spans)], N, K,
+                                          lA.nstates, dev)
+                        q = em.em_step(lA, mu0.copy(order="F"), sig_m)
+                        stats["em_sharded"] = stats.get("em_sharded", 0) + 1
+                        oks = bool(np.all(np.abs(q[0] - r[0]) <= 10 * tol) and np.all(np.nanmax(np.abs(q[2] - r[2]), axis=0) <= 10 * tol)
+                                   and abs(q[3] - r[3]) <= 1e-8 and abs(q[4] - r[4]) <= 1e-9 * abs(r[4]))
+                        if not oks:
+                            stats["failures"].append(dict(case, mode=f"em sharded x{n_sh} chunk {cl}",
+                                                          lp_err=float(np.abs(q[0] - r[0]).max()),
+                                                          mu_err=np.nanmax(np.abs(q[2] - r[2]), axis=0).tolist(),
+                                                          sigma=[q[3], r[3]], ll=[q[4], r[4]], lp=r[0].tolist()))
+                    except (hm.HmmError, RuntimeError, ValueError) as e:
+                        stats.setdefault("em_sharded_refused", []).append(repr(e)[:120])
+                    finally:
+                        if em is not None:
+                            em.close()
                 if not ok:
                     dmu = np.abs(r[2] - o[2])
                     stats["failures"].append(dict(case, mode="em", err=err, ll_rel=rel, lp_gpu=r[0].tolist(), lp_oracle=o[0].tolist(),
