@@ -163,10 +163,20 @@ void dense_update_run(const double *alpha_dev, const double *beta_dev, const dou
     HMM_CUDA(cudaFuncSetAttribute(dense_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
     dense_update_kernel<<<nblk, threads, smb, st>>>(p);
     HMM_CUDA(cudaGetLastError());
-    std::vector<double> part(pstride * nblk), pp(ns);
+    std::vector<double> part(pstride * nblk), pp(ns), alast(ns);
     HMM_CUDA(cudaMemcpyAsync(part.data(), p.part, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, st));
     HMM_CUDA(cudaMemcpyAsync(pp.data(), p.pp, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
+    HMM_CUDA(cudaMemcpyAsync(alast.data(), alpha_dev + (size_t)(T - 1) * ns, sizeof(double) * ns, cudaMemcpyDeviceToHost, st));
     HMM_CUDA(cudaStreamSynchronize(st));
+    {  // log-likelihood = LSE_j alpha[j,T], accumulated in state order with logsumexpl (src/utils.jl:24-32)
+        double g = -INFINITY;
+        for (int j = 0; j < ns; j++) {
+            const double v = alast[j];
+            if (g == -INFINITY) g = v;
+            else if (v != -INFINITY) g = g > v ? g + std::log1p(std::exp(v - g)) : v + std::log1p(std::exp(g - v));
+        }
+        out.loglik = g;
+    }
     // fixed-order host reduction of the per-CTA partials
     std::vector<double> S(4 * (size_t)ns, 0.0);
     double bb = 0.0;
@@ -212,7 +222,6 @@ void dense_update_run(const double *alpha_dev, const double *beta_dev, const dou
         qq += S0[j];
     }
     out.sigma = std::sqrt(x2 / qq);  // :306-307
-    out.loglik = 0.0;
 }
 
 }  // namespace hmm

@@ -177,3 +177,4 @@ def test_em_step_generic_path_overlap(hm, O):
     assert r[5]["engine"] == 1
     assert np.abs(r[0] - o[0]).max() < 1e-8 and np.abs(r[2] - o[2]).max() < 1e-8
     assert abs(r[3] - o[3]) < 1e-9
+    assert abs(r[4] - o[4]) <= 1e-12 * abs(o[4])  # loglik = LSE_j alpha[j,T] on this path too (found missing by tools/fuzz_wide.py)

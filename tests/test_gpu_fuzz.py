@@ -18,3 +18,12 @@ def test_randomised_sweep_has_no_failures(hm, O, seed):
     stats = fuzz_parity.run(budget=25.0, seed=seed, max_cases=120)
     assert stats["cases"] >= 20 and not stats["failures"], stats["failures"][:3]
     assert stats["generic"] >= 20 and stats["ring"] >= 10
+
+
+def test_wide_sweep_has_no_failures(hm, O):
+    """tools/fuzz_wide.py: dense forward / backward of both engines, batches, three-neuron overlap models, E/M steps
+    of overlap models, the library-side training loop against the oracle's loop, reconstruct / unroll."""
+    import fuzz_wide
+
+    stats = fuzz_wide.run(budget=25.0, seed=21, max_cases=400)
+    assert stats["cases"] >= 50 and not stats["failures"], stats["failures"][:3]
