@@ -2130,7 +2130,10 @@ int hmm_emshard_create(const double *X_local, int32_t x_is_host, int64_t local_b
             fail(HMM_EINVAL, "shard spans must be multiples of chunk_len from local_begin");
         if (first != (local_begin == 0)) fail(HMM_EINVAL, "only the first shard may start at sample 0");
         if (!first && main_begin - local_begin < chunk_len) fail(HMM_EINVAL, "left ghost must be at least one chunk");
-        if (!last && local_end - main_end < chunk_len) fail(HMM_EINVAL, "right ghost must be at least one chunk");
+        // a right ghost clipped by the end of the recording is complete whatever its length (the backward pass starts
+        // from the true end there); it only has to be a chunk of its own for the kernels (>= 256 samples)
+        if (!last && local_end - main_end < chunk_len && !(local_end == T_global && local_end - main_end >= 256))
+            fail(HMM_EINVAL, "right ghost must be at least one chunk (or reach the end of the recording)");
         require_device();
         std::unique_ptr<hmm_emshard> h(new hmm_emshard);
         HMM_CUDA(cudaGetDevice(&h->device));

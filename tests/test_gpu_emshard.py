@@ -54,3 +54,20 @@ def test_sharded_iterations_follow_the_single_gpu_fit(hm, O, case_factory):
             assert np.abs(mu - mu1).max() < FIT_ATOL and abs(sig - sig1) < FIT_ATOL and abs(ll - r[4]) <= 1e-9 * abs(r[4])
     finally:
         em.close()
+
+
+def test_last_shard_of_one_partial_chunk(hm, O, case_factory):
+    """T = 12 chunks + 1000 samples, 7 shards: the last main span ends in a partial chunk, so the shard before the last
+    has a right ghost shorter than a chunk -- complete all the same, because it ends where the recording ends
+    (hmm_emshard_create used to refuse it; tools/fuzz_parity.py ran into that)."""
+    N, K, cl = 3, 40, 4096
+    T = 12 * cl + 1000
+    S, lA, mu0, s0, em, keep = _setup(hm, case_factory, N, K, T, 403, 7, cl)  # 2 chunks per shard, the last one: the partial chunk
+    try:
+        lp, pp, mu, sig, ll = em.em_step(lA, mu0, s0)
+    finally:
+        em.close()
+    o = O.em_step(S, O.OracleStateMatrix(N, K, np.log(np.full(N, 0.01)), False), mu0.copy(order="F"), s0)
+    assert em.last_check is True
+    assert np.abs(lp - o[0]).max() < FIT_ATOL and np.abs(mu - o[2]).max() < FIT_ATOL and abs(sig - o[3]) < FIT_ATOL
+    assert abs(ll - o[4]) <= 1e-9 * abs(o[4]), (ll, o[4])

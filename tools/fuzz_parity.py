@@ -2,6 +2,7 @@
 the ring, generic and sequential engines against the CPU oracle (x identical, ll within 1e-9), plus one E/M step
 (1e-9 per step).  Usage: python tools/fuzz_parity.py [seconds] [seed]."""
 import json
+import os
 import sys
 import time
 
@@ -52,6 +53,14 @@ def _sweep(hm, O, rng, t_end, stats, em_only, max_cases):
             if T > 40_000 and "faithful" in modes:
                 modes.remove("faithful")
             hm.set_ring_params(chunk, warm)
+            # a third of the cases exercise the repair paths: forced flags, or a warm-up of zero (real mis-speculation)
+            dbg = rng.random()
+            os.environ.pop("HMMCUDA_DEBUG_FLAG_EVERY", None)
+            os.environ.pop("HMMCUDA_DEBUG_WARMUP", None)
+            if dbg < 0.2:
+                os.environ["HMMCUDA_DEBUG_FLAG_EVERY"] = str(int(rng.integers(2, 6)))
+            elif dbg < 0.33:
+                os.environ["HMMCUDA_DEBUG_WARMUP"] = "0"
             for mode in modes:
                 x, ll, info = hm.viterbi(S, lA, mu, sig_m, mode=mode, return_info=True)
                 ok = np.array_equal(x, xo) and abs(ll - llo) <= 1e-9 * abs(llo)
@@ -61,6 +70,8 @@ def _sweep(hm, O, rng, t_end, stats, em_only, max_cases):
                 if not ok:
                     stats["failures"].append(dict(case, mode=mode, mismatches=int(np.sum(x != xo)), ll=ll, llo=llo, info=info))
             hm.set_ring_params(0, 0)
+            os.environ.pop("HMMCUDA_DEBUG_FLAG_EVERY", None)
+            os.environ.pop("HMMCUDA_DEBUG_WARMUP", None)
             # the same recording as time shards (hmm_vshard_*: ghost chunks, boundary exchange, verify rounds)
             if not em_only and "ring" in modes and T >= 30_000:
                 n_sh = int(rng.integers(2, 6))
@@ -123,6 +134,8 @@ def _sweep(hm, O, rng, t_end, stats, em_only, max_cases):
         except Exception as e:  # noqa: BLE001
             stats["failures"].append(dict(case, error=repr(e)))
             hm.set_ring_params(0, 0)
+            os.environ.pop("HMMCUDA_DEBUG_FLAG_EVERY", None)
+            os.environ.pop("HMMCUDA_DEBUG_WARMUP", None)
         stats["cases"] += 1
 
 
