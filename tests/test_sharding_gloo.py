@@ -79,6 +79,27 @@ WORKER = textwrap.dedent("""
 """)
 
 
+def test_boundary_vectors_agree_rule(hm):
+    """Shard-level boundary check of the time-sharded E/M step: equal up to a constant over EVERY finite entry.  An entry
+    far below the maximum still counts (at high SNR a pending chain's entry is multiplied by e^(+1000s) later), and the
+    pattern of -inf entries must be the same."""
+    agree = hm.timeshard._vectors_agree
+    a = np.array([0.0, -3.0, -900.0, -np.inf, 5.0])
+    ok, c = agree(a + 7.25, a)
+    assert ok and c == 7.25
+    b = a.copy()
+    b[2] = -870.0  # 900 below the maximum in `a`: used to be ignored
+    assert not agree(a, b)[0]
+    b = a.copy()
+    b[3] = -2000.0  # finite where the other vector has -inf
+    assert not agree(a, b)[0]
+    b = a.copy()
+    b[1] += 1e-6
+    assert not agree(a, b)[0]
+    b[1] = a[1] + 1e-13
+    assert agree(a, b)[0]
+
+
 def test_channel_sharding_world2_gloo(hm, O, tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER.format(root=ROOT))
