@@ -61,6 +61,13 @@ def _sweep(hm, O, rng, t_end, stats, em_only, max_cases):
                 os.environ["HMMCUDA_DEBUG_FLAG_EVERY"] = str(int(rng.integers(2, 6)))
             elif dbg < 0.33:
                 os.environ["HMMCUDA_DEBUG_WARMUP"] = "0"
+            # the generic engine's memory placements (tables / score columns in shared memory or in L2) and its two
+            # traceback forms, as they occur for models of 10 000+ states
+            os.environ.pop("HMMCUDA_DEBUG_GEN_SMEM_KB", None)
+            os.environ.pop("HMMCUDA_DEBUG_GEN_DIRECT_TRACE", None)
+            if rng.random() < 0.4:
+                os.environ["HMMCUDA_DEBUG_GEN_SMEM_KB"] = str(int(rng.choice([3, 8, 16, 32, 64])))
+                os.environ["HMMCUDA_DEBUG_GEN_DIRECT_TRACE"] = str(int(rng.integers(0, 2)))
             for mode in modes:
                 x, ll, info = hm.viterbi(S, lA, mu, sig_m, mode=mode, return_info=True)
                 ok = np.array_equal(x, xo) and abs(ll - llo) <= 1e-9 * abs(llo)
@@ -70,8 +77,8 @@ def _sweep(hm, O, rng, t_end, stats, em_only, max_cases):
                 if not ok:
                     stats["failures"].append(dict(case, mode=mode, mismatches=int(np.sum(x != xo)), ll=ll, llo=llo, info=info))
             hm.set_ring_params(0, 0)
-            os.environ.pop("HMMCUDA_DEBUG_FLAG_EVERY", None)
-            os.environ.pop("HMMCUDA_DEBUG_WARMUP", None)
+            for k in ("HMMCUDA_DEBUG_FLAG_EVERY", "HMMCUDA_DEBUG_WARMUP", "HMMCUDA_DEBUG_GEN_SMEM_KB", "HMMCUDA_DEBUG_GEN_DIRECT_TRACE"):
+                os.environ.pop(k, None)
             # the same recording as time shards (hmm_vshard_*: ghost chunks, boundary exchange, verify rounds)
             if not em_only and "ring" in modes and T >= 30_000:
                 n_sh = int(rng.integers(2, 6))
@@ -134,8 +141,8 @@ def _sweep(hm, O, rng, t_end, stats, em_only, max_cases):
         except Exception as e:  # noqa: BLE001
             stats["failures"].append(dict(case, error=repr(e)))
             hm.set_ring_params(0, 0)
-            os.environ.pop("HMMCUDA_DEBUG_FLAG_EVERY", None)
-            os.environ.pop("HMMCUDA_DEBUG_WARMUP", None)
+            for k in ("HMMCUDA_DEBUG_FLAG_EVERY", "HMMCUDA_DEBUG_WARMUP", "HMMCUDA_DEBUG_GEN_SMEM_KB", "HMMCUDA_DEBUG_GEN_DIRECT_TRACE"):
+                os.environ.pop(k, None)
         stats["cases"] += 1
 
 
