@@ -1886,9 +1886,9 @@ int hmm_train_run(hmm_train_ctx *ctx, const int16_t *states, int32_t N, int32_t 
         }
         hmm_info acc{}, one{};
         double dev_ms = 0, ker_ms = 0;
+        Timer tall(st);  // (one pair of events for the whole loop: creating them costs microseconds per step)
         for (int it = 0; it < nsteps; it++) {
             double ll = 0;
-            Timer tall(st);
             tall.start();
             em_step_dev(ctx->X_dev, ctx->T, states, N, K, nstates, tr_inout, ntrans, mu_inout, sigma_inout, lp_out, pp_out,
                         &ll, HMM_MODE_AUTO, st, &one);

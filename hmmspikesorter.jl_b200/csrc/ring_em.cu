@@ -1277,28 +1277,51 @@ __global__ void __launch_bounds__(128) fb_dense(EmParams p, const double *Zs, co
 }
 
 // ---------------------------------------------------------------------------
+// cudaFuncSetAttribute costs a few microseconds and the E/M step is launch-latency sensitive: set once per host thread
+// and per (device, value)
+#define EM_SMEM_ATTR(bytes, ...)                                                                                     \
+    do {                                                                                                             \
+        static thread_local size_t set_ = 0;                                                                         \
+        static thread_local int dev_ = -1;                                                                           \
+        int cur_ = 0;                                                                                                \
+        HMM_CUDA(cudaGetDevice(&cur_));                                                                              \
+        if (set_ != (size_t)(bytes) || dev_ != cur_) {                                                               \
+            HMM_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            set_ = (size_t)(bytes);                                                                                  \
+            dev_ = cur_;                                                                                             \
+        }                                                                                                            \
+    } while (0)
+
 // mode: 0 = full E/M step; 1 = forward quantities only; 2 = forward + backward quantities
 // Warps of the forward and of the backward kernel that are co-resident on one SM (the smaller of the two):
 // the chunk count is matched to it so that each pass runs as exactly one wave.
 template <int N, int R>
 static int em_warps_per_sm(const RingLayout &RL) {
     constexpr int WPB = 4;
+    // (asked on every E/M step: the answer depends on the model shape only; one host thread = one device)
+    static thread_local int c_L = -1, c_dev = -1, c_val = 0;
+    int dev = 0;
+    HMM_CUDA(cudaGetDevice(&dev));
+    if (c_L == RL.L && c_dev == dev) return c_val;
     const size_t mdl_d = (RL.hot + 1) & ~1;
     const size_t sm_fwd = sizeof(double) * (mdl_d + (size_t)WPB * EmWarpSmem<N, R>::DOUBLES);
     const size_t sm_bwd = sizeof(double) * (mdl_d + (size_t)WPB * N * RING_Q);
-    HMM_CUDA(cudaFuncSetAttribute(em_forward<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
+    EM_SMEM_ATTR(sm_fwd, em_forward<N, R>);
     int nf = 0, nb = 0;
     HMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nf, em_forward<N, R>, 32 * WPB, sm_fwd));
     HMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, em_backward<N>, 32 * WPB, sm_bwd));
     const int n = nf < nb ? nf : nb;
-    return (n > 0 ? n : 1) * WPB;
+    c_L = RL.L;
+    c_dev = dev;
+    c_val = (n > 0 ? n : 1) * WPB;
+    return c_val;
 }
 
 template <int N, int R, int LPC>
 static void em_fir_launch(EmParams &p, const double *hmdl, cudaStream_t st) {
     constexpr int WPB = 4;
     const size_t sm = sizeof(double) * (((p.RL.hot + 1) & ~1) + (size_t)WPB * EmWarpSmem<N, R>::TILE);
-    HMM_CUDA(cudaFuncSetAttribute(em_fir<N, R, LPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    EM_SMEM_ATTR(sm, em_fir<N, R, LPC>);
     FirCoef<N, LPC> coef{};
     if (LPC > 0)
         for (int r = 0; r < LPC; r++)
@@ -1347,13 +1370,13 @@ static void em_launch(EmParams &p, const double *hmdl, cudaStream_t st, hmm_info
     const size_t sm_bwd = sizeof(double) * (mdl_d + (size_t)WPB * N * RING_Q);
     const size_t sm_stats = sizeof(double) * std::max<size_t>((size_t)WPB * (160 + N * 32), (size_t)WPB * p.pstride);
     const size_t sm_fin = sizeof(double) * ((size_t)p.pstride + std::max<size_t>(3 * (size_t)N * S1_LAGS, 4 * (size_t)p.pstride));
-    HMM_CUDA(cudaFuncSetAttribute(em_forward<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fwd));
-    HMM_CUDA(cudaFuncSetAttribute(em_stats<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_stats));
+    EM_SMEM_ATTR(sm_fwd, em_forward<N, R>);
+    EM_SMEM_ATTR(sm_stats, em_stats<N>);
     const int gridc = (p.nchunks + WPB - 1) / WPB;
     const int gchk = (p.nchunks * 32 + 127) / 128;
     const int dirs = mode != 1 ? 3 : 1;  // bit 0 forward, bit 1 backward
     const size_t sm_rep = sizeof(double) * (mdl_d + (size_t)N * RING_Q + EM_SCAN_SMEM);
-    HMM_CUDA(cudaFuncSetAttribute(em_fixup<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rep));
+    EM_SMEM_ATTR(sm_rep, em_fixup<N, R>);
     // FIR pass first: F_i(t0) for every sample, consumed by both recursions and by the statistics pass
     if (N >= 3 && N <= 5 && p.RL.L == 59)
         em_fir_launch<N, R, (N >= 3 && N <= 5) ? 59 : 0>(p, hmdl, st);
@@ -1385,7 +1408,7 @@ static void em_launch(EmParams &p, const double *hmdl, cudaStream_t st, hmm_info
     } else if (mode == 0) {
         em_stats<N><<<p.nblk, 32 * WPB, sm_stats, st>>>(p);
         tm.mark("stats", st);
-        HMM_CUDA(cudaFuncSetAttribute(em_finalize<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_fin));
+        EM_SMEM_ATTR(sm_fin, em_finalize<N>);
         em_reduce<<<(p.pstride + 31) / 32, 1024, 0, st>>>(p);
         tm.mark("reduce", st);
         em_finalize<N><<<1, 1024, sm_fin, st>>>(p);

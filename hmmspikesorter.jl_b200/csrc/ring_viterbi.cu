@@ -1912,7 +1912,25 @@ static void stage_verify_trace(VitParams &p, int C, cudaStream_t st) {
 // (N, LP) -> kernel variant.  LPC > 0: FIR coefficients as constant-bank operands
 // (single channel per launch; K = 48 and K = 60 models); LPC = 0: generic, coefficients
 // in shared memory (any K <= 97, any number of channels per launch).
+// Traceback warps that are resident on the whole device at once (one chunk per warp).
+template <int N>
+static int trace_slots_dev() {
+    static thread_local int c_dev = -1, c_val = 0;
+    int dev = 0;
+    HMM_CUDA(cudaGetDevice(&dev));
+    if (dev == c_dev) return c_val;
+    int sms = 148, nb = 1;
+    const size_t smb = sizeof(uint32_t) * 4 * TR_WARP_U32;
+    HMM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    HMM_CUDA(cudaFuncSetAttribute(ring_vit_trace<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smb));
+    HMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ring_vit_trace<N>, 128, smb));
+    c_dev = dev;
+    c_val = sms * (nb > 0 ? nb : 1) * 4;
+    return c_val;
+}
+
 struct VitVariant {
+    int (*trace_slots)();
     int (*warps_per_sm)(const RingLayout &);
     void (*prepare)(const VitParams &);
     void (*forward)(VitParams &, const double *, int, cudaStream_t, Timer *);
@@ -1922,7 +1940,7 @@ struct VitVariant {
 };
 template <int N, int R, int LPC, typename S>
 static VitVariant make_variant_s() {
-    return VitVariant{&fwd_warps_per_sm<N, R, LPC, S>, &stage_prepare<N, R, LPC, S>, &stage_forward<N, R, LPC, S>,
+    return VitVariant{&trace_slots_dev<N>, &fwd_warps_per_sm<N, R, LPC, S>, &stage_prepare<N, R, LPC, S>, &stage_forward<N, R, LPC, S>,
                       &stage_verify_fwd<N, R, LPC, S>, &stage_trace<N, R, LPC, S>, &stage_verify_trace<N, R, LPC, S>};
 }
 static thread_local bool t_pick_f32 = false;  // set by pick_variant for the helpers below
@@ -2077,14 +2095,32 @@ void VitPlan::build(const double *y_dev, int64_t T, int64_t y_stride, int C_, co
     // Traceback chunks: a divisor of the forward chunk that is a multiple of 32 steps (mask-word alignment) and
     // at least max(1024, 2 W) -- the longest one of at most 4096 steps, else the shortest admissible one -- the walk is latency-bound per warp, so it
     // wants several times more chunks than the forward pass has.
+    // Among the admissible lengths of at most 8192 steps (one staging tile) the one whose chunk count fills whole
+    // waves of resident warps best wins: estimated time = waves x (length + look-ahead).  (At config 2 a third of the
+    // forward chunk -- 3 516 chunks, one wave of 3 552 warps -- beats a quarter -- 4 688 chunks, 1.3 waves -- by 17 us.)
     int tfac = 1;
-    for (int64_t f = 2; f <= 64; f++) {  // f ascending = sub-chunk length descending
-        if (Lc % f) continue;
-        const int64_t lt = Lc / f;
-        if (lt < 1024 || lt < 2 * W) break;
-        if (lt % 32) continue;
-        tfac = (int)f;             // the finest admissible split so far ...
-        if (lt <= 4096) break;     // ... and fine enough
+    {
+        const int64_t slots = std::max<int64_t>(1, (int64_t)impl->variant.trace_slots());
+        const int64_t launches_C = per_channel ? 1 : C_;  // channels per traceback launch
+        double best = 0.0;
+        bool have = false;
+        int f_last = 1;
+        for (int64_t f = 1; f <= 64; f++) {  // f ascending = sub-chunk length descending
+            if (Lc % f) continue;
+            const int64_t lt = Lc / f;
+            if (f > 1 && (lt < 1024 || lt < 2 * W)) break;
+            if (lt % 32) continue;
+            f_last = (int)f;
+            if (lt > 8192) continue;
+            const int64_t n_t = launches_C * ((T + lt - 1) / lt);
+            const double cost = (double)((n_t + slots - 1) / slots) * (double)(lt + W);
+            if (!have || cost < best * 0.98) {  // prefer the longer chunk unless a finer split is clearly better
+                best = cost;
+                tfac = (int)f;
+                have = true;
+            }
+        }
+        if (!have) tfac = f_last;  // nothing of at most 8192 steps divides the forward chunk: the shortest admissible one
     }
     const int64_t Lc_t = Lc / tfac;
     const int nchunks_t = (int)((T + Lc_t - 1) / Lc_t);
