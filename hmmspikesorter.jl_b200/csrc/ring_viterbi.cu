@@ -1578,8 +1578,11 @@ __device__ __forceinline__ long long state_from_xend(int j, int64_t T, int L) {
     return enc_spike(T - sph, i);
 }
 
+#ifndef HMM_TRACE_MIN_CTAS
+#define HMM_TRACE_MIN_CTAS 1
+#endif
 template <int N>
-__global__ void __launch_bounds__(128) ring_vit_trace(VitParams p) {
+__global__ void __launch_bounds__(128, HMM_TRACE_MIN_CTAS) ring_vit_trace(VitParams p) {
     extern __shared__ __align__(16) uint32_t trsm[];
     const int ch = blockIdx.y + p.ch0;
     const int warp = warp_index_uniform();
