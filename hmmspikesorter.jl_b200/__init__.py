@@ -32,7 +32,7 @@ from .timeshard import viterbi_time_sharded
 __all__ = [
     "StateMatrix", "viterbi", "viterbi_batch", "forward", "backward", "update", "train_model", "em_step",
     "reconstruct_signal", "unroll_mlseq", "TrainContext", "create_signal", "create_spike_template", "make_rng",
-    "HmmError", "HmmArgumentError", "device_count", "set_ring_params", "set_devices", "set_precision", "viterbi_f32", "viterbi_rawfile", "save_sort_result", "viterbi_time_sharded",
+    "HmmError", "HmmArgumentError", "device_count", "set_ring_params", "set_devices", "set_precision", "viterbi_f32", "viterbi_rawfile", "save_sort_result", "viterbi_time_sharded", "transition_weights",
 ]
 
 i64, i32, f64 = C.c_int64, C.c_int32, C.c_double
@@ -207,6 +207,19 @@ def backward(V, lA, mu, sigma):
 def _rebuild(lA, lp, pp):
     # src/baumwelch.jl:265: StateMatrix(lA.states .- 1, pp, K, xb[2:end]; allow_overlaps=lA.resolve_overlaps)
     return StateMatrix.from_states(lA.states, pp, lA.K, lp, lA.resolve_overlaps)
+
+
+def transition_weights(lA, lp):
+    """Transition records of `lA` with the weights a new `lp` gives them (hmm_transition_weights: the weight part of the
+    StateMatrix rebuild, src/types.jl:94-127; host arithmetic, no device needed).  Returns None when a weight would
+    not be finite (the set of transitions changes: run the constructor)."""
+    st = np.asfortranarray(lA.states, dtype=np.int16)
+    tr = np.ascontiguousarray(lA.transitions).copy()
+    lp = np.ascontiguousarray(lp, dtype=np.float64)
+    ok = i32(0)
+    check(lib().hmm_transition_weights(_p(st), i32(lA.N), i32(lA.nstates), _p(tr), i64(tr.size), _p(lp), i32(lp.size),
+                                       C.byref(ok)))
+    return tr if ok.value else None
 
 
 def _nxi(lA):

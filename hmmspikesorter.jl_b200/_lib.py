@@ -48,7 +48,7 @@ EXPORTS = [
     "hmm_version", "hmm_last_error", "hmm_device_count", "hmm_set_device", "hmm_get_device", "hmm_set_ring_params",
     "hmm_viterbi_f64", "hmm_viterbi_ex_f64", "hmm_viterbi_batch_f64", "hmm_viterbi_dev_f64",
     "hmm_forward_f64", "hmm_backward_f64", "hmm_update_f64", "hmm_em_step_f64", "hmm_em_step_ex_f64",
-    "hmm_train_create", "hmm_train_create_dev", "hmm_train_em_step", "hmm_train_run", "hmm_train_destroy",
+    "hmm_train_create", "hmm_train_create_dev", "hmm_train_em_step", "hmm_train_run", "hmm_transition_weights", "hmm_train_destroy",
     "hmm_reconstruct_f64", "hmm_reconstruct_dev_f64", "hmm_unroll_mlseq_i16", "hmm_host_alloc", "hmm_host_free",
     "hmm_vshard_chunking", "hmm_vshard_create", "hmm_vshard_bvec", "hmm_vshard_forward", "hmm_vshard_fwd_boundary_get",
     "hmm_vshard_fwd_boundary_set", "hmm_vshard_fwd_verify", "hmm_vshard_trace", "hmm_vshard_trace_boundary_get",

@@ -1857,6 +1857,54 @@ int hmm_train_em_step(hmm_train_ctx *ctx, const int16_t *states, int32_t N, int3
     });
 }
 
+// Weights of an unchanged set of transitions from a new lp vector (src/types.jl:94-127): per transition and neuron the
+// term is lpz (silent -> silent), lp[i] (silent -> first phase) or 0 (advance / return), added in neuron order like
+// `lpt += ...`; lpz = log1p(-exp(sum(lp))) over the WHOLE vector (left-to-right sum).  Host arithmetic only.
+static void transition_term_codes(const int16_t *states, int N, int nstates, const hmm_trans *tr, int64_t ntrans,
+                                  std::vector<unsigned char> &code) {
+    code.resize((size_t)ntrans * N);
+    for (int64_t e = 0; e < ntrans; e++) {
+        const int64_t a = tr[e].src - 1, b = tr[e].dst - 1;
+        if (a < 0 || a >= nstates || b < 0 || b >= nstates) fail(HMM_EINVAL, "transition %lld out of range", (long long)e);
+        for (int i = 0; i < N; i++) {
+            const int s1 = states[(size_t)a * N + i], s2 = states[(size_t)b * N + i];
+            code[(size_t)e * N + i] = (s1 == 1 && s2 == 1) ? 0 : (s1 == 1 && s2 == 2) ? 1 : 2;  // phases are 1-based, 1 = silent
+        }
+    }
+}
+// false (and tr untouched) if a weight is not finite: the set of finite transitions would change
+static bool transition_weights_from_lp(const std::vector<unsigned char> &code, int N, const double *lp, int nlp,
+                                       hmm_trans *tr, int64_t ntrans, std::vector<double> &tmp) {
+    double sum = 0.0;
+    for (int k = 0; k < nlp; k++) sum = k == 0 ? lp[0] : sum + lp[k];
+    const double lpz = log1p(-exp(sum));
+    if (!std::isfinite(lpz)) return false;
+    tmp.resize((size_t)ntrans);
+    for (int64_t e = 0; e < ntrans; e++) {
+        double w = 0.0;
+        for (int i = 0; i < N; i++) {
+            const unsigned char c = code[(size_t)e * N + i];
+            w += c == 0 ? lpz : c == 1 ? lp[i] : 0.0;
+        }
+        if (!std::isfinite(w)) return false;
+        tmp[(size_t)e] = w;
+    }
+    for (int64_t e = 0; e < ntrans; e++) tr[e].lp = tmp[(size_t)e];
+    return true;
+}
+
+int hmm_transition_weights(const int16_t *states, int32_t N, int32_t nstates, hmm_trans *tr_inout, int64_t ntrans,
+                           const double *lp, int32_t nlp, int32_t *all_finite) {
+    return guarded([&] {
+        if (!states || !tr_inout || !lp || nlp < N || N < 1) fail(HMM_EINVAL, "null argument or lp shorter than N");
+        std::vector<unsigned char> code;
+        std::vector<double> tmp;
+        transition_term_codes(states, N, nstates, tr_inout, ntrans, code);
+        const bool ok = transition_weights_from_lp(code, N, lp, nlp, tr_inout, ntrans, tmp);
+        if (all_finite) *all_finite = ok ? 1 : 0;
+    });
+}
+
 // The E/M loop of src/baumwelch.jl:325-335 in one call (no callback between the steps): each step's lp goes
 // straight into the next step's transition weights -- the StateMatrix rebuild of src/baumwelch.jl:265 /
 // src/types.jl:94-127 restricted to what it can change, the WEIGHTS: which transitions are finite depends on the
@@ -1874,16 +1922,9 @@ int hmm_train_run(hmm_train_ctx *ctx, const int16_t *states, int32_t N, int32_t 
         if (nsteps < 0 || nlp < N) fail(HMM_EINVAL, "nsteps must be >= 0 and lp_out must hold at least N entries");
         require_device();
         cudaStream_t st = main_stream();
-        // term codes per (transition, neuron): 0 -> lpz, 1 -> lp[i], 2 -> 0.0
-        std::vector<unsigned char> code((size_t)ntrans * N);
-        for (int64_t e = 0; e < ntrans; e++) {
-            const int a = tr_inout[e].src - 1, b = tr_inout[e].dst - 1;
-            if (a < 0 || a >= nstates || b < 0 || b >= nstates) fail(HMM_EINVAL, "transition %lld out of range", (long long)e);
-            for (int i = 0; i < N; i++) {
-                const int s1 = states[(size_t)a * N + i], s2 = states[(size_t)b * N + i];
-                code[(size_t)e * N + i] = (s1 == 1 && s2 == 1) ? 0 : (s1 == 1 && s2 == 2) ? 1 : 2;  // phases are 1-based, 1 = silent
-            }
-        }
+        std::vector<unsigned char> code;  // term codes per (transition, neuron): 0 -> lpz, 1 -> lp[i], 2 -> 0.0
+        std::vector<double> wtmp;
+        transition_term_codes(states, N, nstates, tr_inout, ntrans, code);
         hmm_info acc{}, one{};
         double dev_ms = 0, ker_ms = 0;
         Timer tall(st);  // (one pair of events for the whole loop: creating them costs microseconds per step)
@@ -1904,20 +1945,7 @@ int hmm_train_run(hmm_train_ctx *ctx, const int16_t *states, int32_t N, int32_t 
             memset(&one, 0, sizeof one);
             if (loglik_out) loglik_out[it] = ll;
             if (steps_done) *steps_done = it + 1;
-            double sum = 0.0;
-            for (int k = 0; k < nlp; k++) sum = k == 0 ? lp_out[0] : sum + lp_out[k];
-            const double lpz = log1p(-exp(sum));
-            bool finite = std::isfinite(lpz);
-            for (int64_t e = 0; e < ntrans && finite; e++) {
-                double w = 0.0;
-                for (int i = 0; i < N; i++) {
-                    const unsigned char c = code[(size_t)e * N + i];
-                    w += c == 0 ? lpz : c == 1 ? lp_out[i] : 0.0;
-                }
-                finite = std::isfinite(w);
-                tr_inout[e].lp = w;
-            }
-            if (!finite) break;
+            if (!transition_weights_from_lp(code, N, lp_out, nlp, tr_inout, ntrans, wtmp)) break;
         }
         if (info) {
             *info = acc;

@@ -302,6 +302,17 @@ int hmm_train_run(hmm_train_ctx *ctx, const int16_t *states, int32_t N, int32_t 
                   double *loglik_out, int32_t nsteps, int32_t *steps_done, hmm_info *info);
 int hmm_train_destroy(hmm_train_ctx *ctx);
 
+/*
+ * Host-only model management helper (no device needed): the WEIGHTS of an unchanged set of transitions for a new lp
+ * vector -- what `StateMatrix(states, pp, K, lp; ...)` (src/types.jl:94-127, called by `update` at
+ * src/baumwelch.jl:265) changes when the state layout stays the same, without its O(nstates^2 N) scan.  Per
+ * transition and neuron the term is lpz = log1p(-exp(sum(lp))) (silent -> silent), lp[i] (silent -> first phase) or 0,
+ * added in neuron order.  *all_finite = 0 (and tr_inout untouched) when a weight would not be finite: the set of
+ * transitions changes and the caller has to run the constructor.  hmm_train_run uses the same routine between steps.
+ */
+int hmm_transition_weights(const int16_t *states, int32_t N, int32_t nstates, hmm_trans *tr_inout, int64_t ntrans,
+                           const double *lp, int32_t nlp, int32_t *all_finite);
+
 /* ---- I/O front-end (src/hmmsort.jl:36-104: data file -> Float64 -> decode -> unrolled sequence) ------------------
  * Decodes C channels of a raw recording FILE without the samples ever passing through a caller array: the file is read
  * block by block into pinned staging by a reader thread, every block crosses PCIe while the next is read, one kernel

@@ -71,3 +71,25 @@ def test_product_does_not_reach_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile", ".jl")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "liboracle" not in txt and "hmm_oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_transition_weights_host_helper_matches_the_constructor(hm, O):
+    """hmm_transition_weights (host only, what hmm_train_run applies between E/M steps): for ring and overlap layouts
+    and random lp it must give the records the StateMatrix constructor builds (src/types.jl:94-127) -- bit for bit
+    those of the oracle's constructor (same libm), within an ulp of log1p those of the numpy mirror -- including lpz
+    over the WHOLE lp vector for overlap models, and refuse a degenerate lp."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    for N, K, overlap in [(3, 12, False), (1, 5, False), (5, 9, False), (2, 7, True), (3, 5, True)]:
+        lA = hm.StateMatrix(N, K, np.log(np.full(N, 0.01)), overlap)
+        nlp = int((lA.transitions["src"] == 1).sum()) - 1
+        for _ in range(5):
+            lp = np.log(rng.uniform(1e-6, 0.05, size=nlp))
+            tr = hm.transition_weights(lA, lp)
+            ref = hm.StateMatrix(N, K, lp, overlap).transitions
+            assert tr is not None and np.array_equal(tr["src"], ref["src"]) and np.array_equal(tr["dst"], ref["dst"])
+            assert np.allclose(tr["lp"], ref["lp"], rtol=1e-14, atol=0)
+            assert np.array_equal(tr["lp"], O.OracleStateMatrix(N, K, lp, overlap).transitions["lp"])
+        lp = np.log(np.full(nlp, 0.01))
+        lp[0] = -np.inf
+        assert hm.transition_weights(lA, lp) is None
