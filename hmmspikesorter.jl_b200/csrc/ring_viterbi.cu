@@ -1623,7 +1623,6 @@ __global__ void __launch_bounds__(128) ring_vit_verify_trace(VitParams p) {
     }
     int any = 0;
     if (!last_cta_of_row_any(p.sync_cnt + ch * 4 + 1, s_flag, bad, &any)) return;
-    const int lane = threadIdx.x & 31;
     int repaired = 0;
     if (any && threadIdx.x < 32) {
         uint32_t *tws = trsm;
