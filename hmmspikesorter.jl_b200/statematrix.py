@@ -89,17 +89,58 @@ def _topology(states0: np.ndarray, K: int, allow_overlaps: bool):
     hit = _TOPOLOGY_CACHE.get(key)
     if hit is not None:
         return hit
+    out = _enumerate_topology(states0, K)
+    if len(_TOPOLOGY_CACHE) > 32:
+        _TOPOLOGY_CACHE.clear()
+    _TOPOLOGY_CACHE[key] = out
+    return out
+
+
+def _enumerate_topology(states0: np.ndarray, K: int):
+    """The finite transitions of a state layout by direct enumeration instead of the reference's O(nstates^2 N) scan of
+    all pairs (src/types.jl:114-127; 45 s in numpy for the CLI's 21 123-state model, 13 M checks for the 3 600-state
+    one): from a source state every neuron has one or two admissible next phases -- silent: stay silent or start;
+    active: advance, or return to silence from the last phase (src/types.jl:94-113) -- and a combination is a
+    transition iff it is a state of the layout.  Same records in the same (src, dst) order; `tests/test_oracle.py`
+    compares it with the literal scan."""
+    N, n = states0.shape
+    cols = [tuple(int(v) for v in states0[:, j]) for j in range(n)]
+    index = {c: j for j, c in enumerate(cols)}
+    src, dst, codes = [], [], []
+    for j, c in enumerate(cols):
+        combos = [((), ())]
+        for s1 in c:
+            if s1 == 0:
+                opts = ((0, 0), (1, 1))
+            elif s1 == K - 1:
+                opts = ((0, 2),)
+            else:
+                opts = ((s1 + 1, 2),)
+            combos = [(st + (s2,), cd + (code,)) for st, cd in combos for s2, code in opts]
+        found = []
+        for st, cd in combos:
+            k = index.get(st)
+            if k is not None:
+                found.append((k, cd))
+        found.sort(key=lambda q: q[0])
+        for k, cd in found:
+            src.append(j)
+            dst.append(k)
+            codes.append(cd)
+    return (np.asarray(src, dtype=np.int64) + 1, np.asarray(dst, dtype=np.int64) + 1,
+            np.asarray(codes, dtype=np.int8).reshape(len(src), N))
+
+
+def _scan_topology(states0: np.ndarray, K: int):
+    """The same by the literal all-pairs scan (kept for the cross-check)."""
+    N = states0.shape[0]
     tr = get_valid_transitions(states0, K, np.full(N, np.log(0.5 / max(N, 1))))
     src = tr["src"].astype(np.int64) - 1
     dst = tr["dst"].astype(np.int64) - 1
     s1 = states0[:, src].astype(np.int32).T  # [ntrans, N]
     s2 = states0[:, dst].astype(np.int32).T
     codes = np.where((s1 == 0) & (s2 == 0), 0, np.where((s1 == 0) & (s2 == 1), 1, 2)).astype(np.int8)
-    out = (tr["src"].copy(), tr["dst"].copy(), codes)
-    if len(_TOPOLOGY_CACHE) > 32:
-        _TOPOLOGY_CACHE.clear()
-    _TOPOLOGY_CACHE[key] = out
-    return out
+    return tr["src"].copy(), tr["dst"].copy(), codes
 
 
 def transitions_fast(states0: np.ndarray, K: int, lp, allow_overlaps: bool) -> np.ndarray:

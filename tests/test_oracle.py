@@ -325,3 +325,20 @@ def test_overlap_rebuild_uses_the_full_lp_vector(hm, O):
     # the truncated sum (first N entries only) gives different noise->noise weights: the test can tell
     trunc = np.log1p(-np.exp(lp3[:N].sum()))
     assert got_h["lp"][0] != N * trunc
+
+
+@pytest.mark.parametrize("N,K,overlap", [(1, 2, False), (1, 5, False), (3, 12, False), (7, 9, False), (2, 2, True), (2, 7, True),
+                                         (3, 5, True), (4, 4, True), (3, 2, True), (2, 24, True)])
+def test_transition_enumeration_equals_the_all_pairs_scan(hm, O, N, K, overlap):
+    """The host mirror finds the finite transitions of a layout by enumerating each state's admissible successors
+    instead of testing all pairs (src/types.jl:114-127 is O(nstates^2 N): 45 s in numpy for the CLI's 21 123-state
+    model).  Same records, same order, as the literal scan and as the oracle's constructor."""
+    sm = hm.statematrix
+    st0 = sm.generate_states(N, K, overlap)
+    a, b = sm._enumerate_topology(st0, K), sm._scan_topology(st0, K)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    lp = np.log(np.linspace(0.002, 0.01, N))
+    tr = hm.StateMatrix(N, K, lp, overlap).transitions
+    tro = O.OracleStateMatrix(N, K, lp, overlap).transitions
+    assert np.array_equal(tr["src"], tro["src"]) and np.array_equal(tr["dst"], tro["dst"])
+    assert np.allclose(tr["lp"], tro["lp"], rtol=1e-14, atol=0)
