@@ -128,3 +128,17 @@ def test_cli_sized_overlap_model_three_templates(hm, O):
     mu = np.asfortranarray(temps)
     _check(hm, O, S, lA, mu, 0.3, mode="auto")
     _check(hm, O, S[:2500], lA, mu, 0.3, mode="auto")  # short: still this engine (the sequential one cannot hold it)
+
+
+def test_cli_sized_overlap_model_four_templates(hm, O):
+    """Four K=60 templates with overlaps (src/hmmsort.jl:54, max_templates = 4): 21 123 states.  Neither the score
+    columns nor the tables fit shared memory -- columns in a per-CTA global scratch, tables read from L2, traceback
+    straight from global memory (939 multi-predecessor states)."""
+    K, T = 60, 5000
+    pars = [(3.0, 0.8, 0.2), (4.0, 0.3, 0.2), (2.0, 0.5, 0.3), (2.5, 0.6, 0.25)]
+    temps = np.stack([hm.create_spike_template(K, *p) for p in pars], 1)
+    pp = np.array([0.004, 0.002, 0.003, 0.002])
+    S = hm.create_signal(T, 0.3, pp, temps, hm.make_rng(12))
+    lA = hm.StateMatrix(4, K, np.log(pp), True)
+    assert lA.nstates == 21123
+    _check(hm, O, S, lA, np.asfortranarray(temps), 0.3, mode="auto")
